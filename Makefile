@@ -1,0 +1,26 @@
+# Builds libMiniCVNative.so (sm_100a only) in-tree.  `make` needs nvcc; no GPU required.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function \
+             -cudart static --expt-relaxed-constexpr
+CSRC      := minicv_b200/csrc
+OBJDIR    := build/obj
+LIB       := minicv_b200/lib/libMiniCVNative.so
+SRCS      := $(wildcard $(CSRC)/*.cu)
+OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
+HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/MiniCVNative.h
+
+all: $(LIB)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) $(EXTRA) -c $< -o $@
+
+$(LIB): $(OBJS)
+	@mkdir -p $(dir $(LIB))
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(OBJS) -ldl -lpthread
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all clean

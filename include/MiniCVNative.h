@@ -1,0 +1,161 @@
+/*
+ * MiniCVNative.h -- C ABI of the B200-native drop-in for MiniCV's native library.
+ *
+ * Library identity: the F# layer binds `[<Literal>] lib = "MiniCVNative"`
+ * (reference src/MiniCV/OpenCV.fs:340-341), so this header describes
+ * libMiniCVNative.so.  Symbol convention follows the reference's DllExport macro
+ * (src/MiniCVNative/stdafx.h:20-26): extern "C", default visibility, unmangled,
+ * everything else hidden.  All buffers are caller-allocated and caller-owned; the
+ * callee reads inputs during the call and writes outputs before it returns; no
+ * pointer is retained.  No export throws; failure is 0 / -1 with outputs untouched
+ * (the reference's convention).
+ *
+ * Three groups of exports:
+ *   (1) EXISTING exports on the hot path, re-implemented on the GPU with their
+ *       reference signatures unchanged: cvRecoverPose, cvRecoverPoses, cvFivePoint.
+ *   (2) NEW exports the north-star path needs and the reference does not ship
+ *       (no matcher, no findHomography/findFundamentalMat in the reference):
+ *       cvMatchKnn2*, cvFindHomography*, cvFindFundamentalMat*, batched forms and
+ *       the test-only *WithHypotheses forms used by the parity contract.
+ *   (3) The ten remaining reference exports (PnP, detectors, fiducials, cvTest) are
+ *       out of scope for acceleration; they are forwarded to a side-by-side original
+ *       library so every DllImport keeps resolving.
+ *
+ * There is NO CPU fallback: every compute export returns the failure value and
+ * records an error string (mcvLastError) when no CUDA device is usable.
+ */
+#ifndef MINICV_NATIVE_H
+#define MINICV_NATIVE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_MSC_VER)
+#define MCV_API __declspec(dllexport)
+#else
+#define MCV_API __attribute__((visibility("default")))
+#endif
+
+/* ---- blittable types shared with the F# side -------------------------------- */
+
+/* cv::Point2d / Aardvark V2d: 16 bytes. */
+typedef struct { double X, Y; } McvPoint2d;
+/* cv::Matx33d / Aardvark M33d: 9 doubles, row-major, 72 bytes. */
+typedef struct { double M[9]; } McvMatx33d;
+/* cv::Vec3d / Aardvark V3d: 24 bytes. */
+typedef struct { double V[3]; } McvVec3d;
+
+/* Reference: src/MiniCVNative/MiniCVNative.cpp:39-46 <-> src/MiniCV/OpenCV.fs:16-36.
+ * 40 bytes, sequential, no padding. */
+typedef struct {
+    double     FocalLength;
+    McvPoint2d PrincipalPoint;
+    double     Probability;
+    double     InlierThreshold;
+} RecoverPoseConfig;
+
+/* Reference: src/MiniCVNative/MiniCVNative.h:14-29 (KeyPoint2d, DetectorResult):
+ * the descriptor wire format a matcher consumes. */
+typedef struct {
+    float ptX, ptY;
+    float size;
+    float angle;
+    float response;
+    int   octave;
+    int   class_id;
+} McvKeyPoint2d;
+
+typedef struct {
+    int            PointCount;
+    int            DescriptorEntries;      /* rows * cols of the descriptor Mat  */
+    int            DescriptorElementType;  /* OpenCV depth code: 0 = u8, 5 = f32 */
+    McvKeyPoint2d* Points;
+    uint8_t*       Descriptors;            /* row-major PointCount x descBytes   */
+} McvDetectorResult;
+
+/* OpenCV norm codes accepted by the matcher. */
+enum { MCV_NORM_L2 = 4, MCV_NORM_HAMMING = 6 };
+
+/* RANSAC sampling / termination modes for the batched estimators. */
+enum {
+    MCV_SAMPLE_OPENCV_MWC = 0, /* OpenCV's per-call RNG(-1) multiply-with-carry stream   */
+    MCV_SAMPLE_COUNTER    = 1, /* counter-based hash RNG, one hypothesis per thread      */
+    MCV_SAMPLE_INJECTED   = 2  /* caller supplies the sample index sets                  */
+};
+enum {
+    MCV_STOP_ADAPTIVE = 0,     /* OpenCV's RANSACUpdateNumIters semantics (confidence)   */
+    MCV_STOP_FIXED    = 1      /* score exactly maxIters hypotheses                      */
+};
+
+/* ---- diagnostics ------------------------------------------------------------ */
+
+/* Last error message of the calling thread ("" when none).  Never NULL. */
+MCV_API const char* mcvLastError(void);
+/* Number of usable CUDA devices (0 when none); never throws. */
+MCV_API int mcvDeviceCount(void);
+/* Kernels launched by this library since load (all threads); used by bench.py. */
+MCV_API int64_t mcvKernelLaunchCount(void);
+/* Library build tag: "minicv_b200 sm_100a <date>". */
+MCV_API const char* mcvBuildInfo(void);
+
+/* ---- (2) descriptor matching -------------------------------------------------
+ * New exports (absent in the reference).  Semantics == cv2.BFMatcher(norm)
+ * .knnMatch(query, train, k=2) followed by the Lowe test d1 < ratio*d2 in float32.
+ *   query/train : row-major nQuery/nTrain x descBytes (HAMMING: bytes; L2: descBytes
+ *                 is the row size in BYTES of float32 rows)
+ *   trainIdx    : 2*nQuery ints  (k-th neighbour of query i at [2*i+k]; -1 if absent)
+ *   dist        : 2*nQuery floats (Hamming distance stored as float like DMatch;
+ *                 FLT_MAX if absent)
+ *   ratioPass   : nQuery bytes (1 = passes the ratio test); may be NULL
+ * Returns the number of queries passing the ratio test, or -1 on error. */
+MCV_API int cvMatchKnn2(const uint8_t* query, int nQuery,
+                        const uint8_t* train, int nTrain,
+                        int descBytes, int normType, float ratio,
+                        int* trainIdx, float* dist, uint8_t* ratioPass);
+
+/* Batched form: pair p matches query rows [queryOffsets[p], queryOffsets[p+1]) against
+ * train rows [trainOffsets[p], trainOffsets[p+1]).  Offsets have nPairs+1 entries and
+ * count ROWS.  trainIdx is relative to the pair's own train block.  Outputs are indexed
+ * by global query row.  device = CUDA ordinal (-1: current/default).
+ * Returns total ratio-passing queries or -1. */
+MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
+                             const uint8_t* train, const int64_t* trainOffsets,
+                             int nPairs, int descBytes, int normType, float ratio,
+                             int* trainIdx, float* dist, uint8_t* ratioPass, int device);
+
+/* Same, with every pointer (except the offsets, which stay on the host) already in
+ * device memory of `device` and the work enqueued on CUDA stream `stream`
+ * (cudaStream_t, may be NULL = legacy default stream).  Asynchronous; returns 0 or -1.
+ * Rows must be 16-byte aligned when descBytes is a multiple of 16. */
+MCV_API int cvMatchKnn2BatchDevice(const uint8_t* dQuery, const int64_t* queryOffsets,
+                                   const uint8_t* dTrain, const int64_t* trainOffsets,
+                                   int nPairs, int descBytes, int normType, float ratio,
+                                   int* dTrainIdx, float* dDist, uint8_t* dRatioPass,
+                                   int device, void* stream);
+
+/* Matcher over two detector results in the reference's own container
+ * (src/MiniCVNative/MiniCVNative.h:23-29) -- SURVEY.md section 8f next-1. */
+MCV_API int cvMatchFeatures(const McvDetectorResult* query, const McvDetectorResult* train,
+                            float ratio, int* trainIdx, float* dist, uint8_t* ratioPass);
+
+/* Sharded large-database matching: local top-2 of
+ * `nQuery` queries against this rank's train shard, emitted as packed keys
+ * (dist << 32) | (globalIdxBase + localIdx), 2 per query (UINT64_MAX if absent);
+ * device pointers, asynchronous on `stream`. */
+MCV_API int cvMatchKnn2ShardKeysDevice(const uint8_t* dQuery, int nQuery,
+                                       const uint8_t* dTrainShard, int nTrainShard,
+                                       int64_t globalIdxBase, int descBytes,
+                                       uint64_t* dKeys, int device, void* stream);
+/* Merge `nShards` gathered key lists ([nShards][nQuery][2], e.g. the ncclAllGather
+ * output) into the global top-2 and apply the ratio test.  Device pointers. */
+MCV_API int cvMergeShardKeysDevice(const uint64_t* dKeys, int nShards, int nQuery, float ratio,
+                                   int64_t* dTrainIdx64, float* dDist, uint8_t* dRatioPass,
+                                   int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINICV_NATIVE_H */

@@ -1,0 +1,9 @@
+"""minicv_b200 -- B200-native match + two-view-estimation path behind MiniCV's native ABI.
+
+The product is ``lib/libMiniCVNative.so`` (C ABI in ``include/MiniCVNative.h``, CUDA kernels
+in ``csrc/``).  This Python package is the host-side mirror of the reference's F# wrappers
+(``src/MiniCV/OpenCV.fs``) used by the tests and the benchmark; it never computes on the CPU.
+"""
+from . import native  # noqa: F401
+from .matching import (KnnResult, NORM_HAMMING, NORM_L2, match_features, match_knn2,  # noqa: F401
+                       match_knn2_batch, match_knn2_batch_device)

@@ -1,0 +1,42 @@
+// knn.cuh -- internal interface of the descriptor kNN (k=2) engines.
+#pragma once
+#include "common.cuh"
+
+namespace mcv {
+
+// What the launcher should emit.
+enum KnnEmit {
+    KNN_EMIT_MATCHES = 0,  // trainIdx(int32) / dist / ratioPass, indices local to the pair
+    KNN_EMIT_KEYS    = 1   // packed u64 keys (dist << 32) | (globalIdxBase + idx), 2 per query
+};
+
+struct KnnArgs {
+    const uint8_t* dQuery = nullptr;   // device, row-major
+    const uint8_t* dTrain = nullptr;   // device, row-major
+    const int64_t* hQOff = nullptr;    // host, nPairs+1 row offsets
+    const int64_t* hTOff = nullptr;    // host, nPairs+1 row offsets
+    int     nPairs = 0;
+    int     descBytes = 0;
+    float   ratio = 0.f;
+    int     emit = KNN_EMIT_MATCHES;
+    int64_t globalIdxBase = 0;         // KNN_EMIT_KEYS only
+    int*      dTrainIdx = nullptr;     // 2 per query
+    float*    dDist = nullptr;         // 2 per query
+    uint8_t*  dRatioPass = nullptr;    // 1 per query, may be null
+    uint64_t* dKeys = nullptr;         // KNN_EMIT_KEYS: 2 per query
+    int*      dPassCount = nullptr;    // device counter (pre-zeroed by the launcher) or null
+};
+
+// Hamming kNN-2 on the integer pipe (XOR + POPC, shared-memory tiled train set).
+// Asynchronous on `stream`; uses ctx workspaces 0..3 and pinned buffer 0.
+int launch_hamming_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a);
+
+// L2 kNN-2 for float32 descriptors (difference form, fp32).
+int launch_l2_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a);
+
+// Merge nShards x nQuery x 2 packed keys into global top-2 (+ ratio test).
+int launch_merge_keys(Context* ctx, cudaStream_t stream, const uint64_t* dKeys, int nShards,
+                      int nQuery, float ratio, int64_t* dTrainIdx64, float* dDist,
+                      uint8_t* dRatioPass);
+
+}  // namespace mcv

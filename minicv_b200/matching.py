@@ -1,0 +1,133 @@
+"""Descriptor matching -- host-side mirror of the (new) matcher surface of ``MiniCV.OpenCV``.
+
+The reference has no matcher; these wrappers follow the style of its
+F# wrappers (``src/MiniCV/OpenCV.fs:855-920``): allocate outputs, pin arrays, call native,
+return plain arrays.  Inputs are the descriptor blobs ``detectFeatures`` yields
+(``OpenCV.fs:440-535``: row-major ``points x descriptorDimension``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import native
+
+NORM_L2 = 4
+NORM_HAMMING = 6
+
+
+@dataclass
+class KnnResult:
+    train_idx: np.ndarray   # [nq, 2] int32, -1 where the neighbour does not exist
+    distance: np.ndarray    # [nq, 2] float32 (Hamming distances stored as float, like DMatch)
+    ratio_pass: np.ndarray  # [nq] uint8
+    n_pass: int
+
+
+def _rows(a: np.ndarray, norm: int) -> tuple[np.ndarray, int]:
+    if norm == NORM_HAMMING:
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        return a, a.shape[1] if a.ndim == 2 else 0
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, (a.shape[1] * 4 if a.ndim == 2 else 0)
+
+
+def _ptr(a: np.ndarray) -> int:
+    return a.ctypes.data if a.size else 0
+
+
+def match_knn2(query: np.ndarray, train: np.ndarray, ratio: float = 0.8,
+               norm: int = NORM_HAMMING) -> KnnResult:
+    """``BFMatcher(norm).knnMatch(query, train, 2)`` + Lowe ratio test, on the GPU."""
+    lib = native.load()
+    q, db = _rows(query, norm)
+    t, dbt = _rows(train, norm)
+    if t.shape[0] and q.shape[0] and db != dbt:
+        raise ValueError("query/train descriptor sizes differ")
+    nq, nt = q.shape[0], t.shape[0]
+    idx = np.full((nq, 2), -1, dtype=np.int32)
+    dist = np.full((nq, 2), np.finfo(np.float32).max, dtype=np.float32)
+    ok = np.zeros(nq, dtype=np.uint8)
+    n = native.check(lib.cvMatchKnn2(_ptr(q), nq, _ptr(t), nt, db or dbt, norm, ratio,
+                                     _ptr(idx), _ptr(dist), _ptr(ok)), "cvMatchKnn2")
+    return KnnResult(idx, dist, ok, n)
+
+
+def match_knn2_batch(query: np.ndarray, query_offsets, train: np.ndarray, train_offsets,
+                     ratio: float = 0.8, norm: int = NORM_HAMMING, device: int = -1,
+                     out: KnnResult | None = None) -> KnnResult:
+    """Batched matcher over host buffers (pinned buffers make the copies asynchronous).
+
+    ``query_offsets`` / ``train_offsets``: ``nPairs+1`` row offsets.  ``train_idx`` is relative
+    to each pair's own train block."""
+    lib = native.load()
+    q, db = _rows(query, norm)
+    t, dbt = _rows(train, norm)
+    qo = np.ascontiguousarray(query_offsets, dtype=np.int64)
+    to = np.ascontiguousarray(train_offsets, dtype=np.int64)
+    if qo.shape != to.shape or qo.ndim != 1 or qo.size < 1:
+        raise ValueError("offset arrays must both have nPairs+1 entries")
+    n_pairs = qo.size - 1
+    nq = q.shape[0]
+    if out is None:
+        out = KnnResult(np.full((nq, 2), -1, dtype=np.int32),
+                        np.full((nq, 2), np.finfo(np.float32).max, dtype=np.float32),
+                        np.zeros(nq, dtype=np.uint8), 0)
+    out.n_pass = native.check(
+        lib.cvMatchKnn2Batch(_ptr(q), _ptr(qo), _ptr(t), _ptr(to), n_pairs, db or dbt, norm, ratio,
+                             _ptr(out.train_idx), _ptr(out.distance), _ptr(out.ratio_pass), device),
+        "cvMatchKnn2Batch")
+    return out
+
+
+def match_knn2_batch_device(d_query, query_offsets, d_train, train_offsets, desc_bytes: int,
+                            ratio: float, d_train_idx, d_dist, d_ratio_pass, norm: int = NORM_HAMMING,
+                            device: int = -1, stream: int = 0) -> None:
+    """Device-resident batched matcher: arguments are torch CUDA tensors (or raw device
+    pointers as ints); work is enqueued on ``stream`` (a ``cudaStream_t`` as int)."""
+    lib = native.load()
+
+    def dp(x):
+        return x if isinstance(x, int) else (x.data_ptr() if x is not None else 0)
+
+    qo = np.ascontiguousarray(query_offsets, dtype=np.int64)
+    to = np.ascontiguousarray(train_offsets, dtype=np.int64)
+    native.check(
+        lib.cvMatchKnn2BatchDevice(dp(d_query), _ptr(qo), dp(d_train), _ptr(to), qo.size - 1,
+                                   desc_bytes, norm, ratio, dp(d_train_idx), dp(d_dist),
+                                   dp(d_ratio_pass), device, stream),
+        "cvMatchKnn2BatchDevice")
+
+
+def match_features(query_desc: np.ndarray, train_desc: np.ndarray, ratio: float = 0.8) -> KnnResult:
+    """Matcher over two ``DetectorResult`` containers (reference layout
+    ``src/MiniCVNative/MiniCVNative.h:23-29``): u8 blobs match with Hamming, f32 with L2."""
+    lib = native.load()
+
+    def make(a: np.ndarray):
+        if a.dtype == np.uint8:
+            ty = 0
+        elif a.dtype == np.float32:
+            ty = 5
+        else:
+            raise ValueError("descriptors must be uint8 or float32")
+        a = np.ascontiguousarray(a)
+        r = native.DetectorResult()
+        r.PointCount = a.shape[0]
+        r.DescriptorEntries = a.size
+        r.DescriptorElementType = ty
+        r.Points = None
+        r.Descriptors = C.cast(a.ctypes.data, C.POINTER(C.c_uint8)) if a.size else None
+        return r, a
+
+    rq, keep_q = make(query_desc)
+    rt, keep_t = make(train_desc)
+    nq = keep_q.shape[0]
+    idx = np.full((nq, 2), -1, dtype=np.int32)
+    dist = np.full((nq, 2), np.finfo(np.float32).max, dtype=np.float32)
+    ok = np.zeros(nq, dtype=np.uint8)
+    n = native.check(lib.cvMatchFeatures(C.byref(rq), C.byref(rt), ratio, _ptr(idx), _ptr(dist),
+                                         _ptr(ok)), "cvMatchFeatures")
+    return KnnResult(idx, dist, ok, n)

@@ -1,0 +1,108 @@
+"""ctypes binding of libMiniCVNative.so -- the stand-in for MiniCV's F# P/Invoke layer.
+
+Mirrors ``module Native`` of the reference (``src/MiniCV/OpenCV.fs:339-382``): the same
+library name, the same entry-point names, blittable structs passed by pointer.  There is no
+``dotnet`` in this image, so this module plays the role of the managed caller.
+
+The library is built in-tree by ``make`` (see ``__graft_entry__.build``).  Loading fails
+loudly when it is missing; nothing here falls back to a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "libMiniCVNative.so"
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class Point2d(C.Structure):
+    _fields_ = [("X", C.c_double), ("Y", C.c_double)]
+
+
+class Matx33d(C.Structure):
+    _fields_ = [("M", C.c_double * 9)]
+
+
+class Vec3d(C.Structure):
+    _fields_ = [("V", C.c_double * 3)]
+
+
+class RecoverPoseConfig(C.Structure):
+    """Reference: ``src/MiniCVNative/MiniCVNative.cpp:39-46`` / ``OpenCV.fs:16-36`` (40 bytes)."""
+    _fields_ = [("FocalLength", C.c_double), ("PrincipalPoint", Point2d),
+                ("Probability", C.c_double), ("InlierThreshold", C.c_double)]
+
+
+class KeyPoint2d(C.Structure):
+    _fields_ = [("ptX", C.c_float), ("ptY", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int), ("class_id", C.c_int)]
+
+
+class DetectorResult(C.Structure):
+    """Reference: ``src/MiniCVNative/MiniCVNative.h:23-29``."""
+    _fields_ = [("PointCount", C.c_int), ("DescriptorEntries", C.c_int),
+                ("DescriptorElementType", C.c_int), ("Points", C.POINTER(KeyPoint2d)),
+                ("Descriptors", C.POINTER(C.c_uint8))]
+
+
+assert C.sizeof(RecoverPoseConfig) == 40 and C.sizeof(Point2d) == 16
+assert C.sizeof(Matx33d) == 72 and C.sizeof(Vec3d) == 24
+
+_vp, _i, _f, _d, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64
+
+# name -> (restype, argtypes).  Every symbol include/MiniCVNative.h declares is listed here;
+# tests/test_abi.py checks the two stay in step.
+SIGNATURES = {
+    "mcvLastError": (C.c_char_p, []),
+    "mcvDeviceCount": (_i, []),
+    "mcvKernelLaunchCount": (_i64, []),
+    "mcvBuildInfo": (C.c_char_p, []),
+    "cvMatchKnn2": (_i, [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "cvMatchKnn2Batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i]),
+    "cvMatchKnn2BatchDevice": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp]),
+    "cvMatchFeatures": (_i, [C.POINTER(DetectorResult), C.POINTER(DetectorResult), _f, _vp, _vp, _vp]),
+    "cvMatchKnn2ShardKeysDevice": (_i, [_vp, _i, _vp, _i, _i64, _i, _vp, _i, _vp]),
+    "cvMergeShardKeysDevice": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _i, _vp]),
+}
+
+_lib = None
+
+
+def load(path: os.PathLike | str | None = None) -> C.CDLL:
+    """Load libMiniCVNative.so and attach signatures.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else Path(os.environ.get("MINICV_NATIVE_LIB", LIB_PATH))
+    if not p.exists():
+        raise NativeLibraryMissing(
+            f"{p} not found: build it with `make` (or __graft_entry__.build()). "
+            "minicv_b200 has no CPU fallback for the match/estimate path.")
+    lib = C.CDLL(str(p))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means header/library drift
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().mcvLastError().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> int:
+    if rc < 0:
+        raise NativeError(f"{what} failed: {last_error()}")
+    return rc
