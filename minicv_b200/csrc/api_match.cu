@@ -54,11 +54,12 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
                              int descBytes, int normType, float ratio, int* trainIdx, float* dist,
                              uint8_t* ratioPass, int device) {
     clear_error();
-    if (nPairs < 0 || !queryOffsets || !trainOffsets || !trainIdx || !dist) {
+    if (nPairs < 0 || !queryOffsets || !trainOffsets) {
         set_error("cvMatchKnn2Batch: bad arguments");
         return -1;
     }
-    if (nPairs == 0) return 0;
+    if (nPairs == 0 || queryOffsets[nPairs] == 0) return 0;
+    if (!trainIdx || !dist) { set_error("cvMatchKnn2Batch: null output buffers"); return -1; }
     if (check_norm(normType, descBytes)) return -1;
     if (queryOffsets[0] != 0 || trainOffsets[0] != 0) { set_error("offsets must start at 0"); return -1; }
     const int64_t totalQ = queryOffsets[nPairs], totalT = trainOffsets[nPairs];

@@ -63,3 +63,63 @@ def ragged_descriptor_batch(seed: int, n_pairs: int, desc_bytes: int = 32, max_r
     q_off = np.concatenate([[0], np.cumsum(nq)]).astype(np.int64)
     t_off = np.concatenate([[0], np.cumsum(nt)]).astype(np.int64)
     return q, q_off, t, t_off
+
+
+# ---------------------------------------------------------------------------------------------
+# two-view correspondences (C3: homography / fundamental; C4: essential + recoverPose)
+# ---------------------------------------------------------------------------------------------
+H_GT = np.array([[1.02, 0.08, 12.0], [-0.09, 1.03, -7.0], [-1.6e-4, -0.7e-4, 1.0]])
+
+
+def homography_pair(seed: int, n: int = 2000, inlier_frac: float = 0.30, noise: float = 0.5,
+                    jitter: bool = True):
+    """C3 homography pair: src uniform in [0,1000)^2, inliers follow a (per-seed jittered)
+    ground-truth H with N(0, noise px) noise, outliers uniform.  Returns (a, b, gt_inlier, H)."""
+    rng = np.random.default_rng(2000 + seed)
+    H = H_GT.copy()
+    if jitter:
+        H[:2, :2] += rng.normal(0, 0.01, (2, 2))
+        H[:2, 2] += rng.normal(0, 3.0, 2)
+        H[2, :2] += rng.normal(0, 2e-5, 2)
+    a = rng.uniform(0, 1000, (n, 2))
+    ah = np.concatenate([a, np.ones((n, 1))], axis=1) @ H.T
+    b = ah[:, :2] / ah[:, 2:3] + rng.normal(0, noise, (n, 2))
+    n_in = int(round(n * inlier_frac))
+    gt = np.zeros(n, dtype=bool)
+    gt[rng.permutation(n)[:n_in]] = True
+    b[~gt] = rng.uniform(0, 1000, (int((~gt).sum()), 2))
+    return np.ascontiguousarray(a), np.ascontiguousarray(b), gt, H
+
+
+def rodrigues(axis, angle):
+    axis = np.asarray(axis, float)
+    axis = axis / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * (K @ K)
+
+
+def two_view_pair(seed: int, n: int = 2000, inlier_frac: float = 0.30, noise: float = 0.3,
+                  focal: float = 800.0, pp=(320.0, 240.0), normalized: bool = False):
+    """C3(F)/C4(E) pair: 3-D points in [-2,2]^2 x [4,8], second camera rotated 0.15 rad about
+    (0.1,1,0.2) and translated along unit(0.8,0.1,0.2); pixel noise sigma; outliers uniform in
+    the 640x480 image.  normalized=True returns coordinates already divided by the intrinsics
+    (MiniCV's default RecoverPoseConfig{1,(0,0),0.999,0.005}).  Returns (a, b, gt, R, t)."""
+    rng = np.random.default_rng(3000 + seed)
+    R = rodrigues((0.1, 1.0, 0.2), 0.15 + 0.02 * rng.standard_normal())
+    t = np.array([0.8, 0.1, 0.2]) + 0.05 * rng.standard_normal(3)
+    t /= np.linalg.norm(t)
+    X = np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n), rng.uniform(4, 8, n)], axis=1)
+    X2 = X @ R.T + t
+    a = X[:, :2] / X[:, 2:3] * focal + np.asarray(pp)
+    b = X2[:, :2] / X2[:, 2:3] * focal + np.asarray(pp)
+    a = a + rng.normal(0, noise, (n, 2))
+    b = b + rng.normal(0, noise, (n, 2))
+    n_in = int(round(n * inlier_frac))
+    gt = np.zeros(n, dtype=bool)
+    gt[rng.permutation(n)[:n_in]] = True
+    n_out = int((~gt).sum())
+    b[~gt] = np.stack([rng.uniform(0, 640, n_out), rng.uniform(0, 480, n_out)], axis=1)
+    if normalized:
+        a = (a - np.asarray(pp)) / focal
+        b = (b - np.asarray(pp)) / focal
+    return np.ascontiguousarray(a), np.ascontiguousarray(b), gt, R, t
