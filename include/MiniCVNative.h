@@ -155,6 +155,93 @@ MCV_API int cvMergeShardKeysDevice(const uint64_t* dKeys, int nShards, int nQuer
                                    int64_t* dTrainIdx64, float* dDist, uint8_t* dRatioPass,
                                    int device, void* stream);
 
+
+/* ---- (1) existing hot-path exports, re-implemented on the GPU -------------------------
+ * Signatures are the reference's (C++ references are pointers at the ABI).  cvRecoverPoses
+ * returns a C++ bool in the reference, read by .NET as a 4-byte BOOL (no MarshalAs on the
+ * import, src/MiniCV/OpenCV.fs:347): the implementation returns a zero-extended int32 0/1. */
+
+/* Reference: src/MiniCVNative/MiniCVNative.cpp:197-215.  findEssentialMat(RANSAC, prob, thr,
+ * maxIters 1000) -> ms = RANSAC inlier mask (N bytes, 0/1) -> recoverPose -> R, t; returns the
+ * number of points passing the cheirality check.  On failure returns 0, outputs untouched. */
+MCV_API int cvRecoverPose(const RecoverPoseConfig* config, int N, const McvPoint2d* pa,
+                          const McvPoint2d* pb, McvMatx33d* rMat, McvVec3d* tVec, uint8_t* ms);
+
+/* Reference: src/MiniCVNative/MiniCVNative.cpp:165-194.  Same RANSAC; R1, R2, t from
+ * decomposeEssentialMat; false if N < 5 or no unique E. */
+MCV_API int32_t cvRecoverPoses(const RecoverPoseConfig* config, int N, const McvPoint2d* pa,
+                               const McvPoint2d* pb, McvMatx33d* rMat1, McvMatx33d* rMat2,
+                               McvVec3d* tVec, uint8_t* ms);
+
+/* Reference: src/MiniCVNative/MiniCVNative.cpp:368-382 -> fivepoint.cpp:233-339.  All real
+ * essential matrices through 5 correspondences; Es has room for 10; returns the count. */
+MCV_API int cvFivePoint(const McvPoint2d* pa, const McvPoint2d* pb, McvMatx33d* Es);
+
+/* ---- (2) two-view estimation: new exports ---------------------------------------------- */
+
+typedef struct {
+    int32_t  model;        /* 0 homography (4-pt), 1 fundamental (7-pt), 2 essential (5-pt)      */
+    int32_t  sampleMode;   /* MCV_SAMPLE_*                                                        */
+    int32_t  stopMode;     /* MCV_STOP_*                                                          */
+    int32_t  maxIters;     /* hypotheses per pair (OpenCV: maxIters)                              */
+    double   threshold;    /* reprojection / epipolar threshold in the units of the points        */
+    double   confidence;   /* (0,1) exclusive, as OpenCV asserts                                  */
+    uint64_t seed;         /* MCV_SAMPLE_COUNTER only                                             */
+    double   focal, ppx, ppy; /* essential only (findEssentialMat(focal, pp) overload)            */
+    int32_t  refine;       /* homography: 1 = findHomography's refit + 10 LM iterations + re-mask */
+    int32_t  reserved;
+} McvRansacParams;
+
+/* == cv2.findHomography(a, b, RANSAC, thr, maxIters=, confidence=): H (h33 = 1) and mask.
+ * Returns 1 on success, 0 on failure (outputs untouched). */
+MCV_API int cvFindHomography(const McvPoint2d* a, const McvPoint2d* b, int N, double thr,
+                             int maxIters, double conf, McvMatx33d* H, uint8_t* mask);
+/* == cv2.findFundamentalMat(a, b, FM_RANSAC, thr, conf, maxIters): best 7-point model. */
+MCV_API int cvFindFundamentalMat(const McvPoint2d* a, const McvPoint2d* b, int N, double thr,
+                                 double conf, int maxIters, McvMatx33d* F, uint8_t* mask);
+
+/* Batched estimator over packed correspondences: pair p owns rows [offsets[p], offsets[p+1]).
+ * Covers the batched forms and the test-only *WithHypotheses forms of SURVEY.md section 8b:
+ *   injSamples : [nPairs][maxIters][modelPoints] sample indices (MCV_SAMPLE_INJECTED) or NULL
+ *   injModels  : [nPairs][maxIters][9] model matrices scored as given (skips the solver) or NULL
+ * Outputs (host): models [nPairs], masks [total rows], inlierCounts/ok/itersRun [nPairs] and
+ * best [nPairs][2] = (iteration, model index) of the winner; optional parity taps
+ * dbgCounts [nPairs][maxIters][maxModels] (-1 = no model), dbgModels [...][9],
+ * dbgSamples [nPairs][maxIters][modelPoints].  Returns the number of pairs with ok = 1, or -1. */
+MCV_API int cvRansacBatch(const McvRansacParams* prm, const McvPoint2d* a, const McvPoint2d* b,
+                          const int64_t* offsets, int nPairs, const int32_t* injSamples,
+                          const double* injModels, McvMatx33d* models, uint8_t* masks,
+                          int32_t* inlierCounts, uint8_t* ok, int32_t* itersRun, int32_t* best,
+                          int32_t* dbgCounts, double* dbgModels, int32_t* dbgSamples, int device);
+/* Device-resident form (offsets on the host, everything else in device memory; asynchronous). */
+MCV_API int cvRansacBatchDevice(const McvRansacParams* prm, const double* dA, const double* dB,
+                                const int64_t* offsets, int nPairs, double* dModels, uint8_t* dMasks,
+                                int32_t* dInlierCounts, uint8_t* dOk, int device, void* stream);
+
+/* Batched cvRecoverPose (config C4): essential RANSAC + recoverPose per pair.
+ * R [nPairs], t [nPairs], ms [total rows] (RANSAC masks), good [nPairs] (cheirality counts),
+ * ok [nPairs].  Returns pairs with ok = 1, or -1. */
+MCV_API int cvRecoverPoseBatch(const RecoverPoseConfig* config, const McvPoint2d* a,
+                               const McvPoint2d* b, const int64_t* offsets, int nPairs,
+                               int sampleMode, int maxIters, McvMatx33d* R, McvVec3d* t,
+                               uint8_t* ms, int32_t* good, uint8_t* ok, int device);
+MCV_API int cvRecoverPoseBatchDevice(const RecoverPoseConfig* config, const double* dA,
+                                     const double* dB, const int64_t* offsets, int nPairs,
+                                     int sampleMode, int maxIters, double* dE, double* dR, double* dT,
+                                     uint8_t* dMs, int32_t* dGood, uint8_t* dOk, int device,
+                                     void* stream);
+
+/* == cv2.recoverPose(E, a, b, focal=, pp=, mask=) for a given E (parity tap): mask is in/out
+ * (NULL = all points), good4 receives the four candidate counts.  Returns the count. */
+MCV_API int cvRecoverPoseFromE(const McvMatx33d* E, const McvPoint2d* a, const McvPoint2d* b, int N,
+                               double focal, double ppx, double ppy, uint8_t* mask,
+                               McvMatx33d* R, McvVec3d* t, int32_t* good4);
+/* == cv2.decomposeEssentialMat(E). */
+MCV_API int cvDecomposeEssentialMat(const McvMatx33d* E, McvMatx33d* R1, McvMatx33d* R2, McvVec3d* t);
+/* Batched cvFivePoint: nSets x 5 correspondences -> Es [nSets][10], counts [nSets]. */
+MCV_API int cvFivePointBatch(const McvPoint2d* pa, const McvPoint2d* pb, int nSets,
+                             McvMatx33d* Es, int32_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,7 +70,7 @@ struct Context {
     cudaStream_t stream2 = nullptr;      // host->device copy stream (copy/compute overlap)
     cudaStream_t stream3 = nullptr;      // device->host copy stream
     cudaEvent_t  ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DevBuf       ws[24];                 // numbered workspaces, meaning fixed per call site
+    DevBuf       ws[48];                 // numbered workspaces, meaning fixed per call site
     PinBuf       pin[4];
 };
 

@@ -1,0 +1,824 @@
+// cvmath.cuh -- register/local-memory resident numerical building blocks of the two-view
+// estimators, written as __host__ __device__ templates so the SAME source is unit-tested on
+// the host (tests/hostmath, a test-only library) and runs inside the CUDA kernels.
+//
+// What each block mirrors (OpenCV 4.13.0, the un-vendored dependency the reference shim
+// forwards to at src/MiniCVNative/MiniCVNative.cpp:177,186,204,212 and re-uses inside its
+// vendored solver at src/MiniCVNative/fivepoint.cpp:252,297,323):
+//   * Mwc                 cv::RNG (multiply-with-carry), seeded (uint64)-1 per RANSAC call
+//   * jacobi_svd_rows     JacobiSVDImpl_ (one-sided Jacobi + pseudo-random completion); the
+//                         basis/sign conventions of every null space used below come from it
+//   * jacobi_eigen_sym    symmetric eigen-decomposition (cyclic Jacobi)
+//   * scoring functions   bit-exact restatements (explicit _rn intrinsics: no FMA contraction)
+//   * minimal solvers     4-point homography, 7-point fundamental, 5-point essential
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define MCV_HD __host__ __device__ __forceinline__
+#define MCV_HDN __host__ __device__
+#else
+#define MCV_HD inline
+#define MCV_HDN
+#endif
+
+namespace mcv {
+namespace cvm {
+
+// ---- rounding-exact arithmetic (no contraction into FMA on either side) -------------------
+#if defined(__CUDA_ARCH__)
+MCV_HD float  fmul(float a, float b)   { return __fmul_rn(a, b); }
+MCV_HD float  fadd(float a, float b)   { return __fadd_rn(a, b); }
+MCV_HD float  fsub(float a, float b)   { return __fsub_rn(a, b); }
+MCV_HD float  fdiv(float a, float b)   { return __fdiv_rn(a, b); }
+MCV_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+MCV_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+MCV_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+MCV_HD double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+#else
+// host build: compiled without -mfma / with -ffp-contract=off, plain operators are exact
+MCV_HD float  fmul(float a, float b)   { volatile float r = a * b; return r; }
+MCV_HD float  fadd(float a, float b)   { volatile float r = a + b; return r; }
+MCV_HD float  fsub(float a, float b)   { volatile float r = a - b; return r; }
+MCV_HD float  fdiv(float a, float b)   { volatile float r = a / b; return r; }
+MCV_HD double dmul(double a, double b) { volatile double r = a * b; return r; }
+MCV_HD double dadd(double a, double b) { volatile double r = a + b; return r; }
+MCV_HD double dsub(double a, double b) { volatile double r = a - b; return r; }
+MCV_HD double ddiv(double a, double b) { volatile double r = a / b; return r; }
+#endif
+
+// ---- cv::RNG --------------------------------------------------------------------------------
+struct Mwc {
+    uint64_t state;
+    MCV_HD Mwc() : state(0xFFFFFFFFFFFFFFFFull) {}
+    MCV_HD explicit Mwc(uint64_t s) : state(s) {}
+    MCV_HD uint32_t next() {
+        state = (uint64_t)(uint32_t)state * 4164903690ull + (state >> 32);
+        return (uint32_t)state;
+    }
+    MCV_HD int uniform(int n) { return (int)(next() % (uint32_t)n); }
+};
+
+// counter-based generator for the native (non-OpenCV) sampling mode: splitmix64 of the key
+MCV_HD uint64_t mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// RANSACUpdateNumIters (calib3d/src/ptsetreg.cpp)
+MCV_HDN inline int update_num_iters(double p, double ep, int modelPoints, int maxIters) {
+    p = fmax(p, 0.); p = fmin(p, 1.);
+    ep = fmax(ep, 0.); ep = fmin(ep, 1.);
+    double num = fmax(1. - p, DBL_MIN);
+    double denom = 1. - pow(1. - ep, (double)modelPoints);
+    if (denom < DBL_MIN) return 0;
+    num = log(num);
+    denom = log(denom);
+    if (denom >= 0 || -num >= maxIters * (-denom)) return maxIters;
+    return (int)rint(num / denom);   // cvRound: round half to even
+}
+
+// ---- one-sided Jacobi SVD, OpenCV's JacobiSVDImpl_ -----------------------------------------
+// At: N1 rows of length M (row-major, leading dimension M); the first N rows hold the vectors
+// to orthogonalise.  On return rows 0..N1-1 are unit "left" vectors (rows >= N fabricated by
+// OpenCV's fixed pseudo-random completion), W[N] the singular values (descending), Vt (N x N)
+// the accumulated rotations.  WANT_V = false skips Vt.
+template <int M, int N, int N1, bool WANT_V>
+MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
+    const double eps = DBL_EPSILON * 10, minval = DBL_MIN;
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+        for (int k = 0; k < M; ++k) sd += At[i * M + k] * At[i * M + k];
+        W[i] = sd;
+        if (WANT_V) {
+            for (int k = 0; k < N; ++k) Vt[i * N + k] = 0;
+            Vt[i * N + i] = 1;
+        }
+    }
+    const int max_iter = M > 30 ? M : 30;
+    for (int iter = 0; iter < max_iter; ++iter) {
+        bool changed = false;
+        for (int i = 0; i < N - 1; ++i)
+            for (int j = i + 1; j < N; ++j) {
+                double* Ai = At + i * M;
+                double* Aj = At + j * M;
+                double a = W[i], p = 0, b = W[j];
+                for (int k = 0; k < M; ++k) p += Ai[k] * Aj[k];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                double beta = a - b, gamma = hypot(p, beta), c, s;
+                if (beta < 0) {
+                    double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+                a = b = 0;
+                for (int k = 0; k < M; ++k) {
+                    double t0 = c * Ai[k] + s * Aj[k];
+                    double t1 = -s * Ai[k] + c * Aj[k];
+                    Ai[k] = t0; Aj[k] = t1;
+                    a += t0 * t0; b += t1 * t1;
+                }
+                W[i] = a; W[j] = b;
+                changed = true;
+                if (WANT_V) {
+                    double* Vi = Vt + i * N;
+                    double* Vj = Vt + j * N;
+                    for (int k = 0; k < N; ++k) {
+                        double t0 = c * Vi[k] + s * Vj[k];
+                        double t1 = -s * Vi[k] + c * Vj[k];
+                        Vi[k] = t0; Vj[k] = t1;
+                    }
+                }
+            }
+        if (!changed) break;
+    }
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+        for (int k = 0; k < M; ++k) sd += At[i * M + k] * At[i * M + k];
+        W[i] = sqrt(sd);
+    }
+    for (int i = 0; i < N - 1; ++i) {
+        int j = i;
+        for (int k = i + 1; k < N; ++k)
+            if (W[j] < W[k]) j = k;
+        if (i != j) {
+            double t = W[i]; W[i] = W[j]; W[j] = t;
+            for (int k = 0; k < M; ++k) { t = At[i * M + k]; At[i * M + k] = At[j * M + k]; At[j * M + k] = t; }
+            if (WANT_V)
+                for (int k = 0; k < N; ++k) { t = Vt[i * N + k]; Vt[i * N + k] = Vt[j * N + k]; Vt[j * N + k] = t; }
+        }
+    }
+    Mwc rng(0x12345678ull);
+    for (int i = 0; i < N1; ++i) {
+        double sd = i < N ? W[i] : 0;
+        for (int ii = 0; ii < 100 && sd <= minval; ++ii) {
+            const double val0 = 1. / M;
+            for (int k = 0; k < M; ++k) At[i * M + k] = (rng.next() & 256) != 0 ? val0 : -val0;
+            for (int it = 0; it < 2; ++it)
+                for (int j = 0; j < i; ++j) {
+                    sd = 0;
+                    for (int k = 0; k < M; ++k) sd += At[i * M + k] * At[j * M + k];
+                    double asum = 0;
+                    for (int k = 0; k < M; ++k) {
+                        double t = At[i * M + k] - sd * At[j * M + k];
+                        At[i * M + k] = t;
+                        asum += fabs(t);
+                    }
+                    asum = asum > eps * 100 ? 1 / asum : 0;
+                    for (int k = 0; k < M; ++k) At[i * M + k] *= asum;
+                }
+            sd = 0;
+            for (int k = 0; k < M; ++k) sd += At[i * M + k] * At[i * M + k];
+            sd = sqrt(sd);
+        }
+        const double s = sd > minval ? 1 / sd : 0.;
+        for (int k = 0; k < M; ++k) At[i * M + k] *= s;
+    }
+}
+
+// cv::SVD::compute(A, w, u, vt) for a square K x K matrix (row-major).  u and vt row-major.
+template <int K>
+MCV_HDN inline void svd_square(const double* A, double* w, double* u, double* vt) {
+    double At[K * K];
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) At[i * K + j] = A[j * K + i];   // rows of At = columns of A
+    jacobi_svd_rows<K, K, K, true>(At, w, vt);
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) u[j * K + i] = At[i * K + j];   // u = At^T
+}
+
+// symmetric eigen-decomposition by cyclic Jacobi.  A (N x N, row-major, destroyed) -> eigen
+// values w (unsorted) and eigenvectors as ROWS of V.
+template <int N>
+MCV_HDN inline void jacobi_eigen_sym(double* A, double* w, double* V) {
+    for (int i = 0; i < N; ++i) {
+        for (int j = 0; j < N; ++j) V[i * N + j] = 0;
+        V[i * N + i] = 1;
+    }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0, diag = 0;
+        for (int i = 0; i < N; ++i) {
+            diag += A[i * N + i] * A[i * N + i];
+            for (int j = i + 1; j < N; ++j) off += A[i * N + j] * A[i * N + j];
+        }
+        if (off <= 1e-32 * diag || off == 0) break;
+        for (int p = 0; p < N - 1; ++p)
+            for (int q = p + 1; q < N; ++q) {
+                const double apq = A[p * N + q];
+                if (apq == 0) continue;
+                const double app = A[p * N + p], aqq = A[q * N + q];
+                const double theta = (aqq - app) / (2 * apq);
+                const double t = (theta >= 0 ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1));
+                const double c = 1 / sqrt(t * t + 1), s = t * c;
+                for (int k = 0; k < N; ++k) {
+                    const double akp = A[k * N + p], akq = A[k * N + q];
+                    A[k * N + p] = c * akp - s * akq;
+                    A[k * N + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < N; ++k) {
+                    const double apk = A[p * N + k], aqk = A[q * N + k];
+                    A[p * N + k] = c * apk - s * aqk;
+                    A[q * N + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < N; ++k) {
+                    const double vp = V[p * N + k], vq = V[q * N + k];
+                    V[p * N + k] = c * vp - s * vq;
+                    V[q * N + k] = s * vp + c * vq;
+                }
+            }
+    }
+    for (int i = 0; i < N; ++i) w[i] = A[i * N + i];
+}
+
+// cv::solve(A, b, x, DECOMP_EIG) for symmetric A: x = sum_i (v_i . b / w_i) v_i over
+// eigenvalues above eps*2*sum|w| (SVBkSb's threshold).
+template <int N>
+MCV_HDN inline void solve_sym_eig(const double* A, const double* b, double* x) {
+    double M[N * N], w[N], V[N * N];
+    for (int i = 0; i < N * N; ++i) M[i] = A[i];
+    jacobi_eigen_sym<N>(M, w, V);
+    double sum = 0;
+    for (int i = 0; i < N; ++i) sum += fabs(w[i]);
+    const double thr = DBL_EPSILON * 2 * sum;
+    for (int i = 0; i < N; ++i) x[i] = 0;
+    for (int i = 0; i < N; ++i) {
+        if (fabs(w[i]) <= thr) continue;
+        double s = 0;
+        for (int k = 0; k < N; ++k) s += V[i * N + k] * b[k];
+        s /= w[i];
+        for (int k = 0; k < N; ++k) x[k] += s * V[i * N + k];
+    }
+}
+
+// max |diag| of pinv(A) for symmetric A (LMSolver's lambda re-seed: invert(A, Ap, DECOMP_EIG))
+template <int N>
+MCV_HDN inline double max_diag_pinv_sym(const double* A) {
+    double M[N * N], w[N], V[N * N];
+    for (int i = 0; i < N * N; ++i) M[i] = A[i];
+    jacobi_eigen_sym<N>(M, w, V);
+    double sum = 0;
+    for (int i = 0; i < N; ++i) sum += fabs(w[i]);
+    const double thr = DBL_EPSILON * 2 * sum;
+    double maxval = DBL_EPSILON;
+    for (int k = 0; k < N; ++k) {
+        double d = 0;
+        for (int i = 0; i < N; ++i)
+            if (fabs(w[i]) > thr) d += V[i * N + k] * V[i * N + k] / w[i];
+        maxval = fmax(maxval, fabs(d));
+    }
+    return maxval;
+}
+
+// ---- scoring (bit-exact) --------------------------------------------------------------------
+// Homography reprojection error, float32 (HomographyEstimatorCallback::computeError).
+// Hf = first 8 entries of H cast to float (h33 taken as 1).
+MCV_HD float h_error(const float* Hf, float Mx, float My, float mx, float my) {
+    const float ww = fdiv(1.f, fadd(fadd(fmul(Hf[6], Mx), fmul(Hf[7], My)), 1.f));
+    const float dx = fsub(fmul(fadd(fadd(fmul(Hf[0], Mx), fmul(Hf[1], My)), Hf[2]), ww), mx);
+    const float dy = fsub(fmul(fadd(fadd(fmul(Hf[3], Mx), fmul(Hf[4], My)), Hf[5]), ww), my);
+    return fadd(fmul(dx, dx), fmul(dy, dy));
+}
+
+// Fundamental matrix: max of the two squared point-line distances, float64 -> float32
+// (FMEstimatorCallback::computeError).  Points are float32 promoted to double.
+MCV_HD float f_error(const double* F, double x1, double y1, double x2, double y2) {
+    double a = dadd(dadd(dmul(F[0], x1), dmul(F[1], y1)), F[2]);
+    double b = dadd(dadd(dmul(F[3], x1), dmul(F[4], y1)), F[5]);
+    double c = dadd(dadd(dmul(F[6], x1), dmul(F[7], y1)), F[8]);
+    const double s2 = ddiv(1., dadd(dmul(a, a), dmul(b, b)));
+    const double d2 = dadd(dadd(dmul(x2, a), dmul(y2, b)), c);
+    a = dadd(dadd(dmul(F[0], x2), dmul(F[3], y2)), F[6]);
+    b = dadd(dadd(dmul(F[1], x2), dmul(F[4], y2)), F[7]);
+    c = dadd(dadd(dmul(F[2], x2), dmul(F[5], y2)), F[8]);
+    const double s1 = ddiv(1., dadd(dmul(a, a), dmul(b, b)));
+    const double d1 = dadd(dadd(dmul(x1, a), dmul(y1, b)), c);
+    const double e1 = dmul(dmul(d1, d1), s1), e2 = dmul(dmul(d2, d2), s2);
+    return (float)((e1 < e2) ? e2 : e1);   // std::max(e1, e2)
+}
+
+// Essential matrix Sampson error, float64 -> float32 (EMEstimatorCallback::computeError).
+MCV_HD float e_error(const double* E, double x1, double y1, double x2, double y2) {
+    const double Ex0 = dadd(dadd(dmul(E[0], x1), dmul(E[1], y1)), E[2]);
+    const double Ex1 = dadd(dadd(dmul(E[3], x1), dmul(E[4], y1)), E[5]);
+    const double Ex2 = dadd(dadd(dmul(E[6], x1), dmul(E[7], y1)), E[8]);
+    const double Et0 = dadd(dadd(dmul(E[0], x2), dmul(E[3], y2)), E[6]);
+    const double Et1 = dadd(dadd(dmul(E[1], x2), dmul(E[4], y2)), E[7]);
+    const double xe = dadd(dadd(dmul(x2, Ex0), dmul(y2, Ex1)), Ex2);
+    const double a = dmul(Ex0, Ex0), b = dmul(Ex1, Ex1), c = dmul(Et0, Et0), d = dmul(Et1, Et1);
+    return (float)ddiv(dmul(xe, xe), dadd(dadd(dadd(a, b), c), d));
+}
+
+// ---- subset checks ----------------------------------------------------------------------------
+// haveCollinearPoints: last point against every earlier pair; pts as float (x,y) pairs.
+MCV_HDN inline bool have_collinear(const float* pts, int count) {
+    const int i = count - 1;
+    for (int j = 0; j < i; ++j) {
+        const double dx1 = (double)pts[2 * j] - (double)pts[2 * i];
+        const double dy1 = (double)pts[2 * j + 1] - (double)pts[2 * i + 1];
+        for (int k = 0; k < j; ++k) {
+            const double dx2 = (double)pts[2 * k] - (double)pts[2 * i];
+            const double dy2 = (double)pts[2 * k + 1] - (double)pts[2 * i + 1];
+            if (fabs(dx2 * dy1 - dy2 * dx1) <=
+                (double)FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2)))
+                return true;
+        }
+    }
+    return false;
+}
+
+MCV_HD double det3pts(const float* p, int i0, int i1, int i2) {
+    const double a00 = p[2 * i0], a01 = p[2 * i0 + 1], a10 = p[2 * i1], a11 = p[2 * i1 + 1],
+                 a20 = p[2 * i2], a21 = p[2 * i2 + 1];
+    return a00 * (a11 * 1. - a21 * 1.) - a01 * (a10 * 1. - a20 * 1.) + 1. * (a10 * a21 - a20 * a11);
+}
+
+// HomographyEstimatorCallback::checkSubset for count == 4
+MCV_HDN inline bool h_check_subset(const float* src, const float* dst) {
+    if (have_collinear(src, 4) || have_collinear(dst, 4)) return false;
+    const int tt[4][3] = {{0, 1, 2}, {1, 2, 3}, {0, 2, 3}, {0, 1, 3}};
+    int negative = 0;
+    for (int i = 0; i < 4; ++i)
+        negative += det3pts(src, tt[i][0], tt[i][1], tt[i][2]) * det3pts(dst, tt[i][0], tt[i][1], tt[i][2]) < 0;
+    return negative == 0 || negative == 4;
+}
+
+// ---- homography from 4 correspondences ------------------------------------------------------
+// Same normalisation as HomographyEstimatorCallback::runKernel; the exact interpolating H
+// is obtained from the 8x9 DLT system by elimination with complete pivoting (OpenCV takes the
+// smallest eigenvector of the 9x9 normal matrix -- same H up to rounding for a minimal set).
+// src/dst: 4 (x,y) float pairs.  H: 9 doubles, scaled so H[8] = 1.  Returns false if degenerate.
+MCV_HDN inline bool h_solve4(const float* src, const float* dst, double* H) {
+    double cMx = 0, cMy = 0, cmx = 0, cmy = 0;
+    for (int i = 0; i < 4; ++i) { cmx += dst[2 * i]; cmy += dst[2 * i + 1]; cMx += src[2 * i]; cMy += src[2 * i + 1]; }
+    cmx /= 4; cmy /= 4; cMx /= 4; cMy /= 4;
+    double smx = 0, smy = 0, sMx = 0, sMy = 0;
+    for (int i = 0; i < 4; ++i) {
+        smx += fabs(dst[2 * i] - cmx); smy += fabs(dst[2 * i + 1] - cmy);
+        sMx += fabs(src[2 * i] - cMx); sMy += fabs(src[2 * i + 1] - cMy);
+    }
+    if (fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON)
+        return false;
+    smx = 4 / smx; smy = 4 / smy; sMx = 4 / sMx; sMy = 4 / sMy;
+    double A[8][9];
+    for (int i = 0; i < 4; ++i) {
+        const double x = (dst[2 * i] - cmx) * smx, y = (dst[2 * i + 1] - cmy) * smy;
+        const double X = (src[2 * i] - cMx) * sMx, Y = (src[2 * i + 1] - cMy) * sMy;
+        double* r0 = A[2 * i];
+        double* r1 = A[2 * i + 1];
+        r0[0] = X; r0[1] = Y; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -x * X; r0[7] = -x * Y; r0[8] = -x;
+        r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = X; r1[4] = Y; r1[5] = 1; r1[6] = -y * X; r1[7] = -y * Y; r1[8] = -y;
+    }
+    int perm[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
+    for (int c = 0; c < 8; ++c) {
+        int pr = c, pc = c;
+        double best = -1;
+        for (int r = c; r < 8; ++r)
+            for (int k = c; k < 9; ++k) {
+                const double v = fabs(A[r][k]);
+                if (v > best) { best = v; pr = r; pc = k; }
+            }
+        if (!(best > 1e-14)) return false;
+        if (pr != c) for (int k = 0; k < 9; ++k) { double t = A[c][k]; A[c][k] = A[pr][k]; A[pr][k] = t; }
+        if (pc != c) {
+            for (int r = 0; r < 8; ++r) { double t = A[r][c]; A[r][c] = A[r][pc]; A[r][pc] = t; }
+            int t = perm[c]; perm[c] = perm[pc]; perm[pc] = t;
+        }
+        const double inv = 1 / A[c][c];
+        for (int r = c + 1; r < 8; ++r) {
+            const double f = A[r][c] * inv;
+            if (f != 0) for (int k = c; k < 9; ++k) A[r][k] -= f * A[c][k];
+        }
+    }
+    double h[9], sol[9];
+    sol[8] = 1;
+    for (int c = 7; c >= 0; --c) {
+        double s = 0;
+        for (int k = c + 1; k < 9; ++k) s += A[c][k] * sol[k];
+        sol[c] = -s / A[c][c];
+    }
+    for (int k = 0; k < 9; ++k) h[perm[k]] = sol[k];
+    // H = invHnorm * h0 * Hnorm2
+    const double iH[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
+    const double N2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
+    double T[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) T[i * 3 + j] = iH[i * 3] * h[j] + iH[i * 3 + 1] * h[3 + j] + iH[i * 3 + 2] * h[6 + j];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) H[i * 3 + j] = T[i * 3] * N2[j] + T[i * 3 + 1] * N2[3 + j] + T[i * 3 + 2] * N2[6 + j];
+    if (H[8] == 0 || !(fabs(H[8]) > 0)) return false;
+    const double sc = 1. / H[8];
+    for (int k = 0; k < 9; ++k) H[k] *= sc;
+    for (int k = 0; k < 9; ++k) if (!(fabs(H[k]) < 1e300)) return false;
+    return true;
+}
+
+// ---- cv::solveCubic (closed form); coeffs c[0] x^3 + c[1] x^2 + c[2] x + c[3] -----------------
+MCV_HDN inline int solve_cubic(const double* cf, double* roots) {
+    double a0 = cf[0], a1 = cf[1], a2 = cf[2], a3 = cf[3];
+    double x0 = 0, x1 = 0, x2 = 0;
+    int n = 0;
+    if (a0 == 0) {
+        if (a1 == 0) {
+            if (a2 == 0) n = a3 == 0 ? -1 : 0;
+            else { x0 = -a3 / a2; n = 1; }
+        } else {
+            double d = a2 * a2 - 4 * a1 * a3;
+            if (d >= 0) {
+                d = sqrt(d);
+                const double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+                if (fabs(q1) > fabs(q2)) { x0 = q1 / a1; x1 = a3 / q1; }
+                else { x0 = q2 / a1; x1 = a3 / q2; }
+                n = d > 0 ? 2 : 1;
+            }
+        }
+    } else {
+        a0 = 1. / a0; a1 *= a0; a2 *= a0; a3 *= a0;
+        const double Q = (a1 * a1 - 3 * a2) * (1. / 9);
+        const double R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
+        const double Qcubed = Q * Q * Q;
+        double d = Qcubed - R * R;
+        const double PI = 3.14159265358979323846;
+        if (d > 0) {
+            const double theta = acos(R / sqrt(Qcubed));
+            const double sqrtQ = sqrt(Q);
+            const double t0 = -2 * sqrtQ, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
+            x0 = t0 * cos(t1) - t2;
+            x1 = t0 * cos(t1 + (2. * PI / 3)) - t2;
+            x2 = t0 * cos(t1 + (4. * PI / 3)) - t2;
+            n = 3;
+        } else if (d == 0) {
+            if (R >= 0) { x0 = -2 * pow(R, 1. / 3) - a1 / 3; x1 = pow(R, 1. / 3) - a1 / 3; }
+            else { x0 = 2 * pow(-R, 1. / 3) - a1 / 3; x1 = -pow(-R, 1. / 3) - a1 / 3; }
+            x2 = 0;
+            n = x0 == x1 ? 1 : 2;
+            x1 = x0 == x1 ? 0 : x1;
+        } else {
+            d = sqrt(-d);
+            double e = pow(d + fabs(R), 1. / 3);
+            if (R > 0) e = -e;
+            x0 = (e + Q / e) - a1 * (1. / 3);
+            n = 1;
+        }
+    }
+    roots[0] = x0; roots[1] = x1; roots[2] = x2;
+    return n;
+}
+
+// ---- 7-point fundamental matrix (run7Point) ----------------------------------------------------
+// m1/m2: 7 (x,y) float pairs.  F: up to 3 matrices (9 doubles each).  Returns the count.
+MCV_HDN inline int f_solve7(const float* m1, const float* m2, double* Fout) {
+    double At[9 * 9];
+    for (int i = 0; i < 7; ++i) {
+        const double x0 = m1[2 * i], y0 = m1[2 * i + 1], x1 = m2[2 * i], y1 = m2[2 * i + 1];
+        double* a = At + i * 9;
+        a[0] = x1 * x0; a[1] = x1 * y0; a[2] = x1; a[3] = y1 * x0; a[4] = y1 * y0; a[5] = y1;
+        a[6] = x0; a[7] = y0; a[8] = 1;
+    }
+    for (int k = 63; k < 81; ++k) At[k] = 0;
+    double W[7];
+    jacobi_svd_rows<9, 7, 9, false>(At, W, nullptr);   // rows 7, 8 = null-space basis (Vt rows)
+    double* f1 = At + 7 * 9;
+    double* f2 = At + 8 * 9;
+    for (int i = 0; i < 9; ++i) f1[i] -= f2[i];
+    double c[4], r[3] = {0, 0, 0};
+    const double t0 = f2[4] * f2[8] - f2[5] * f2[7];
+    const double t1 = f2[3] * f2[8] - f2[5] * f2[6];
+    const double t2 = f2[3] * f2[7] - f2[4] * f2[6];
+    c[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+    c[2] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 -
+           f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) + f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) -
+           f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) + f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) -
+           f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) + f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+    const double u0 = f1[4] * f1[8] - f1[5] * f1[7];
+    const double u1 = f1[3] * f1[8] - f1[5] * f1[6];
+    const double u2 = f1[3] * f1[7] - f1[4] * f1[6];
+    c[1] = f2[0] * u0 - f2[1] * u1 + f2[2] * u2 -
+           f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) + f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) -
+           f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) + f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) -
+           f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) + f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+    c[0] = f1[0] * u0 - f1[1] * u1 + f1[2] * u2;
+    const int n = solve_cubic(c, r);
+    if (n < 1 || n > 3) return n < 0 ? 0 : (n > 3 ? 0 : n);
+    for (int k = 0; k < n; ++k) {
+        double* F = Fout + 9 * k;
+        double lambda = r[k], mu = 1.;
+        const double s = f1[8] * r[k] + f2[8];
+        if (fabs(s) > DBL_EPSILON) { mu = 1. / s; lambda *= mu; F[8] = 1.; }
+        else F[8] = 0.;
+        for (int i = 0; i < 8; ++i) F[i] = f1[i] * lambda + f2[i] * mu;
+    }
+    return n;
+}
+
+// ---- 5-point essential matrix ------------------------------------------------------------------
+// Small dense polynomials in (x, y, z): deg1 = [x, y, z, 1]; deg2 (10) and deg3 (20) indexed by
+// the tables below.  deg3 order = the elimination order used by the solver:
+//   x3 y3 x2y xy2 x2z x2 y2z y2 xyz xy | xz2 xz x yz2 yz y z3 z2 z 1
+namespace p5 {
+// deg2 order: x2 y2 z2 xy xz yz x y z 1
+MCV_HD void mul11(const double* a, const double* b, double* r) {
+    r[0] = a[0] * b[0]; r[1] = a[1] * b[1]; r[2] = a[2] * b[2];
+    r[3] = a[0] * b[1] + a[1] * b[0];
+    r[4] = a[0] * b[2] + a[2] * b[0];
+    r[5] = a[1] * b[2] + a[2] * b[1];
+    r[6] = a[0] * b[3] + a[3] * b[0];
+    r[7] = a[1] * b[3] + a[3] * b[1];
+    r[8] = a[2] * b[3] + a[3] * b[2];
+    r[9] = a[3] * b[3];
+}
+// deg2 (a) x deg1 (b) accumulated into deg3 r (+= s * a*b)
+MCV_HD void mul21_acc(const double* a, const double* b, double s, double* r) {
+    const double bx = b[0] * s, by = b[1] * s, bz = b[2] * s, b1 = b[3] * s;
+    // a: 0 x2, 1 y2, 2 z2, 3 xy, 4 xz, 5 yz, 6 x, 7 y, 8 z, 9 one
+    r[0] += a[0] * bx;                              // x3
+    r[1] += a[1] * by;                              // y3
+    r[2] += a[0] * by + a[3] * bx;                  // x2y
+    r[3] += a[1] * bx + a[3] * by;                  // xy2
+    r[4] += a[0] * bz + a[4] * bx;                  // x2z
+    r[5] += a[0] * b1 + a[6] * bx;                  // x2
+    r[6] += a[1] * bz + a[5] * by;                  // y2z
+    r[7] += a[1] * b1 + a[7] * by;                  // y2
+    r[8] += a[3] * bz + a[4] * by + a[5] * bx;      // xyz
+    r[9] += a[3] * b1 + a[6] * by + a[7] * bx;      // xy
+    r[10] += a[2] * bx + a[4] * bz;                 // xz2
+    r[11] += a[4] * b1 + a[6] * bz + a[8] * bx;     // xz
+    r[12] += a[6] * b1 + a[9] * bx;                 // x
+    r[13] += a[2] * by + a[5] * bz;                 // yz2
+    r[14] += a[5] * b1 + a[7] * bz + a[8] * by;     // yz
+    r[15] += a[7] * b1 + a[9] * by;                 // y
+    r[16] += a[2] * bz;                             // z3
+    r[17] += a[2] * b1 + a[8] * bz;                 // z2
+    r[18] += a[8] * b1 + a[9] * bz;                 // z
+    r[19] += a[9] * b1;                             // 1
+}
+}  // namespace p5
+
+// univariate polynomial helpers (coefficients in DESCENDING powers, like the reference's b[])
+MCV_HD void upoly_mul(const double* a, int na, const double* b, int nb, double* r) {
+    for (int i = 0; i < na + nb - 1; ++i) r[i] = 0;
+    for (int i = 0; i < na; ++i)
+        for (int j = 0; j < nb; ++j) r[i + j] += a[i] * b[j];
+}
+
+// Real roots of a degree-10 polynomial c[0] z^10 + ... + c[10]: simultaneous Aberth-Ehrlich
+// iteration in complex arithmetic, then the reference's filter |Im| <= 1e-10
+// (fivepoint.cpp:301; the reference calls cv::solvePoly, a Durand-Kerner iteration).
+MCV_HDN inline int real_roots10(const double* c, double* out) {
+    int deg = 10, lead = 0;
+    while (deg > 0 && c[lead] == 0) { ++lead; --deg; }
+    if (deg == 0) return 0;
+    const double* a = c + lead;   // a[0] z^deg + ... + a[deg]
+    double zr[10], zi[10];
+    // Cauchy bound for the starting radius
+    double bound = 0;
+    for (int i = 1; i <= deg; ++i) bound = fmax(bound, fabs(a[i] / a[0]));
+    const double rad = 1 + bound > 1e3 ? pow(fabs(a[deg] / a[0]), 1.0 / deg) + 1 : 1 + bound;
+    for (int i = 0; i < deg; ++i) {
+        const double ang = 2 * 3.14159265358979323846 * i / deg + 0.4;
+        zr[i] = rad * 0.5 * cos(ang);
+        zi[i] = rad * 0.5 * sin(ang);
+    }
+    for (int iter = 0; iter < 200; ++iter) {
+        double maxd = 0;
+        for (int i = 0; i < deg; ++i) {
+            // Horner for p and p'
+            double pr = a[0], pi = 0, dr = 0, di = 0;
+            const double xr = zr[i], xi = zi[i];
+            for (int k = 1; k <= deg; ++k) {
+                const double ndr = dr * xr - di * xi + pr, ndi = dr * xi + di * xr + pi;
+                dr = ndr; di = ndi;
+                const double npr = pr * xr - pi * xi + a[k], npi = pr * xi + pi * xr;
+                pr = npr; pi = npi;
+            }
+            // w = p / p'
+            double den = dr * dr + di * di;
+            if (den == 0) { dr = 1e-300; den = dr * dr; }
+            const double wr = (pr * dr + pi * di) / den, wi = (pi * dr - pr * di) / den;
+            // s = sum_{j != i} 1 / (z_i - z_j)
+            double sr = 0, si = 0;
+            for (int j = 0; j < deg; ++j) {
+                if (j == i) continue;
+                const double er = xr - zr[j], ei = xi - zi[j];
+                const double d2 = er * er + ei * ei;
+                if (d2 == 0) continue;
+                sr += er / d2; si -= ei / d2;
+            }
+            // delta = w / (1 - w * s)
+            const double qr = 1 - (wr * sr - wi * si), qi = -(wr * si + wi * sr);
+            double qd = qr * qr + qi * qi;
+            if (qd == 0) qd = 1e-300;
+            const double der = (wr * qr + wi * qi) / qd, dei = (wi * qr - wr * qi) / qd;
+            zr[i] = xr - der; zi[i] = xi - dei;
+            maxd = fmax(maxd, fabs(der) + fabs(dei));
+        }
+        if (maxd <= 1e-15 * rad) break;
+    }
+    int n = 0;
+    for (int i = 0; i < deg; ++i) {
+        if (fabs(zi[i]) > 1e-10) continue;
+        // two real Newton steps on the real polynomial polish the accepted root
+        double x = zr[i];
+        for (int it = 0; it < 2; ++it) {
+            double p = a[0], d = 0;
+            for (int k = 1; k <= deg; ++k) { d = d * x + p; p = p * x + a[k]; }
+            if (d != 0 && fabs(p / d) < 1e-6 * (1 + fabs(x))) x -= p / d;
+        }
+        out[n++] = x;
+    }
+    // ascending order (deterministic model order inside an iteration)
+    for (int i = 1; i < n; ++i) {
+        const double v = out[i];
+        int j = i - 1;
+        while (j >= 0 && out[j] > v) { out[j + 1] = out[j]; --j; }
+        out[j + 1] = v;
+    }
+    return n;
+}
+
+// pa/pb: 5 points each as (x,y) doubles (already normalised by the intrinsics).
+// Es: up to 10 matrices, 9 doubles each, row-major, unit Frobenius norm.  Returns the count.
+// Follows the reference's runFivepoint (src/MiniCVNative/fivepoint.cpp:233-339); the
+// generated coefficient table of getCoeffMat (:10-231) is replaced by polynomial arithmetic.
+MCV_HDN inline int e_solve5(const double* pa, const double* pb, double* Es) {
+    // 1. null space of the 5x9 system: rows 5..8 of Vt (OpenCV basis, incl. its completion)
+    double At[9 * 9];
+    for (int i = 0; i < 5; ++i) {
+        const double x1 = pa[2 * i], y1 = pa[2 * i + 1], x2 = pb[2 * i], y2 = pb[2 * i + 1];
+        double* q = At + 9 * i;
+        q[0] = x1 * x2; q[1] = y1 * x2; q[2] = x2; q[3] = x1 * y2; q[4] = y1 * y2; q[5] = y2;
+        q[6] = x1; q[7] = y1; q[8] = 1.0;
+    }
+    for (int k = 45; k < 81; ++k) At[k] = 0;
+    double Wsv[5];
+    jacobi_svd_rows<9, 5, 9, false>(At, Wsv, nullptr);
+    const double* EE = At + 5 * 9;   // 4 x 9: X, Y, Z, W
+
+    // 2. cubic constraints.  E[i][j] as deg1 polys: coefficient c of basis b at e1[i*3+j][b]
+    double e1[9][4];
+    for (int k = 0; k < 9; ++k)
+        for (int b = 0; b < 4; ++b) e1[k][b] = EE[b * 9 + k];
+    double A[10][20];
+    for (int r = 0; r < 10; ++r)
+        for (int k = 0; k < 20; ++k) A[r][k] = 0;
+    {
+        // det(E)
+        double m[10];
+        p5::mul11(e1[4], e1[8], m); p5::mul21_acc(m, e1[0], 1., A[0]);
+        p5::mul11(e1[5], e1[7], m); p5::mul21_acc(m, e1[0], -1., A[0]);
+        p5::mul11(e1[3], e1[8], m); p5::mul21_acc(m, e1[1], -1., A[0]);
+        p5::mul11(e1[5], e1[6], m); p5::mul21_acc(m, e1[1], 1., A[0]);
+        p5::mul11(e1[3], e1[7], m); p5::mul21_acc(m, e1[2], 1., A[0]);
+        p5::mul11(e1[4], e1[6], m); p5::mul21_acc(m, e1[2], -1., A[0]);
+        // EEt (symmetric), trace
+        double eet[3][3][10], tr[10];
+        for (int i = 0; i < 3; ++i)
+            for (int j = i; j < 3; ++j) {
+                double t0[10], t1[10], t2[10];
+                p5::mul11(e1[i * 3], e1[j * 3], t0);
+                p5::mul11(e1[i * 3 + 1], e1[j * 3 + 1], t1);
+                p5::mul11(e1[i * 3 + 2], e1[j * 3 + 2], t2);
+                for (int k = 0; k < 10; ++k) { eet[i][j][k] = t0[k] + t1[k] + t2[k]; eet[j][i][k] = eet[i][j][k]; }
+            }
+        for (int k = 0; k < 10; ++k) tr[k] = eet[0][0][k] + eet[1][1][k] + eet[2][2][k];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double* row = A[1 + i * 3 + j];
+                for (int k = 0; k < 3; ++k) p5::mul21_acc(eet[i][k], e1[k * 3 + j], 2., row);
+                p5::mul21_acc(tr, e1[i * 3 + j], -1., row);
+            }
+    }
+    // 3. Gauss-Jordan on the ten leading monomials (partial pivoting)
+    for (int c = 0; c < 10; ++c) {
+        int pr = c;
+        double best = fabs(A[c][c]);
+        for (int r = c + 1; r < 10; ++r)
+            if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); pr = r; }
+        if (!(best > 0)) return 0;
+        if (pr != c) for (int k = 0; k < 20; ++k) { double t = A[c][k]; A[c][k] = A[pr][k]; A[pr][k] = t; }
+        const double inv = 1 / A[c][c];
+        for (int k = c; k < 20; ++k) A[c][k] *= inv;
+        for (int r = 0; r < 10; ++r) {
+            if (r == c) continue;
+            const double f = A[r][c];
+            if (f != 0) for (int k = c; k < 20; ++k) A[r][k] -= f * A[c][k];
+        }
+    }
+    // 4. B(z) from rows (4,5), (6,7), (8,9): [x-part (4) | y-part (4) | 1-part (5)], descending
+    double b[3][13];
+    for (int i = 0; i < 3; ++i) {
+        const double* r1 = A[2 * i + 4] + 10;
+        const double* r2 = A[2 * i + 5] + 10;
+        double row1[13], row2[13];
+        for (int k = 0; k < 13; ++k) { row1[k] = 0; row2[k] = 0; }
+        row1[1] = r1[0]; row1[2] = r1[1]; row1[3] = r1[2];
+        row1[5] = r1[3]; row1[6] = r1[4]; row1[7] = r1[5];
+        row1[9] = r1[6]; row1[10] = r1[7]; row1[11] = r1[8]; row1[12] = r1[9];
+        row2[0] = r2[0]; row2[1] = r2[1]; row2[2] = r2[2];
+        row2[4] = r2[3]; row2[5] = r2[4]; row2[6] = r2[5];
+        row2[8] = r2[6]; row2[9] = r2[7]; row2[10] = r2[8]; row2[11] = r2[9];
+        for (int k = 0; k < 13; ++k) b[i][k] = row1[k] - row2[k];
+    }
+    // det B(z): degree 10, descending coefficients
+    double coef[11];
+    for (int k = 0; k < 11; ++k) coef[k] = 0;
+    {
+        const int perm[6][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 0}};
+        for (int t = 0; t < 6; ++t) {
+            const double sgn = t < 3 ? 1. : -1.;
+            // columns: 0 -> x-part (deg 3), 1 -> y-part (deg 3), 2 -> 1-part (deg 4)
+            double xy[7], full[11];
+            upoly_mul(b[perm[t][0]] + 0, 4, b[perm[t][1]] + 4, 4, xy);
+            upoly_mul(xy, 7, b[perm[t][2]] + 8, 5, full);
+            for (int k = 0; k < 11; ++k) coef[k] += sgn * full[k];
+        }
+    }
+    double roots[10];
+    const int nr = real_roots10(coef, roots);
+    int count = 0;
+    for (int ri = 0; ri < nr; ++ri) {
+        const double z1 = roots[ri], z2 = z1 * z1, z3 = z2 * z1, z4 = z3 * z1;
+        double bz[9];
+        for (int j = 0; j < 3; ++j) {
+            const double* br = b[j];
+            bz[j * 3 + 0] = br[0] * z3 + br[1] * z2 + br[2] * z1 + br[3];
+            bz[j * 3 + 1] = br[4] * z3 + br[5] * z2 + br[6] * z1 + br[7];
+            bz[j * 3 + 2] = br[8] * z4 + br[9] * z3 + br[10] * z2 + br[11] * z1 + br[12];
+        }
+        // SVD::solveZ(Bz): right singular vector of the smallest singular value
+        double w3[3], u3[9], vt3[9];
+        svd_square<3>(bz, w3, u3, vt3);
+        const double vx = vt3[6], vy = vt3[7], vw = vt3[8];
+        if (fabs(vw) < 1e-10) continue;
+        const double xs = vx / vw, ys = vy / vw;
+        double* E = Es + 9 * count;
+        double nrm = 0;
+        for (int k = 0; k < 9; ++k) {
+            E[k] = EE[k] * xs + EE[9 + k] * ys + EE[18 + k] * z1 + EE[27 + k];
+            nrm += E[k] * E[k];
+        }
+        nrm = sqrt(nrm);
+        if (!(nrm > 0)) continue;
+        for (int k = 0; k < 9; ++k) E[k] /= nrm;
+        ++count;
+    }
+    return count;
+}
+
+// ---- decomposeEssentialMat ----------------------------------------------------------------------
+MCV_HD double det3(const double* m) {
+    return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+MCV_HD void mat3mul(const double* a, const double* b, double* r) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+}
+MCV_HDN inline void decompose_essential(const double* E, double* R1, double* R2, double* t) {
+    double w[3], U[9], Vt[9];
+    svd_square<3>(E, w, U, Vt);
+    if (det3(U) < 0) for (int k = 0; k < 9; ++k) U[k] *= -1.;
+    if (det3(Vt) < 0) for (int k = 0; k < 9; ++k) Vt[k] *= -1.;
+    const double Wm[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+    const double Wt[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};
+    double T[9];
+    mat3mul(U, Wm, T); mat3mul(T, Vt, R1);
+    mat3mul(U, Wt, T); mat3mul(T, Vt, R2);
+    t[0] = U[2]; t[1] = U[5]; t[2] = U[8];
+}
+
+// ---- recoverPose cheirality test for one correspondence and one candidate (R, t) ---------------
+// DLT triangulation (cv::triangulatePoints): 4x4 system, right singular vector of the smallest
+// singular value; then z*w > 0, z/w < dist, 0 < z2 < dist in the second camera.
+MCV_HDN inline bool cheirality_ok(const double* R, const double* t, double x1, double y1, double x2,
+                                  double y2, double dist) {
+    double A[16];
+    // P0 = [I | 0], P1 = [R | t]
+    A[0] = x1 * 0 - 1; A[1] = x1 * 0 - 0; A[2] = x1 * 1 - 0; A[3] = x1 * 0 - 0;
+    A[4] = y1 * 0 - 0; A[5] = y1 * 0 - 1; A[6] = y1 * 1 - 0; A[7] = y1 * 0 - 0;
+    for (int k = 0; k < 3; ++k) {
+        A[8 + k] = x2 * R[6 + k] - R[k];
+        A[12 + k] = y2 * R[6 + k] - R[3 + k];
+    }
+    A[11] = x2 * t[2] - t[0];
+    A[15] = y2 * t[2] - t[1];
+    double w[4], U[16], Vt[16];
+    svd_square<4>(A, w, U, Vt);
+    double Q0 = Vt[12], Q1 = Vt[13], Q2 = Vt[14], Q3 = Vt[15];
+    bool ok = (Q2 * Q3) > 0;
+    Q0 /= Q3; Q1 /= Q3; Q2 /= Q3; Q3 /= Q3;
+    ok = ok && (Q2 < dist);
+    const double z2 = R[6] * Q0 + R[7] * Q1 + R[8] * Q2 + t[2] * Q3;
+    ok = ok && (z2 > 0) && (z2 < dist);
+    return ok;
+}
+
+}  // namespace cvm
+}  // namespace mcv

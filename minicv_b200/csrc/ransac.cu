@@ -1,0 +1,928 @@
+// ransac.cu -- batched RANSAC for homography / fundamental / essential matrices.
+//
+// The reference exports only the essential-matrix form (cvRecoverPose / cvRecoverPoses,
+// src/MiniCVNative/MiniCVNative.cpp:165-215 -> cv::findEssentialMat(..., RANSAC, ...)); the
+// H and F forms are the new exports the north-star path adds.  All three run through one
+// engine that restates OpenCV's RANSACPointSetRegistrator::run as data-parallel stages:
+//
+//   prep      points -> float32 (H, F) or intrinsics-normalised float64 (E)        [HBM-bound]
+//   sample    all maxIters subsets up front: OpenCV's MWC stream (one thread per pair, the
+//             stream is sequential by construction), a counter-based hash RNG (one thread per
+//             hypothesis) or injected index sets; degeneracy checks as in checkSubset
+//   solve     one hypothesis per thread: 4-point H / 7-point F / 5-point E (cvmath.cuh)
+//   compact   per pair prefix over the model counts -> dense model list in OpenCV's order
+//   score     one model per thread x all correspondences staged through shared memory and
+//             read as 128-bit broadcasts; inlier count in a register              [FP pipe bound]
+//   select    replays OpenCV's sequential accept / RANSACUpdateNumIters logic over the counts,
+//             so the winner is the model OpenCV's loop would have stopped with
+//   finalize  inlier mask of the winner; homography: refit on inliers (normalised DLT) +
+//             10 Levenberg-Marquardt iterations + mask from the refined H (findHomography)
+#include "ransac.cuh"
+#include "cvmath.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace mcv {
+namespace {
+
+using namespace cvm;
+
+template <int MODEL> struct MT;
+template <> struct MT<RM_HOMOGRAPHY>  { static constexpr int MP = 4, MAXM = 1; };
+template <> struct MT<RM_FUNDAMENTAL> { static constexpr int MP = 7, MAXM = 3; };
+template <> struct MT<RM_ESSENTIAL>   { static constexpr int MP = 5, MAXM = 10; };
+
+constexpr int PAIR_FAIL = 1;     // sampling failed at iteration 0 / N < modelPoints
+constexpr int PAIR_DIRECT = 2;   // N == modelPoints: kernel on all points, mask all ones
+
+// ---------------------------------------------------------------------------------------------
+// prep: double (x,y) pairs -> working layout
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prep_points_kernel(const double2* __restrict__ a, const double2* __restrict__ b, int64_t total,
+                   int isE, double invf, double nx, double ny, float4* __restrict__ pf,
+                   double* __restrict__ pd) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const double2 pa = a[i], pb = b[i];
+    if (!isE) {
+        pf[i] = make_float4((float)pa.x, (float)pa.y, (float)pb.x, (float)pb.y);
+    } else {
+        // (x - pp) / f as x*(1/f) + (-pp*(1/f)), unfused (oracle/essential.py normalize_points)
+        double* o = pd + 4 * i;
+        o[0] = dadd(dmul(pa.x, invf), nx);
+        o[1] = dadd(dmul(pa.y, invf), ny);
+        o[2] = dadd(dmul(pb.x, invf), nx);
+        o[3] = dadd(dmul(pb.y, invf), ny);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampling
+// ---------------------------------------------------------------------------------------------
+template <int MODEL>
+__device__ __forceinline__ bool check_subset(const float4* pf, int64_t base, const int* idx) {
+    if (MODEL == RM_ESSENTIAL) return true;
+    constexpr int MP = MT<MODEL>::MP;
+    float s[2 * MP], d[2 * MP];
+#pragma unroll
+    for (int i = 0; i < MP; ++i) {
+        const float4 p = pf[base + idx[i]];
+        s[2 * i] = p.x; s[2 * i + 1] = p.y; d[2 * i] = p.z; d[2 * i + 1] = p.w;
+    }
+    if (MODEL == RM_HOMOGRAPHY) return h_check_subset(s, d);
+    return !(have_collinear(s, MP) || have_collinear(d, MP));
+}
+
+// OpenCV's stream: RNG((uint64)-1) per call, subsets drawn one after another (getSubset).
+template <int MODEL>
+__global__ void __launch_bounds__(64)
+sample_mwc_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off, int nPairs,
+                  int maxIters, int* __restrict__ samples, int* __restrict__ nIter,
+                  int* __restrict__ flags) {
+    constexpr int MP = MT<MODEL>::MP;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nPairs) return;
+    const int64_t base = off[p];
+    const int n = (int)(off[p + 1] - base);
+    int* out = samples + (int64_t)p * maxIters * MP;
+    if (n < MP) { nIter[p] = 0; flags[p] = PAIR_FAIL; return; }
+    if (n == MP) {
+        for (int i = 0; i < MP; ++i) out[i] = i;
+        nIter[p] = 1; flags[p] = PAIR_DIRECT; return;
+    }
+    Mwc rng;
+    int it = 0;
+    int fl = 0;
+    for (; it < maxIters; ++it) {
+        int idx[MP];
+        bool found = false;
+        for (int attempt = 0; attempt < 10000; ++attempt) {
+            for (int i = 0; i < MP; ++i) {
+                int v;
+                bool dup;
+                do {
+                    v = rng.uniform(n);
+                    dup = false;
+                    for (int k = 0; k < i; ++k) dup |= (idx[k] == v);
+                } while (dup);
+                idx[i] = v;
+            }
+            if (check_subset<MODEL>(pf, base, idx)) { found = true; break; }
+        }
+        if (!found) { if (it == 0) fl = PAIR_FAIL; break; }
+        for (int i = 0; i < MP; ++i) out[it * MP + i] = idx[i];
+    }
+    nIter[p] = it;
+    flags[p] = fl;
+}
+
+// Native mode: hypothesis (pair, it) draws from its own counter-based stream -- no sequential
+// dependency, same duplicate / degeneracy rules.
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+sample_counter_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off, int nPairs,
+                      int maxIters, uint64_t seed, int64_t pairBase, int* __restrict__ samples,
+                      int* __restrict__ nIter, int* __restrict__ flags) {
+    constexpr int MP = MT<MODEL>::MP;
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y;
+    if (it >= maxIters) return;
+    const int64_t base = off[p];
+    const int n = (int)(off[p + 1] - base);
+    int* out = samples + ((int64_t)p * maxIters + it) * MP;
+    if (n < MP) { if (it == 0) { nIter[p] = 0; flags[p] = PAIR_FAIL; } return; }
+    if (n == MP) {
+        if (it == 0) { for (int i = 0; i < MP; ++i) out[i] = i; nIter[p] = 1; flags[p] = PAIR_DIRECT; }
+        return;
+    }
+    if (it == 0) { nIter[p] = maxIters; flags[p] = 0; }
+    uint64_t ctr = mix64(seed ^ mix64((uint64_t)(pairBase + p) * 0x100000001B3ull + (uint64_t)it));
+    int idx[MP];
+    for (int attempt = 0; attempt < 64; ++attempt) {
+        for (int i = 0; i < MP; ++i) {
+            int v;
+            bool dup;
+            do {
+                ctr = mix64(ctr);
+                v = (int)((uint32_t)(ctr >> 32) % (uint32_t)n);
+                dup = false;
+                for (int k = 0; k < i; ++k) dup |= (idx[k] == v);
+            } while (dup);
+            idx[i] = v;
+        }
+        if (check_subset<MODEL>(pf, base, idx)) break;   // after 64 tries keep the last subset
+    }
+    for (int i = 0; i < MP; ++i) out[i] = idx[i];
+}
+
+__global__ void __launch_bounds__(256)
+injected_setup_kernel(const int64_t* __restrict__ off, int nPairs, int maxIters, int mp,
+                      int* __restrict__ nIter, int* __restrict__ flags) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nPairs) return;
+    const int n = (int)(off[p + 1] - off[p]);
+    if (n < mp) { nIter[p] = 0; flags[p] = PAIR_FAIL; }
+    else { nIter[p] = maxIters; flags[p] = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// solve: one hypothesis per thread
+// ---------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(64)
+solve_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
+             const int64_t* __restrict__ off, int maxIters, const int* __restrict__ samples,
+             const int* __restrict__ nIter, double* __restrict__ models,
+             uint8_t* __restrict__ nModels) {
+    constexpr int MP = MT<MODEL>::MP, MAXM = MT<MODEL>::MAXM;
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y;
+    if (it >= maxIters) return;
+    uint8_t* nm = nModels + (int64_t)p * maxIters + it;
+    if (it >= nIter[p]) { *nm = 0; return; }
+    const int64_t base = off[p];
+    const int n = (int)(off[p + 1] - base);
+    const int* idx = samples + ((int64_t)p * maxIters + it) * MP;
+    double* out = models + ((int64_t)p * maxIters + it) * MAXM * 9;
+    int cnt = 0;
+    bool bad = false;
+    for (int i = 0; i < MP; ++i) bad |= (idx[i] < 0 || idx[i] >= n);
+    if (bad) { *nm = 0; return; }
+    if (MODEL == RM_ESSENTIAL) {
+        double a[2 * MP], b[2 * MP];
+        for (int i = 0; i < MP; ++i) {
+            const double* q = pd + 4 * (base + idx[i]);
+            a[2 * i] = q[0]; a[2 * i + 1] = q[1]; b[2 * i] = q[2]; b[2 * i + 1] = q[3];
+        }
+        double Es[MAXM * 9];
+        cnt = e_solve5(a, b, Es);
+        for (int k = 0; k < cnt * 9; ++k) out[k] = Es[k];
+    } else {
+        float s[2 * MP], d[2 * MP];
+        for (int i = 0; i < MP; ++i) {
+            const float4 q = pf[base + idx[i]];
+            s[2 * i] = q.x; s[2 * i + 1] = q.y; d[2 * i] = q.z; d[2 * i + 1] = q.w;
+        }
+        if (MODEL == RM_HOMOGRAPHY) {
+            double H[9];
+            cnt = h_solve4(s, d, H) ? 1 : 0;
+            if (cnt) for (int k = 0; k < 9; ++k) out[k] = H[k];
+        } else {
+            double F[27];
+            cnt = f_solve7(s, d, F);
+            if (cnt < 0 || cnt > 3) cnt = 0;
+            for (int k = 0; k < cnt * 9; ++k) out[k] = F[k];
+        }
+    }
+    *nm = (uint8_t)cnt;
+}
+
+// injected models: one model per iteration, copied into slot 0
+__global__ void __launch_bounds__(256)
+inject_models_kernel(const double* __restrict__ inj, int64_t nHyp, int maxm,
+                     double* __restrict__ models, uint8_t* __restrict__ nModels) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nHyp) return;
+    for (int k = 0; k < 9; ++k) models[h * maxm * 9 + k] = inj[h * 9 + k];
+    nModels[h] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// compact: dense model list per pair in (iteration, model) order
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+compact_kernel(const uint8_t* __restrict__ nModels, const int* __restrict__ nIter, int maxIters,
+               int maxm, int* __restrict__ iterStart, int* __restrict__ slotList,
+               int* __restrict__ nTotal) {
+    const int p = blockIdx.x;
+    const uint8_t* nm = nModels + (int64_t)p * maxIters;
+    int* is = iterStart + (int64_t)p * (maxIters + 1);
+    int* sl = slotList + (int64_t)p * maxIters * maxm;
+    __shared__ int sPart[256];
+    __shared__ int sBase;
+    const int tid = threadIdx.x;
+    const int ni = nIter[p];
+    if (tid == 0) sBase = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < maxIters; c0 += 256) {
+        const int it = c0 + tid;
+        const int v = (it < ni) ? nm[it] : 0;
+        sPart[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {          // inclusive Hillis-Steele scan
+            const int t = tid >= o ? sPart[tid - o] : 0;
+            __syncthreads();
+            sPart[tid] += t;
+            __syncthreads();
+        }
+        const int start = sBase + sPart[tid] - v;
+        if (it < maxIters) {
+            is[it] = start;
+            for (int m = 0; m < v; ++m) sl[start + m] = it * maxm + m;
+        }
+        __syncthreads();
+        if (tid == 255) sBase += sPart[255];
+        __syncthreads();
+    }
+    if (tid == 0) { is[maxIters] = sBase; nTotal[p] = sBase; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// score: one model per thread, correspondences through shared memory
+// ---------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
+             const int64_t* __restrict__ off, const double* __restrict__ models,
+             const int* __restrict__ slotList, const int* __restrict__ nTotal, int maxSlots,
+             float thr2, int chunkPts, int* __restrict__ counts) {
+    constexpr int TP = (MODEL == RM_ESSENTIAL) ? 512 : 1024;   // 16 KB per stage
+    __shared__ __align__(16) unsigned char sraw[16384];
+    const int p = blockIdx.y;
+    const int total = nTotal[p];
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    if (blockIdx.x * 128 >= total) return;
+    const bool active = k < total;
+    const int64_t base = off[p];
+    const int n = (int)(off[p + 1] - base);
+    const int i0 = blockIdx.z * chunkPts;
+    const int i1 = min(n, i0 + chunkPts);
+
+    double m[9];
+    float Hf[8];
+    if (active) {
+        const int slot = slotList[(int64_t)p * maxSlots + k];
+        const double* src = models + ((int64_t)p * maxSlots + slot) * 9;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) m[j] = src[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) m[j] = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Hf[j] = (float)m[j];
+
+    int cnt = 0;
+    for (int s0 = i0; s0 < i1; s0 += TP) {
+        const int rows = min(TP, i1 - s0);
+        if (MODEL == RM_ESSENTIAL) {
+            double4* sp = reinterpret_cast<double4*>(sraw);
+            const double4* g = reinterpret_cast<const double4*>(pd) + base + s0;
+            for (int j = threadIdx.x; j < rows; j += 128) sp[j] = g[j];
+        } else {
+            float4* sp = reinterpret_cast<float4*>(sraw);
+            const float4* g = pf + base + s0;
+            for (int j = threadIdx.x; j < rows; j += 128) sp[j] = g[j];
+        }
+        __syncthreads();
+        if (MODEL == RM_HOMOGRAPHY) {
+            const float4* sp = reinterpret_cast<const float4*>(sraw);
+#pragma unroll 4
+            for (int j = 0; j < rows; ++j) {
+                const float4 q = sp[j];
+                cnt += (h_error(Hf, q.x, q.y, q.z, q.w) <= thr2) ? 1 : 0;
+            }
+        } else if (MODEL == RM_FUNDAMENTAL) {
+            const float4* sp = reinterpret_cast<const float4*>(sraw);
+#pragma unroll 2
+            for (int j = 0; j < rows; ++j) {
+                const float4 q = sp[j];
+                cnt += (f_error(m, (double)q.x, (double)q.y, (double)q.z, (double)q.w) <= thr2) ? 1 : 0;
+            }
+        } else {
+            const double4* sp = reinterpret_cast<const double4*>(sraw);
+#pragma unroll 2
+            for (int j = 0; j < rows; ++j) {
+                const double4 q = sp[j];
+                cnt += (e_error(m, q.x, q.y, q.z, q.w) <= thr2) ? 1 : 0;
+            }
+        }
+        __syncthreads();
+    }
+    if (active) {
+        int* c = counts + (int64_t)p * maxSlots + k;
+        if (gridDim.z == 1) *c = cnt; else atomicAdd(c, cnt);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// select: OpenCV's sequential accept rule + adaptive iteration count, replayed over the counts
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+select_kernel(const int64_t* __restrict__ off, int nPairs, int maxIters, int maxm, int mp,
+              int adaptive, double confidence, const int* __restrict__ nIter,
+              const int* __restrict__ flags, const int* __restrict__ iterStart,
+              const int* __restrict__ counts, int* __restrict__ best /*[nPairs][4]*/) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nPairs) return;
+    const int n = (int)(off[p + 1] - off[p]);
+    int* o = best + 4 * p;   // compacted index, count, iterations run, iteration*maxm+model
+    o[0] = -1; o[1] = 0; o[2] = 0; o[3] = -1;
+    if (flags[p] & PAIR_FAIL) return;
+    const int* is = iterStart + (int64_t)p * (maxIters + 1);
+    const int* c = counts + (int64_t)p * maxIters * maxm;
+    if (flags[p] & PAIR_DIRECT) {
+        const int nm = is[1] - is[0];
+        if (nm > 0) { o[0] = 0; o[1] = n; o[2] = 1; o[3] = 0; }
+        return;
+    }
+    int niters = max(maxIters, 1);
+    const int ni = nIter[p];
+    int maxGood = 0, bestK = -1, bestSlot = -1;
+    int it = 0;
+    for (; it < niters && it < ni; ++it) {
+        const int k0 = is[it], k1 = is[it + 1];
+        for (int k = k0; k < k1; ++k) {
+            const int good = c[k];
+            if (good > max(maxGood, mp - 1)) {
+                maxGood = good; bestK = k; bestSlot = it * maxm + (k - k0);
+                if (adaptive) niters = update_num_iters(confidence, (double)(n - good) / n, mp, niters);
+            }
+        }
+    }
+    o[0] = bestK; o[1] = maxGood; o[2] = it; o[3] = bestSlot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize
+// ---------------------------------------------------------------------------------------------
+constexpr int FB = 256;   // finalize block size
+
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double* sred /*[K * 8]*/, double* sout /*[K]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        if (lane == 0) sred[warp * K + k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double s = 0;
+        for (int w = 0; w < FB / 32; ++w) s += sred[w * K + threadIdx.x];
+        sout[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double block_max(double x, double* sred) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xFFFFFFFFu, x, o));
+    if (lane == 0) sred[warp] = x;
+    __syncthreads();
+    double r = sred[0];
+    for (int w = 1; w < FB / 32; ++w) r = fmax(r, sred[w]);
+    __syncthreads();
+    return r;
+}
+
+// F / E (and H without refinement): mask of the winner, model copied out.
+template <int MODEL>
+__global__ void __launch_bounds__(FB)
+finalize_plain_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
+                      const int64_t* __restrict__ off, const double* __restrict__ models,
+                      int maxSlots, const int* __restrict__ best, const int* __restrict__ flags,
+                      const int* __restrict__ nTotal, float thr2, double* __restrict__ outModels,
+                      uint8_t* __restrict__ masks,
+                      int* __restrict__ inlierCounts, uint8_t* __restrict__ ok,
+                      int* __restrict__ itersRun, int* __restrict__ bestOut) {
+    const int p = blockIdx.x;
+    const int64_t base = off[p];
+    const int n = (int)(off[p + 1] - base);
+    const int* b = best + 4 * p;
+    const int slot = b[3];
+    __shared__ int sCnt[FB / 32];
+    if (threadIdx.x == 0 && itersRun) itersRun[p] = b[2];
+    if (slot < 0) {
+        for (int i = threadIdx.x; i < n; i += FB) masks[base + i] = 0;
+        if (threadIdx.x == 0) {
+            ok[p] = 0;
+            if (inlierCounts) inlierCounts[p] = 0;
+            if (bestOut) { bestOut[2 * p] = -1; bestOut[2 * p + 1] = -1; }
+        }
+        return;
+    }
+    const double* src = models + ((int64_t)p * maxSlots + slot) * 9;
+    double m[9];
+    float Hf[8];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) m[j] = src[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Hf[j] = (float)m[j];
+    const bool direct = (flags[p] & PAIR_DIRECT) != 0;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n; i += FB) {
+        bool in;
+        if (direct) in = true;
+        else if (MODEL == RM_HOMOGRAPHY) { const float4 q = pf[base + i]; in = h_error(Hf, q.x, q.y, q.z, q.w) <= thr2; }
+        else if (MODEL == RM_FUNDAMENTAL) { const float4 q = pf[base + i]; in = f_error(m, (double)q.x, (double)q.y, (double)q.z, (double)q.w) <= thr2; }
+        else { const double* q = pd + 4 * (base + i); in = e_error(m, q[0], q[1], q[2], q[3]) <= thr2; }
+        masks[base + i] = in ? 1 : 0;
+        cnt += in ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if ((threadIdx.x & 31) == 0) sCnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < FB / 32; ++w) t += sCnt[w];
+        if (inlierCounts) inlierCounts[p] = t;
+        // E with N == 5 and several solutions: OpenCV returns them stacked and the reference
+        // then reports failure (E not 3x3, MiniCVNative.cpp:184-193)
+        ok[p] = (MODEL == RM_ESSENTIAL && direct && nTotal[p] != 1) ? 0 : 1;
+        for (int j = 0; j < 9; ++j) outModels[9 * p + j] = m[j];
+        if (bestOut) { bestOut[2 * p] = slot / MT<MODEL>::MAXM; bestOut[2 * p + 1] = slot % MT<MODEL>::MAXM; }
+    }
+}
+
+// Homography with OpenCV's post-processing: runKernel on the inliers, LMSolver(10), mask
+// recomputed from the refined H, H /= h33 (cv::findHomography, calib3d/src/fundam.cpp).
+__global__ void __launch_bounds__(FB)
+finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off,
+                           const double* __restrict__ models, int maxSlots,
+                           const int* __restrict__ best, const int* __restrict__ flags, float thr2,
+                           double* __restrict__ outModels, uint8_t* __restrict__ masks,
+                           int* __restrict__ inlierCounts, uint8_t* __restrict__ ok,
+                           int* __restrict__ itersRun, int* __restrict__ bestOut) {
+    const int p = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int64_t base = off[p];
+    const int n = (int)(off[p + 1] - base);
+    const int* b = best + 4 * p;
+    const int slot = b[3];
+    __shared__ double sred[45 * (FB / 32)];
+    __shared__ double sout[48];
+    __shared__ double sH[9];      // current parameters x (8) + 1
+    __shared__ double sXd[9];     // trial parameters
+    __shared__ double sCtl[8];    // [0] continue flag
+    if (tid == 0) {
+        if (itersRun) itersRun[p] = b[2];
+        if (bestOut) { bestOut[2 * p] = slot; bestOut[2 * p + 1] = slot < 0 ? -1 : 0; }
+    }
+    if (slot < 0) {
+        for (int i = tid; i < n; i += FB) masks[base + i] = 0;
+        if (tid == 0) { ok[p] = 0; if (inlierCounts) inlierCounts[p] = 0; }
+        return;
+    }
+    const double* src = models + ((int64_t)p * maxSlots + slot) * 9;
+    if (tid < 9) sH[tid] = src[tid];
+    __syncthreads();
+    const bool direct = (flags[p] & PAIR_DIRECT) != 0;
+    float Hf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Hf[j] = (float)sH[j];
+
+    // RANSAC mask of the winner
+    for (int i = tid; i < n; i += FB) {
+        const float4 q = pf[base + i];
+        masks[base + i] = (direct || h_error(Hf, q.x, q.y, q.z, q.w) <= thr2) ? 1 : 0;
+    }
+    __syncthreads();
+    if (direct) {   // 4 points: kernel only, no refinement
+        if (tid == 0) {
+            ok[p] = 1;
+            if (inlierCounts) inlierCounts[p] = n;
+            for (int j = 0; j < 9; ++j) outModels[9 * p + j] = sH[j];
+        }
+        return;
+    }
+
+    // ---- runKernel on the inliers: centroids, mean absolute deviations, LtL ----
+    {
+        double v[5] = {0, 0, 0, 0, 0};
+        for (int i = tid; i < n; i += FB)
+            if (masks[base + i]) {
+                const float4 q = pf[base + i];
+                v[0] += q.z; v[1] += q.w; v[2] += q.x; v[3] += q.y; v[4] += 1;
+            }
+        block_sum<5>(v, sred, sout);
+    }
+    const double cnt = sout[4];
+    const double cmx = sout[0] / cnt, cmy = sout[1] / cnt, cMx = sout[2] / cnt, cMy = sout[3] / cnt;
+    __syncthreads();
+    {
+        double v[4] = {0, 0, 0, 0};
+        for (int i = tid; i < n; i += FB)
+            if (masks[base + i]) {
+                const float4 q = pf[base + i];
+                v[0] += fabs(q.z - cmx); v[1] += fabs(q.w - cmy);
+                v[2] += fabs(q.x - cMx); v[3] += fabs(q.y - cMy);
+            }
+        block_sum<4>(v, sred, sout);
+    }
+    double smx = sout[0], smy = sout[1], sMx = sout[2], sMy = sout[3];
+    __syncthreads();
+    const bool kernel_ok = !(fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON ||
+                             fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON);
+    if (kernel_ok) {
+        smx = cnt / smx; smy = cnt / smy; sMx = cnt / sMx; sMy = cnt / sMy;
+        double v[45];
+#pragma unroll
+        for (int k = 0; k < 45; ++k) v[k] = 0;
+        for (int i = tid; i < n; i += FB)
+            if (masks[base + i]) {
+                const float4 q = pf[base + i];
+                const double x = (q.z - cmx) * smx, y = (q.w - cmy) * smy;
+                const double X = (q.x - cMx) * sMx, Y = (q.y - cMy) * sMy;
+                const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
+                const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+                int k = 0;
+#pragma unroll
+                for (int r = 0; r < 9; ++r)
+#pragma unroll
+                    for (int c = r; c < 9; ++c) { v[k] += Lx[r] * Lx[c] + Ly[r] * Ly[c]; ++k; }
+            }
+        block_sum<45>(v, sred, sout);
+        if (tid == 0) {
+            double L[81], w[9], V[81];
+            int k = 0;
+            for (int r = 0; r < 9; ++r)
+                for (int c = r; c < 9; ++c) { L[r * 9 + c] = sout[k]; L[c * 9 + r] = sout[k]; ++k; }
+            jacobi_eigen_sym<9>(L, w, V);
+            int mi = 0;
+            for (int i = 1; i < 9; ++i) if (w[i] < w[mi]) mi = i;
+            const double* h = V + 9 * mi;
+            const double iH[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
+            const double N2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
+            double T[9], Hn[9];
+            mat3mul(iH, h, T);
+            mat3mul(T, N2, Hn);
+            if (Hn[8] != 0) {
+                const double sc = 1. / Hn[8];
+                for (int j = 0; j < 9; ++j) sH[j] = Hn[j] * sc;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- LMSolver, 10 iterations, on the 8 free parameters ----
+    // state held by thread 0: A (8x8), v (8), D (8), S, lambda, lc; everyone helps with sums
+    __shared__ double sA[64], sV[8], sD[8], sS, sLam, sLc, sRmax;
+    auto accumulate = [&](const double* x) {   // A, v, S, max|r| at parameters x
+        double v[45];
+#pragma unroll
+        for (int k = 0; k < 45; ++k) v[k] = 0;
+        double rmax = 0;
+        for (int i = tid; i < n; i += FB)
+            if (masks[base + i]) {
+                const float4 q = pf[base + i];
+                const double Mx = q.x, My = q.y;
+                double ww = x[6] * Mx + x[7] * My + 1.;
+                ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+                const double xi = (x[0] * Mx + x[1] * My + x[2]) * ww;
+                const double yi = (x[3] * Mx + x[4] * My + x[5]) * ww;
+                const double r0 = xi - q.z, r1 = yi - q.w;
+                const double J0[8] = {Mx * ww, My * ww, ww, 0, 0, 0, -Mx * ww * xi, -My * ww * xi};
+                const double J1[8] = {0, 0, 0, Mx * ww, My * ww, ww, -Mx * ww * yi, -My * ww * yi};
+                int k = 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = r; c < 8; ++c) { v[k] += J0[r] * J0[c] + J1[r] * J1[c]; ++k; }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) v[36 + r] += J0[r] * r0 + J1[r] * r1;
+                v[44] += r0 * r0 + r1 * r1;
+                rmax = fmax(rmax, fmax(fabs(r0), fabs(r1)));
+            }
+        block_sum<45>(v, sred, sout);
+        const double rm = block_max(rmax, sred);
+        if (tid == 0) {
+            int k = 0;
+            for (int r = 0; r < 8; ++r)
+                for (int c = r; c < 8; ++c) { sA[r * 8 + c] = sout[k]; sA[c * 8 + r] = sout[k]; ++k; }
+            for (int r = 0; r < 8; ++r) sV[r] = sout[36 + r];
+            sS = sout[44];
+            sRmax = rm;
+        }
+        __syncthreads();
+    };
+    auto residual_sq = [&](const double* x) -> double {   // Sd at trial parameters
+        double v[1] = {0};
+        for (int i = tid; i < n; i += FB)
+            if (masks[base + i]) {
+                const float4 q = pf[base + i];
+                const double Mx = q.x, My = q.y;
+                double ww = x[6] * Mx + x[7] * My + 1.;
+                ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+                const double r0 = (x[0] * Mx + x[1] * My + x[2]) * ww - q.z;
+                const double r1 = (x[3] * Mx + x[4] * My + x[5]) * ww - q.w;
+                v[0] += r0 * r0 + r1 * r1;
+            }
+        block_sum<1>(v, sred, sout);
+        const double r = sout[0];
+        __syncthreads();
+        return r;
+    };
+
+    accumulate(sH);
+    if (tid == 0) {
+        for (int r = 0; r < 8; ++r) sD[r] = sA[r * 8 + r];
+        sLam = 1; sLc = 0.75;
+    }
+    __syncthreads();
+    __shared__ double sDvec[8];
+    for (int iter = 0; iter < 10; ++iter) {
+        if (tid == 0) {
+            double Ap[64];
+            for (int k = 0; k < 64; ++k) Ap[k] = sA[k];
+            for (int r = 0; r < 8; ++r) Ap[r * 8 + r] += sLam * sD[r];
+            double d[8];
+            solve_sym_eig<8>(Ap, sV, d);
+            for (int r = 0; r < 8; ++r) { sDvec[r] = d[r]; sXd[r] = sH[r] - d[r]; }
+        }
+        __syncthreads();
+        const double Sd = residual_sq(sXd);
+        if (tid == 0) {
+            const double S = sS;
+            double dS = 0, tdv = 0;
+            for (int r = 0; r < 8; ++r) {
+                double Ad = 0;
+                for (int c = 0; c < 8; ++c) Ad += sA[r * 8 + c] * sDvec[c];
+                dS += sDvec[r] * (-Ad + 2 * sV[r]);
+                tdv += sDvec[r] * sV[r];
+            }
+            const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
+            if (R > 0.75) {
+                sLam *= 0.5;
+                if (sLam < sLc) sLam = 0;
+            } else if (R < 0.25) {
+                double nu = (Sd - S) / (fabs(tdv) > DBL_EPSILON ? tdv : 1) + 2;
+                nu = fmin(fmax(nu, 2.), 10.);
+                if (sLam == 0) {
+                    const double maxval = max_diag_pinv_sym<8>(sA);
+                    sLam = sLc = 1. / maxval;
+                    nu *= 0.5;
+                }
+                sLam *= nu;
+            }
+            sCtl[0] = (Sd < S) ? 1 : 0;
+            if (Sd < S) for (int r = 0; r < 8; ++r) sH[r] = sXd[r];
+        }
+        __syncthreads();
+        if (sCtl[0] != 0) accumulate(sH);
+        if (tid == 0) {
+            double dinf = 0;
+            for (int r = 0; r < 8; ++r) dinf = fmax(dinf, fabs(sDvec[r]));
+            const bool proceed = (iter + 1 < 10) && dinf >= (double)FLT_EPSILON && sRmax >= (double)FLT_EPSILON;
+            sCtl[1] = proceed ? 1 : 0;
+        }
+        __syncthreads();
+        if (sCtl[1] == 0) break;
+    }
+    if (tid == 0) sH[8] = 1.0;
+    __syncthreads();
+
+    // ---- mask recomputed from the refined H ----
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Hf[j] = (float)sH[j];
+    int c2 = 0;
+    for (int i = tid; i < n; i += FB) {
+        const float4 q = pf[base + i];
+        const bool in = h_error(Hf, q.x, q.y, q.z, q.w) <= thr2;
+        masks[base + i] = in ? 1 : 0;
+        c2 += in ? 1 : 0;
+    }
+    {
+        double v[1] = {(double)c2};
+        block_sum<1>(v, sred, sout);
+    }
+    if (tid == 0) {
+        ok[p] = 1;
+        if (inlierCounts) inlierCounts[p] = (int)sout[0];
+        for (int j = 0; j < 9; ++j) outModels[9 * p + j] = sH[j];
+    }
+}
+
+// debug taps: expand compacted counts back to [maxIters][MAXM] (-1 = no model)
+__global__ void __launch_bounds__(256)
+dbg_counts_kernel(const int* __restrict__ iterStart, const int* __restrict__ counts, int maxIters,
+                  int maxm, int* __restrict__ out) {
+    const int p = blockIdx.y;
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= maxIters) return;
+    const int* is = iterStart + (int64_t)p * (maxIters + 1);
+    const int k0 = is[it], k1 = is[it + 1];
+    for (int m = 0; m < maxm; ++m)
+        out[((int64_t)p * maxIters + it) * maxm + m] = (m < k1 - k0) ? counts[(int64_t)p * maxIters * maxm + k0 + m] : -1;
+}
+
+template <int MODEL>
+int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const RansacIO& io) {
+    constexpr int MP = MT<MODEL>::MP, MAXM = MT<MODEL>::MAXM;
+    const int nPairs = io.nPairs;
+    const int maxIters = std::max(prm.maxIters, 1);
+    const int64_t total = io.hOff[nPairs];
+    const float thr2 = MODEL == RM_ESSENTIAL
+                           ? (float)((prm.threshold / ((prm.focal + prm.focal) / 2)) * (prm.threshold / ((prm.focal + prm.focal) / 2)))
+                           : (float)(prm.threshold * prm.threshold);
+
+    // device offsets (whole batch), staged through pinned memory
+    const size_t n1 = (size_t)nPairs + 1;
+    if (ctx->pin[1].reserve(n1 * 8) || ctx->ws[10].reserve(n1 * 8)) return -1;
+    MCV_CUDA_TRY(cudaEventSynchronize(ctx->ev[1]));
+    memcpy(ctx->pin[1].p, io.hOff, n1 * 8);
+    MCV_CUDA_TRY(cudaMemcpyAsync(ctx->ws[10].p, ctx->pin[1].p, n1 * 8, cudaMemcpyHostToDevice, st));
+    MCV_CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+    const int64_t* dOff = ctx->ws[10].as<int64_t>();
+
+    // working point layout
+    float4* pf = nullptr;
+    double* pd = nullptr;
+    if (MODEL == RM_ESSENTIAL) {
+        if (ctx->ws[11].reserve((size_t)std::max<int64_t>(total, 1) * 32)) return -1;
+        pd = ctx->ws[11].as<double>();
+    } else {
+        if (ctx->ws[11].reserve((size_t)std::max<int64_t>(total, 1) * 16)) return -1;
+        pf = ctx->ws[11].as<float4>();
+    }
+    if (total > 0) {
+        const double invf = 1.0 / prm.focal;
+        prep_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const double2*>(io.dA), reinterpret_cast<const double2*>(io.dB), total,
+            MODEL == RM_ESSENTIAL ? 1 : 0, invf, -prm.ppx * invf, -prm.ppy * invf, pf, pd);
+        MCV_LAUNCH_CHECK();
+    }
+
+    // pair chunks bound the per-hypothesis workspaces (~1 GB of models at most)
+    const size_t perPair = (size_t)maxIters * MAXM * 72;
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nPairs, ((size_t)1 << 30) / std::max<size_t>(perPair, 1)));
+    const size_t slots = (size_t)maxIters * MAXM;
+    if (ctx->ws[12].reserve((size_t)chunk * maxIters * MP * 4) ||       // samples
+        ctx->ws[13].reserve((size_t)chunk * 8 + 64) ||                  // nIter, flags
+        ctx->ws[14].reserve((size_t)chunk * slots * 72) ||              // models
+        ctx->ws[15].reserve((size_t)chunk * maxIters) ||                // nModels
+        ctx->ws[16].reserve((size_t)chunk * (maxIters + 1) * 4) ||      // iterStart
+        ctx->ws[17].reserve((size_t)chunk * slots * 4) ||               // slotList
+        ctx->ws[18].reserve((size_t)chunk * slots * 4) ||               // counts
+        ctx->ws[19].reserve((size_t)chunk * 4 + 64) ||                  // nTotal
+        ctx->ws[20].reserve((size_t)chunk * 16))                        // best
+        return -1;
+    int* dSamples = ctx->ws[12].as<int>();
+    int* dNIter = ctx->ws[13].as<int>();
+    int* dFlags = dNIter + chunk;
+    double* dModels = ctx->ws[14].as<double>();
+    uint8_t* dNModels = ctx->ws[15].as<uint8_t>();
+    int* dIterStart = ctx->ws[16].as<int>();
+    int* dSlotList = ctx->ws[17].as<int>();
+    int* dCounts = ctx->ws[18].as<int>();
+    int* dNTotal = ctx->ws[19].as<int>();
+    int* dBest = ctx->ws[20].as<int>();
+
+    for (int p0 = 0; p0 < nPairs; p0 += chunk) {
+        const int np = std::min(chunk, nPairs - p0);
+        const int64_t* off = dOff + p0;
+        int64_t maxN = 0;
+        for (int p = p0; p < p0 + np; ++p) maxN = std::max(maxN, io.hOff[p + 1] - io.hOff[p]);
+
+        // ---- sample
+        if (io.dInjModels) {
+            injected_setup_kernel<<<(np + 255) / 256, 256, 0, st>>>(off, np, maxIters, MP, dNIter, dFlags);
+            MCV_LAUNCH_CHECK();
+        } else if (prm.sampleMode == MCV_SAMPLE_INJECTED) {
+            if (!io.dInjSamples) { set_error("MCV_SAMPLE_INJECTED without sample indices"); return -1; }
+            MCV_CUDA_TRY(cudaMemcpyAsync(dSamples, io.dInjSamples + (size_t)p0 * maxIters * MP,
+                                         (size_t)np * maxIters * MP * 4, cudaMemcpyDeviceToDevice, st));
+            injected_setup_kernel<<<(np + 255) / 256, 256, 0, st>>>(off, np, maxIters, MP, dNIter, dFlags);
+            MCV_LAUNCH_CHECK();
+        } else if (prm.sampleMode == MCV_SAMPLE_COUNTER) {
+            dim3 g((maxIters + 127) / 128, np);
+            sample_counter_kernel<MODEL><<<g, 128, 0, st>>>(pf, off, np, maxIters, prm.seed, p0,
+                                                            dSamples, dNIter, dFlags);
+            MCV_LAUNCH_CHECK();
+        } else {
+            sample_mwc_kernel<MODEL><<<(np + 63) / 64, 64, 0, st>>>(pf, off, np, maxIters, dSamples,
+                                                                    dNIter, dFlags);
+            MCV_LAUNCH_CHECK();
+        }
+        // ---- solve
+        if (io.dInjModels) {
+            const int64_t nh = (int64_t)np * maxIters;
+            inject_models_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(
+                io.dInjModels + (size_t)p0 * maxIters * 9, nh, MAXM, dModels, dNModels);
+            MCV_LAUNCH_CHECK();
+        } else {
+            dim3 g((maxIters + 63) / 64, np);
+            solve_kernel<MODEL><<<g, 64, 0, st>>>(pf, pd, off, maxIters, dSamples, dNIter, dModels, dNModels);
+            MCV_LAUNCH_CHECK();
+        }
+        // ---- compact
+        compact_kernel<<<np, 256, 0, st>>>(dNModels, dNIter, maxIters, MAXM, dIterStart, dSlotList, dNTotal);
+        MCV_LAUNCH_CHECK();
+        // ---- score
+        {
+            const int tiles = (int)((slots + 127) / 128);
+            int zs = 1;
+            const int64_t blocksXY = (int64_t)tiles * np;
+            const int64_t fill = 4ll * ctx->sm_count;
+            const int TPmin = (MODEL == RM_ESSENTIAL) ? 512 : 1024;
+            if (blocksXY < fill) zs = (int)std::min<int64_t>((fill + blocksXY - 1) / blocksXY, std::max<int64_t>(1, (maxN + TPmin - 1) / TPmin));
+            int chunkPts = (int)((std::max<int64_t>(maxN, 1) + zs - 1) / zs);
+            zs = (int)((std::max<int64_t>(maxN, 1) + chunkPts - 1) / chunkPts);
+            if (zs > 1) MCV_CUDA_TRY(cudaMemsetAsync(dCounts, 0, (size_t)np * slots * 4, st));
+            dim3 g(tiles, np, zs);
+            score_kernel<MODEL><<<g, 128, 0, st>>>(pf, pd, off, dModels, dSlotList, dNTotal, (int)slots,
+                                                   thr2, chunkPts, dCounts);
+            MCV_LAUNCH_CHECK();
+        }
+        // ---- select
+        select_kernel<<<(np + 63) / 64, 64, 0, st>>>(off, np, maxIters, MAXM, MP,
+                                                     prm.stopMode == MCV_STOP_ADAPTIVE ? 1 : 0,
+                                                     prm.confidence, dNIter, dFlags, dIterStart, dCounts, dBest);
+        MCV_LAUNCH_CHECK();
+        // ---- finalize
+        double* oM = io.dModels + (size_t)p0 * 9;
+        uint8_t* oOk = io.dOk + p0;
+        int* oCnt = io.dInlierCounts ? io.dInlierCounts + p0 : nullptr;
+        int* oIt = io.dItersRun ? io.dItersRun + p0 : nullptr;
+        int* oBest = io.dBest ? io.dBest + 2 * (size_t)p0 : nullptr;
+        if (MODEL == RM_HOMOGRAPHY && prm.refine) {
+            finalize_homography_kernel<<<np, FB, 0, st>>>(pf, off, dModels, (int)slots, dBest, dFlags, thr2,
+                                                          oM, io.dMasks, oCnt, oOk, oIt, oBest);
+        } else {
+            finalize_plain_kernel<MODEL><<<np, FB, 0, st>>>(pf, pd, off, dModels, (int)slots, dBest, dFlags,
+                                                            dNTotal, thr2, oM, io.dMasks, oCnt, oOk, oIt, oBest);
+        }
+        MCV_LAUNCH_CHECK();
+        // ---- debug taps
+        if (io.dDbgCounts) {
+            dim3 g((maxIters + 255) / 256, np);
+            dbg_counts_kernel<<<g, 256, 0, st>>>(dIterStart, dCounts, maxIters, MAXM,
+                                                 io.dDbgCounts + (size_t)p0 * slots);
+            MCV_LAUNCH_CHECK();
+        }
+        if (io.dDbgModels)
+            MCV_CUDA_TRY(cudaMemcpyAsync(io.dDbgModels + (size_t)p0 * slots * 9, dModels,
+                                         (size_t)np * slots * 72, cudaMemcpyDeviceToDevice, st));
+        if (io.dDbgSamples && !io.dInjModels)
+            MCV_CUDA_TRY(cudaMemcpyAsync(io.dDbgSamples + (size_t)p0 * maxIters * MP, dSamples,
+                                         (size_t)np * maxIters * MP * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+}  // namespace
+
+int ransac_batch_device(Context* ctx, cudaStream_t stream, const RansacParams& prm, const RansacIO& io) {
+    if (io.nPairs <= 0) return 0;
+    if (!io.hOff || io.hOff[0] != 0) { set_error("ransac: offsets must start at 0"); return -1; }
+    if (!io.dModels || !io.dMasks || !io.dOk) { set_error("ransac: null outputs"); return -1; }
+    if (!(prm.confidence > 0 && prm.confidence < 1) && prm.stopMode == MCV_STOP_ADAPTIVE) {
+        set_error("ransac: confidence must be in (0,1) (OpenCV asserts the same)");
+        return -1;
+    }
+    if (prm.maxIters > (1 << 20)) { set_error("ransac: maxIters too large"); return -1; }
+    switch (prm.model) {
+        case RM_HOMOGRAPHY: return run_model<RM_HOMOGRAPHY>(ctx, stream, prm, io);
+        case RM_FUNDAMENTAL: return run_model<RM_FUNDAMENTAL>(ctx, stream, prm, io);
+        case RM_ESSENTIAL: return run_model<RM_ESSENTIAL>(ctx, stream, prm, io);
+    }
+    set_error("ransac: unknown model %d", prm.model);
+    return -1;
+}
+
+}  // namespace mcv

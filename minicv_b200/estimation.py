@@ -1,0 +1,218 @@
+"""Two-view estimation -- host-side mirror of ``MiniCV.OpenCV`` (reference
+``src/MiniCV/OpenCV.fs:855-920``): ``recoverPose``, ``recoverPoses``, ``recoverPoses2``,
+``fivepoint`` with the reference's argument meaning, sentinels and return shapes, plus the
+new ``findHomography`` / ``findFundamentalMat`` and the batched / injected forms.
+Everything calls through the C ABI into the CUDA library; nothing is computed here."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import native
+
+MODEL_H, MODEL_F, MODEL_E = 0, 1, 2
+SAMPLE_MWC, SAMPLE_COUNTER, SAMPLE_INJECTED = 0, 1, 2
+STOP_ADAPTIVE, STOP_FIXED = 0, 1
+MODEL_POINTS = {MODEL_H: 4, MODEL_F: 7, MODEL_E: 5}
+MAX_MODELS = {MODEL_H: 1, MODEL_F: 3, MODEL_E: 10}
+
+
+@dataclass
+class RecoverPoseConfig:
+    """Reference ``RecoverPoseConfig`` (``OpenCV.fs:16-36``); ``Default`` = (1, (0,0), .999, .005)."""
+    FocalLength: float = 1.0
+    PrincipalPoint: tuple = (0.0, 0.0)
+    Probability: float = 0.999
+    InlierThreshold: float = 0.005
+
+    def native(self) -> native.RecoverPoseConfig:
+        c = native.RecoverPoseConfig()
+        c.FocalLength = self.FocalLength
+        c.PrincipalPoint.X, c.PrincipalPoint.Y = self.PrincipalPoint
+        c.Probability = self.Probability
+        c.InlierThreshold = self.InlierThreshold
+        return c
+
+
+def _pts(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a.reshape(-1, 2)
+
+
+def _p(a):
+    return a.ctypes.data if a is not None and a.size else 0
+
+
+def recoverPose(cfg: RecoverPoseConfig, a, b):
+    """``OpenCV.recoverPose`` (``OpenCV.fs:855-861``): returns (res, m, t, ms) with the
+    reference's sentinels m = identity, t = (100,123,432) left untouched on failure."""
+    lib = native.load()
+    a, b = _pts(a), _pts(b)
+    m = np.eye(3)
+    t = np.array([100.0, 123.0, 432.0])
+    ms = np.zeros(a.shape[0], np.uint8)
+    c = cfg.native()
+    res = lib.cvRecoverPose(C.addressof(c), a.shape[0], _p(a), _p(b), _p(m), _p(t), _p(ms))
+    return res, m, t, ms
+
+
+def recoverPoses(cfg: RecoverPoseConfig, a, b):
+    """``OpenCV.recoverPoses`` (``OpenCV.fs:863-870``): (m1, m2, t, ms)."""
+    lib = native.load()
+    a, b = _pts(a), _pts(b)
+    m1, m2 = np.eye(3), np.eye(3)
+    t = np.array([100.0, 123.0, 432.0])
+    ms = np.zeros(a.shape[0], np.uint8)
+    c = cfg.native()
+    lib.cvRecoverPoses(C.addressof(c), a.shape[0], _p(a), _p(b), _p(m1), _p(m2), _p(t), _p(ms))
+    return m1, m2, t, ms
+
+
+def recoverPoses2(cfg: RecoverPoseConfig, a, b):
+    """``OpenCV.recoverPoses2`` (``OpenCV.fs:872-909``): flips y, rescales the config, calls
+    cvRecoverPoses, transposes R and conjugates by C = diag(1,-1,-1).  Returns
+    (list of (R, t) candidate poses, boolean mask)."""
+    scale = 2.0
+    off = np.array([0.0, 0.0])
+    a, b = _pts(a), _pts(b)
+
+    def mp(v):
+        return np.stack([0.5 * v[:, 0] + off[0], off[1] - 0.5 * v[:, 1]], axis=1) * scale
+
+    cfg2 = RecoverPoseConfig(scale * cfg.FocalLength / 2.0, tuple(scale * off), cfg.Probability,
+                             scale * 0.5 * cfg.InlierThreshold)
+    m1, m2, t, ms = recoverPoses(cfg2, mp(a), mp(b))
+    Cm = np.diag([1.0, -1.0, -1.0])
+    m1 = Cm @ m1.T @ Cm
+    m2 = Cm @ m2.T @ Cm
+    t = Cm @ t
+    poses = [(m1, t)] if np.array_equal(m1, m2) else [(m1, t), (m2, t)]
+    return poses, ms != 0
+
+
+def fivepoint(a, b) -> np.ndarray:
+    """``OpenCV.fivepoint`` (``OpenCV.fs:912-920``): all essential matrices through 5 points."""
+    lib = native.load()
+    a, b = _pts(a), _pts(b)
+    if a.shape[0] != 5 or b.shape[0] != 5:
+        raise ValueError("fivepoint takes exactly 5 correspondences")
+    res = np.zeros((10, 3, 3))
+    cnt = lib.cvFivePoint(_p(a), _p(b), _p(res))
+    return res[:cnt].copy() if cnt > 0 else np.zeros((0, 3, 3))
+
+
+def fivepoint_batch(a, b):
+    lib = native.load()
+    a = np.ascontiguousarray(a, np.float64).reshape(-1, 5, 2)
+    b = np.ascontiguousarray(b, np.float64).reshape(-1, 5, 2)
+    n = a.shape[0]
+    res = np.zeros((n, 10, 3, 3))
+    cnt = np.zeros(n, np.int32)
+    native.check(lib.cvFivePointBatch(_p(a), _p(b), n, _p(res), _p(cnt)), "cvFivePointBatch")
+    return res, cnt
+
+
+def findHomography(a, b, thr: float = 3.0, maxIters: int = 2000, confidence: float = 0.995):
+    """== ``cv2.findHomography(a, b, cv2.RANSAC, thr, maxIters=, confidence=)`` -> (H | None, mask)."""
+    lib = native.load()
+    a, b = _pts(a), _pts(b)
+    H = np.zeros((3, 3))
+    mask = np.zeros(a.shape[0], np.uint8)
+    ok = lib.cvFindHomography(_p(a), _p(b), a.shape[0], thr, maxIters, confidence, _p(H), _p(mask))
+    return (H if ok else None), mask
+
+
+def findFundamentalMat(a, b, thr: float = 3.0, confidence: float = 0.99, maxIters: int = 1000):
+    """== ``cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, thr, confidence, maxIters)``."""
+    lib = native.load()
+    a, b = _pts(a), _pts(b)
+    F = np.zeros((3, 3))
+    mask = np.zeros(a.shape[0], np.uint8)
+    ok = lib.cvFindFundamentalMat(_p(a), _p(b), a.shape[0], thr, confidence, maxIters, _p(F), _p(mask))
+    return (F if ok else None), mask
+
+
+@dataclass
+class RansacBatchResult:
+    models: np.ndarray        # [nPairs, 3, 3]
+    masks: np.ndarray         # [total] uint8
+    inliers: np.ndarray       # [nPairs]
+    ok: np.ndarray            # [nPairs] uint8
+    iters_run: np.ndarray     # [nPairs]
+    best: np.ndarray          # [nPairs, 2] (iteration, model index)
+    dbg_counts: np.ndarray | None = None   # [nPairs, maxIters, maxModels]
+    dbg_models: np.ndarray | None = None   # [nPairs, maxIters, maxModels, 3, 3]
+    dbg_samples: np.ndarray | None = None  # [nPairs, maxIters, modelPoints]
+
+
+def ransac_batch(model: int, a, b, offsets, thr: float, maxIters: int, confidence: float = 0.995,
+                 sample_mode: int = SAMPLE_MWC, stop_mode: int = STOP_ADAPTIVE, seed: int = 0,
+                 focal: float = 1.0, pp=(0.0, 0.0), refine: bool = True, samples=None, models=None,
+                 debug: bool = False, device: int = -1) -> RansacBatchResult:
+    """Batched RANSAC (``cvRansacBatch``).  ``samples`` injects index sets
+    [nPairs, maxIters, modelPoints]; ``models`` injects matrices [nPairs, maxIters, 3, 3]."""
+    lib = native.load()
+    a, b = _pts(a), _pts(b)
+    off = np.ascontiguousarray(offsets, np.int64)
+    n_pairs = off.size - 1
+    prm = native.RansacParams(model, sample_mode, stop_mode, maxIters, thr, confidence, seed, focal,
+                              pp[0], pp[1], 1 if refine else 0, 0)
+    mp, mm = MODEL_POINTS[model], MAX_MODELS[model]
+    inj_s = inj_m = None
+    if samples is not None:
+        inj_s = np.ascontiguousarray(samples, np.int32).reshape(n_pairs, maxIters, mp)
+        prm.sampleMode = SAMPLE_INJECTED
+    if models is not None:
+        inj_m = np.ascontiguousarray(models, np.float64).reshape(n_pairs, maxIters, 9)
+    out = RansacBatchResult(np.zeros((n_pairs, 3, 3)), np.zeros(a.shape[0], np.uint8),
+                            np.zeros(n_pairs, np.int32), np.zeros(n_pairs, np.uint8),
+                            np.zeros(n_pairs, np.int32), np.zeros((n_pairs, 2), np.int32))
+    if debug:
+        out.dbg_counts = np.zeros((n_pairs, maxIters, mm), np.int32)
+        out.dbg_models = np.zeros((n_pairs, maxIters, mm, 3, 3))
+        out.dbg_samples = np.zeros((n_pairs, maxIters, mp), np.int32)
+    native.check(lib.cvRansacBatch(C.addressof(prm), _p(a), _p(b), _p(off), n_pairs, _p(inj_s), _p(inj_m),
+                                   _p(out.models), _p(out.masks), _p(out.inliers), _p(out.ok),
+                                   _p(out.iters_run), _p(out.best), _p(out.dbg_counts),
+                                   _p(out.dbg_models), _p(out.dbg_samples), device), "cvRansacBatch")
+    return out
+
+
+def recover_pose_batch(cfg: RecoverPoseConfig, a, b, offsets, sample_mode: int = SAMPLE_MWC,
+                       maxIters: int = 1000, device: int = -1):
+    """Batched ``cvRecoverPose``: returns (R [n,3,3], t [n,3], ms [total], good [n], ok [n])."""
+    lib = native.load()
+    a, b = _pts(a), _pts(b)
+    off = np.ascontiguousarray(offsets, np.int64)
+    n = off.size - 1
+    R = np.zeros((n, 3, 3)); t = np.zeros((n, 3)); ms = np.zeros(a.shape[0], np.uint8)
+    good = np.zeros(n, np.int32); ok = np.zeros(n, np.uint8)
+    c = cfg.native()
+    native.check(lib.cvRecoverPoseBatch(C.addressof(c), _p(a), _p(b), _p(off), n, sample_mode, maxIters,
+                                        _p(R), _p(t), _p(ms), _p(good), _p(ok), device), "cvRecoverPoseBatch")
+    return R, t, ms, good, ok
+
+
+def recover_pose_from_E(E, a, b, focal=1.0, pp=(0.0, 0.0), mask=None):
+    """== ``cv2.recoverPose(E, a, b, focal=, pp=, mask=)`` -> (count, R, t, mask_out, good4)."""
+    lib = native.load()
+    a, b = _pts(a), _pts(b)
+    E = np.ascontiguousarray(E, np.float64).reshape(3, 3)
+    R = np.zeros((3, 3)); t = np.zeros(3); g4 = np.zeros(4, np.int32)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8).reshape(-1).copy()
+    if m is None:
+        m = np.ones(a.shape[0], np.uint8)
+    cnt = native.check(lib.cvRecoverPoseFromE(_p(E), _p(a), _p(b), a.shape[0], focal, pp[0], pp[1], _p(m),
+                                              _p(R), _p(t), _p(g4)), "cvRecoverPoseFromE")
+    return cnt, R, t, m, g4
+
+
+def decompose_essential(E):
+    lib = native.load()
+    E = np.ascontiguousarray(E, np.float64).reshape(3, 3)
+    R1 = np.zeros((3, 3)); R2 = np.zeros((3, 3)); t = np.zeros(3)
+    if not lib.cvDecomposeEssentialMat(_p(E), _p(R1), _p(R2), _p(t)):
+        raise native.NativeError("cvDecomposeEssentialMat failed: " + native.last_error())
+    return R1, R2, t

@@ -73,7 +73,27 @@ SIGNATURES = {
     "cvMatchFeatures": (_i, [C.POINTER(DetectorResult), C.POINTER(DetectorResult), _f, _vp, _vp, _vp]),
     "cvMatchKnn2ShardKeysDevice": (_i, [_vp, _i, _vp, _i, _i64, _i, _vp, _i, _vp]),
     "cvMergeShardKeysDevice": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _i, _vp]),
+    "cvRecoverPose": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cvRecoverPoses": (C.c_int32, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cvFivePoint": (_i, [_vp, _vp, _vp]),
+    "cvFindHomography": (_i, [_vp, _vp, _i, _d, _i, _d, _vp, _vp]),
+    "cvFindFundamentalMat": (_i, [_vp, _vp, _i, _d, _d, _i, _vp, _vp]),
+    "cvRansacBatch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "cvRansacBatchDevice": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "cvRecoverPoseBatch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "cvRecoverPoseBatchDevice": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "cvRecoverPoseFromE": (_i, [_vp, _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp, _vp]),
+    "cvDecomposeEssentialMat": (_i, [_vp, _vp, _vp, _vp]),
+    "cvFivePointBatch": (_i, [_vp, _vp, _i, _vp, _vp]),
 }
+
+
+class RansacParams(C.Structure):
+    """``McvRansacParams`` of include/MiniCVNative.h."""
+    _fields_ = [("model", C.c_int32), ("sampleMode", C.c_int32), ("stopMode", C.c_int32),
+                ("maxIters", C.c_int32), ("threshold", C.c_double), ("confidence", C.c_double),
+                ("seed", C.c_uint64), ("focal", C.c_double), ("ppx", C.c_double), ("ppy", C.c_double),
+                ("refine", C.c_int32), ("reserved", C.c_int32)]
 
 _lib = None
 

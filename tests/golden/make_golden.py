@@ -49,9 +49,76 @@ def golden_knn():
     print("knn_hamming.npz", {k: v.shape for k, v in out.items() if k.endswith("_idx")})
 
 
+def golden_ransac():
+    out = {}
+    # homography: cv2.findHomography(RANSAC, 3.0, maxIters 2000, confidence .995)
+    for k, (seed, n) in enumerate([(0, 400), (1, 700), (4, 2000), (5, 333)]):
+        a, b, gt, H = synth.homography_pair(seed, n)
+        Hc, mc = cv2.findHomography(a, b, cv2.RANSAC, 3.0, maxIters=2000, confidence=0.995)
+        out[f"h{k}_a"] = a; out[f"h{k}_b"] = b; out[f"h{k}_H"] = Hc; out[f"h{k}_mask"] = mc.ravel()
+    # 4-point kernel (method 0 on 4 points == kernel only)
+    A, B, HH = [], [], []
+    for seed in range(24):
+        a, b, gt, H = synth.homography_pair(100 + seed, 4, inlier_frac=1.0)
+        Hc, _ = cv2.findHomography(a.astype(np.float32), b.astype(np.float32), 0)
+        if Hc is None:
+            continue
+        A.append(a.astype(np.float32)); B.append(b.astype(np.float32)); HH.append(Hc)
+    out["h4_a"] = np.array(A); out["h4_b"] = np.array(B); out["h4_H"] = np.array(HH)
+    # fundamental: FM_RANSAC 3.0 / .99 / 1000
+    for k, (seed, n) in enumerate([(0, 300), (1, 500), (3, 2000)]):
+        a, b, gt, R, t = synth.two_view_pair(seed, n)
+        Fc, mc = cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, 3.0, 0.99, 1000)
+        out[f"f{k}_a"] = a; out[f"f{k}_b"] = b; out[f"f{k}_F"] = Fc; out[f"f{k}_mask"] = mc.ravel()
+    # 7-point minimal sets (stacked models; order is OpenCV's)
+    A, B, FF, NN = [], [], [], []
+    for seed in range(24):
+        a, b, gt, R, t = synth.two_view_pair(200 + seed, 7, inlier_frac=1.0)
+        Fc, _ = cv2.findFundamentalMat(a, b, cv2.FM_7POINT)
+        if Fc is None:
+            continue
+        pad = np.zeros((9, 3)); pad[:Fc.shape[0]] = Fc
+        A.append(a.astype(np.float32)); B.append(b.astype(np.float32)); FF.append(pad); NN.append(Fc.shape[0] // 3)
+    out["f7_a"] = np.array(A); out["f7_b"] = np.array(B); out["f7_F"] = np.array(FF); out["f7_n"] = np.array(NN)
+    np.savez_compressed(HERE / "ransac_hf.npz", **out)
+    print("ransac_hf.npz", len(out), "arrays")
+
+    out = {}
+    cfgs = [(800.0, (320.0, 240.0), 0.999, 1.0, False), (1.0, (0.0, 0.0), 0.999, 0.005, True)]
+    k = 0
+    for seed, n in [(0, 300), (1, 600), (2, 1500)]:
+        for (f, pp, prob, thr, norm) in cfgs:
+            a, b, gt, R, t = synth.two_view_pair(seed, n, normalized=norm)
+            Ec, mc = cv2.findEssentialMat(a, b, f, pp, cv2.RANSAC, prob, thr)
+            cnt, Rc, tc, mk = cv2.recoverPose(Ec, a, b, focal=f, pp=pp, mask=mc.copy())
+            R1, R2, tt = cv2.decomposeEssentialMat(Ec)
+            out[f"e{k}_a"] = a; out[f"e{k}_b"] = b; out[f"e{k}_cfg"] = np.array([f, pp[0], pp[1], prob, thr])
+            out[f"e{k}_E"] = Ec; out[f"e{k}_mask"] = mc.ravel(); out[f"e{k}_cnt"] = np.array(cnt)
+            out[f"e{k}_R"] = Rc; out[f"e{k}_t"] = tc.ravel(); out[f"e{k}_posemask"] = mk.ravel()
+            out[f"e{k}_R1"] = R1; out[f"e{k}_R2"] = R2; out[f"e{k}_tdec"] = tt.ravel()
+            k += 1
+    out["e_n"] = np.array(k)
+    # 5-point minimal sets: findEssentialMat on exactly 5 points returns every solution stacked
+    A, B, EE, NN = [], [], [], []
+    for seed in range(40):
+        a, b, gt, R, t = synth.two_view_pair(300 + seed, 5, inlier_frac=1.0,
+                                             noise=0.0 if seed % 2 else 0.3, normalized=True)
+        Ec, _ = cv2.findEssentialMat(a, b, 1.0, (0.0, 0.0), cv2.RANSAC, 0.999, 1.0)
+        n = 0 if Ec is None else Ec.shape[0] // 3
+        pad = np.zeros((30, 3))
+        if n:
+            pad[:3 * n] = Ec
+        A.append(a); B.append(b); EE.append(pad); NN.append(n)
+    out["e5_a"] = np.array(A); out["e5_b"] = np.array(B); out["e5_E"] = np.array(EE); out["e5_n"] = np.array(NN)
+    np.savez_compressed(HERE / "ransac_e.npz", **out)
+    print("ransac_e.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
     print("cv2", cv2.__version__)
     assert cv2.__version__.startswith("4.13"), "goldens are pinned to cv2 4.13.0"
     which = sys.argv[1:] or ["knn"]
     if "knn" in which:
         golden_knn()
+    if "ransac" in which:
+        golden_ransac()

@@ -1,0 +1,43 @@
+// hostmath.cpp -- TEST-ONLY host build of minicv_b200/csrc/cvmath.cuh (the same source the
+// CUDA kernels include), so the solver/scoring math can be checked against the oracle in
+// the CPU test-suite.  Never linked into libMiniCVNative.so; not a fallback path.
+#include "../../minicv_b200/csrc/cvmath.cuh"
+#include <string.h>
+
+using namespace mcv::cvm;
+
+extern "C" {
+
+int hm_h_solve4(const float* src, const float* dst, double* H) { return h_solve4(src, dst, H) ? 1 : 0; }
+int hm_h_check_subset(const float* src, const float* dst) { return h_check_subset(src, dst) ? 1 : 0; }
+int hm_have_collinear(const float* pts, int count) { return have_collinear(pts, count) ? 1 : 0; }
+void hm_h_error(const double* H, const float* a, const float* b, int n, float* err) {
+    float Hf[8];
+    for (int i = 0; i < 8; ++i) Hf[i] = (float)H[i];
+    for (int i = 0; i < n; ++i) err[i] = h_error(Hf, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]);
+}
+int hm_f_solve7(const float* a, const float* b, double* F) { return f_solve7(a, b, F); }
+void hm_f_error(const double* F, const float* a, const float* b, int n, float* err) {
+    for (int i = 0; i < n; ++i) err[i] = f_error(F, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]);
+}
+int hm_e_solve5(const double* a, const double* b, double* Es) { return e_solve5(a, b, Es); }
+void hm_e_error(const double* E, const double* a, const double* b, int n, float* err) {
+    for (int i = 0; i < n; ++i) err[i] = e_error(E, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]);
+}
+void hm_decompose_essential(const double* E, double* R1, double* R2, double* t) { decompose_essential(E, R1, R2, t); }
+void hm_cheirality(const double* R, const double* t, const double* a, const double* b, int n, double dist,
+                   unsigned char* ok) {
+    for (int i = 0; i < n; ++i) ok[i] = cheirality_ok(R, t, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], dist) ? 1 : 0;
+}
+void hm_svd3(const double* A, double* w, double* u, double* vt) { svd_square<3>(A, w, u, vt); }
+void hm_svd4(const double* A, double* w, double* u, double* vt) { svd_square<4>(A, w, u, vt); }
+void hm_solve_sym_eig8(const double* A, const double* b, double* x) { solve_sym_eig<8>(A, b, x); }
+void hm_eigen_sym9(const double* A, double* w, double* V) {
+    double M[81]; memcpy(M, A, sizeof(M));
+    jacobi_eigen_sym<9>(M, w, V);
+}
+int hm_update_num_iters(double p, double ep, int mp, int maxIters) { return update_num_iters(p, ep, mp, maxIters); }
+void hm_mwc(int n, unsigned* out) { Mwc r; for (int i = 0; i < n; ++i) out[i] = r.next(); }
+int hm_real_roots10(const double* c, double* out) { return real_roots10(c, out); }
+
+}

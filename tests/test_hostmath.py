@@ -1,0 +1,114 @@
+"""CPU: the device math header (minicv_b200/csrc/cvmath.cuh) compiled for the host and checked
+against the oracle -- same source the CUDA kernels include.  Test-only build, not a fallback."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from minicv_b200 import synth
+from oracle import essential, fivepoint, ransac
+from conftest import GOLDEN, ROOT
+
+
+@pytest.fixture(scope="module")
+def hm():
+    out = ROOT / "build" / "libmcv_hostmath_test.so"
+    out.parent.mkdir(exist_ok=True)
+    src = ROOT / "tests" / "hostmath" / "hostmath.cpp"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++",
+                    "-o", str(out), str(src)], check=True)
+    lib = C.CDLL(str(out))
+    lib.hm_update_num_iters.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+    return lib
+
+
+def p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_scoring_functions_bit_exact(hm):
+    a, b, gt, H = synth.homography_pair(1, 2000)
+    af, bf = a.astype(np.float32), b.astype(np.float32)
+    Hn = (H / H[2, 2]).ravel().copy()
+    err = np.zeros(2000, np.float32)
+    hm.hm_h_error(p(Hn), p(af), p(bf), 2000, p(err))
+    np.testing.assert_array_equal(err, ransac.HomographyCB.compute_error(af, bf, Hn))
+    g = np.load(GOLDEN / "ransac_hf.npz")
+    af, bf = g["f2_a"].astype(np.float32), g["f2_b"].astype(np.float32)
+    F = g["f2_F"].ravel().copy()
+    err = np.zeros(len(af), np.float32)
+    hm.hm_f_error(p(F), p(af), p(bf), len(af), p(err))
+    np.testing.assert_array_equal(err, ransac.FundamentalCB.compute_error(af, bf, F))
+    ge = np.load(GOLDEN / "ransac_e.npz")
+    x1 = essential.normalize_points(ge["e4_a"], 800.0, (320.0, 240.0))
+    x2 = essential.normalize_points(ge["e4_b"], 800.0, (320.0, 240.0))
+    E = ge["e4_E"].ravel().copy()
+    err = np.zeros(len(x1), np.float32)
+    hm.hm_e_error(p(E), p(x1), p(x2), len(x1), p(err))
+    np.testing.assert_array_equal(err, essential.EssentialCB.compute_error(x1, x2, E))
+
+
+def test_h_solve4_and_check_subset(hm):
+    rng = np.random.default_rng(0)
+    for seed in range(60):
+        a, b, gt, H = synth.homography_pair(seed, 50, inlier_frac=1.0)
+        idx = rng.permutation(50)[:4]
+        s, d = a[idx].astype(np.float32), b[idx].astype(np.float32)
+        assert bool(hm.hm_h_check_subset(p(s), p(d))) == ransac.HomographyCB.check_subset(s, d, 4)
+        Hh = np.zeros(9)
+        ok = hm.hm_h_solve4(p(s), p(d), p(Hh))
+        ms = ransac.HomographyCB.run_kernel(s, d)
+        if ok and ms:
+            assert np.abs(Hh.reshape(3, 3) - ms[0]).max() / np.abs(ms[0]).max() < 1e-6
+
+
+def test_f_solve7_sets(hm):
+    g = np.load(GOLDEN / "ransac_hf.npz")
+    for a, b, Fc, n in zip(g["f7_a"], g["f7_b"], g["f7_F"], g["f7_n"]):
+        F = np.zeros(27)
+        cnt = hm.hm_f_solve7(p(np.ascontiguousarray(a)), p(np.ascontiguousarray(b)), p(F))
+        assert cnt == n
+        for i in range(n):
+            ref = Fc[3 * i:3 * i + 3]
+            assert min(np.abs(F[9 * k:9 * k + 9].reshape(3, 3) - ref).max() for k in range(cnt)) / np.abs(ref).max() < 1e-6
+
+
+def test_e_solve5_golden(hm):
+    g = np.load(GOLDEN / "ransac_e.npz")
+    tot = bad = 0
+    for a, b, Ec, n in zip(g["e5_a"], g["e5_b"], g["e5_E"], g["e5_n"]):
+        Es = np.zeros(90)
+        cnt = hm.hm_e_solve5(p(np.ascontiguousarray(a)), p(np.ascontiguousarray(b)), p(Es))
+        assert cnt == n
+        for i in range(n):
+            tot += 1
+            bad += min(np.abs(Es[9 * k:9 * k + 9].reshape(3, 3) - Ec[3 * i:3 * i + 3]).max() for k in range(cnt)) > 1e-6
+    assert tot > 100 and bad / tot < 0.02
+
+
+def test_pose_math(hm):
+    g = np.load(GOLDEN / "ransac_e.npz")
+    E = g["e0_E"].ravel().copy()
+    R1, R2, t = np.zeros(9), np.zeros(9), np.zeros(3)
+    hm.hm_decompose_essential(p(E), p(R1), p(R2), p(t))
+    Ro1, Ro2, to = essential.decompose_essential(g["e0_E"])
+    pairs = [(R1.reshape(3, 3), R2.reshape(3, 3)), (R2.reshape(3, 3), R1.reshape(3, 3))]
+    assert min(np.abs(x - Ro1).max() + np.abs(y - Ro2).max() for x, y in pairs) < 1e-9
+    x1 = essential.normalize_points(g["e0_a"], 800.0, (320.0, 240.0))
+    x2 = essential.normalize_points(g["e0_b"], 800.0, (320.0, 240.0))
+    for Rr, ts in [(Ro1, to), (Ro2, to), (Ro1, -to), (Ro2, -to)]:
+        ok = np.zeros(len(x1), np.uint8)
+        hm.hm_cheirality(p(Rr.ravel().copy()), p(ts.copy()), p(x1), p(x2), len(x1), C.c_double(50.0), p(ok))
+        np.testing.assert_array_equal(ok.astype(bool), essential.cheirality_mask(Rr, ts, x1, x2))
+
+
+def test_rng_and_iteration_update(hm):
+    out = np.zeros(64, np.uint32)
+    hm.hm_mwc(64, p(out))
+    r = ransac.MWC()
+    assert out.tolist() == [r.next() for _ in range(64)]
+    for ep in np.linspace(0, 1, 401):
+        for mp, mi in ((4, 2000), (7, 1000), (5, 1000)):
+            assert hm.hm_update_num_iters(0.995, ep, mp, mi) == ransac.update_num_iters(0.995, ep, mp, mi)
