@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--pairs", type=int, default=1024, help="image pairs per GPU per step")
     ap.add_argument("--cpu-sample-pairs", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3/C4 RANSAC side measurements")
     return ap.parse_args()
 
 
@@ -125,6 +126,124 @@ def cpu_match_pairs(pairs, threads: int):
             idx, dist = bf_knn.bf_knn2_hamming(q, t)
             bf_knn.ratio_test(dist, idx, RATIO)
         return time.perf_counter() - t0, "port"
+
+
+# ---------------------------------------------------------------------------------------------
+# extra (not the headline `value`): the RANSAC configs C3 / C4 of BASELINE.json, device-resident,
+# next to the same OpenCV calls on the host cores (one pair per task, cv2.setNumThreads(1),
+# a pool of `cores` workers -- OpenCV's RANSAC loops do not multi-thread)
+# ---------------------------------------------------------------------------------------------
+def _cpu_ransac_init():
+    import cv2
+    cv2.setNumThreads(1)
+
+
+def _cpu_ransac_task(task):
+    import cv2
+    kind, a, b = task
+    t0 = time.perf_counter()
+    if kind == "H":
+        cv2.findHomography(a, b, cv2.RANSAC, 3.0, maxIters=4096, confidence=0.995)
+    elif kind == "F":
+        cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, 3.0, 0.99, 4096)
+    else:
+        E, m = cv2.findEssentialMat(a, b, 800.0, (320.0, 240.0), cv2.RANSAC, 0.999, 1.0)
+        cv2.recoverPose(E, a, b, focal=800.0, pp=(320.0, 240.0), mask=m)
+    return time.perf_counter() - t0
+
+
+def cpu_ransac_pairs_per_s(kind, pairs, cores):
+    """pairs/s of the OpenCV CPU path over `pairs` with a pool of `cores` single-thread workers."""
+    try:
+        import cv2  # noqa: F401
+    except ImportError:
+        return None
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores, initializer=_cpu_ransac_init) as pool:
+        pool.map(_cpu_ransac_task, [(kind, a, b) for a, b in pairs[:cores]])     # warm-up / page-in
+        t0 = time.perf_counter()
+        per = pool.map(_cpu_ransac_task, [(kind, a, b) for a, b in pairs])
+        wall = time.perf_counter() - t0
+    return {"pairs_per_s": len(pairs) / wall, "ms_per_pair_one_core": 1e3 * float(np.mean(per)),
+            "cores": cores, "sample_pairs": len(pairs)}
+
+
+def extra_ransac(local, with_cpu=True):
+    import torch
+    from minicv_b200 import estimation as est, synth
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    cores = os.cpu_count() or 1
+    out = {}
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps / 1e3
+
+    # ---- C3: homography 4-pt and fundamental 7-pt, 2000 correspondences, 4096 hypotheses, 1024 pairs
+    P, N, HYP = 1024, 2000, 4096
+    off = np.arange(P + 1, dtype=np.int64) * N
+    for kind, model, gen, thr, conf in (("H", est.MODEL_H, synth.homography_pair, 3.0, 0.995),
+                                        ("F", est.MODEL_F, synth.two_view_pair, 3.0, 0.99)):
+        A = np.empty((P * N, 2)); B = np.empty((P * N, 2))
+        gts = []
+        for p in range(P):
+            r = gen(p, N)
+            A[p * N:(p + 1) * N] = r[0]; B[p * N:(p + 1) * N] = r[1]; gts.append(r[2])
+        dA = torch.from_numpy(A).to(dev); dB = torch.from_numpy(B).to(dev)
+        dM = torch.empty((P, 9), dtype=torch.float64, device=dev)
+        dMask = torch.empty(P * N, dtype=torch.uint8, device=dev)
+        dCnt = torch.empty(P, dtype=torch.int32, device=dev)
+        dOk = torch.empty(P, dtype=torch.uint8, device=dev)
+
+        def run():
+            est.ransac_batch_device(model, dA, dB, off, thr, HYP, dM, dMask, dCnt, dOk, confidence=conf,
+                                    sample_mode=est.SAMPLE_COUNTER, stop_mode=est.STOP_FIXED, seed=1,
+                                    device=local, stream=stream.cuda_stream)
+        t = timed(run)
+        mask = dMask.cpu().numpy().reshape(P, N).astype(bool)
+        gt = np.array(gts)
+        recall = float((mask & gt).sum() / gt.sum())
+        out[f"C3_{kind}"] = {"pairs_per_s": P / t, "ms_per_batch": t * 1e3, "pairs": P, "correspondences": N,
+                             "hypotheses_per_pair": HYP, "ghyp_x_corr_per_s": P * N * HYP / t / 1e9,
+                             "ok_pairs": int(dOk.sum().item()), "gt_inlier_recall": recall,
+                             "mode": "counter-based sampling, fixed hypothesis count"}
+        if with_cpu:
+            k = max(cores, 8) if kind == "H" else cores
+            out[f"C3_{kind}"]["cpu"] = cpu_ransac_pairs_per_s(kind, [(A[p * N:(p + 1) * N], B[p * N:(p + 1) * N]) for p in range(k)], cores)
+        del dA, dB
+    # ---- C4: essential 5-pt RANSAC + recoverPose, 5000 correspondences, 512 pairs (cvRecoverPose semantics)
+    P, N = 512, 5000
+    off = np.arange(P + 1, dtype=np.int64) * N
+    A = np.empty((P * N, 2)); B = np.empty((P * N, 2))
+    for p in range(P):
+        r = synth.two_view_pair(p, N)
+        A[p * N:(p + 1) * N] = r[0]; B[p * N:(p + 1) * N] = r[1]
+    dA = torch.from_numpy(A).to(dev); dB = torch.from_numpy(B).to(dev)
+    dE = torch.empty((P, 9), dtype=torch.float64, device=dev); dR = torch.empty((P, 9), dtype=torch.float64, device=dev)
+    dT = torch.empty((P, 3), dtype=torch.float64, device=dev); dMs = torch.empty(P * N, dtype=torch.uint8, device=dev)
+    dGood = torch.empty(P, dtype=torch.int32, device=dev); dOk = torch.empty(P, dtype=torch.uint8, device=dev)
+    cfg = est.RecoverPoseConfig(800.0, (320.0, 240.0), 0.999, 1.0)
+
+    def run_e():
+        est.recover_pose_batch_device(cfg, dA, dB, off, dE, dR, dT, dMs, dGood, dOk, sample_mode=est.SAMPLE_MWC,
+                                      maxIters=1000, device=local, stream=stream.cuda_stream)
+    t = timed(run_e, reps=2)
+    out["C4_E_pose"] = {"pairs_per_s": P / t, "ms_per_batch": t * 1e3, "pairs": P, "correspondences": N,
+                        "max_iters": 1000, "ok_pairs": int(dOk.sum().item()),
+                        "mean_cheirality_inliers": float(dGood.float().mean().item()),
+                        "mode": "OpenCV MWC sampling + adaptive stop (cvRecoverPose semantics)"}
+    if with_cpu:
+        out["C4_E_pose"]["cpu"] = cpu_ransac_pairs_per_s("E", [(A[p * N:(p + 1) * N], B[p * N:(p + 1) * N]) for p in range(cores)], cores)
+    return out
 
 
 def run_reference(args):
@@ -295,6 +414,12 @@ def run_ours(args):
                          f"{'cv2.BFMatcher(NORM_HAMMING).knnMatch k=2' if kind == 'reference' else 'numpy oracle port'}"
                          f" + ratio test, {cores} threads"}
 
+    extra = None
+    if not args.no_extra:
+        del dq, dt, didx, ddist, dok
+        torch.cuda.empty_cache()
+        extra = extra_ransac(local, with_cpu=not args.no_cpu_baseline)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -305,7 +430,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(out.train_idx.nbytes + out.distance.nbytes + out.ratio_pass.nbytes),
                 "steps": e2e_steps, "api": "cvMatchKnn2Batch (host buffers, pinned)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "ratio_pass_per_pair": n_pass_dev / P,
+        "ratio_pass_per_pair": n_pass_dev / P, "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -7,3 +7,6 @@ in ``csrc/``).  This Python package is the host-side mirror of the reference's F
 from . import native  # noqa: F401
 from .matching import (KnnResult, NORM_HAMMING, NORM_L2, match_features, match_knn2,  # noqa: F401
                        match_knn2_batch, match_knn2_batch_device)
+from . import estimation  # noqa: F401
+from .estimation import (RecoverPoseConfig, findFundamentalMat, findHomography, fivepoint,  # noqa: F401
+                         recoverPose, recoverPoses, recoverPoses2)

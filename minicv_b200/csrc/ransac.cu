@@ -480,6 +480,45 @@ finalize_plain_kernel(const float4* __restrict__ pf, const double* __restrict__ 
     }
 }
 
+// Thread-0 helpers of the homography refit, kept out of line so the kernel's register and
+// stack footprint stay small.
+__device__ __noinline__ void h_from_ltl(const double* ltl45, double cmx, double cmy, double cMx, double cMy,
+                                        double smx, double smy, double sMx, double sMy, double* H) {
+    double L[81], w[9], V[81];
+    int k = 0;
+    for (int r = 0; r < 9; ++r)
+        for (int c = r; c < 9; ++c) { L[r * 9 + c] = ltl45[k]; L[c * 9 + r] = ltl45[k]; ++k; }
+    jacobi_eigen_sym<9>(L, w, V);
+    int mi = 0;
+    for (int i = 1; i < 9; ++i) if (w[i] < w[mi]) mi = i;
+    const double* h = V + 9 * mi;
+    const double iH[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
+    const double N2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
+    double T[9], Hn[9];
+    mat3mul(iH, h, T);
+    mat3mul(T, N2, Hn);
+    if (Hn[8] != 0) {
+        const double sc = 1. / Hn[8];
+        for (int j = 0; j < 9; ++j) H[j] = Hn[j] * sc;
+    }
+}
+
+// one LM trial step: d = solve(A + lambda*diag(D), v), xd = x - d
+__device__ __noinline__ void lm_trial(const double* A, const double* v, const double* D, double lam,
+                                      const double* x, double* d, double* xd) {
+    double Ap[64], vv[8], dd[8];
+    for (int k = 0; k < 64; ++k) Ap[k] = A[k];
+    for (int r = 0; r < 8; ++r) { Ap[r * 8 + r] += lam * D[r]; vv[r] = v[r]; }
+    solve_sym_eig<8>(Ap, vv, dd);
+    for (int r = 0; r < 8; ++r) { d[r] = dd[r]; xd[r] = x[r] - dd[r]; }
+}
+
+__device__ __noinline__ double lm_reseed(const double* A) {
+    double M[64];
+    for (int k = 0; k < 64; ++k) M[k] = A[k];
+    return max_diag_pinv_sym<8>(M);
+}
+
 // Homography with OpenCV's post-processing: runKernel on the inliers, LMSolver(10), mask
 // recomputed from the refined H, H /= h33 (cv::findHomography, calib3d/src/fundam.cpp).
 __global__ void __launch_bounds__(FB)
@@ -578,25 +617,7 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
                     for (int c = r; c < 9; ++c) { v[k] += Lx[r] * Lx[c] + Ly[r] * Ly[c]; ++k; }
             }
         block_sum<45>(v, sred, sout);
-        if (tid == 0) {
-            double L[81], w[9], V[81];
-            int k = 0;
-            for (int r = 0; r < 9; ++r)
-                for (int c = r; c < 9; ++c) { L[r * 9 + c] = sout[k]; L[c * 9 + r] = sout[k]; ++k; }
-            jacobi_eigen_sym<9>(L, w, V);
-            int mi = 0;
-            for (int i = 1; i < 9; ++i) if (w[i] < w[mi]) mi = i;
-            const double* h = V + 9 * mi;
-            const double iH[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
-            const double N2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
-            double T[9], Hn[9];
-            mat3mul(iH, h, T);
-            mat3mul(T, N2, Hn);
-            if (Hn[8] != 0) {
-                const double sc = 1. / Hn[8];
-                for (int j = 0; j < 9; ++j) sH[j] = Hn[j] * sc;
-            }
-        }
+        if (tid == 0) h_from_ltl(sout, cmx, cmy, cMx, cMy, smx, smy, sMx, sMy, sH);
         __syncthreads();
     }
 
@@ -667,14 +688,7 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
     __syncthreads();
     __shared__ double sDvec[8];
     for (int iter = 0; iter < 10; ++iter) {
-        if (tid == 0) {
-            double Ap[64];
-            for (int k = 0; k < 64; ++k) Ap[k] = sA[k];
-            for (int r = 0; r < 8; ++r) Ap[r * 8 + r] += sLam * sD[r];
-            double d[8];
-            solve_sym_eig<8>(Ap, sV, d);
-            for (int r = 0; r < 8; ++r) { sDvec[r] = d[r]; sXd[r] = sH[r] - d[r]; }
-        }
+        if (tid == 0) lm_trial(sA, sV, sD, sLam, sH, sDvec, sXd);
         __syncthreads();
         const double Sd = residual_sq(sXd);
         if (tid == 0) {
@@ -694,12 +708,15 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
                 double nu = (Sd - S) / (fabs(tdv) > DBL_EPSILON ? tdv : 1) + 2;
                 nu = fmin(fmax(nu, 2.), 10.);
                 if (sLam == 0) {
-                    const double maxval = max_diag_pinv_sym<8>(sA);
+                    const double maxval = lm_reseed(sA);
                     sLam = sLc = 1. / maxval;
                     nu *= 0.5;
                 }
                 sLam *= nu;
             }
+#ifdef MCV_DEBUG_REFIT
+            printf(" lm iter=%d S=%g Sd=%g dS=%g R=%g lam=%g d0=%g\n", iter, S, Sd, dS, R, sLam, sDvec[0]);
+#endif
             sCtl[0] = (Sd < S) ? 1 : 0;
             if (Sd < S) for (int r = 0; r < 8; ++r) sH[r] = sXd[r];
         }

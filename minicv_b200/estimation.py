@@ -216,3 +216,35 @@ def decompose_essential(E):
     if not lib.cvDecomposeEssentialMat(_p(E), _p(R1), _p(R2), _p(t)):
         raise native.NativeError("cvDecomposeEssentialMat failed: " + native.last_error())
     return R1, R2, t
+
+
+def _dp(x):
+    return x if isinstance(x, int) else (x.data_ptr() if x is not None else 0)
+
+
+def ransac_batch_device(model: int, d_a, d_b, offsets, thr: float, maxIters: int, d_models, d_masks,
+                        d_inliers, d_ok, confidence: float = 0.995, sample_mode: int = SAMPLE_COUNTER,
+                        stop_mode: int = STOP_FIXED, seed: int = 0, focal: float = 1.0, pp=(0.0, 0.0),
+                        refine: bool = True, device: int = -1, stream: int = 0) -> None:
+    """Device-resident batched RANSAC (``cvRansacBatchDevice``): torch CUDA tensors (float64
+    [total, 2] points) or raw device pointers; asynchronous on ``stream``."""
+    lib = native.load()
+    off = np.ascontiguousarray(offsets, np.int64)
+    prm = native.RansacParams(model, sample_mode, stop_mode, maxIters, thr, confidence, seed, focal,
+                              pp[0], pp[1], 1 if refine else 0, 0)
+    native.check(lib.cvRansacBatchDevice(C.addressof(prm), _dp(d_a), _dp(d_b), _p(off), off.size - 1,
+                                         _dp(d_models), _dp(d_masks), _dp(d_inliers), _dp(d_ok), device,
+                                         stream), "cvRansacBatchDevice")
+
+
+def recover_pose_batch_device(cfg: RecoverPoseConfig, d_a, d_b, offsets, d_E, d_R, d_t, d_ms, d_good, d_ok,
+                              sample_mode: int = SAMPLE_MWC, maxIters: int = 1000, device: int = -1,
+                              stream: int = 0) -> None:
+    """Device-resident batched ``cvRecoverPose`` (``cvRecoverPoseBatchDevice``)."""
+    lib = native.load()
+    off = np.ascontiguousarray(offsets, np.int64)
+    c = cfg.native()
+    native.check(lib.cvRecoverPoseBatchDevice(C.addressof(c), _dp(d_a), _dp(d_b), _p(off), off.size - 1,
+                                              sample_mode, maxIters, _dp(d_E), _dp(d_R), _dp(d_t), _dp(d_ms),
+                                              _dp(d_good), _dp(d_ok), device, stream),
+                 "cvRecoverPoseBatchDevice")

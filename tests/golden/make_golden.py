@@ -109,7 +109,7 @@ def golden_ransac():
         if n:
             pad[:3 * n] = Ec
         A.append(a); B.append(b); EE.append(pad); NN.append(n)
-    out["e5_a"] = np.array(A); out["e5_b"] = np.array(B); out["e5_E"] = np.array(EE); out["e5_n"] = np.array(NN)
+    out["min5_a"] = np.array(A); out["min5_b"] = np.array(B); out["min5_E"] = np.array(EE); out["min5_n"] = np.array(NN)
     np.savez_compressed(HERE / "ransac_e.npz", **out)
     print("ransac_e.npz", len(out), "arrays")
 

@@ -78,7 +78,7 @@ def test_f_solve7_sets(hm):
 def test_e_solve5_golden(hm):
     g = np.load(GOLDEN / "ransac_e.npz")
     tot = bad = 0
-    for a, b, Ec, n in zip(g["e5_a"], g["e5_b"], g["e5_E"], g["e5_n"]):
+    for a, b, Ec, n in zip(g["min5_a"], g["min5_b"], g["min5_E"], g["min5_n"]):
         Es = np.zeros(90)
         cnt = hm.hm_e_solve5(p(np.ascontiguousarray(a)), p(np.ascontiguousarray(b)), p(Es))
         assert cnt == n

@@ -42,7 +42,7 @@ def test_find_fundamental_oracle(ghf, k):
 
 def test_five_point_oracle(ge):
     tot = bad = 0
-    for a, b, Ec, n in zip(ge["e5_a"], ge["e5_b"], ge["e5_E"], ge["e5_n"]):
+    for a, b, Ec, n in zip(ge["min5_a"], ge["min5_b"], ge["min5_E"], ge["min5_n"]):
         Es = fivepoint.five_point(a, b)
         assert len(Es) == n
         for i in range(n):

@@ -146,7 +146,7 @@ def test_fundamental_seven_point_models_as_sets(ghf):
 
 # ----------------------------------------------------------------------------- essential / pose
 def test_five_point_vs_cv2_golden(ge):
-    A, B, EE, NN = ge["e5_a"], ge["e5_b"], ge["e5_E"], ge["e5_n"]
+    A, B, EE, NN = ge["min5_a"], ge["min5_b"], ge["min5_E"], ge["min5_n"]
     tot = bad = 0
     for a, b, Ec, n in zip(A, B, EE, NN):
         Es = est.fivepoint(a, b)
@@ -226,7 +226,7 @@ def test_recover_pose_from_golden_E_exact(ge, k):
     np.testing.assert_array_equal(m, ge[f"e{k}_posemask"])
     assert rel_err(R, ge[f"e{k}_R"]) < 1e-9 and rel_err(t, ge[f"e{k}_t"]) < 1e-9
     co, Ro, to, mo, good = essential.recover_pose(ge[f"e{k}_E"], a, b, f, (px, py), ge[f"e{k}_mask"])
-    assert list(g4) == good
+    assert sorted(int(x) for x in g4) == sorted(good)   # candidate order follows the noise-decided SVD sign
 
 
 def test_recover_pose_sentinels_and_small_n():
