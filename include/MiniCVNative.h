@@ -98,6 +98,9 @@ MCV_API const char* mcvLastError(void);
 MCV_API int mcvDeviceCount(void);
 /* Kernels launched by this library since load (all threads); used by bench.py. */
 MCV_API int64_t mcvKernelLaunchCount(void);
+/* Hamming matcher engine: 0 = auto (default), 1 = integer pipe (XOR + POPC), 2 = tcgen05
+ * tensor cores.  Both engines are bit-identical in their results; returns 0, or -1 if bad. */
+MCV_API int mcvSetHammingEngine(int engine);
 /* Library build tag: "minicv_b200 sm_100a <date>". */
 MCV_API const char* mcvBuildInfo(void);
 

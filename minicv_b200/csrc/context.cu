@@ -1,5 +1,6 @@
 // context.cu -- error string, per-thread contexts, diagnostics exports.
 #include "common.cuh"
+#include "knn.cuh"
 
 #include <map>
 #include <memory>
@@ -114,6 +115,12 @@ MCV_API int mcvDeviceCount(void) {
 }
 
 MCV_API int64_t mcvKernelLaunchCount(void) { return mcv::g_launches.load(); }
+
+MCV_API int mcvSetHammingEngine(int engine) {
+    if (engine < 0 || engine > 2) return -1;
+    mcv::g_hamming_engine.store(engine);
+    return 0;
+}
 
 MCV_API const char* mcvBuildInfo(void) { return "minicv_b200 sm_100a " __DATE__ " " __TIME__; }
 

@@ -250,8 +250,32 @@ int launch_kernel_w(cudaStream_t stream, dim3 grid, const uint4* q, const uint4*
 
 }  // namespace
 
+std::atomic<int> g_hamming_engine{0};
+
+int launch_knn2_finalize(cudaStream_t stream, const uint64_t* dSplitKeys, int nSplits, int64_t totalQ,
+                         const KnnArgs& a) {
+    knn2_finalize_kernel<<<(unsigned)((totalQ + 255) / 256), 256, 0, stream>>>(
+        dSplitKeys, nSplits, totalQ, a.ratio, a.emit == KNN_EMIT_KEYS ? 1 : 0, a.globalIdxBase,
+        a.dTrainIdx, a.dDist, a.dRatioPass, a.dPassCount, a.dKeys);
+    MCV_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_hamming_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     if (a.nPairs <= 0) return 0;
+    {
+        // engine choice: the tensor-core path pays a bit-expansion pass, so small problems stay
+        // on the integer pipe
+        const int eng = g_hamming_engine.load(std::memory_order_relaxed);
+        bool tc = false;
+        if (eng == 2) tc = hamming_tc_supported(a.descBytes);
+        else if (eng == 0 && hamming_tc_supported(a.descBytes)) {
+            const double q = (double)(a.hQOff[a.nPairs] - a.hQOff[0]);
+            const double t = (double)(a.hTOff[a.nPairs] - a.hTOff[0]) / std::max(a.nPairs, 1);
+            tc = q * t >= 64.0 * 1024 * 1024;
+        }
+        if (tc) return launch_hamming_knn2_tc(ctx, stream, a);
+    }
     if (a.descBytes <= 0 || a.descBytes > 128) {
         set_error("Hamming matcher supports 1..128-byte descriptors (got %d)", a.descBytes);
         return -1;
@@ -360,12 +384,7 @@ int launch_hamming_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     }
 #undef MCV_W
     if (rc) return rc;
-    if (twoStage) {
-        knn2_finalize_kernel<<<(unsigned)((totalQ + 255) / 256), 256, 0, stream>>>(
-            dSplitKeys, nSplits, totalQ, a.ratio, a.emit == KNN_EMIT_KEYS ? 1 : 0,
-            a.globalIdxBase, a.dTrainIdx, a.dDist, a.dRatioPass, a.dPassCount, a.dKeys);
-        MCV_LAUNCH_CHECK();
-    }
+    if (twoStage) return launch_knn2_finalize(stream, dSplitKeys, nSplits, totalQ, a);
     return 0;
 }
 

@@ -31,6 +31,15 @@ struct KnnArgs {
 // Asynchronous on `stream`; uses ctx workspaces 0..3 and pinned buffer 0.
 int launch_hamming_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a);
 
+// Same contract on the tensor cores (tcgen05 int8 +-1 GEMM, hamming_tc.cu).
+bool hamming_tc_supported(int descBytes);
+int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a);
+// Engine choice: 0 = auto, 1 = integer pipe (XOR + POPC), 2 = tensor cores.
+extern std::atomic<int> g_hamming_engine;
+// Shared second stage: merges nSplits key pairs per query and emits matches or keys.
+int launch_knn2_finalize(cudaStream_t stream, const uint64_t* dSplitKeys, int nSplits, int64_t totalQ,
+                         const KnnArgs& a);
+
 // L2 kNN-2 for float32 descriptors (difference form, fp32).
 int launch_l2_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a);
 

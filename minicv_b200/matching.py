@@ -131,3 +131,13 @@ def match_features(query_desc: np.ndarray, train_desc: np.ndarray, ratio: float 
     n = native.check(lib.cvMatchFeatures(C.byref(rq), C.byref(rt), ratio, _ptr(idx), _ptr(dist),
                                          _ptr(ok)), "cvMatchFeatures")
     return KnnResult(idx, dist, ok, n)
+
+
+ENGINE_AUTO, ENGINE_POPC, ENGINE_TENSOR = 0, 1, 2
+
+
+def set_hamming_engine(engine: int) -> None:
+    """Choose the Hamming matcher engine (results are bit-identical): 0 auto, 1 integer pipe
+    (XOR + POPC), 2 tcgen05 tensor cores."""
+    if native.load().mcvSetHammingEngine(engine) != 0:
+        raise ValueError("engine must be 0, 1 or 2")
