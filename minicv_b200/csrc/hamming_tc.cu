@@ -10,8 +10,10 @@
 // a group maximum filters each 8-column group against the current second best, so the exact
 // (index-carrying, lowest-index-wins) update only runs for groups that can change the result.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  One CTA sweeps the train rows of its
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter take one
+// query tile each, or one half of the columns each when there is a single query tile, and
+// software-pipeline tcgen05.ld of the next 32 columns under the top-2 work of the current 32).  One CTA sweeps the train rows of its
 // split for 256 queries (two M = 128 tiles share every train stage, halving L2 -> SM traffic).
 // Results leave the kernel as packed keys (dist << 32) | trainIdx and go through the same
 // finalize kernel as the integer-pipe engine (hamming_knn.cu), so tie-breaking is identical.
@@ -24,7 +26,8 @@
 namespace mcv {
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int EPI_WARPS = 8;       // two epilogue warps per TMEM lane quarter
+constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
 constexpr int TILE_M = 128;        // rows per MMA (queries)
 constexpr int TILE_N = 128;        // train rows per stage
 constexpr int CHUNK_BYTES = TILE_M * 128;   // one 128-row x 128-byte swizzle-128B panel = 16 KB
@@ -177,7 +180,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, EPI_WARPS * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -236,66 +239,76 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             }
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4 =====
         const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;          // accumulator row within an M tile
-        int b1[ATILES], i1[ATILES], b2[ATILES], i2[ATILES];
+        const int grp = (warp - 2) >> 2;                 // 0 or 1
+        const int row = quarter * 32 + lane;             // accumulator row within an M tile
+        // ATILES == 2: this warp owns query tile `grp`, all four 32-column chunks of a stage.
+        // ATILES == 1: it owns column chunks [2*grp, 2*grp+2) and reports as its own split slot.
+        const int myTile = ATILES == 2 ? grp : 0;
+        constexpr int NCHUNK = ATILES == 2 ? 4 : 2;
+        const int chunk0 = ATILES == 2 ? 0 : 2 * grp;
+        int b1 = INT_MIN, i1 = -1, b2 = INT_MIN, i2 = -1;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+        auto process = [&](int (&v)[32], int nv, int cb) {
+            if (nv < 32) {
 #pragma unroll
-        for (int t = 0; t < ATILES; ++t) { b1[t] = INT_MIN; b2[t] = INT_MIN; i1[t] = -1; i2[t] = -1; }
+                for (int i = 0; i < 32; ++i) if (i >= nv) v[i] = INT_MIN;
+            }
+            int g[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int m01 = max(v[q * 8 + 0], v[q * 8 + 1]), m23 = max(v[q * 8 + 2], v[q * 8 + 3]);
+                const int m45 = max(v[q * 8 + 4], v[q * 8 + 5]), m67 = max(v[q * 8 + 6], v[q * 8 + 7]);
+                g[q] = max(max(m01, m23), max(m45, m67));
+            }
+            const int gm = max(max(g[0], g[1]), max(g[2], g[3]));
+            if (gm > b2) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (g[q] > b2) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) top2_insert(v[q * 8 + i], cb + q * 8 + i, b1, i1, b2, i2);
+                    }
+                }
+            }
+        };
+
         for (int j = 0; j < nStagesTotal; ++j) {
             const int as = j & 1;
             mbar_wait(acc_full + as, (j >> 1) & 1);
             tc_fence_after();
             const int colBase = j * TILE_N;               // within the split
             const int valid = min(TILE_N, nT - colBase);  // train rows of this stage that exist
+            const uint32_t tcol = tlane + (uint32_t)(as * (ATILES * TILE_N) + myTile * TILE_N + chunk0 * 32);
+            const int cb0 = t0 + colBase + chunk0 * 32;
+            int va[32], vb[32];
+            // software pipeline: the load of chunk c+1 is in flight while chunk c is processed
+            tc_ld32(tcol, va);
+            tc_wait_ld();
 #pragma unroll
-            for (int t = 0; t < ATILES; ++t) {
-#pragma unroll 1
-                for (int c = 0; c < TILE_N / 32; ++c) {
-                    if (c * 32 >= valid) break;
-                    int v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                                           (uint32_t)(as * (ATILES * TILE_N) + t * TILE_N + c * 32);
-                    tc_ld32(taddr, v);
+            for (int c = 0; c < NCHUNK; c += 2) {
+                if (c + 1 < NCHUNK) tc_ld32(tcol + (c + 1) * 32, vb);
+                process(va, valid - (chunk0 + c) * 32, cb0 + c * 32);
+                tc_wait_ld();
+                if (c + 1 < NCHUNK) {
+                    if (c + 2 < NCHUNK) tc_ld32(tcol + (c + 2) * 32, va);
+                    else { tc_fence_before(); mbar_arrive(acc_empty + as); }   // all loads landed
+                    process(vb, valid - (chunk0 + c + 1) * 32, cb0 + (c + 1) * 32);
                     tc_wait_ld();
-                    const int nv = valid - c * 32;
-                    if (nv < 32) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) if (i >= nv) v[i] = INT_MIN;
-                    }
-                    int g[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int m01 = max(v[q * 8 + 0], v[q * 8 + 1]), m23 = max(v[q * 8 + 2], v[q * 8 + 3]);
-                        const int m45 = max(v[q * 8 + 4], v[q * 8 + 5]), m67 = max(v[q * 8 + 6], v[q * 8 + 7]);
-                        g[q] = max(max(m01, m23), max(m45, m67));
-                    }
-                    const int gm = max(max(g[0], g[1]), max(g[2], g[3]));
-                    if (gm > b2[t]) {
-                        const int cb = t0 + colBase + c * 32;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (g[q] > b2[t]) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    top2_insert(v[q * 8 + i], cb + q * 8 + i, b1[t], i1[t], b2[t], i2[t]);
-                            }
-                        }
-                    }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(acc_empty + as);
         }
         // emit packed keys (dist << 32) | pair-local train index
-#pragma unroll
-        for (int t = 0; t < ATILES; ++t) {
-            const int64_t qRow = qTile0 + t * TILE_M + row;
+        {
+            const int64_t qRow = qTile0 + myTile * TILE_M + row;
+            const int slot = ATILES == 2 ? split : split * 2 + grp;
             if (qRow < qEnd) {
                 uint64_t k1 = ~0ull, k2 = ~0ull;
-                if (i1[t] >= 0) k1 = ((uint64_t)(uint32_t)((KBITS - b1[t]) >> 1) << 32) | (uint64_t)(uint32_t)i1[t];
-                if (i2[t] >= 0) k2 = ((uint64_t)(uint32_t)((KBITS - b2[t]) >> 1) << 32) | (uint64_t)(uint32_t)i2[t];
-                uint64_t* o = splitKeys + ((int64_t)split * totalQ + qRow) * 2;
+                if (i1 >= 0) k1 = ((uint64_t)(uint32_t)((KBITS - b1) >> 1) << 32) | (uint64_t)(uint32_t)i1;
+                if (i2 >= 0) k2 = ((uint64_t)(uint32_t)((KBITS - b2) >> 1) << 32) | (uint64_t)(uint32_t)i2;
+                uint64_t* o = splitKeys + ((int64_t)slot * totalQ + qRow) * 2;
                 reinterpret_cast<ulonglong2*>(o)[0] = make_ulonglong2(k1, k2);
             }
         }
@@ -425,7 +438,8 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
     splitRows = (splitRows + TILE_N - 1) / TILE_N * TILE_N;
     const int nSplits = (int)std::max<int64_t>(1, (maxT + splitRows - 1) / splitRows);
     if (nSplits > 65535) { set_error("train set too large for one launch"); return -1; }
-    if (ctx->ws[3].reserve((size_t)nSplits * totalQ * 16)) return -1;
+    const int nSlots = ATILES == 2 ? nSplits : 2 * nSplits;   // single-tile config: column halves report separately
+    if (ctx->ws[3].reserve((size_t)nSlots * totalQ * 16)) return -1;
     uint64_t* dSplitKeys = ctx->ws[3].as<uint64_t>();
 
     dim3 grid((unsigned)tiles, (unsigned)nSplits);
@@ -434,7 +448,7 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
     else if (KC == 2) rc = launch_cfg<2, 2, 4>(stream, grid, mq, mt, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dSplitKeys);
     else rc = launch_cfg<4, 1, 2>(stream, grid, mq, mt, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dSplitKeys);
     if (rc) return rc;
-    return launch_knn2_finalize(stream, dSplitKeys, nSplits, totalQ, a);
+    return launch_knn2_finalize(stream, dSplitKeys, nSlots, totalQ, a);
 }
 
 }  // namespace mcv
