@@ -248,6 +248,47 @@ def extra_ransac(local, with_cpu=True):
     return out
 
 
+def extra_large_db(local, rank, world, n_train=4 * 1024 * 1024, n_query=10000):
+    """C5: train set sharded by contiguous range over the ranks, queries replicated, local top-2
+    keys all_gathered over NCCL and merged on the device.  Time = max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from minicv_b200 import sharding
+    dev = torch.device("cuda", local)
+    lo, hi = sharding.block_range(n_train, world, rank)
+    g = torch.Generator(device=dev)
+    g.manual_seed(7 + rank)
+    shard = torch.randint(0, 256, (hi - lo, DESC_BYTES), dtype=torch.uint8, device=dev, generator=g)
+    gq = torch.Generator(device=dev)
+    gq.manual_seed(99)
+    q = torch.randint(0, 256, (n_query, DESC_BYTES), dtype=torch.uint8, device=dev, generator=gq)
+    if lo == 0:
+        q[: n_query // 2] = shard[: n_query // 2] ^ 1       # half the queries have a near-duplicate in shard 0
+    if world > 1:
+        dist.broadcast(q, 0)
+    stream = torch.cuda.current_stream()
+    sharding.match_large_db(q, shard, lo, DESC_BYTES, RATIO, device=local)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record(stream)
+    for _ in range(reps):
+        idx, dd, ok = sharding.match_large_db(q, shard, lo, DESC_BYTES, RATIO, device=local)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    found = int((idx[: n_query // 2, 0] == torch.arange(n_query // 2, device=dev)).sum().item())
+    return {"ms_per_image": ms, "images_per_s": 1e3 / ms, "n_train_total": n_train, "n_query": n_query,
+            "shards": world, "gdist_per_s": n_query * n_train / ms / 1e6,
+            "planted_matches_found": found, "planted": n_query // 2,
+            "collective": "all_gather of Q x 2 x 8 B per rank" if world > 1 else "none (1 rank)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -377,6 +418,11 @@ def run_ours(args):
     e2e_value = world * P / float(te.item())
     assert out.n_pass == n_pass_dev, "host-path and device-path results differ"
 
+    # --- C5 (all ranks): 4 Mi train descriptors sharded over the ranks, 10 000 queries, keys all_gathered
+    c5 = None
+    if not args.no_extra:
+        c5 = extra_large_db(local, rank, world)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -440,6 +486,7 @@ def run_ours(args):
         del dq, dt, didx, ddist, dok
         torch.cuda.empty_cache()
         extra = extra_ransac(local, with_cpu=not args.no_cpu_baseline)
+        extra["C5_large_db"] = c5
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
