@@ -1,12 +1,203 @@
-// l2_knn.cu -- L2 kNN (k = 2) for float32 descriptors.  (placeholder until the kernel lands)
+// l2_knn.cu -- brute-force L2 kNN (k = 2) + ratio test for float32 descriptors (SIFT-style).
+//
+// Contract: cv2.BFMatcher(NORM_L2).knnMatch(q, t, 2) (the reference
+// ships no matcher).  Distance = sqrt(sum_k (a_k - b_k)^2) in float32, accumulated in index order
+// with separate multiply and add (the oracle's definition, oracle/bf_knn.py l2_matrix_seq), so the
+// kernel is bit-exact against the oracle; against OpenCV's SIMD accumulation order it agrees to a
+// few ulp (tests state the tolerance).
+//
+// Mapping: 64 queries x 64 train rows per block step, 16 x 16 threads with a 4 x 4 register
+// micro-tile each; operands staged through shared memory 32 dimensions at a time.  Every thread
+// keeps the top-2 of its 4 queries as packed keys (float bits << 32 | trainIdx) -- non-negative
+// floats order like their bit patterns, so one unsigned min/max pair updates both ranks with the
+// lowest index winning ties; the 16 column threads of a query merge through shared memory.
+// This is the fp32 CUDA-core engine (FP32-pipe bound: 3 flops per dimension, no FMA); the
+// tcgen05 GEMM + rescoring engine of the north-star plan replaces it for large batches later.
 #include "knn.cuh"
 
+#include <algorithm>
+#include <float.h>
+
 namespace mcv {
+namespace {
+
+constexpr int LT = 64;    // tile edge (queries and train rows)
+constexpr int LK = 32;    // dimensions per shared-memory stage
+
+__device__ __forceinline__ void top2_u64(uint64_t& m1, uint64_t& m2, uint64_t key) {
+    const uint64_t hi = m1 > key ? m1 : key;
+    m1 = m1 < key ? m1 : key;
+    m2 = m2 < hi ? m2 : hi;
+}
+
+__global__ void __launch_bounds__(256)
+l2_knn2_kernel(const float* __restrict__ query, const float* __restrict__ train,
+               const int64_t* __restrict__ qOff, const int64_t* __restrict__ tOff,
+               const int* __restrict__ tileStart, int nPairs, int dim, int splitRows, int64_t totalQ,
+               uint64_t* __restrict__ splitKeys) {
+    __shared__ float sQ[LK][LT + 1];
+    __shared__ float sT[LK][LT + 1];
+    __shared__ uint64_t sM[LT][16][2];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    int lo = 0, hi = nPairs;
+    const int tile = blockIdx.x;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tileStart[mid] <= tile) lo = mid; else hi = mid;
+    }
+    const int p = lo;
+    const int64_t q0 = qOff[p] + (int64_t)(tile - tileStart[p]) * LT, qEnd = qOff[p + 1];
+    const int64_t tRow0 = tOff[p];
+    const int tCount = (int)(tOff[p + 1] - tRow0);
+    const int split = blockIdx.y;
+    const int t0 = min(tCount, split * splitRows), t1 = min(tCount, t0 + splitRows);
+
+    uint64_t m1[4], m2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m1[i] = ~0ull; m2[i] = ~0ull; }
+
+    for (int tb = t0; tb < t1; tb += LT) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int k0 = 0; k0 < dim; k0 += LK) {
+            // stage 64 x 32 floats of each operand, transposed to [k][row]
+            for (int e = threadIdx.x; e < LT * LK; e += 256) {
+                const int r = e / LK, k = e - r * LK;
+                const int64_t qr = q0 + r;
+                const int tr = tb + r;
+                sQ[k][r] = (qr < qEnd && k0 + k < dim) ? query[qr * dim + k0 + k] : 0.f;
+                sT[k][r] = (tr < t1 && k0 + k < dim) ? train[(tRow0 + tr) * dim + k0 + k] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int k = 0; k < LK; ++k) {
+                float a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] = sQ[k][ty * 4 + i]; b[i] = sT[k][tx * 4 + i]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float d = __fsub_rn(a[i], b[j]);
+                        acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(d, d));
+                    }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int tr = tb + tx * 4 + j;
+                if (tr < t1) {
+                    const float dist = __fsqrt_rn(acc[i][j]);
+                    top2_u64(m1[i], m2[i], ((uint64_t)__float_as_uint(dist) << 32) | (uint32_t)tr);
+                }
+            }
+    }
+    // merge the 16 column threads of each query
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { sM[ty * 4 + i][tx][0] = m1[i]; sM[ty * 4 + i][tx][1] = m2[i]; }
+    __syncthreads();
+    if (threadIdx.x < LT) {
+        const int r = threadIdx.x;
+        uint64_t a = ~0ull, b = ~0ull;
+        for (int c = 0; c < 16; ++c) { top2_u64(a, b, sM[r][c][0]); top2_u64(a, b, sM[r][c][1]); }
+        const int64_t qr = q0 + r;
+        if (qr < qEnd)
+            reinterpret_cast<ulonglong2*>(splitKeys + ((int64_t)split * totalQ + qr) * 2)[0] = make_ulonglong2(a, b);
+    }
+}
+
+// keys carry float bits: same merge as the Hamming finalize, but the distance word is a float
+__global__ void __launch_bounds__(256)
+l2_finalize_kernel(const uint64_t* __restrict__ splitKeys, int nSplits, int64_t totalQ, float ratio,
+                   int* __restrict__ trainIdx, float* __restrict__ dist, uint8_t* __restrict__ ratioPass,
+                   int* __restrict__ passCount) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool pass = false;
+    if (q < totalQ) {
+        uint64_t m1 = ~0ull, m2 = ~0ull;
+        for (int s = 0; s < nSplits; ++s) {
+            const ulonglong2 k = reinterpret_cast<const ulonglong2*>(splitKeys + ((int64_t)s * totalQ + q) * 2)[0];
+            top2_u64(m1, m2, k.x);
+            top2_u64(m1, m2, k.y);
+        }
+        int i1 = -1, i2 = -1;
+        float d1 = FLT_MAX, d2 = FLT_MAX;
+        if (m1 != ~0ull) { i1 = (int)(uint32_t)m1; d1 = __uint_as_float((uint32_t)(m1 >> 32)); }
+        if (m2 != ~0ull) { i2 = (int)(uint32_t)m2; d2 = __uint_as_float((uint32_t)(m2 >> 32)); }
+        reinterpret_cast<int2*>(trainIdx)[q] = make_int2(i1, i2);
+        reinterpret_cast<float2*>(dist)[q] = make_float2(d1, d2);
+        pass = (i2 >= 0) && (d1 < __fmul_rn(ratio, d2));
+        if (ratioPass) ratioPass[q] = pass ? 1 : 0;
+    }
+    if (passCount) {
+        const unsigned b = __ballot_sync(0xFFFFFFFFu, pass);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(passCount, __popc(b));
+    }
+}
+
+}  // namespace
 
 int launch_l2_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
-    (void)ctx; (void)stream; (void)a;
-    set_error("NORM_L2 matcher kernel is not built into this library yet");
-    return -1;
+    if (a.nPairs <= 0) return 0;
+    if (a.descBytes <= 0 || a.descBytes % 4 != 0) { set_error("L2 matcher needs float32 rows"); return -1; }
+    if (a.emit != KNN_EMIT_MATCHES) { set_error("L2 matcher has no shard-key mode"); return -1; }
+    if ((reinterpret_cast<uintptr_t>(a.dQuery) & 3) || (reinterpret_cast<uintptr_t>(a.dTrain) & 3)) {
+        set_error("L2 matcher needs 4-byte aligned descriptor blobs");
+        return -1;
+    }
+    const int dim = a.descBytes / 4;
+    const int64_t totalQ = a.hQOff[a.nPairs];
+    if (a.hQOff[0] != 0 || a.hTOff[0] != 0) { set_error("offset arrays must start at 0"); return -1; }
+    if (totalQ == 0) return 0;
+    const size_t n1 = (size_t)a.nPairs + 1;
+    const size_t ctlBytes = n1 * (8 + 8 + 4);
+    if (ctx->pin[0].reserve(ctlBytes) || ctx->ws[0].reserve(ctlBytes)) return -1;
+    MCV_CUDA_TRY(cudaEventSynchronize(ctx->ev[0]));
+    int64_t* hQ = ctx->pin[0].as<int64_t>();
+    int64_t* hT = hQ + n1;
+    int* hTile = reinterpret_cast<int*>(hT + n1);
+    int64_t tiles = 0, maxT = 0;
+    for (int p = 0; p < a.nPairs; ++p) {
+        const int64_t nq = a.hQOff[p + 1] - a.hQOff[p], nt = a.hTOff[p + 1] - a.hTOff[p];
+        if (nq < 0 || nt < 0 || nt > 0x7FFFFFFFll) { set_error("bad offsets at pair %d", p); return -1; }
+        hQ[p] = a.hQOff[p]; hT[p] = a.hTOff[p]; hTile[p] = (int)tiles;
+        tiles += (nq + LT - 1) / LT;
+        maxT = std::max(maxT, nt);
+    }
+    hQ[a.nPairs] = a.hQOff[a.nPairs]; hT[a.nPairs] = a.hTOff[a.nPairs]; hTile[a.nPairs] = (int)tiles;
+    if (tiles > 0x7FFFFFFFll) { set_error("too many query tiles"); return -1; }
+    MCV_CUDA_TRY(cudaMemcpyAsync(ctx->ws[0].p, hQ, ctlBytes, cudaMemcpyHostToDevice, stream));
+    MCV_CUDA_TRY(cudaEventRecord(ctx->ev[0], stream));
+    const int64_t* dQOff = ctx->ws[0].as<int64_t>();
+    const int64_t* dTOff = dQOff + n1;
+    const int* dTile = reinterpret_cast<const int*>(dTOff + n1);
+
+    int64_t wantSplits = 1;
+    const int64_t fill = 4ll * ctx->sm_count;
+    if (tiles < fill) wantSplits = (fill + tiles - 1) / tiles;
+    wantSplits = std::min<int64_t>(wantSplits, std::max<int64_t>(1, (maxT + LT - 1) / LT));
+    int64_t splitRows = (std::max<int64_t>(maxT, 1) + wantSplits - 1) / wantSplits;
+    splitRows = (splitRows + LT - 1) / LT * LT;
+    const int nSplits = (int)std::max<int64_t>(1, (maxT + splitRows - 1) / splitRows);
+    if (nSplits > 65535) { set_error("train set too large for one launch"); return -1; }
+    if (ctx->ws[3].reserve((size_t)nSplits * totalQ * 16)) return -1;
+    uint64_t* dKeys = ctx->ws[3].as<uint64_t>();
+    dim3 grid((unsigned)tiles, (unsigned)nSplits);
+    l2_knn2_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(a.dQuery),
+                                             reinterpret_cast<const float*>(a.dTrain), dQOff, dTOff, dTile,
+                                             a.nPairs, dim, (int)splitRows, totalQ, dKeys);
+    MCV_LAUNCH_CHECK();
+    l2_finalize_kernel<<<(unsigned)((totalQ + 255) / 256), 256, 0, stream>>>(dKeys, nSplits, totalQ, a.ratio,
+                                                                            a.dTrainIdx, a.dDist, a.dRatioPass,
+                                                                            a.dPassCount);
+    MCV_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // namespace mcv

@@ -49,6 +49,25 @@ def golden_knn():
     print("knn_hamming.npz", {k: v.shape for k, v in out.items() if k.endswith("_idx")})
 
 
+def golden_l2():
+    out = {}
+    rng = np.random.default_rng(5)
+    # SIFT-like: integer-valued float32 in [0, 255] -> every partial sum is exact in float32
+    t = rng.integers(0, 120, (700, 128)).astype(np.float32)
+    q = rng.integers(0, 120, (300, 128)).astype(np.float32)
+    q[:100] = t[rng.permutation(700)[:100]] + rng.integers(-3, 4, (100, 128)).astype(np.float32)
+    t[9] = t[3]; q[0] = t[3]                       # exact tie -> lowest index
+    idx, dist = cv_knn2(q, t, cv2.NORM_L2)
+    out["sift_q"] = q; out["sift_t"] = t; out["sift_idx"] = idx; out["sift_dist"] = dist
+    # general floats
+    t = rng.normal(size=(500, 64)).astype(np.float32)
+    q = rng.normal(size=(200, 64)).astype(np.float32)
+    idx, dist = cv_knn2(q, t, cv2.NORM_L2)
+    out["gen_q"] = q; out["gen_t"] = t; out["gen_idx"] = idx; out["gen_dist"] = dist
+    np.savez_compressed(HERE / "knn_l2.npz", **out)
+    print("knn_l2.npz")
+
+
 def golden_ransac():
     out = {}
     # homography: cv2.findHomography(RANSAC, 3.0, maxIters 2000, confidence .995)
@@ -122,3 +141,5 @@ if __name__ == "__main__":
         golden_knn()
     if "ransac" in which:
         golden_ransac()
+    if "l2" in which:
+        golden_l2()

@@ -42,3 +42,14 @@ def test_empty_inputs():
     assert (idx == -1).all() and (dist == bf_knn.FLT_MAX).all()
     idx, dist = bf_knn.bf_knn2_hamming(np.zeros((0, 32), np.uint8), np.zeros((5, 32), np.uint8))
     assert idx.shape == (0, 2)
+
+
+def test_l2_oracle_vs_cv2_golden():
+    g = np.load(GOLDEN / "knn_l2.npz")
+    idx, dist = bf_knn.bf_knn2_l2(g["sift_q"], g["sift_t"])          # integer-valued: bit-exact
+    np.testing.assert_array_equal(idx, g["sift_idx"])
+    np.testing.assert_array_equal(dist, g["sift_dist"])
+    assert tuple(idx[0]) == (3, 9)
+    idx, dist = bf_knn.bf_knn2_l2(g["gen_q"], g["gen_t"])            # general floats: few ulp
+    np.testing.assert_array_equal(idx, g["gen_idx"])
+    np.testing.assert_allclose(dist, g["gen_dist"], rtol=2e-6)
