@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample-pairs", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the C3/C4 RANSAC side measurements")
-    ap.add_argument("--engine", default="auto", choices=["auto", "popc", "tensor"],
+    ap.add_argument("--engine", default="auto", choices=["auto", "popc", "tensor", "packed"],
                     help="Hamming engine: auto (tensor cores for large batches), popc, tensor")
     return ap.parse_args()
 
@@ -345,9 +345,9 @@ def run_ours(args):
     lib = native.load()
     if lib.mcvDeviceCount() < 1:
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback): " + native.last_error())
-    engine = {"auto": 0, "popc": 1, "tensor": 2}[args.engine]
+    engine = {"auto": 0, "popc": 1, "tensor": 2, "packed": 3}[args.engine]
     mcv.set_hamming_engine(engine)
-    use_tc = engine == 2 or (engine == 0 and args.pairs * NQ * NT >= 64 * 1024 * 1024)
+    use_tc = engine >= 2 or (engine == 0 and args.pairs * NQ * NT >= 64 * 1024 * 1024)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

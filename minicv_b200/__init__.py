@@ -5,7 +5,7 @@ in ``csrc/``).  This Python package is the host-side mirror of the reference's F
 (``src/MiniCV/OpenCV.fs``) used by the tests and the benchmark; it never computes on the CPU.
 """
 from . import native  # noqa: F401
-from .matching import (ENGINE_AUTO, ENGINE_POPC, ENGINE_TENSOR, KnnResult, NORM_HAMMING, NORM_L2,  # noqa: F401
+from .matching import (ENGINE_AUTO, ENGINE_POPC, ENGINE_TENSOR, ENGINE_TENSOR_PACKED, KnnResult, NORM_HAMMING, NORM_L2,  # noqa: F401
                        match_features, match_knn2, set_hamming_engine,
                        match_knn2_batch, match_knn2_batch_device)
 from . import estimation  # noqa: F401

@@ -117,7 +117,7 @@ MCV_API int mcvDeviceCount(void) {
 MCV_API int64_t mcvKernelLaunchCount(void) { return mcv::g_launches.load(); }
 
 MCV_API int mcvSetHammingEngine(int engine) {
-    if (engine < 0 || engine > 2) return -1;
+    if (engine < 0 || engine > 3) return -1;
     mcv::g_hamming_engine.store(engine);
     return 0;
 }

@@ -268,7 +268,8 @@ int launch_hamming_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
         // on the integer pipe
         const int eng = g_hamming_engine.load(std::memory_order_relaxed);
         bool tc = false;
-        if (eng == 2) tc = hamming_tc_supported(a.descBytes);
+        if (eng == 3 && hamming_tc2_supported(a.descBytes)) return launch_hamming_knn2_tc2(ctx, stream, a);
+        if (eng == 2 || eng == 3) tc = hamming_tc_supported(a.descBytes);
         else if (eng == 0 && hamming_tc_supported(a.descBytes)) {
             const double q = (double)(a.hQOff[a.nPairs] - a.hQOff[0]);
             const double t = (double)(a.hTOff[a.nPairs] - a.hTOff[0]) / std::max(a.nPairs, 1);

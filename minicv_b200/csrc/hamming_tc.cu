@@ -18,6 +18,7 @@
 // Results leave the kernel as packed keys (dist << 32) | trainIdx and go through the same
 // finalize kernel as the integer-pipe engine (hamming_knn.cu), so tie-breaking is identical.
 #include "knn.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda.h>
 #include <algorithm>
@@ -28,71 +29,7 @@ namespace {
 
 constexpr int EPI_WARPS = 8;       // two epilogue warps per TMEM lane quarter
 constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
-constexpr int TILE_M = 128;        // rows per MMA (queries)
-constexpr int TILE_N = 128;        // train rows per stage
-constexpr int CHUNK_BYTES = TILE_M * 128;   // one 128-row x 128-byte swizzle-128B panel = 16 KB
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory operand descriptor (sm_100 format): start address >> 4,
-// LBO = 1 (ignored for swizzled K-major), SBO = 1024 B between 8-row groups, version 1, layout 2.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
+using namespace tc;
 
 // ---------------------------------------------------------------------------------------------
 // bit expansion: packed descriptor bits -> int8 +-1 rows of KC*128 bytes (zero bits -> -1;
@@ -340,20 +277,6 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int rowBytes) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return -1; }
-    const cuuint64_t dims[2] = {(cuuint64_t)rowBytes, (cuuint64_t)std::max<int64_t>(rows, 1)};
-    const cuuint64_t strides[1] = {(cuuint64_t)rowBytes};
-    const cuuint32_t box[2] = {128, (cuuint32_t)TILE_M};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
-    return 0;
-}
-
 template <int KC, int ATILES, int STAGES>
 int launch_cfg(cudaStream_t stream, dim3 grid, const CUtensorMap& mq, const CUtensorMap& mt, const int64_t* qOff,
                const int64_t* tOff, const int* tileStart, int nPairs, int splitRows, int64_t totalQ,
@@ -366,7 +289,27 @@ int launch_cfg(cudaStream_t stream, dim3 grid, const CUtensorMap& mq, const CUte
     return 0;
 }
 
+EncodeTiledFn get_encode_fn_public_impl() { return get_encode_fn(); }
+
 }  // namespace
+
+namespace tc {
+static inline EncodeTiledFn get_encode_fn_public() { return get_encode_fn_public_impl(); }
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int rowBytes) {
+    EncodeTiledFn fn = get_encode_fn_public();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return -1; }
+    const cuuint64_t dims[2] = {(cuuint64_t)rowBytes, (cuuint64_t)std::max<int64_t>(rows, 1)};
+    const cuuint64_t strides[1] = {(cuuint64_t)rowBytes};
+    const cuuint32_t box[2] = {128, (cuuint32_t)TILE_M};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+    return 0;
+}
+
+}  // namespace tc
 
 bool hamming_tc_supported(int descBytes) { return descBytes >= 1 && descBytes <= 64; }
 

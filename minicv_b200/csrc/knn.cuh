@@ -34,7 +34,11 @@ int launch_hamming_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a);
 // Same contract on the tensor cores (tcgen05 int8 +-1 GEMM, hamming_tc.cu).
 bool hamming_tc_supported(int descBytes);
 int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a);
-// Engine choice: 0 = auto, 1 = integer pipe (XOR + POPC), 2 = tensor cores.
+// Packed-accumulator tensor-core engine (two distances per TMEM word, <= 256 bit), hamming_tc2.cu.
+bool hamming_tc2_supported(int descBytes);
+int launch_hamming_knn2_tc2(Context* ctx, cudaStream_t stream, const KnnArgs& a);
+// Engine choice: 0 = auto, 1 = integer pipe (XOR + POPC), 2 = tensor cores (int8),
+// 3 = tensor cores with packed accumulators (fp8).
 extern std::atomic<int> g_hamming_engine;
 // Shared second stage: merges nSplits key pairs per query and emits matches or keys.
 int launch_knn2_finalize(cudaStream_t stream, const uint64_t* dSplitKeys, int nSplits, int64_t totalQ,

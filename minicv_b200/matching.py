@@ -133,11 +133,11 @@ def match_features(query_desc: np.ndarray, train_desc: np.ndarray, ratio: float 
     return KnnResult(idx, dist, ok, n)
 
 
-ENGINE_AUTO, ENGINE_POPC, ENGINE_TENSOR = 0, 1, 2
+ENGINE_AUTO, ENGINE_POPC, ENGINE_TENSOR, ENGINE_TENSOR_PACKED = 0, 1, 2, 3
 
 
 def set_hamming_engine(engine: int) -> None:
     """Choose the Hamming matcher engine (results are bit-identical): 0 auto, 1 integer pipe
-    (XOR + POPC), 2 tcgen05 tensor cores."""
+    (XOR + POPC), 2 tcgen05 int8 tensor cores, 3 tcgen05 fp8 with packed accumulators."""
     if native.load().mcvSetHammingEngine(engine) != 0:
-        raise ValueError("engine must be 0, 1 or 2")
+        raise ValueError("engine must be 0..3")

@@ -11,9 +11,9 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True)
-def tensor_engine():
-    mcv.set_hamming_engine(mcv.ENGINE_TENSOR)
+@pytest.fixture(autouse=True, params=[mcv.ENGINE_TENSOR, mcv.ENGINE_TENSOR_PACKED], ids=["int8", "fp8-packed"])
+def tensor_engine(request):
+    mcv.set_hamming_engine(request.param)
     yield
     mcv.set_hamming_engine(mcv.ENGINE_AUTO)
 
@@ -63,6 +63,13 @@ def test_ragged_batch_vs_oracle():
         idx, dist = bf_knn.bf_knn2_hamming(q[qo[p]:qo[p + 1]], t[to[p]:to[p + 1]])
         np.testing.assert_array_equal(r.train_idx[qo[p]:qo[p + 1]], idx)
         np.testing.assert_array_equal(r.distance[qo[p]:qo[p + 1]], dist)
+
+
+def test_split_tail_and_hi_lo_boundaries():
+    # train counts around the 128/256-row stage and half-split boundaries, few queries (forces splits)
+    for nt in (127, 128, 129, 255, 256, 257, 383, 1023, 1025, 4097):
+        q, t, _ = synth.descriptor_pair(900 + nt, 70, nt, 32)
+        check(q, t)
 
 
 def test_engines_agree_on_batch():
