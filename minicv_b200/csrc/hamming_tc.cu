@@ -27,7 +27,7 @@
 namespace mcv {
 namespace {
 
-constexpr int EPI_WARPS = 8;       // two epilogue warps per TMEM lane quarter
+constexpr int EPI_WARPS = 16;      // four epilogue warps per TMEM lane quarter (latency hiding)
 constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
 using namespace tc;
 
@@ -178,13 +178,17 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     } else {
         // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4 =====
         const int quarter = warp & 3;
-        const int grp = (warp - 2) >> 2;                 // 0 or 1
+        const int grp = (warp - 2) >> 2;                 // 0 .. 3
         const int row = quarter * 32 + lane;             // accumulator row within an M tile
-        // ATILES == 2: this warp owns query tile `grp`, all four 32-column chunks of a stage.
-        // ATILES == 1: it owns column chunks [2*grp, 2*grp+2) and reports as its own split slot.
-        const int myTile = ATILES == 2 ? grp : 0;
-        constexpr int NCHUNK = ATILES == 2 ? 4 : 2;
-        const int chunk0 = ATILES == 2 ? 0 : 2 * grp;
+        // The four warps of a lane quarter split a stage's work; every warp reports its own
+        // partial top-2 as a separate key slot (merged exactly by the finalize kernel).
+        // ATILES == 2: query tile = grp & 1, column half = grp >> 1 (two 32-column chunks).
+        // ATILES == 1: one 32-column chunk each.
+        const int myTile = ATILES == 2 ? (grp & 1) : 0;
+        constexpr int NCHUNK = ATILES == 2 ? 2 : 1;
+        constexpr int SLOTS = ATILES == 2 ? 2 : 4;       // key slots per split
+        const int colPart = ATILES == 2 ? (grp >> 1) : grp;
+        const int chunk0 = colPart * NCHUNK;
         int b1 = INT_MIN, i1 = -1, b2 = INT_MIN, i2 = -1;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
@@ -224,23 +228,23 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             // software pipeline: the load of chunk c+1 is in flight while chunk c is processed
             tc_ld32(tcol, va);
             tc_wait_ld();
-#pragma unroll
-            for (int c = 0; c < NCHUNK; c += 2) {
-                if (c + 1 < NCHUNK) tc_ld32(tcol + (c + 1) * 32, vb);
-                process(va, valid - (chunk0 + c) * 32, cb0 + c * 32);
+            if (NCHUNK == 2) {
+                tc_ld32(tcol + 32, vb);
+                process(va, valid - chunk0 * 32, cb0);
                 tc_wait_ld();
-                if (c + 1 < NCHUNK) {
-                    if (c + 2 < NCHUNK) tc_ld32(tcol + (c + 2) * 32, va);
-                    else { tc_fence_before(); mbar_arrive(acc_empty + as); }   // all loads landed
-                    process(vb, valid - (chunk0 + c + 1) * 32, cb0 + (c + 1) * 32);
-                    tc_wait_ld();
-                }
+                tc_fence_before();
+                mbar_arrive(acc_empty + as);                 // all of this warp's loads have landed
+                process(vb, valid - (chunk0 + 1) * 32, cb0 + 32);
+            } else {
+                tc_fence_before();
+                mbar_arrive(acc_empty + as);
+                process(va, valid - chunk0 * 32, cb0);
             }
         }
         // emit packed keys (dist << 32) | pair-local train index
         {
             const int64_t qRow = qTile0 + myTile * TILE_M + row;
-            const int slot = ATILES == 2 ? split : split * 2 + grp;
+            const int slot = split * SLOTS + colPart;
             if (qRow < qEnd) {
                 uint64_t k1 = ~0ull, k2 = ~0ull;
                 if (i1 >= 0) k1 = ((uint64_t)(uint32_t)((KBITS - b1) >> 1) << 32) | (uint64_t)(uint32_t)i1;
@@ -381,7 +385,7 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
     splitRows = (splitRows + TILE_N - 1) / TILE_N * TILE_N;
     const int nSplits = (int)std::max<int64_t>(1, (maxT + splitRows - 1) / splitRows);
     if (nSplits > 65535) { set_error("train set too large for one launch"); return -1; }
-    const int nSlots = ATILES == 2 ? nSplits : 2 * nSplits;   // single-tile config: column halves report separately
+    const int nSlots = (ATILES == 2 ? 2 : 4) * nSplits;   // every epilogue warp of a lane quarter reports its own slot
     if (ctx->ws[3].reserve((size_t)nSlots * totalQ * 16)) return -1;
     uint64_t* dSplitKeys = ctx->ws[3].as<uint64_t>();
 

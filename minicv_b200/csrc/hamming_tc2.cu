@@ -70,13 +70,6 @@ expand_fp8_kernel(const uint8_t* __restrict__ src, int srcBytes, int64_t nRows, 
     dst[dstRow * per + g] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__device__ __forceinline__ void top2_ins(int x, int col, int& b1, int& i1, int& b2, int& i2) {
-    if (x > b2) {
-        if (x > b1) { b2 = b1; i2 = i1; b1 = x; i1 = col; }
-        else { b2 = x; i2 = col; }
-    }
-}
-
 template <int KC, int STAGES>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 hamming_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapT,
@@ -192,63 +185,90 @@ hamming_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         const int quarter = warp & 3;
         const int myTile = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
-        // lo stream state lives in the shifted domain (value << 22); hi stream in plain integers
-        int lb1 = INT_MIN, li1 = -1, lb2 = INT_MIN, li2 = -1;
+        // lo stream: values kept as exact-integer floats; hi stream: integers + a float threshold
+        float lb1 = -3.0e38f, lb2 = -3.0e38f;
+        int li1 = -1, li2 = -1;
         int hb1 = INT_MIN, hi1 = -1, hb2 = INT_MIN, hi2 = -1;
         float hiThr = -3.0e38f;            // D > hiThr  <=>  hi(D) > hb2
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
-        auto process = [&](int (&raw)[32], int nvLo, int nvHi, int cbLo, int cbHi) {
-            float f[32];
-            int L[32];
+        // one 32-column chunk: split every accumulator D = 1024*hi + lo on the FMA pipe
+        // (hi = rint(D/1024) via the magic-number add, lo = D - 1024*hi, both exact), filter
+        // 8-column groups by their maxima, and run the exact insert only where it can matter
+        auto process = [&](const int (&raw)[32], int nvLo, int nvHi, int cbLo, int cbHi) {
+            float f[32], lf[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 f[i] = __int_as_float(raw[i]);
-                L[i] = (int)((uint32_t)__float_as_int(__fadd_rn(f[i], MAGIC)) << 22);
+                const float hf = __fsub_rn(__fmaf_rn(f[i], 0.0009765625f, MAGIC), MAGIC);
+                lf[i] = __fmaf_rn(hf, -1024.0f, f[i]);
             }
             if (nvLo < 32 || nvHi < 32) {          // tail stage only
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    if (i >= nvLo) L[i] = INT_MIN;
+                    if (i >= nvLo) lf[i] = -3.0e38f;
                     if (i >= nvHi) f[i] = -3.0e38f;
                 }
             }
-            int gl[4];
-            float gf[4];
+            float gl[4], gf[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int a01 = max(L[q * 8 + 0], L[q * 8 + 1]), a23 = max(L[q * 8 + 2], L[q * 8 + 3]);
-                const int a45 = max(L[q * 8 + 4], L[q * 8 + 5]), a67 = max(L[q * 8 + 6], L[q * 8 + 7]);
-                gl[q] = max(max(a01, a23), max(a45, a67));
+                const float a01 = fmaxf(lf[q * 8 + 0], lf[q * 8 + 1]), a23 = fmaxf(lf[q * 8 + 2], lf[q * 8 + 3]);
+                const float a45 = fmaxf(lf[q * 8 + 4], lf[q * 8 + 5]), a67 = fmaxf(lf[q * 8 + 6], lf[q * 8 + 7]);
+                gl[q] = fmaxf(fmaxf(a01, a23), fmaxf(a45, a67));
                 const float f01 = fmaxf(f[q * 8 + 0], f[q * 8 + 1]), f23 = fmaxf(f[q * 8 + 2], f[q * 8 + 3]);
                 const float f45 = fmaxf(f[q * 8 + 4], f[q * 8 + 5]), f67 = fmaxf(f[q * 8 + 6], f[q * 8 + 7]);
                 gf[q] = fmaxf(fmaxf(f01, f23), fmaxf(f45, f67));
             }
-            const int gml = max(max(gl[0], gl[1]), max(gl[2], gl[3]));
+            const float gml = fmaxf(fmaxf(gl[0], gl[1]), fmaxf(gl[2], gl[3]));
             const float gmf = fmaxf(fmaxf(gf[0], gf[1]), fmaxf(gf[2], gf[3]));
+            // exact updates: one code instance per stream, the triggered group is copied into x[]
             if (gml > lb2) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (gl[q] > lb2) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) top2_ins(L[q * 8 + i], cbLo + q * 8 + i, lb1, li1, lb2, li2);
-                    }
-            }
-            if (gmf > hiThr) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (gf[q] > hiThr) {
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    const float g = q == 0 ? gl[0] : q == 1 ? gl[1] : q == 2 ? gl[2] : gl[3];
+                    if (g > lb2) {
+                        float x[8];
+                        if (q == 0) { _Pragma("unroll") for (int i = 0; i < 8; ++i) x[i] = lf[i]; }
+                        else if (q == 1) { _Pragma("unroll") for (int i = 0; i < 8; ++i) x[i] = lf[8 + i]; }
+                        else if (q == 2) { _Pragma("unroll") for (int i = 0; i < 8; ++i) x[i] = lf[16 + i]; }
+                        else { _Pragma("unroll") for (int i = 0; i < 8; ++i) x[i] = lf[24 + i]; }
+                        const int cb = cbLo + q * 8;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            if (f[q * 8 + i] > hiThr) {
-                                // exact integer image of D, then hi = round(D / 1024)
-                                const int d = __float_as_int(__fadd_rn(f[q * 8 + i], MAGIC)) - MAGIC_BITS;
+                            if (x[i] > lb2) {
+                                const bool top = x[i] > lb1;
+                                lb2 = top ? lb1 : x[i]; li2 = top ? li1 : cb + i;
+                                lb1 = top ? x[i] : lb1; li1 = top ? cb + i : li1;
+                            }
+                        }
+                    }
+                }
+            }
+            if (gmf > hiThr) {
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    const float g = q == 0 ? gf[0] : q == 1 ? gf[1] : q == 2 ? gf[2] : gf[3];
+                    if (g > hiThr) {
+                        float x[8];
+                        if (q == 0) { _Pragma("unroll") for (int i = 0; i < 8; ++i) x[i] = f[i]; }
+                        else if (q == 1) { _Pragma("unroll") for (int i = 0; i < 8; ++i) x[i] = f[8 + i]; }
+                        else if (q == 2) { _Pragma("unroll") for (int i = 0; i < 8; ++i) x[i] = f[16 + i]; }
+                        else { _Pragma("unroll") for (int i = 0; i < 8; ++i) x[i] = f[24 + i]; }
+                        const int cb = cbHi + q * 8;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (x[i] > hiThr) {
+                                const int d = __float_as_int(__fadd_rn(x[i], MAGIC)) - MAGIC_BITS;
                                 const int hv = (d + 512) >> 10;
-                                top2_ins(hv, cbHi + q * 8 + i, hb1, hi1, hb2, hi2);
+                                const bool top = hv > hb1;
+                                hb2 = top ? hb1 : hv; hi2 = top ? hi1 : cb + i;
+                                hb1 = top ? hv : hb1; hi1 = top ? cb + i : hi1;
                                 hiThr = hb2 == INT_MIN ? -3.0e38f : (float)(hb2 * 1024 + 512);
                             }
                         }
                     }
+                }
             }
         };
 
@@ -261,26 +281,26 @@ hamming_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
             const int validHi = max(0, min(TILE_N, hiCount - colBase));
             const uint32_t tcol = tlane + (uint32_t)(as * (ATILES * TILE_N) + myTile * TILE_N);
             const int cbLo = t0 + colBase, cbHi = t0 + H + colBase;
-            int va[32], vb[32];
-            tc_ld32(tcol, va);
+            int cur[32], nxt[32];
+            tc_ld32(tcol, cur);
             tc_wait_ld();
+            // one code instance of process(): the next chunk's tcgen05.ld is in flight under it
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                if (c < 3) tc_ld32(tcol + (c + 1) * 32, nxt);
+                process(cur, validLo - c * 32, validHi - c * 32, cbLo + c * 32, cbHi + c * 32);
+                tc_wait_ld();
+                if (c == 2) { tc_fence_before(); mbar_arrive(acc_empty + as); }   // every load has landed
 #pragma unroll
-            for (int c = 0; c < 4; c += 2) {
-                tc_ld32(tcol + (c + 1) * 32, vb);
-                process(va, validLo - c * 32, validHi - c * 32, cbLo + c * 32, cbHi + c * 32);
-                tc_wait_ld();
-                if (c + 2 < 4) tc_ld32(tcol + (c + 2) * 32, va);
-                else { tc_fence_before(); mbar_arrive(acc_empty + as); }
-                process(vb, validLo - (c + 1) * 32, validHi - (c + 1) * 32, cbLo + (c + 1) * 32, cbHi + (c + 1) * 32);
-                tc_wait_ld();
+                for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
             }
         }
         // emit: lo stream -> slot 2*split, hi stream -> slot 2*split + 1
         const int64_t qRow = qTile0 + myTile * TILE_M + row;
         if (qRow < qEnd) {
             uint64_t k1 = ~0ull, k2 = ~0ull, k3 = ~0ull, k4 = ~0ull;
-            if (li1 >= 0) k1 = ((uint64_t)(uint32_t)((KBITS - (lb1 >> 22)) >> 1) << 32) | (uint64_t)(uint32_t)li1;
-            if (li2 >= 0) k2 = ((uint64_t)(uint32_t)((KBITS - (lb2 >> 22)) >> 1) << 32) | (uint64_t)(uint32_t)li2;
+            if (li1 >= 0) k1 = ((uint64_t)(uint32_t)((KBITS - (int)lb1) >> 1) << 32) | (uint64_t)(uint32_t)li1;
+            if (li2 >= 0) k2 = ((uint64_t)(uint32_t)((KBITS - (int)lb2) >> 1) << 32) | (uint64_t)(uint32_t)li2;
             if (hi1 >= 0) k3 = ((uint64_t)(uint32_t)((KBITS - hb1) >> 1) << 32) | (uint64_t)(uint32_t)hi1;
             if (hi2 >= 0) k4 = ((uint64_t)(uint32_t)((KBITS - hb2) >> 1) << 32) | (uint64_t)(uint32_t)hi2;
             uint64_t* o = splitKeys + ((int64_t)(2 * split) * totalQ + qRow) * 2;
