@@ -569,79 +569,111 @@ MCV_HD void upoly_mul(const double* a, int na, const double* b, int nb, double* 
         for (int j = 0; j < nb; ++j) r[i + j] += a[i] * b[j];
 }
 
-// Real roots of a degree-10 polynomial c[0] z^10 + ... + c[10]: simultaneous Aberth-Ehrlich
-// iteration in complex arithmetic, then the reference's filter |Im| <= 1e-10
-// (fivepoint.cpp:301; the reference calls cv::solvePoly, a Durand-Kerner iteration).
+// Real roots of a degree-10 polynomial c[0] z^10 + ... + c[10] (real coefficients).
+// The reference calls cv::solvePoly (Durand-Kerner on all complex roots) and keeps roots with
+// |Im| <= 1e-10 (fivepoint.cpp:296-303).  Here: Laguerre iterations with deflation by real
+// linear / real quadratic factors (coefficients stay real), every root then polished on the
+// ORIGINAL polynomial before the same |Im| <= 1e-10 filter.  ~10x fewer flops than a
+// simultaneous all-roots iteration, and all state fits in registers.
+MCV_HDN inline void laguerre_step_poly(const double* a, int deg, double& xr, double& xi, int maxIter) {
+    // a[0] z^deg + ... + a[deg]; iterates (xr, xi) towards a root of this polynomial
+    for (int iter = 0; iter < maxIter; ++iter) {
+        double br = a[0], bi = 0, dr = 0, di = 0, fr = 0, fi = 0;
+        double err = fabs(br);
+        const double ax = sqrt(xr * xr + xi * xi);
+        for (int j = 1; j <= deg; ++j) {
+            // f = x*f + d; d = x*d + b; b = x*b + a[j]
+            const double nfr = xr * fr - xi * fi + dr, nfi = xr * fi + xi * fr + di;
+            const double ndr = xr * dr - xi * di + br, ndi = xr * di + xi * dr + bi;
+            const double nbr = xr * br - xi * bi + a[j], nbi = xr * bi + xi * br;
+            fr = nfr; fi = nfi; dr = ndr; di = ndi; br = nbr; bi = nbi;
+            err = sqrt(br * br + bi * bi) + ax * err;
+        }
+        const double babs = sqrt(br * br + bi * bi);
+        if (babs <= err * 2e-16) return;                      // at the rounding floor of p(x)
+        // G = d/b, G2 = G^2, H = G2 - 2 f / b
+        const double b2 = br * br + bi * bi;
+        const double gr = (dr * br + di * bi) / b2, gi = (di * br - dr * bi) / b2;
+        const double g2r = gr * gr - gi * gi, g2i = 2 * gr * gi;
+        const double qr = (fr * br + fi * bi) / b2, qi = (fi * br - fr * bi) / b2;
+        const double hr = g2r - 2 * qr, hi = g2i - 2 * qi;
+        // sq = sqrt((deg-1) * (deg*H - G2))
+        const double tr = (deg - 1) * (deg * hr - g2r), ti = (deg - 1) * (deg * hi - g2i);
+        const double tm = sqrt(tr * tr + ti * ti);
+        double sr = sqrt(fmax(0.0, 0.5 * (tm + tr))), si = sqrt(fmax(0.0, 0.5 * (tm - tr)));
+        if (ti < 0) si = -si;
+        double p1r = gr + sr, p1i = gi + si, p2r = gr - sr, p2i = gi - si;
+        const double m1 = p1r * p1r + p1i * p1i, m2 = p2r * p2r + p2i * p2i;
+        if (m2 > m1) { p1r = p2r; p1i = p2i; }
+        const double pm = fmax(m1, m2);
+        double dxr, dxi;
+        if (pm > 0) { dxr = deg * p1r / pm; dxi = -deg * p1i / pm; }
+        else { dxr = (1 + ax) * cos((double)iter); dxi = (1 + ax) * sin((double)iter); }
+        const double nxr = xr - dxr, nxi = xi - dxi;
+        if (nxr == xr && nxi == xi) return;
+        xr = nxr; xi = nxi;
+        if (fabs(dxr) + fabs(dxi) <= 1e-16 * (fabs(xr) + fabs(xi))) return;
+    }
+}
+
 MCV_HDN inline int real_roots10(const double* c, double* out) {
     int deg = 10, lead = 0;
     while (deg > 0 && c[lead] == 0) { ++lead; --deg; }
     if (deg == 0) return 0;
-    const double* a = c + lead;   // a[0] z^deg + ... + a[deg]
-    double zr[10], zi[10];
-    // Cauchy bound for the starting radius
-    double bound = 0;
-    for (int i = 1; i <= deg; ++i) bound = fmax(bound, fabs(a[i] / a[0]));
-    const double rad = 1 + bound > 1e3 ? pow(fabs(a[deg] / a[0]), 1.0 / deg) + 1 : 1 + bound;
-    for (int i = 0; i < deg; ++i) {
-        const double ang = 2 * 3.14159265358979323846 * i / deg + 0.4;
-        zr[i] = rad * 0.5 * cos(ang);
-        zi[i] = rad * 0.5 * sin(ang);
-    }
-    for (int iter = 0; iter < 200; ++iter) {
-        double maxd = 0;
-        for (int i = 0; i < deg; ++i) {
-            // Horner for p and p'
-            double pr = a[0], pi = 0, dr = 0, di = 0;
-            const double xr = zr[i], xi = zi[i];
-            for (int k = 1; k <= deg; ++k) {
-                const double ndr = dr * xr - di * xi + pr, ndi = dr * xi + di * xr + pi;
-                dr = ndr; di = ndi;
-                const double npr = pr * xr - pi * xi + a[k], npi = pr * xi + pi * xr;
-                pr = npr; pi = npi;
-            }
-            // w = p / p'
-            double den = dr * dr + di * di;
-            if (den == 0) { dr = 1e-300; den = dr * dr; }
-            const double wr = (pr * dr + pi * di) / den, wi = (pi * dr - pr * di) / den;
-            // s = sum_{j != i} 1 / (z_i - z_j)
-            double sr = 0, si = 0;
-            for (int j = 0; j < deg; ++j) {
-                if (j == i) continue;
-                const double er = xr - zr[j], ei = xi - zi[j];
-                const double d2 = er * er + ei * ei;
-                if (d2 == 0) continue;
-                sr += er / d2; si -= ei / d2;
-            }
-            // delta = w / (1 - w * s)
-            const double qr = 1 - (wr * sr - wi * si), qi = -(wr * si + wi * sr);
-            double qd = qr * qr + qi * qi;
-            if (qd == 0) qd = 1e-300;
-            const double der = (wr * qr + wi * qi) / qd, dei = (wi * qr - wr * qi) / qd;
-            zr[i] = xr - der; zi[i] = xi - dei;
-            maxd = fmax(maxd, fabs(der) + fabs(dei));
-        }
-        if (maxd <= 1e-15 * rad) break;
-    }
+    double a0[11], w[11];
+    for (int i = 0; i <= deg; ++i) { a0[i] = c[lead + i]; w[i] = a0[i]; }
+    const int deg0 = deg;
     int n = 0;
-    for (int i = 0; i < deg; ++i) {
-        if (fabs(zi[i]) > 1e-10) continue;
-        // two real Newton steps on the real polynomial polish the accepted root
-        double x = zr[i];
-        for (int it = 0; it < 2; ++it) {
-            double p = a[0], d = 0;
-            for (int k = 1; k <= deg; ++k) { d = d * x + p; p = p * x + a[k]; }
-            if (d != 0 && fabs(p / d) < 1e-6 * (1 + fabs(x))) x -= p / d;
+    while (deg >= 1) {
+        double xr = 0, xi = 0;
+        if (deg == 1) { xr = -w[1] / w[0]; xi = 0; }
+        else laguerre_step_poly(w, deg, xr, xi, 80);
+        // polish on the original polynomial: complex Newton steps (local, so the polished value
+        // stays with the root the deflated estimate belongs to)
+        double pr = xr, pi = xi;
+        for (int it = 0; it < 4; ++it) {
+            double br = a0[0], bi = 0, dr = 0, di = 0;
+            for (int j = 1; j <= deg0; ++j) {
+                const double ndr = pr * dr - pi * di + br, ndi = pr * di + pi * dr + bi;
+                const double nbr = pr * br - pi * bi + a0[j], nbi = pr * bi + pi * br;
+                dr = ndr; di = ndi; br = nbr; bi = nbi;
+            }
+            const double d2 = dr * dr + di * di;
+            if (d2 == 0) break;
+            const double sr = (br * dr + bi * di) / d2, si = (bi * dr - br * di) / d2;
+            // accept the step only while it stays a small correction of the estimate
+            if (fabs(sr) + fabs(si) > 1e-3 * (fabs(pr) + fabs(pi)) + 1e-300) break;
+            pr -= sr; pi -= si;
+            if (fabs(sr) + fabs(si) <= 1e-16 * (fabs(pr) + fabs(pi))) break;
         }
-        out[n++] = x;
+        const bool real_root = fabs(pi) <= 1e-10;
+        if (real_root) out[n++] = pr;
+        // deflate the working polynomial by a real factor
+        if (fabs(xi) <= 1e-12 * (1 + fabs(xr)) || deg == 1) {
+            double rem = w[0];
+            for (int j = 1; j < deg; ++j) { const double t = w[j] + rem * xr; w[j] = t; rem = t; }
+            // w[0..deg-1] now holds the quotient (w[0] unchanged)
+            deg -= 1;
+        } else {
+            // quadratic z^2 - 2 Re(x) z + |x|^2 ; the conjugate is a root too
+            const double pcoef = 2 * xr, qcoef = -(xr * xr + xi * xi);
+            double b0 = w[0], b1 = w[1] + pcoef * b0;
+            w[1] = b1;
+            for (int j = 2; j <= deg - 2; ++j) { const double t = w[j] + pcoef * b1 + qcoef * b0; b0 = b1; b1 = t; w[j] = t; }
+            deg -= 2;
+        }
     }
-    // ascending order (deterministic model order inside an iteration)
-    for (int i = 1; i < n; ++i) {
+    for (int i = 1; i < n; ++i) {           // ascending order: deterministic model order
         const double v = out[i];
         int j = i - 1;
         while (j >= 0 && out[j] > v) { out[j + 1] = out[j]; --j; }
         out[j + 1] = v;
     }
-    return n;
+    // two deflated estimates that polish onto the same root would double-count it
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if (m == 0 || fabs(out[i] - out[m - 1]) > 1e-13 * (fabs(out[i]) + fabs(out[m - 1]))) out[m++] = out[i];
+    return m;
 }
 
 // pa/pb: 5 points each as (x,y) doubles (already normalised by the intrinsics).

@@ -350,39 +350,71 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
 // ---------------------------------------------------------------------------------------------
 // select: OpenCV's sequential accept rule + adaptive iteration count, replayed over the counts
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+// One warp per pair.  A window of 32 compacted models is examined at once: a warp prefix-max marks
+// the strict records (the only candidates OpenCV's loop would accept), which are then replayed in
+// order so RANSACUpdateNumIters shrinks the horizon exactly as in the sequential loop.
+__global__ void __launch_bounds__(128)
 select_kernel(const int64_t* __restrict__ off, int nPairs, int maxIters, int maxm, int mp,
               int adaptive, double confidence, const int* __restrict__ nIter,
               const int* __restrict__ flags, const int* __restrict__ iterStart,
-              const int* __restrict__ counts, int* __restrict__ best /*[nPairs][4]*/) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+              const int* __restrict__ slotList, const int* __restrict__ counts,
+              int* __restrict__ best /*[nPairs][4]*/) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= nPairs) return;
     const int n = (int)(off[p + 1] - off[p]);
     int* o = best + 4 * p;   // compacted index, count, iterations run, iteration*maxm+model
-    o[0] = -1; o[1] = 0; o[2] = 0; o[3] = -1;
-    if (flags[p] & PAIR_FAIL) return;
+    const int fl = flags[p];
     const int* is = iterStart + (int64_t)p * (maxIters + 1);
     const int* c = counts + (int64_t)p * maxIters * maxm;
-    if (flags[p] & PAIR_DIRECT) {
-        const int nm = is[1] - is[0];
-        if (nm > 0) { o[0] = 0; o[1] = n; o[2] = 1; o[3] = 0; }
+    const int* sl = slotList + (int64_t)p * maxIters * maxm;
+    if (fl & (PAIR_FAIL | PAIR_DIRECT)) {
+        if (lane == 0) {
+            o[0] = -1; o[1] = 0; o[2] = 0; o[3] = -1;
+            if ((fl & PAIR_DIRECT) && !(fl & PAIR_FAIL) && is[1] - is[0] > 0) { o[0] = 0; o[1] = n; o[2] = 1; o[3] = 0; }
+        }
         return;
     }
+    // OpenCV checks `iter < niters` once per iteration: every model of an iteration that was
+    // started is evaluated even if an earlier model of the same iteration shrank niters.
     int niters = max(maxIters, 1);
-    const int ni = nIter[p];
-    int maxGood = 0, bestK = -1, bestSlot = -1;
-    int it = 0;
-    for (; it < niters && it < ni; ++it) {
-        const int k0 = is[it], k1 = is[it + 1];
-        for (int k = k0; k < k1; ++k) {
-            const int good = c[k];
-            if (good > max(maxGood, mp - 1)) {
-                maxGood = good; bestK = k; bestSlot = it * maxm + (k - k0);
-                if (adaptive) niters = update_num_iters(confidence, (double)(n - good) / n, mp, niters);
-            }
+    const int total = is[min(nIter[p], maxIters)];
+    int maxGood = 0, bestK = -1, bestSlot = -1, curIt = -1;
+    bool done = false;
+    for (int w = 0; w < total && !done; w += 32) {
+        const int k = w + lane;
+        const int slot = k < total ? sl[k] : 0x7FFFFFFF;
+        const int itk = slot == 0x7FFFFFFF ? 0x7FFFFFFF : slot / maxm;
+        const bool valid = k < total && (itk < niters || itk == curIt);
+        const int x = valid ? c[k] : -1;
+        int pm = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, pm, d);
+            if (lane >= d) pm = max(pm, t);
         }
+        int excl = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
+        if (lane == 0) excl = -1;
+        const bool rec = valid && x > max(max(excl, maxGood), mp - 1);
+        unsigned recs = __ballot_sync(0xFFFFFFFFu, rec);
+        const unsigned inval = __ballot_sync(0xFFFFFFFFu, !valid);
+        while (recs) {
+            const int b = __ffs(recs) - 1;
+            recs &= recs - 1;
+            const int xb = __shfl_sync(0xFFFFFFFFu, x, b);
+            const int itb = __shfl_sync(0xFFFFFFFFu, itk, b);
+            const int sb = __shfl_sync(0xFFFFFFFFu, slot, b);
+            if (itb != curIt && itb >= niters) { done = true; break; }   // horizon shrank past this iteration
+            curIt = itb;
+            maxGood = xb; bestK = w + b; bestSlot = sb;
+            if (adaptive) niters = min(niters, update_num_iters(confidence, (double)(n - xb) / n, mp, niters));
+        }
+        if (inval) done = true;                              // reached the end of the horizon
     }
-    o[0] = bestK; o[1] = maxGood; o[2] = it; o[3] = bestSlot;
+    if (lane == 0) {
+        // iterations OpenCV's loop would have executed
+        o[0] = bestK; o[1] = maxGood; o[2] = min(niters, nIter[p]); o[3] = bestSlot;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -887,9 +919,10 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             MCV_LAUNCH_CHECK();
         }
         // ---- select
-        select_kernel<<<(np + 63) / 64, 64, 0, st>>>(off, np, maxIters, MAXM, MP,
-                                                     prm.stopMode == MCV_STOP_ADAPTIVE ? 1 : 0,
-                                                     prm.confidence, dNIter, dFlags, dIterStart, dCounts, dBest);
+        select_kernel<<<(np + 3) / 4, 128, 0, st>>>(off, np, maxIters, MAXM, MP,
+                                                    prm.stopMode == MCV_STOP_ADAPTIVE ? 1 : 0,
+                                                    prm.confidence, dNIter, dFlags, dIterStart, dSlotList,
+                                                    dCounts, dBest);
         MCV_LAUNCH_CHECK();
         // ---- finalize
         double* oM = io.dModels + (size_t)p0 * 9;
