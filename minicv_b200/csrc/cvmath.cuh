@@ -317,6 +317,49 @@ MCV_HD float e_error(const double* E, double x1, double y1, double x2, double y2
     return (float)ddiv(dmul(xe, xe), dadd(dadd(dadd(a, b), c), d));
 }
 
+// Division-free inlier tests, decision-identical to `x_error(...) <= thr`.
+// err = (float)(q * (1/n)) differs from the real quotient q/n by < 4 ulp(double) plus the final
+// rounding to float (2^-24 relative), so q <= thr*n*(1 - 2e-7) proves "inlier" and
+// q > thr*n*(1 + 2e-7) proves "outlier"; only the sliver in between (and non-finite or zero
+// denominators) takes the exact path with the division.  thr is the float threshold (float)(t*t).
+MCV_HD bool f_inlier(const double* F, double x1, double y1, double x2, double y2, float thr) {
+    const double t = (double)thr, tl = t * (1.0 - 2e-7), th = t * (1.0 + 2e-7);
+    double a = dadd(dadd(dmul(F[0], x1), dmul(F[1], y1)), F[2]);
+    double b = dadd(dadd(dmul(F[3], x1), dmul(F[4], y1)), F[5]);
+    double c = dadd(dadd(dmul(F[6], x1), dmul(F[7], y1)), F[8]);
+    const double n2 = dadd(dmul(a, a), dmul(b, b));
+    const double d2 = dadd(dadd(dmul(x2, a), dmul(y2, b)), c);
+    a = dadd(dadd(dmul(F[0], x2), dmul(F[3], y2)), F[6]);
+    b = dadd(dadd(dmul(F[1], x2), dmul(F[4], y2)), F[7]);
+    c = dadd(dadd(dmul(F[2], x2), dmul(F[5], y2)), F[8]);
+    const double n1 = dadd(dmul(a, a), dmul(b, b));
+    const double d1 = dadd(dadd(dmul(x1, a), dmul(y1, b)), c);
+    const double q1 = dmul(d1, d1), q2 = dmul(d2, d2);
+    if (n1 > 0 && n2 > 0) {
+        if (q1 <= tl * n1 && q2 <= tl * n2) return true;
+        if (q1 > th * n1 || q2 > th * n2) return false;
+    }
+    const double e1 = dmul(q1, ddiv(1., n1)), e2 = dmul(q2, ddiv(1., n2));
+    return (float)((e1 < e2) ? e2 : e1) <= thr;
+}
+
+MCV_HD bool e_inlier(const double* E, double x1, double y1, double x2, double y2, float thr) {
+    const double t = (double)thr, tl = t * (1.0 - 2e-7), th = t * (1.0 + 2e-7);
+    const double Ex0 = dadd(dadd(dmul(E[0], x1), dmul(E[1], y1)), E[2]);
+    const double Ex1 = dadd(dadd(dmul(E[3], x1), dmul(E[4], y1)), E[5]);
+    const double Ex2 = dadd(dadd(dmul(E[6], x1), dmul(E[7], y1)), E[8]);
+    const double Et0 = dadd(dadd(dmul(E[0], x2), dmul(E[3], y2)), E[6]);
+    const double Et1 = dadd(dadd(dmul(E[1], x2), dmul(E[4], y2)), E[7]);
+    const double xe = dadd(dadd(dmul(x2, Ex0), dmul(y2, Ex1)), Ex2);
+    const double den = dadd(dadd(dadd(dmul(Ex0, Ex0), dmul(Ex1, Ex1)), dmul(Et0, Et0)), dmul(Et1, Et1));
+    const double q = dmul(xe, xe);
+    if (den > 0) {
+        if (q <= tl * den) return true;
+        if (q > th * den) return false;
+    }
+    return (float)ddiv(q, den) <= thr;
+}
+
 // ---- subset checks ----------------------------------------------------------------------------
 // haveCollinearPoints: last point against every earlier pair; pts as float (x,y) pairs.
 MCV_HDN inline bool have_collinear(const float* pts, int count) {

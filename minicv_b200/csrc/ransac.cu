@@ -329,14 +329,14 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
 #pragma unroll 2
             for (int j = 0; j < rows; ++j) {
                 const float4 q = sp[j];
-                cnt += (f_error(m, (double)q.x, (double)q.y, (double)q.z, (double)q.w) <= thr2) ? 1 : 0;
+                cnt += f_inlier(m, (double)q.x, (double)q.y, (double)q.z, (double)q.w, thr2) ? 1 : 0;
             }
         } else {
             const double4* sp = reinterpret_cast<const double4*>(sraw);
 #pragma unroll 2
             for (int j = 0; j < rows; ++j) {
                 const double4 q = sp[j];
-                cnt += (e_error(m, q.x, q.y, q.z, q.w) <= thr2) ? 1 : 0;
+                cnt += e_inlier(m, q.x, q.y, q.z, q.w, thr2) ? 1 : 0;
             }
         }
         __syncthreads();
@@ -492,8 +492,8 @@ finalize_plain_kernel(const float4* __restrict__ pf, const double* __restrict__ 
         bool in;
         if (direct) in = true;
         else if (MODEL == RM_HOMOGRAPHY) { const float4 q = pf[base + i]; in = h_error(Hf, q.x, q.y, q.z, q.w) <= thr2; }
-        else if (MODEL == RM_FUNDAMENTAL) { const float4 q = pf[base + i]; in = f_error(m, (double)q.x, (double)q.y, (double)q.z, (double)q.w) <= thr2; }
-        else { const double* q = pd + 4 * (base + i); in = e_error(m, q[0], q[1], q[2], q[3]) <= thr2; }
+        else if (MODEL == RM_FUNDAMENTAL) { const float4 q = pf[base + i]; in = f_inlier(m, (double)q.x, (double)q.y, (double)q.z, (double)q.w, thr2); }
+        else { const double* q = pd + 4 * (base + i); in = e_inlier(m, q[0], q[1], q[2], q[3], thr2); }
         masks[base + i] = in ? 1 : 0;
         cnt += in ? 1 : 0;
     }

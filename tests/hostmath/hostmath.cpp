@@ -24,6 +24,12 @@ int hm_e_solve5(const double* a, const double* b, double* Es) { return e_solve5(
 void hm_e_error(const double* E, const double* a, const double* b, int n, float* err) {
     for (int i = 0; i < n; ++i) err[i] = e_error(E, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]);
 }
+void hm_f_inlier(const double* F, const float* a, const float* b, int n, float thr, unsigned char* out) {
+    for (int i = 0; i < n; ++i) out[i] = f_inlier(F, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], thr) ? 1 : 0;
+}
+void hm_e_inlier(const double* E, const double* a, const double* b, int n, float thr, unsigned char* out) {
+    for (int i = 0; i < n; ++i) out[i] = e_inlier(E, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], thr) ? 1 : 0;
+}
 void hm_decompose_essential(const double* E, double* R1, double* R2, double* t) { decompose_essential(E, R1, R2, t); }
 void hm_cheirality(const double* R, const double* t, const double* a, const double* b, int n, double dist,
                    unsigned char* ok) {

@@ -112,3 +112,31 @@ def test_rng_and_iteration_update(hm):
     for ep in np.linspace(0, 1, 401):
         for mp, mi in ((4, 2000), (7, 1000), (5, 1000)):
             assert hm.hm_update_num_iters(0.995, ep, mp, mi) == ransac.update_num_iters(0.995, ep, mp, mi)
+
+
+def test_division_free_inlier_tests_match_exact_errors(hm):
+    """f_inlier / e_inlier == (error <= thr) for every point, including thresholds placed exactly
+    on, one ulp below and one ulp above individual error values (the borderline sliver)."""
+    g = np.load(GOLDEN / "ransac_hf.npz")
+    af, bf = g["f2_a"].astype(np.float32), g["f2_b"].astype(np.float32)
+    F = g["f2_F"].ravel().copy()
+    err = ransac.FundamentalCB.compute_error(af, bf, F)
+    n = len(af)
+    picks = np.concatenate([[np.float32(9.0)], err[:40], np.nextafter(err[:40], np.float32(0)),
+                            np.nextafter(err[:40], np.float32(np.inf))]).astype(np.float32)
+    for thr in picks:
+        out = np.zeros(n, np.uint8)
+        hm.hm_f_inlier(p(F), p(af), p(bf), n, C.c_float(float(thr)), p(out))
+        np.testing.assert_array_equal(out.astype(bool), err <= thr)
+    ge = np.load(GOLDEN / "ransac_e.npz")
+    x1 = essential.normalize_points(ge["e4_a"], 800.0, (320.0, 240.0))
+    x2 = essential.normalize_points(ge["e4_b"], 800.0, (320.0, 240.0))
+    E = ge["e4_E"].ravel().copy()
+    err = essential.EssentialCB.compute_error(x1, x2, E)
+    n = len(x1)
+    picks = np.concatenate([[np.float32((1.0 / 800) ** 2)], err[:40], np.nextafter(err[:40], np.float32(0)),
+                            np.nextafter(err[:40], np.float32(np.inf))]).astype(np.float32)
+    for thr in picks:
+        out = np.zeros(n, np.uint8)
+        hm.hm_e_inlier(p(E), p(x1), p(x2), n, C.c_float(float(thr)), p(out))
+        np.testing.assert_array_equal(out.astype(bool), err <= thr)
