@@ -68,6 +68,44 @@ def golden_l2():
     print("knn_l2.npz")
 
 
+def golden_c1():
+    """Config C1 (BASELINE.json configs[0]): procedurally textured plane seen under a known
+    homography; ORB and AKAZE detect+describe on the CPU (cv2 -- detection is out of scope of the
+    path), then BFMatcher k=2 + ratio 0.8 and findHomography RANSAC as the reference results."""
+    rng = np.random.default_rng(42)
+    h, w = 480, 640
+    img = np.zeros((h, w), np.float32)
+    for _ in range(900):                                  # random blobs, rectangles and strokes
+        x, y = int(rng.integers(0, w)), int(rng.integers(0, h))
+        r = int(rng.integers(3, 22)); v = float(rng.uniform(40, 255))
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            cv2.circle(img, (x, y), r, v, -1)
+        elif kind == 1:
+            cv2.rectangle(img, (x, y), (x + r * 2, y + r), v, -1)
+        else:
+            cv2.line(img, (x, y), (int(x + rng.integers(-60, 60)), int(y + rng.integers(-60, 60))), v, int(rng.integers(1, 4)))
+    img = cv2.GaussianBlur(img, (0, 0), 1.0)
+    img1 = np.clip(img + rng.normal(0, 2, img.shape), 0, 255).astype(np.uint8)
+    Hgt = np.array([[0.96, 0.07, 18.0], [-0.06, 1.02, 9.0], [-6e-5, 4e-5, 1.0]])
+    img2 = cv2.warpPerspective(img1, Hgt, (w, h), flags=cv2.INTER_LINEAR, borderValue=0)
+    img2 = np.clip(img2.astype(np.float32) + rng.normal(0, 2, img2.shape), 0, 255).astype(np.uint8)
+    out = {"Hgt": Hgt}
+    for name, det in (("orb", cv2.ORB_create(nfeatures=3000)), ("akaze", cv2.AKAZE_create())):
+        k1, d1 = det.detectAndCompute(img1, None)
+        k2, d2 = det.detectAndCompute(img2, None)
+        p1 = np.array([k.pt for k in k1], np.float64); p2 = np.array([k.pt for k in k2], np.float64)
+        idx, dist = cv_knn2(d1, d2, cv2.NORM_HAMMING)
+        ok = (idx[:, 1] >= 0) & (dist[:, 0] < np.float32(0.8) * dist[:, 1])
+        a = p1[ok]; b = p2[idx[ok, 0]]
+        Hc, mc = cv2.findHomography(a, b, cv2.RANSAC, 3.0, maxIters=2000, confidence=0.995)
+        out[f"{name}_d1"] = d1; out[f"{name}_d2"] = d2; out[f"{name}_p1"] = p1; out[f"{name}_p2"] = p2
+        out[f"{name}_idx"] = idx; out[f"{name}_dist"] = dist; out[f"{name}_H"] = Hc; out[f"{name}_mask"] = mc.ravel()
+        print(name, d1.shape, d2.shape, "ratio-pass", int(ok.sum()), "inliers", int(mc.sum()),
+              "H err", np.abs(Hc - Hgt).max())
+    np.savez_compressed(HERE / "c1_planar.npz", **out)
+
+
 def golden_ransac():
     out = {}
     # homography: cv2.findHomography(RANSAC, 3.0, maxIters 2000, confidence .995)
@@ -143,3 +181,5 @@ if __name__ == "__main__":
         golden_ransac()
     if "l2" in which:
         golden_l2()
+    if "c1" in which:
+        golden_c1()

@@ -90,3 +90,17 @@ def test_update_num_iters_edges():
     assert ransac.update_num_iters(0.995, 1.0, 4, 2000) == 2000
     assert ransac.update_num_iters(0.995, 0.0, 4, 2000) == 0
     assert ransac.update_num_iters(0.995, 0.7, 4, 2000) == 651
+
+
+def test_c1_planar_pair_oracle_chain():
+    from oracle import bf_knn
+    g = np.load(GOLDEN / "c1_planar.npz")
+    for name in ("orb", "akaze"):
+        idx, dist = bf_knn.bf_knn2_hamming(g[f"{name}_d1"], g[f"{name}_d2"])
+        np.testing.assert_array_equal(idx, g[f"{name}_idx"])
+        np.testing.assert_array_equal(dist, g[f"{name}_dist"])
+        ok = bf_knn.ratio_test(dist, idx, 0.8).astype(bool)
+        a = g[f"{name}_p1"][ok]; b = g[f"{name}_p2"][idx[ok, 0]]
+        H, mask = ransac.find_homography(a, b, 3.0, 2000, 0.995)
+        assert rel(H, g[f"{name}_H"]) < 1e-8
+        np.testing.assert_array_equal(mask, g[f"{name}_mask"])
