@@ -28,6 +28,7 @@
 #define MINICV_NATIVE_H
 
 #include <stdint.h>
+#include <stdbool.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -244,6 +245,34 @@ MCV_API int cvDecomposeEssentialMat(const McvMatx33d* E, McvMatx33d* R1, McvMatx
 /* Batched cvFivePoint: nSets x 5 correspondences -> Es [nSets][10], counts [nSets]. */
 MCV_API int cvFivePointBatch(const McvPoint2d* pa, const McvPoint2d* pb, int nSets,
                              McvMatx33d* Es, int32_t* counts);
+
+
+/* ---- (3) reference exports that are not on the path: forwarded, not implemented -----------
+ * Signatures are the reference's (src/MiniCVNative/MiniCVNative.cpp:48,93,140,152,221,347,384,
+ * 439,504; ap3p.cpp:282).  Each call is forwarded to a side-by-side build of the original shim
+ * ($MINICV_ORIGINAL_NATIVE, default "libMiniCVNativeCv.so"); without it the reference's failure
+ * value is returned.  See INTEGRATION.md section 3. */
+typedef struct { double X, Y, Z; } McvPoint3d;
+MCV_API bool cvSolvePnP(const McvPoint2d* imgPoints, const McvPoint3d* worldPoints, const int N,
+                        const McvMatx33d K, const double* distortionCoeffs, const int solverKind,
+                        McvVec3d* tVec, McvVec3d* rVec);
+MCV_API bool cvSolvePnPRansac(const McvPoint2d* imgPoints, const McvPoint3d* worldPoints, const int N,
+                              const McvMatx33d K, const double* distortionCoeffs, const int solverKind,
+                              const int iterationsCount, const float reprojectionError,
+                              const double confidence, McvVec3d* tVec, McvVec3d* rVec,
+                              int* inlierCount, int* outInliers);
+MCV_API void cvRefinePnPLM(const McvPoint2d* imgPoints, const McvPoint3d* worldPoints, const int N,
+                           const McvMatx33d K, const double* distortionCoeffs, McvVec3d* tVec, McvVec3d* rVec);
+MCV_API void cvRefinePnPVVS(const McvPoint2d* imgPoints, const McvPoint3d* worldPoints, const int N,
+                            const McvMatx33d K, const double* distortionCoeffs, McvVec3d* tVec, McvVec3d* rVec);
+MCV_API McvDetectorResult* cvDetectFeatures(char* data, int width, int height, int channels, int mode, void* config);
+MCV_API void cvFreeFeatures(McvDetectorResult* res);
+MCV_API bool cvDetectQRCode(char* data, int width, int height, int channels, int* positions, int* count);
+MCV_API bool cvDetectArucoMarkers(char* data, int width, int height, int channels, int* infoCount, void* infos);
+MCV_API void cvTest(void);
+MCV_API int solveAp3p(McvMatx33d* R, McvVec3d* t, double mu0, double mv0, double X0, double Y0, double Z0,
+                      double mu1, double mv1, double X1, double Y1, double Z1, double mu2, double mv2,
+                      double X2, double Y2, double Z2, double inv_fx, double inv_fy, double cx_fx, double cy_fy);
 
 #ifdef __cplusplus
 }

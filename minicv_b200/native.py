@@ -86,6 +86,17 @@ SIGNATURES = {
     "cvRecoverPoseFromE": (_i, [_vp, _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp, _vp]),
     "cvDecomposeEssentialMat": (_i, [_vp, _vp, _vp, _vp]),
     "cvFivePointBatch": (_i, [_vp, _vp, _i, _vp, _vp]),
+    # group (3): forwarded to the original shim when present
+    "cvSolvePnP": (C.c_bool, [_vp, _vp, _i, Matx33d, _vp, _i, _vp, _vp]),
+    "cvSolvePnPRansac": (C.c_bool, [_vp, _vp, _i, Matx33d, _vp, _i, _i, _f, _d, _vp, _vp, _vp, _vp]),
+    "cvRefinePnPLM": (None, [_vp, _vp, _i, Matx33d, _vp, _vp, _vp]),
+    "cvRefinePnPVVS": (None, [_vp, _vp, _i, Matx33d, _vp, _vp, _vp]),
+    "cvDetectFeatures": (_vp, [_vp, _i, _i, _i, _i, _vp]),
+    "cvFreeFeatures": (None, [_vp]),
+    "cvDetectQRCode": (C.c_bool, [_vp, _i, _i, _i, _vp, _vp]),
+    "cvDetectArucoMarkers": (C.c_bool, [_vp, _i, _i, _i, _vp, _vp]),
+    "cvTest": (None, []),
+    "solveAp3p": (_i, [_vp, _vp] + [_d] * 19),
 }
 
 

@@ -53,3 +53,18 @@ def test_no_device_means_loud_failure_not_fallback():
                          dist.ctypes.data, 0)
     assert rc == -1
     assert b"no usable CUDA device" in lib.mcvLastError()
+
+
+def test_out_of_scope_exports_resolve_and_fail_cleanly():
+    """The ten non-path reference exports exist (DllImports keep resolving) and, with no original
+    shim loaded, return the reference's failure values without computing anything."""
+    lib = native.load()
+    import numpy as np
+    t = np.zeros(3); r = np.zeros(3)
+    K = native.Matx33d()
+    assert lib.cvSolvePnP(0, 0, 0, K, 0, 0, t.ctypes.data, r.ctypes.data) is False
+    assert b"not part of the GPU path" in lib.mcvLastError()
+    assert lib.cvDetectFeatures(0, 0, 0, 0, 1, 0) is None
+    assert lib.solveAp3p(0, 0, *([0.0] * 19)) == 0
+    lib.cvTest()
+    lib.cvFreeFeatures(0)
