@@ -450,12 +450,18 @@ def run_ours(args):
         bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
         ops = 2.0 * P * NQ * NT * (DESC_BYTES * 8)
         ach = ops / kern_s / 1e12
+        traffic = None
+        tj = ROOT / "profiles" / "r01_tc_traffic.json"
+        if tj.exists() and P == 1024:
+            traffic = json.loads(tj.read_text()).get("traffic_bytes_per_launch")
         roofline = {
             "bound": "tensor", "achieved": ach, "peak": 2 * bf16_peak, "unit": "TFLOP/s", "frac": ach / (2 * bf16_peak),
-            "traffic": None, "peak_source": ("measured" if "bf16_tflops" in peaks else "fallback") + " bf16 x2 (int8 rate)",
+            "traffic": traffic, "peak_source": ("measured" if "bf16_tflops" in peaks else "fallback") + " bf16 x2 (int8 rate)",
             "kernel": "hamming_tc_kernel<2,2,4> (tcgen05.mma.kind::i8 + top-2 epilogue)",
-            "note": "achieved uses the whole step (bit-expansion + GEMM/top-2 + finalize kernels); "
-                    "the same step needs >= 1/0.97 of the POPC-pipe roof on the integer engine",
+            "note": "achieved = 2*Q*T*K int8 operations of one step / step time (bit-expansion + GEMM/top-2 + "
+                    "finalize kernels; the GEMM kernel is 93 % of it, profiles/r01_hamming_tc_ncu.md); the kernel "
+                    "is bound by TMEM accumulator read-out (~64 B/clk/SM), at ~97 % of that rate; traffic = DRAM "
+                    "bytes of the dominant kernel from the ncu capture of this same command",
             "hbm": {"achieved_gbs": alg_bytes / kern_s / 1e9, "peak_gbs": hbm_peak},
             "vs_int_pipe_roof": gdist / world / pipe_peak,
         }
