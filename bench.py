@@ -222,6 +222,53 @@ def extra_ransac(local, with_cpu=True):
             k = max(cores, 8) if kind == "H" else cores
             out[f"C3_{kind}"]["cpu"] = cpu_ransac_pairs_per_s(kind, [(A[p * N:(p + 1) * N], B[p * N:(p + 1) * N]) for p in range(k)], cores)
         del dA, dB
+    # ---- match -> gather -> homography, device resident (the "match + H-RANSAC" pipeline of north_star)
+    Pp = 256
+    qs, ts, kqs, kts = [], [], [], []
+    for p in range(Pp):
+        q, t, gt, kq, kt, H = synth.descriptor_pair_geo(p)
+        qs.append(q); ts.append(t); kqs.append(kq); kts.append(kt)
+    qo = np.arange(Pp + 1, dtype=np.int64) * NQ; to = np.arange(Pp + 1, dtype=np.int64) * NT
+    dq = torch.from_numpy(np.concatenate(qs)).to(dev); dt = torch.from_numpy(np.concatenate(ts)).to(dev)
+    dkq = torch.from_numpy(np.concatenate(kqs)).to(dev); dkt = torch.from_numpy(np.concatenate(kts)).to(dev)
+    didx = torch.empty((Pp * NQ, 2), dtype=torch.int32, device=dev)
+    ddist = torch.empty((Pp * NQ, 2), dtype=torch.float32, device=dev)
+    dok = torch.empty(Pp * NQ, dtype=torch.uint8, device=dev)
+    da = torch.empty((Pp * NQ, 2), dtype=torch.float64, device=dev); db = torch.empty((Pp * NQ, 2), dtype=torch.float64, device=dev)
+    dM = torch.empty((Pp, 9), dtype=torch.float64, device=dev); dMask = torch.empty(Pp * NQ, dtype=torch.uint8, device=dev)
+    dCnt = torch.empty(Pp, dtype=torch.int32, device=dev); dOkp = torch.empty(Pp, dtype=torch.uint8, device=dev)
+    import minicv_b200 as mcv
+
+    def run_pipe():
+        mcv.match_knn2_batch_device(dq, qo, dt, to, DESC_BYTES, RATIO, didx, ddist, dok, device=local,
+                                    stream=stream.cuda_stream)
+        off2 = mcv.gather_matches_device(dkq, dkt, qo, to, didx, dok, da, db, device=local, stream=stream.cuda_stream)
+        est.ransac_batch_device(est.MODEL_H, da, db, off2, 3.0, 2000, dM, dMask, dCnt, dOkp, confidence=0.995,
+                                sample_mode=est.SAMPLE_MWC, stop_mode=est.STOP_ADAPTIVE, device=local,
+                                stream=stream.cuda_stream)
+    t = timed(run_pipe)
+    out["C2_match_plus_H"] = {"pairs_per_s": Pp / t, "ms_per_batch": t * 1e3, "pairs": Pp,
+                              "ok_pairs": int(dOkp.sum().item()), "mean_inliers": float(dCnt.float().mean().item()),
+                              "mode": "device-resident: kNN-2 + ratio -> gather -> findHomography semantics "
+                                      "(OpenCV MWC sampling, maxIters 2000, conf .995, refit + LM)"}
+    if with_cpu:
+        try:
+            import cv2
+            cv2.setNumThreads(cores)
+            bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+            k = 12
+            t0 = time.perf_counter()
+            for p in range(k):
+                m = bf.knnMatch(qs[p], ts[p], 2)
+                good = [(a.queryIdx, a.trainIdx) for a, b_ in m if a.distance < RATIO * b_.distance]
+                gi = np.array(good)
+                cv2.findHomography(kqs[p][gi[:, 0]], kts[p][gi[:, 1]], cv2.RANSAC, 3.0, maxIters=2000, confidence=0.995)
+            dtc = time.perf_counter() - t0
+            out["C2_match_plus_H"]["cpu"] = {"pairs_per_s": k / dtc, "cores": cores, "sample_pairs": k,
+                                             "note": "cv2 knnMatch (all cores) + findHomography per pair"}
+        except ImportError:
+            pass
+    del dq, dt, dkq, dkt, didx, ddist, dok, da, db, dMask
     # ---- C4: essential 5-pt RANSAC + recoverPose, 5000 correspondences, 512 pairs (cvRecoverPose semantics)
     P, N = 512, 5000
     off = np.arange(P + 1, dtype=np.int64) * N

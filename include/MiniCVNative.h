@@ -145,6 +145,19 @@ MCV_API int cvMatchKnn2BatchDevice(const uint8_t* dQuery, const int64_t* queryOf
 MCV_API int cvMatchFeatures(const McvDetectorResult* query, const McvDetectorResult* train,
                             float ratio, int* trainIdx, float* dist, uint8_t* ratioPass);
 
+/* Device-resident hand-off matcher -> estimators: builds the packed
+ * correspondence lists of a batch from its match results.  Pair p yields one correspondence per
+ * ratio-passing query, in query order: a = query keypoint, b = keypoint of its nearest train row.
+ *   dKpQuery / dKpTrain : [totalQ][2] / [totalT][2] doubles (device), rows as in the matcher call
+ *   dTrainIdx, dRatioPass: the matcher's device outputs
+ *   dA, dB               : [totalQ][2] doubles capacity (device)
+ *   outOffsets           : nPairs+1 correspondence offsets (HOST, written before return)
+ * Returns the total number of correspondences or -1.  Synchronises `stream` once (the offsets). */
+MCV_API int cvGatherMatchesDevice(const double* dKpQuery, const double* dKpTrain,
+                                  const int64_t* queryOffsets, const int64_t* trainOffsets, int nPairs,
+                                  const int* dTrainIdx, const uint8_t* dRatioPass, double* dA, double* dB,
+                                  int64_t* outOffsets, int device, void* stream);
+
 /* Sharded large-database matching: local top-2 of
  * `nQuery` queries against this rank's train shard, emitted as packed keys
  * (dist << 32) | (globalIdxBase + localIdx), 2 per query (UINT64_MAX if absent);

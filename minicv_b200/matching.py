@@ -101,6 +101,24 @@ def match_knn2_batch_device(d_query, query_offsets, d_train, train_offsets, desc
         "cvMatchKnn2BatchDevice")
 
 
+def gather_matches_device(d_kp_query, d_kp_train, query_offsets, train_offsets, d_train_idx, d_ratio_pass,
+                          d_a, d_b, device: int = -1, stream: int = 0):
+    """Device-resident hand-off matcher -> estimators (``cvGatherMatchesDevice``): returns the host
+    array of nPairs+1 correspondence offsets; ``d_a`` / ``d_b`` receive the packed (x, y) doubles."""
+    lib = native.load()
+
+    def dp(x):
+        return x if isinstance(x, int) else x.data_ptr()
+
+    qo = np.ascontiguousarray(query_offsets, dtype=np.int64)
+    to = np.ascontiguousarray(train_offsets, dtype=np.int64)
+    out = np.zeros(qo.size, dtype=np.int64)
+    native.check(lib.cvGatherMatchesDevice(dp(d_kp_query), dp(d_kp_train), _ptr(qo), _ptr(to), qo.size - 1,
+                                           dp(d_train_idx), dp(d_ratio_pass), dp(d_a), dp(d_b), _ptr(out),
+                                           device, stream), "cvGatherMatchesDevice")
+    return out
+
+
 def match_features(query_desc: np.ndarray, train_desc: np.ndarray, ratio: float = 0.8) -> KnnResult:
     """Matcher over two ``DetectorResult`` containers (reference layout
     ``src/MiniCVNative/MiniCVNative.h:23-29``): u8 blobs match with Hamming, f32 with L2."""

@@ -72,6 +72,7 @@ SIGNATURES = {
     "cvMatchKnn2Batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i]),
     "cvMatchKnn2BatchDevice": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp]),
     "cvMatchFeatures": (_i, [C.POINTER(DetectorResult), C.POINTER(DetectorResult), _f, _vp, _vp, _vp]),
+    "cvGatherMatchesDevice": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "cvMatchKnn2ShardKeysDevice": (_i, [_vp, _i, _vp, _i, _i64, _i, _vp, _i, _vp]),
     "cvMergeShardKeysDevice": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _i, _vp]),
     "cvRecoverPose": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -123,3 +123,22 @@ def two_view_pair(seed: int, n: int = 2000, inlier_frac: float = 0.30, noise: fl
         a = (a - np.asarray(pp)) / focal
         b = (b - np.asarray(pp)) / focal
     return np.ascontiguousarray(a), np.ascontiguousarray(b), gt, R, t
+
+
+def descriptor_pair_geo(seed: int, n_query: int = 8192, n_train: int = 8192, desc_bytes: int = 32,
+                        noise: float = 0.5):
+    """C2 pair with geometry for the match -> homography pipeline: descriptors as descriptor_pair;
+    every true-match query sits at a position whose image under a (per-seed) homography is its train
+    keypoint (+ N(0, noise) px); all other keypoints are uniform in [0, 1000)^2.
+    Returns (query, train, gt, kp_query [nq,2], kp_train [nt,2], H)."""
+    q, t, gt = descriptor_pair(seed, n_query, n_train, desc_bytes)
+    rng = np.random.default_rng(5000 + seed)
+    H = H_GT.copy()
+    H[:2, :2] += rng.normal(0, 0.01, (2, 2))
+    H[:2, 2] += rng.normal(0, 3.0, 2)
+    kq = rng.uniform(0, 1000, (n_query, 2))
+    kt = rng.uniform(0, 1000, (n_train, 2))
+    m = gt >= 0
+    ph = np.concatenate([kq[m], np.ones((int(m.sum()), 1))], axis=1) @ H.T
+    kt[gt[m]] = ph[:, :2] / ph[:, 2:3] + rng.normal(0, noise, (int(m.sum()), 2))
+    return q, t, gt, np.ascontiguousarray(kq), np.ascontiguousarray(kt), H
