@@ -53,56 +53,113 @@ def parse():
 # clocks: sample nvidia-smi DURING the timed region (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Polls NVML (SM clock, max SM clock, power, throttle reasons) every few milliseconds from a
+    thread; start() before the timed region, mark_begin()/mark_end() bracket it, and only samples
+    inside the bracket are reported.  Falls back to `nvidia-smi -lms` when pynvml is missing."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, uuid: str | None = None):
         self.gpu = gpu_index
-        self.lines: list[str] = []
-        self.proc = None
+        self.uuid = uuid
+        self.samples: list[tuple] = []       # (t, sm_mhz, power_w, reasons_mask)
+        self.max_mhz = None
+        self.t0 = self.t1 = None
+        self._stop = threading.Event()
         self.thread = None
+        self.mode = None
+        self.proc = None
+        self.lines: list[str] = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
-            return
-        self.thread = threading.Thread(target=self._pump, daemon=True)
-        self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.perf_counter(), float(mhz), pw, int(rs)))
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "smi"
+
+            def pump():
+                for line in self.proc.stdout:
+                    self.lines.append((time.perf_counter(), line.strip()))
+            self.thread = threading.Thread(target=pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.mode = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (pynvml / nvidia-smi unavailable)"]}
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        sm, pw, reasons = [], [], set()
+        if self.mode == "nvml":
+            for (t, mhz, p, rs) in self.samples:
+                if t0 <= t <= t1:
+                    sm.append(mhz); pw.append(p)
+                    for bit, name in self.REASONS.items():
+                        if rs & bit:
+                            reasons.add(name)
+            mx = self.max_mhz
+        else:
+            mxs = []
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for (t, ln) in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 7 or not (t0 <= t <= t1):
+                    continue
+                try:
+                    sm.append(float(f[0])); mxs.append(float(f[1])); pw.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            mx = max(mxs) if mxs else None
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": ["no samples inside the timed region"],
+                    "source": self.mode}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": mx,
+                "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons), "source": self.mode}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -422,21 +479,27 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    try:
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = lib.mcvKernelLaunchCount()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     launches = lib.mcvKernelLaunchCount() - launches0
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
