@@ -326,6 +326,22 @@ def extra_ransac(local, with_cpu=True):
         except ImportError:
             pass
     del dq, dt, dkq, dkt, didx, ddist, dok, da, db, dMask
+    # ---- single-pair calls through the reference-style exports (what one F# call costs)
+    lat = {}
+    qq, tt, _ = synth.descriptor_pair(1)
+    a_h, b_h, _, _ = synth.homography_pair(1, 2000)
+    a_e, b_e, _, _, _ = synth.two_view_pair(1, 5000)
+    cfg1 = est.RecoverPoseConfig(800.0, (320.0, 240.0), 0.999, 1.0)
+    for name, fn in (("cvMatchKnn2_8192x8192", lambda: mcv.match_knn2(qq, tt, RATIO)),
+                     ("cvFindHomography_2000", lambda: est.findHomography(a_h, b_h, 3.0, 2000, 0.995)),
+                     ("cvFindFundamentalMat_2000", lambda: est.findFundamentalMat(a_h, b_h, 3.0, 0.99, 1000)),
+                     ("cvRecoverPose_5000", lambda: est.recoverPose(cfg1, a_e, b_e))):
+        fn(); fn()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            fn()
+        lat[name] = (time.perf_counter() - t0) / 5 * 1e3
+    out["single_call_ms"] = lat
     # ---- C4: essential 5-pt RANSAC + recoverPose, 5000 correspondences, 512 pairs (cvRecoverPose semantics)
     P, N = 512, 5000
     off = np.arange(P + 1, dtype=np.int64) * N

@@ -49,3 +49,23 @@ def test_sharded_keys_merge_equals_unsharded(engine):
         np.testing.assert_array_equal(i2.cpu().numpy(), ridx.astype(np.int64))
     finally:
         mcv.set_hamming_engine(mcv.ENGINE_AUTO)
+
+
+@pytest.mark.parametrize("engine", [mcv.ENGINE_POPC, mcv.ENGINE_TENSOR])
+def test_train_set_beyond_packed_key_range(engine):
+    """More than 2^22 train rows: the integer-pipe engine must split (22-bit packed index), the
+    tensor engine sweeps >32k stages; both must keep exact indices and the lowest-index tie-break."""
+    rng = np.random.default_rng(3)
+    nt = (1 << 22) + 1000
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (12, 32), dtype=np.uint8)
+    q[0] = t[nt - 1]; q[1] = t[5]; t[(1 << 22) + 7] = t[5]      # tie across the 2^22 boundary
+    mcv.set_hamming_engine(engine)
+    try:
+        r = mcv.match_knn2(q, t, 0.8)
+    finally:
+        mcv.set_hamming_engine(mcv.ENGINE_AUTO)
+    idx, dist = bf_knn.bf_knn2_hamming(q, t)
+    np.testing.assert_array_equal(r.train_idx, idx)
+    np.testing.assert_array_equal(r.distance, dist)
+    assert r.train_idx[0, 0] == nt - 1 and tuple(r.train_idx[1]) == (5, (1 << 22) + 7)
