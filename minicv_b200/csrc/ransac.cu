@@ -76,16 +76,38 @@ __device__ __forceinline__ bool check_subset(const float4* pf, int64_t base, con
 }
 
 // OpenCV's stream: RNG((uint64)-1) per call, subsets drawn one after another (getSubset).
+// One warp per pair: the warp stages the pair's points in shared memory (the degeneracy checks of
+// every draw would otherwise be chains of dependent global loads), then lane 0 replays the
+// sequential stream.
 template <int MODEL>
-__global__ void __launch_bounds__(64)
+__device__ __forceinline__ bool check_subset_pts(const float4* pts, const int* idx) {
+    if (MODEL == RM_ESSENTIAL) return true;
+    constexpr int MP = MT<MODEL>::MP;
+    float s[2 * MP], d[2 * MP];
+#pragma unroll
+    for (int i = 0; i < MP; ++i) {
+        const float4 p = pts[idx[i]];
+        s[2 * i] = p.x; s[2 * i + 1] = p.y; d[2 * i] = p.z; d[2 * i + 1] = p.w;
+    }
+    if (MODEL == RM_HOMOGRAPHY) return h_check_subset(s, d);
+    return !(have_collinear(s, MP) || have_collinear(d, MP));
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(32)
 sample_mwc_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off, int nPairs,
-                  int maxIters, int* __restrict__ samples, int* __restrict__ nIter,
+                  int maxIters, int smemPoints, int* __restrict__ samples, int* __restrict__ nIter,
                   int* __restrict__ flags) {
     constexpr int MP = MT<MODEL>::MP;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nPairs) return;
+    extern __shared__ float4 sPts[];
+    const int p = blockIdx.x;
     const int64_t base = off[p];
     const int n = (int)(off[p + 1] - base);
+    const bool staged = MODEL != RM_ESSENTIAL && n <= smemPoints;
+    if (staged) for (int i = threadIdx.x; i < n; i += 32) sPts[i] = pf[base + i];
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const float4* pts = staged ? sPts : (MODEL == RM_ESSENTIAL ? nullptr : pf + base);
     int* out = samples + (int64_t)p * maxIters * MP;
     if (n < MP) { nIter[p] = 0; flags[p] = PAIR_FAIL; return; }
     if (n == MP) {
@@ -109,7 +131,7 @@ sample_mwc_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off
                 } while (dup);
                 idx[i] = v;
             }
-            if (check_subset<MODEL>(pf, base, idx)) { found = true; break; }
+            if (check_subset_pts<MODEL>(pts, idx)) { found = true; break; }
         }
         if (!found) { if (it == 0) fl = PAIR_FAIL; break; }
         for (int i = 0; i < MP; ++i) out[it * MP + i] = idx[i];
@@ -884,8 +906,12 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
                                                             dSamples, dNIter, dFlags);
             MCV_LAUNCH_CHECK();
         } else {
-            sample_mwc_kernel<MODEL><<<(np + 63) / 64, 64, 0, st>>>(pf, off, np, maxIters, dSamples,
-                                                                    dNIter, dFlags);
+            const int smemPts = (int)std::min<int64_t>(maxN, 12288);       // up to 192 KB of float4 points
+            auto kern = sample_mwc_kernel<MODEL>;
+            const size_t smemBytes = MODEL == RM_ESSENTIAL ? 0 : (size_t)smemPts * 16;
+            if (smemBytes > 48 * 1024)
+                MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+            kern<<<np, 32, smemBytes, st>>>(pf, off, np, maxIters, smemPts, dSamples, dNIter, dFlags);
             MCV_LAUNCH_CHECK();
         }
         // ---- solve
