@@ -44,8 +44,11 @@ extern std::atomic<int> g_hamming_engine;
 int launch_knn2_finalize(cudaStream_t stream, const uint64_t* dSplitKeys, int nSplits, int64_t totalQ,
                          const KnnArgs& a);
 
-// L2 kNN-2 for float32 descriptors (difference form, fp32).
+// L2 kNN-2 for float32 descriptors: fp32 CUDA-core engine (difference form) and the tcgen05
+// bf16x2-split GEMM + exact re-scoring engine (l2_tc.cu); launch_l2_knn2 picks by the engine switch.
 int launch_l2_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a);
+bool l2_tc_supported(int descBytes);
+int launch_l2_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a);
 
 // Merge nShards x nQuery x 2 packed keys into global top-2 (+ ratio test).
 int launch_merge_keys(Context* ctx, cudaStream_t stream, const uint64_t* dKeys, int nShards,

@@ -147,6 +147,19 @@ int launch_l2_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     if (a.nPairs <= 0) return 0;
     if (a.descBytes <= 0 || a.descBytes % 4 != 0) { set_error("L2 matcher needs float32 rows"); return -1; }
     if (a.emit != KNN_EMIT_MATCHES) { set_error("L2 matcher has no shard-key mode"); return -1; }
+    {
+        // engine switch shared with the Hamming matcher: 1 = CUDA cores, >= 2 = tensor cores, 0 = auto
+        const int eng = g_hamming_engine.load(std::memory_order_relaxed);
+        bool tcEng = false;
+        if (eng >= 2) tcEng = l2_tc_supported(a.descBytes);
+        else if (eng == 0 && l2_tc_supported(a.descBytes)) {
+            const double q = (double)a.hQOff[a.nPairs];
+            const double t = (double)a.hTOff[a.nPairs] / std::max(a.nPairs, 1);
+            tcEng = q * t >= 16.0 * 1024 * 1024;
+        }
+        if (tcEng && (reinterpret_cast<uintptr_t>(a.dQuery) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dTrain) & 3) == 0)
+            return launch_l2_knn2_tc(ctx, stream, a);
+    }
     if ((reinterpret_cast<uintptr_t>(a.dQuery) & 3) || (reinterpret_cast<uintptr_t>(a.dTrain) & 3)) {
         set_error("L2 matcher needs 4-byte aligned descriptor blobs");
         return -1;

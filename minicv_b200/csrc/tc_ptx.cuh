@@ -85,6 +85,20 @@ __device__ __forceinline__ void tc_mma_f8(uint32_t tmem_d, uint64_t desc_a, uint
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes multiple of 16, 16-byte aligned)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // host: 2-D tensor map over `rows` x `rowBytes` uint8, box 128 bytes x 128 rows, SWIZZLE_128B
 int make_map(CUtensorMap* map, const void* base, int64_t rows, int rowBytes);
 
