@@ -326,6 +326,40 @@ def extra_ransac(local, with_cpu=True):
         except ImportError:
             pass
     del dq, dt, dkq, dkt, didx, ddist, dok, da, db, dMask
+    # ---- M2: L2 kNN for float descriptors (SIFT-shaped: 128-d, 2048 x 2048 per pair, 256 pairs)
+    Pl, nl, dl = 256, 2048, 128
+    rngl = np.random.default_rng(11)
+    ql = rngl.integers(0, 160, (Pl * nl, dl)).astype(np.float32)
+    tl = rngl.integers(0, 160, (Pl * nl, dl)).astype(np.float32)
+    ql[::2] = tl[::2] + rngl.integers(-2, 3, (Pl * nl // 2, dl)).astype(np.float32)
+    lo_ = np.arange(Pl + 1, dtype=np.int64) * nl
+    dql = torch.from_numpy(ql).to(dev); dtl = torch.from_numpy(tl).to(dev)
+    dil = torch.empty((Pl * nl, 2), dtype=torch.int32, device=dev); ddl = torch.empty((Pl * nl, 2), dtype=torch.float32, device=dev)
+    dol = torch.empty(Pl * nl, dtype=torch.uint8, device=dev)
+    l2 = {}
+    for ename, eng in (("fp32_cuda_core", 1), ("tcgen05_bf16_split_rescore", 2)):
+        mcv.set_hamming_engine(eng)
+        tl2 = timed(lambda: mcv.match_knn2_batch_device(dql, lo_, dtl, lo_, dl * 4, RATIO, dil, ddl, dol, norm=mcv.NORM_L2,
+                                                        device=local, stream=stream.cuda_stream))
+        l2[ename] = {"pairs_per_s": Pl / tl2, "ms_per_batch": tl2 * 1e3, "gdist_per_s": Pl * nl * nl / tl2 / 1e9,
+                     "planted_found": int((dil[::2, 0] == torch.arange(0, Pl * nl, 2, device=dev) % nl).sum().item())}
+    mcv.set_hamming_engine(0)
+    l2["pairs"] = Pl; l2["shape"] = f"{nl} x {nl} x {dl} f32"
+    l2["pairs_per_s"] = max(l2["fp32_cuda_core"]["pairs_per_s"], l2["tcgen05_bf16_split_rescore"]["pairs_per_s"])
+    l2["ms_per_batch"] = min(l2["fp32_cuda_core"]["ms_per_batch"], l2["tcgen05_bf16_split_rescore"]["ms_per_batch"])
+    if with_cpu:
+        try:
+            import cv2
+            cv2.setNumThreads(cores)
+            bfl = cv2.BFMatcher(cv2.NORM_L2)
+            t0 = time.perf_counter()
+            for p in range(8):
+                bfl.knnMatch(ql[p * nl:(p + 1) * nl], tl[p * nl:(p + 1) * nl], 2)
+            l2["cpu"] = {"pairs_per_s": 8 / (time.perf_counter() - t0), "cores": cores, "sample_pairs": 8}
+        except ImportError:
+            pass
+    out["M2_l2_knn"] = l2
+    del dql, dtl, dil, ddl, dol
     # ---- single-pair calls through the reference-style exports (what one F# call costs)
     lat = {}
     qq, tt, _ = synth.descriptor_pair(1)
