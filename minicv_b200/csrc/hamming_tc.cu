@@ -264,23 +264,6 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    });
-    return fn;
-}
-
 template <int KC, int ATILES, int STAGES>
 int launch_cfg(cudaStream_t stream, dim3 grid, const CUtensorMap& mq, const CUtensorMap& mt, const int64_t* qOff,
                const int64_t* tOff, const int* tileStart, int nPairs, int splitRows, int64_t totalQ,
@@ -293,27 +276,7 @@ int launch_cfg(cudaStream_t stream, dim3 grid, const CUtensorMap& mq, const CUte
     return 0;
 }
 
-EncodeTiledFn get_encode_fn_public_impl() { return get_encode_fn(); }
-
 }  // namespace
-
-namespace tc {
-static inline EncodeTiledFn get_encode_fn_public() { return get_encode_fn_public_impl(); }
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int rowBytes) {
-    EncodeTiledFn fn = get_encode_fn_public();
-    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return -1; }
-    const cuuint64_t dims[2] = {(cuuint64_t)rowBytes, (cuuint64_t)std::max<int64_t>(rows, 1)};
-    const cuuint64_t strides[1] = {(cuuint64_t)rowBytes};
-    const cuuint32_t box[2] = {128, (cuuint32_t)TILE_M};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
-    return 0;
-}
-
-}  // namespace tc
 
 bool hamming_tc_supported(int descBytes) { return descBytes >= 1 && descBytes <= 64; }
 
