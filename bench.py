@@ -474,6 +474,27 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local: int):
+    """One process per GPU: pin the rank's host threads (and therefore its first-touch pinned
+    staging buffers) to the CPUs NVML reports as local to the GPU, so the e2e copies of 8 ranks do
+    not all cross the socket interconnect.  Best effort; returns a short description or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and w * 64 + b < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {idx}"
+    except Exception:
+        return None
+    return None
+
+
 def workload_config(args, sample_pairs=None):
     c = {"workload": "C2: Hamming kNN k=2 + ratio 0.8, 256-bit descriptors, 8192x8192 per pair",
          "pairs_per_gpu": args.pairs, "n_query": NQ, "n_train": NT, "desc_bytes": DESC_BYTES,
@@ -499,6 +520,7 @@ def run_ours(args):
     lib = native.load()
     if lib.mcvDeviceCount() < 1:
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback): " + native.last_error())
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     engine = {"auto": 0, "popc": 1, "tensor": 2, "packed": 3}[args.engine]
     mcv.set_hamming_engine(engine)
     use_tc = engine >= 2 or (engine == 0 and args.pairs * NQ * NT >= 64 * 1024 * 1024)
@@ -664,7 +686,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(q_np.nbytes + t_np.nbytes),
                 "d2h_bytes_per_step": int(out.train_idx.nbytes + out.distance.nbytes + out.ratio_pass.nbytes),
                 "steps": e2e_steps, "api": "cvMatchKnn2Batch (host buffers, pinned)"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "numa_binding": numa, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "ratio_pass_per_pair": n_pass_dev / P, "extra": extra,
     }
     print(json.dumps(line), flush=True)
