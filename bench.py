@@ -326,6 +326,33 @@ def extra_ransac(local, with_cpu=True):
         except ImportError:
             pass
     del dq, dt, dkq, dkt, didx, ddist, dok, da, db, dMask
+    # ---- M1 at 488 bit (AKAZE-MLDB, 61-byte rows): both Hamming engines, 128 pairs of 8192 x 8192
+    Pa = 128
+    qa = np.empty((Pa * NQ, 61), np.uint8); ta = np.empty((Pa * NT, 61), np.uint8)
+    for p in range(Pa):
+        qq_, tt_, _ = synth.descriptor_pair(3000 + p, NQ, NT, 61)
+        qa[p * NQ:(p + 1) * NQ] = qq_; ta[p * NT:(p + 1) * NT] = tt_
+    oa = np.arange(Pa + 1, dtype=np.int64) * NQ
+    dqa = torch.from_numpy(qa).to(dev); dta = torch.from_numpy(ta).to(dev)
+    dia = torch.empty((Pa * NQ, 2), dtype=torch.int32, device=dev); dda = torch.empty((Pa * NQ, 2), dtype=torch.float32, device=dev)
+    doa = torch.empty(Pa * NQ, dtype=torch.uint8, device=dev)
+    ak = {}
+    ref_idx = None
+    for ename, eng in (("popc", 1), ("tcgen05_int8", 2)):
+        mcv.set_hamming_engine(eng)
+        ta_ = timed(lambda: mcv.match_knn2_batch_device(dqa, oa, dta, oa, 61, RATIO, dia, dda, doa, device=local,
+                                                        stream=stream.cuda_stream))
+        ak[ename] = {"pairs_per_s": Pa / ta_, "ms_per_batch": ta_ * 1e3, "gdist_per_s": Pa * NQ * NT / ta_ / 1e9}
+        if ref_idx is None:
+            ref_idx = dia.clone()
+        else:
+            ak["engines_identical"] = bool(torch.equal(ref_idx, dia))
+    mcv.set_hamming_engine(0)
+    ak["pairs"] = Pa; ak["shape"] = f"{NQ} x {NT} x 488 bit (61-byte rows)"
+    ak["pairs_per_s"] = max(ak["popc"]["pairs_per_s"], ak["tcgen05_int8"]["pairs_per_s"])
+    ak["ms_per_batch"] = min(ak["popc"]["ms_per_batch"], ak["tcgen05_int8"]["ms_per_batch"])
+    out["M1_hamming_488bit"] = ak
+    del dqa, dta, dia, dda, doa, ref_idx
     # ---- M2: L2 kNN for float descriptors (SIFT-shaped: 128-d, 2048 x 2048 per pair, 256 pairs)
     Pl, nl, dl = 256, 2048, 128
     rngl = np.random.default_rng(11)
