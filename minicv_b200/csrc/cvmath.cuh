@@ -259,6 +259,41 @@ MCV_HDN inline void solve_sym_eig(const double* A, const double* b, double* x) {
     }
 }
 
+// Same solve, fast path: Cholesky when A is comfortably positive definite (the usual LM case:
+// J^T J + lambda diag), where it equals the eigen-solve to rounding; the thresholded eigen-solve
+// stays for ill-conditioned systems, where its pseudo-inverse semantics matter.
+template <int N>
+MCV_HDN inline void solve_sym_chol_or_eig(const double* A, const double* b, double* x) {
+    double L[N * N];
+    double dmax = 0;
+    for (int i = 0; i < N; ++i) dmax = fmax(dmax, fabs(A[i * N + i]));
+    bool ok = dmax > 0;
+    for (int j = 0; j < N && ok; ++j) {
+        double d = A[j * N + j];
+        for (int k = 0; k < j; ++k) d -= L[j * N + k] * L[j * N + k];
+        if (!(d > 1e-12 * dmax)) { ok = false; break; }
+        const double ljj = sqrt(d);
+        L[j * N + j] = ljj;
+        for (int i = j + 1; i < N; ++i) {
+            double s = A[i * N + j];
+            for (int k = 0; k < j; ++k) s -= L[i * N + k] * L[j * N + k];
+            L[i * N + j] = s / ljj;
+        }
+    }
+    if (!ok) { solve_sym_eig<N>(A, b, x); return; }
+    double y[N];
+    for (int i = 0; i < N; ++i) {
+        double s = b[i];
+        for (int k = 0; k < i; ++k) s -= L[i * N + k] * y[k];
+        y[i] = s / L[i * N + i];
+    }
+    for (int i = N - 1; i >= 0; --i) {
+        double s = y[i];
+        for (int k = i + 1; k < N; ++k) s -= L[k * N + i] * x[k];
+        x[i] = s / L[i * N + i];
+    }
+}
+
 // max |diag| of pinv(A) for symmetric A (LMSolver's lambda re-seed: invert(A, Ap, DECOMP_EIG))
 template <int N>
 MCV_HDN inline double max_diag_pinv_sym(const double* A) {

@@ -442,7 +442,7 @@ select_kernel(const int64_t* __restrict__ off, int nPairs, int maxIters, int max
 // ---------------------------------------------------------------------------------------------
 // finalize
 // ---------------------------------------------------------------------------------------------
-constexpr int FB = 256;   // finalize block size
+constexpr int FB = 128;   // finalize block size (several blocks per SM overlap the serial thread-0 phases)
 
 template <int K>
 __device__ __forceinline__ void block_sum(double (&v)[K], double* sred /*[K * 8]*/, double* sout /*[K]*/) {
@@ -563,7 +563,7 @@ __device__ __noinline__ void lm_trial(const double* A, const double* v, const do
     double Ap[64], vv[8], dd[8];
     for (int k = 0; k < 64; ++k) Ap[k] = A[k];
     for (int r = 0; r < 8; ++r) { Ap[r * 8 + r] += lam * D[r]; vv[r] = v[r]; }
-    solve_sym_eig<8>(Ap, vv, dd);
+    solve_sym_chol_or_eig<8>(Ap, vv, dd);
     for (int r = 0; r < 8; ++r) { d[r] = dd[r]; xd[r] = x[r] - dd[r]; }
 }
 

@@ -38,6 +38,7 @@ void hm_cheirality(const double* R, const double* t, const double* a, const doub
 void hm_svd3(const double* A, double* w, double* u, double* vt) { svd_square<3>(A, w, u, vt); }
 void hm_svd4(const double* A, double* w, double* u, double* vt) { svd_square<4>(A, w, u, vt); }
 void hm_solve_sym_eig8(const double* A, const double* b, double* x) { solve_sym_eig<8>(A, b, x); }
+void hm_solve_sym_chol8(const double* A, const double* b, double* x) { solve_sym_chol_or_eig<8>(A, b, x); }
 void hm_eigen_sym9(const double* A, double* w, double* V) {
     double M[81]; memcpy(M, A, sizeof(M));
     jacobi_eigen_sym<9>(M, w, V);

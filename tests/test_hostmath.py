@@ -140,3 +140,21 @@ def test_division_free_inlier_tests_match_exact_errors(hm):
         out = np.zeros(n, np.uint8)
         hm.hm_e_inlier(p(E), p(x1), p(x2), n, C.c_float(float(thr)), p(out))
         np.testing.assert_array_equal(out.astype(bool), err <= thr)
+
+
+def test_symmetric_solvers(hm):
+    rng = np.random.default_rng(2)
+    for cond in (1.0, 1e2, 1e13):
+        B = rng.normal(size=(30, 8))
+        B[:, 7] = B[:, 6] + B[:, 7] / cond          # near-dependent columns for the large cond cases
+        A = B.T @ B
+        b = rng.normal(size=8)
+        x1 = np.zeros(8); x2 = np.zeros(8)
+        hm.hm_solve_sym_eig8(p(A.copy()), p(b), p(x1))
+        hm.hm_solve_sym_chol8(p(A.copy()), p(b), p(x2))
+        if cond < 1e10:
+            ref = np.linalg.solve(A, b)
+            assert np.abs(x1 - ref).max() / np.abs(ref).max() < 1e-6
+            assert np.abs(x2 - ref).max() / np.abs(ref).max() < 1e-6
+        else:   # ill-conditioned: the Cholesky guard must hand over to the eigen-solve
+            np.testing.assert_array_equal(x1, x2)
