@@ -1,22 +1,34 @@
 // hamming_tc.cu -- Hamming kNN (k = 2) on the 5th-generation tensor cores (tcgen05, sm_100a).
 //
-// Formulation: bits are expanded to int8 +-1 (one pass, HBM-bound), so for K-bit descriptors
-//     a . b = K - 2 * hamming(a, b)          (exact in int32)
+// Formulation: bits are expanded to int8 (one pass, HBM-bound): query bits to +-1, train bits to
+// +-S (S = 64, or 32 for 512-bit rows), so for K-bit descriptors
+//     a . b = S * (K - 2 * hamming(a, b))     (exact in int32, and it fits in int16)
 // and the distance matrix of a pair is a K-major int8 GEMM  D = Q * T^T  issued as
 // tcgen05.mma.kind::i8 (M = 128, N = 128, K = 32 per instruction), operands staged in shared
-// memory by TMA (SWIZZLE_128B), accumulators in TMEM (2 query tiles x 2 stages x 128 columns
-// = all 512 columns).  The epilogue warps read the accumulators with tcgen05.ld (one query row
-// per thread, 32 train columns per load) and keep the running top-2 per row in registers:
-// a group maximum filters each 8-column group against the current second best, so the exact
-// (index-carrying, lowest-index-wins) update only runs for groups that can change the result.
+// memory by TMA (SWIZZLE_128B), accumulators in TMEM (four 128-column buffers = all 512 columns:
+// 2 query tiles x 2 stages, or 1 tile x 4 stages for 512-bit rows).
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..9 = epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter take one
-// query tile each, or one half of the columns each when there is a single query tile, and
-// software-pipeline tcgen05.ld of the next 32 columns under the top-2 work of the current 32).  One CTA sweeps the train rows of its
-// split for 256 queries (two M = 128 tiles share every train stage, halving L2 -> SM traffic).
-// Results leave the kernel as packed keys (dist << 32) | trainIdx and go through the same
-// finalize kernel as the integer-pipe engine (hamming_knn.cu), so tie-breaking is identical.
+// Epilogue = the binding resource (the ALU pipe issues 64 min/max per clock per SM, while
+// tcgen05.ld delivers > 1 KB/clk/SM, tools/tmem_bench.cu), so it is built to spend ~1.5 ALU
+// lane-operations per distance and never diverge:
+//   * tcgen05.ld.32x32b.x32.pack::16b returns the low 16 bits of two adjacent accumulator
+//     columns per register (the values fit in int16), so every DPX instruction
+//     (VIADDMNMX.S16x2 / VIMNMX3.S16x2) works on two distances;
+//   * a . b is a multiple of 2S, so adding (CH - 1 - column) < 2S to it makes a 16-bit key that
+//     carries its own column: max() of keys = smallest distance, lowest column on ties.  The add
+//     is fused into the min/max (VIADDMNMX), and the exact top-2 of a chunk of CH columns is the
+//     branch-free recurrence  t = min(b1, x); b1 = max(b1, x); b2 = max(b2, t);
+//   * once per chunk the four surviving candidates are widened to 32-bit keys
+//     (value, 0xFFFF - chunk number, column) and merged into the row's running top-2 with six
+//     more min/max -- again no branch, so a warp never serialises on the rows that improve.
+//
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..17 = epilogue.  TMEM lane quarter = warp % 4; each group of four warps owns one of the
+// four accumulator buffers, i.e. one (query tile, stage parity), and reads all 128 columns of it.
+// One CTA sweeps the train rows of its split for 256 queries (two M = 128 tiles share every train
+// stage, halving L2 -> SM traffic).  Results leave the kernel as packed keys
+// (dist << 32) | trainIdx and go through the same finalize kernel as the integer-pipe engine
+// (hamming_knn.cu), so tie-breaking is identical.
 #include "knn.cuh"
 #include "tc_ptx.cuh"
 
@@ -32,12 +44,12 @@ constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
 using namespace tc;
 
 // ---------------------------------------------------------------------------------------------
-// bit expansion: packed descriptor bits -> int8 +-1 rows of KC*128 bytes (zero bits -> -1;
-// padding bits are "zero" on both sides, so they never contribute to the distance)
+// bit expansion: packed descriptor bits -> int8 +-scale rows of KC*128 bytes (zero bits ->
+// -scale; padding bits are "zero" on both sides, so they never contribute to the distance)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 expand_bits_kernel(const uint8_t* __restrict__ src, int srcBytes, int64_t nRows, int rowBytesOut,
-                   uint4* __restrict__ dst) {
+                   uint32_t scale, uint4* __restrict__ dst) {
     // one thread -> 16 output bytes (16 bits = 2 source bytes)
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int per = rowBytesOut / 16;
@@ -47,13 +59,15 @@ expand_bits_kernel(const uint8_t* __restrict__ src, int srcBytes, int64_t nRows,
     const uint8_t* s = src + row * srcBytes;
     const int b0 = 2 * g, b1 = 2 * g + 1;
     const uint32_t bits = (b0 < srcBytes ? (uint32_t)s[b0] : 0u) | ((b1 < srcBytes ? (uint32_t)s[b1] : 0u) << 8);
+    const uint32_t neg = (256u - scale) * 0x01010101u;          // -scale in every byte
+    const uint32_t flip = (scale ^ (256u - scale)) & 0xFFu;     // -scale ^ flip = +scale
     uint32_t w[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const uint32_t nib = (bits >> (4 * q)) & 0xFu;
-        // spread 4 bits to 4 bytes of 0/1, then 1 -> 0x01 (+1), 0 -> 0xFF (-1)
+        // spread 4 bits to 4 bytes of 0/1, then 1 -> +scale, 0 -> -scale
         const uint32_t sp = (nib * 0x00204081u) & 0x01010101u;
-        w[q] = 0xFFFFFFFFu ^ (sp * 0xFEu);
+        w[q] = neg ^ (sp * flip);
     }
     dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -65,10 +79,86 @@ struct TcSmem {      // carved from dynamic shared memory (1024-byte aligned)
     static constexpr int BAR_BYTES = 256;
 };
 
-__device__ __forceinline__ void top2_insert(int x, int col, int& b1, int& i1, int& b2, int& i2) {
-    if (x > b2) {
-        if (x > b1) { b2 = b1; i2 = i1; b1 = x; i1 = col; }
-        else { b2 = x; i2 = col; }
+// Per-configuration key layout.  A chunk is CH accumulator columns whose 16-bit keys are
+//     key16 = S * (a . b) + (CH - 1 - column)         S * (a . b) is a multiple of 2S >= CH
+// i.e. key16 = (m << IDXB) | (CH - 1 - column) with m = (a . b) / 2 = K/2 - hamming.
+template <int KC> struct KeyCfg {
+    static constexpr int SCALE = KC == 4 ? 32 : 64;      // train-side int8 magnitude
+    static constexpr int IDXB = KC == 4 ? 6 : 7;         // column bits inside a key
+    static constexpr int CH = 1 << IDXB;                 // columns per chunk (64 or 128)
+    static_assert(SCALE * KC * 128 + CH - 1 <= 32767, "keys must fit in int16");
+    static_assert(2 * SCALE >= CH, "column bits must fit under the value step");
+};
+constexpr uint32_t PACK_NONE = 0x80008000u;              // two int16 minima: "no candidate"
+constexpr bool PACK_LOW_IS_EVEN = true;                  // .pack::16b: even column in the low half
+
+// packed index constants for register r of a chunk whose first column is `base`
+template <int CH> __device__ __forceinline__ constexpr uint32_t idx_const(int base, int r) {
+    const uint32_t e = (uint32_t)(CH - 1 - (base + 2 * r)), o = (uint32_t)(CH - 1 - (base + 2 * r + 1));
+    return PACK_LOW_IS_EVEN ? ((o << 16) | e) : ((e << 16) | o);
+}
+
+// exact top-2 (per 16-bit lane) of b1 >= b2 and two more registers x0, x1 (+ their constants)
+__device__ __forceinline__ void top2_step(uint32_t x0, uint32_t c0, uint32_t x1, uint32_t c1, uint32_t& b1, uint32_t& b2) {
+    const uint32_t t0 = __viaddmin_s16x2(x0, c0, b1);
+    b1 = __viaddmax_s16x2(x0, c0, b1);
+    const uint32_t t1 = __viaddmin_s16x2(x1, c1, b1);
+    b1 = __viaddmax_s16x2(x1, c1, b1);
+    b2 = __vimax3_s16x2(b2, t0, t1);
+}
+// (a1 >= a2) U (b1 >= b2) -> top-2, per 16-bit lane
+__device__ __forceinline__ void top2_merge16(uint32_t& a1, uint32_t& a2, uint32_t b1, uint32_t b2) {
+    const uint32_t lo = __vmins2(a1, b1);
+    a1 = __vmaxs2(a1, b1);
+    a2 = __vimax3_s16x2(lo, a2, b2);
+}
+
+// Widen the two 16-bit keys of `b` to 32-bit keys (m, ctr, column) and return them.
+template <int IDXB> __device__ __forceinline__ void widen(uint32_t b, uint32_t ctrShifted, int& lo, int& hi) {
+    constexpr uint32_t MASKM = ~((1u << (16 + IDXB)) - 1u);
+    constexpr uint32_t MASKI = (1u << IDXB) - 1u;
+    hi = (int)(((b & MASKM) | ctrShifted) | ((b >> 16) & MASKI));
+    lo = (int)((((b << 16) & MASKM) | ctrShifted) | (b & MASKI));
+}
+
+// One chunk of CH columns held in NREG = CH/2 packed registers -> merged into (g1 >= g2).
+template <int IDXB, int NREG>
+__device__ __forceinline__ void chunk_top2(const uint32_t* v, uint32_t chunkNo, int& g1, int& g2) {
+    constexpr int CH = 1 << IDXB;
+    static_assert(NREG * 2 == CH && NREG % 8 == 0, "chunk shape");
+    constexpr int NCHAIN = 4, PER = NREG / NCHAIN;       // four independent dependency chains
+    uint32_t b1[NCHAIN], b2[NCHAIN];
+#pragma unroll
+    for (int c = 0; c < NCHAIN; ++c) { b1[c] = PACK_NONE; b2[c] = PACK_NONE; }
+#pragma unroll
+    for (int i = 0; i < PER; i += 2)
+#pragma unroll
+        for (int c = 0; c < NCHAIN; ++c) {
+            const int r = c * PER + i;
+            top2_step(v[r], idx_const<CH>(0, r), v[r + 1], idx_const<CH>(0, r + 1), b1[c], b2[c]);
+        }
+    top2_merge16(b1[0], b2[0], b1[1], b2[1]);
+    top2_merge16(b1[2], b2[2], b1[3], b2[3]);
+    top2_merge16(b1[0], b2[0], b1[2], b2[2]);
+    // four candidates (top-2 of the even columns, top-2 of the odd columns) -> 32-bit keys
+    const uint32_t ctrShifted = (0xFFFFu - chunkNo) << IDXB;
+    int hA, hB, lA, lB;
+    widen<IDXB>(b1[0], ctrShifted, hA, hB);
+    widen<IDXB>(b2[0], ctrShifted, lA, lB);
+    const int H = max(hA, hB);
+    const int S = __vimax3_s32(min(hA, hB), lA, lB);
+    g2 = __vimax3_s32(g2, min(g1, H), S);
+    g1 = max(g1, H);
+}
+
+// columns >= nv of a 128-column row (64 packed registers) become "no candidate"
+__device__ __forceinline__ void mask_tail(uint32_t (&v)[64], int nv) {
+#pragma unroll
+    for (int r = 0; r < 64; ++r) {
+        const int ce = PACK_LOW_IS_EVEN ? 2 * r : 2 * r + 1;      // column in the low half
+        const int co = PACK_LOW_IS_EVEN ? 2 * r + 1 : 2 * r;      // column in the high half
+        if (ce >= nv) v[r] = (v[r] & 0xFFFF0000u) | 0x8000u;
+        if (co >= nv) v[r] = (v[r] & 0x0000FFFFu) | 0x80000000u;
     }
 }
 
@@ -82,6 +172,9 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     constexpr int A_BYTES = ATILES * KC * CHUNK_BYTES;
     constexpr int B_BYTES = KC * CHUNK_BYTES;
     constexpr int KBITS = KC * 128;
+    constexpr int NSTG = 4 / ATILES;                     // accumulator stages (4 TMEM buffers in all)
+    constexpr int IDXB = KeyCfg<KC>::IDXB;
+    constexpr int CH = KeyCfg<KC>::CH;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -90,9 +183,9 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     uint64_t* a_full = bars;                 // 1
     uint64_t* b_full = bars + 1;             // STAGES
     uint64_t* b_empty = b_full + STAGES;     // STAGES
-    uint64_t* acc_full = b_empty + STAGES;   // 2
-    uint64_t* acc_empty = acc_full + 2;      // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* acc_full = b_empty + STAGES;   // NSTG
+    uint64_t* acc_empty = acc_full + NSTG;   // NSTG
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NSTG);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -117,7 +210,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, EPI_WARPS * 32); }
+        for (int s = 0; s < NSTG; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, ATILES * 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -153,15 +246,15 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             mbar_wait(a_full, 0);
             for (int j = 0; j < nStagesTotal; ++j) {
                 const int s = j % STAGES;
-                const int as = j & 1;
+                const int as = j % NSTG;
                 mbar_wait(b_full + s, (j / STAGES) & 1);
-                mbar_wait(acc_empty + as, ((j >> 1) & 1) ^ 1);
+                mbar_wait(acc_empty + as, ((j / NSTG) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t bBase = smem_u32(sB + s * B_BYTES);
 #pragma unroll
                 for (int t = 0; t < ATILES; ++t) {
                     const uint32_t aBase = smem_u32(sA + t * KC * CHUNK_BYTES);
-                    const uint32_t dcol = tmem_base + (uint32_t)(as * (ATILES * TILE_N) + t * TILE_N);
+                    const uint32_t dcol = tmem_base + (uint32_t)((as * ATILES + t) * TILE_N);
 #pragma unroll
                     for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
@@ -176,81 +269,48 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             }
         }
     } else {
-        // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4 =====
+        // ===== epilogue: warps 2..17, TMEM lane quarter = warp % 4 =====
         const int quarter = warp & 3;
-        const int grp = (warp - 2) >> 2;                 // 0 .. 3
+        const int grp = (warp - 2) >> 2;                 // 0 .. 3 = the accumulator buffer this warp owns
         const int row = quarter * 32 + lane;             // accumulator row within an M tile
-        // The four warps of a lane quarter split a stage's work; every warp reports its own
-        // partial top-2 as a separate key slot (merged exactly by the finalize kernel).
-        // ATILES == 2: query tile = grp & 1, column half = grp >> 1 (two 32-column chunks).
-        // ATILES == 1: one 32-column chunk each.
         const int myTile = ATILES == 2 ? (grp & 1) : 0;
-        constexpr int NCHUNK = ATILES == 2 ? 2 : 1;
-        constexpr int SLOTS = ATILES == 2 ? 2 : 4;       // key slots per split
-        const int colPart = ATILES == 2 ? (grp >> 1) : grp;
-        const int chunk0 = colPart * NCHUNK;
-        int b1 = INT_MIN, i1 = -1, b2 = INT_MIN, i2 = -1;
-        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int myAs = ATILES == 2 ? (grp >> 1) : grp; // stages j = myAs (mod NSTG)
+        int g1 = INT_MIN, g2 = INT_MIN;                  // running top-2 as (m, ctr, column) keys
+        const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((myAs * ATILES + myTile) * TILE_N);
 
-        auto process = [&](int (&v)[32], int nv, int cb) {
-            if (nv < 32) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) if (i >= nv) v[i] = INT_MIN;
-            }
-            int g[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int m01 = max(v[q * 8 + 0], v[q * 8 + 1]), m23 = max(v[q * 8 + 2], v[q * 8 + 3]);
-                const int m45 = max(v[q * 8 + 4], v[q * 8 + 5]), m67 = max(v[q * 8 + 6], v[q * 8 + 7]);
-                g[q] = max(max(m01, m23), max(m45, m67));
-            }
-            const int gm = max(max(g[0], g[1]), max(g[2], g[3]));
-            if (gm > b2) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (g[q] > b2) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) top2_insert(v[q * 8 + i], cb + q * 8 + i, b1, i1, b2, i2);
-                    }
-                }
-            }
-        };
-
-        for (int j = 0; j < nStagesTotal; ++j) {
-            const int as = j & 1;
-            mbar_wait(acc_full + as, (j >> 1) & 1);
+        for (int j = myAs; j < nStagesTotal; j += NSTG) {
+            mbar_wait(acc_full + myAs, (j / NSTG) & 1);
             tc_fence_after();
-            const int colBase = j * TILE_N;               // within the split
-            const int valid = min(TILE_N, nT - colBase);  // train rows of this stage that exist
-            const uint32_t tcol = tlane + (uint32_t)(as * (ATILES * TILE_N) + myTile * TILE_N + chunk0 * 32);
-            const int cb0 = t0 + colBase + chunk0 * 32;
-            int va[32], vb[32];
-            // software pipeline: the load of chunk c+1 is in flight while chunk c is processed
-            tc_ld32(tcol, va);
+            uint32_t v[64];
+            tc_ld32_pack16(tcol, v);                     // columns 0..63 of the buffer
+            tc_ld32_pack16(tcol + 64, v + 32);           // columns 64..127
             tc_wait_ld();
-            if (NCHUNK == 2) {
-                tc_ld32(tcol + 32, vb);
-                process(va, valid - chunk0 * 32, cb0);
-                tc_wait_ld();
-                tc_fence_before();
-                mbar_arrive(acc_empty + as);                 // all of this warp's loads have landed
-                process(vb, valid - (chunk0 + 1) * 32, cb0 + 32);
+            tc_fence_before();
+            mbar_arrive(acc_empty + myAs);               // the buffer can be overwritten now
+            const int valid = nT - j * TILE_N;           // train rows of this stage that exist
+            if (valid < TILE_N) mask_tail(v, valid);
+            if constexpr (CH == 128) {
+                chunk_top2<IDXB, 64>(v, (uint32_t)j, g1, g2);
             } else {
-                tc_fence_before();
-                mbar_arrive(acc_empty + as);
-                process(va, valid - chunk0 * 32, cb0);
+                chunk_top2<IDXB, 32>(v, (uint32_t)(2 * j), g1, g2);
+                chunk_top2<IDXB, 32>(v + 32, (uint32_t)(2 * j + 1), g1, g2);
             }
         }
         // emit packed keys (dist << 32) | pair-local train index
         {
             const int64_t qRow = qTile0 + myTile * TILE_M + row;
-            const int slot = split * SLOTS + colPart;
+            const int slot = split * NSTG + myAs;
             if (qRow < qEnd) {
-                uint64_t k1 = ~0ull, k2 = ~0ull;
-                if (i1 >= 0) k1 = ((uint64_t)(uint32_t)((KBITS - b1) >> 1) << 32) | (uint64_t)(uint32_t)i1;
-                if (i2 >= 0) k2 = ((uint64_t)(uint32_t)((KBITS - b2) >> 1) << 32) | (uint64_t)(uint32_t)i2;
+                auto decode = [&](int g) -> uint64_t {
+                    const int m = g >> (16 + IDXB);                        // K/2 - hamming
+                    const int dist = KBITS / 2 - m;
+                    if (dist > KBITS) return ~0ull;                        // sentinel / masked column
+                    const int chunkNo = 0xFFFF - ((g >> IDXB) & 0xFFFF);
+                    const int col = (CH - 1) - (g & (CH - 1));
+                    return ((uint64_t)(uint32_t)dist << 32) | (uint64_t)(uint32_t)(t0 + chunkNo * CH + col);
+                };
                 uint64_t* o = splitKeys + ((int64_t)slot * totalQ + qRow) * 2;
-                reinterpret_cast<ulonglong2*>(o)[0] = make_ulonglong2(k1, k2);
+                reinterpret_cast<ulonglong2*>(o)[0] = make_ulonglong2(decode(g1), decode(g2));
             }
         }
     }
@@ -326,12 +386,13 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
         return -1;
     {
         const int64_t nq = totalQ * (rowBytes / 16), nt = totalT * (rowBytes / 16);
+        const uint32_t trainScale = KC == 4 ? KeyCfg<4>::SCALE : KeyCfg<2>::SCALE;
         expand_bits_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(a.dQuery, a.descBytes, totalQ, rowBytes,
-                                                                             ctx->ws[24].as<uint4>());
+                                                                             1u, ctx->ws[24].as<uint4>());
         MCV_LAUNCH_CHECK();
         if (nt > 0) {
             expand_bits_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, stream>>>(a.dTrain, a.descBytes, totalT, rowBytes,
-                                                                                 ctx->ws[25].as<uint4>());
+                                                                                 trainScale, ctx->ws[25].as<uint4>());
             MCV_LAUNCH_CHECK();
         }
     }
@@ -344,11 +405,13 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
     if (tiles < fill) wantSplits = (fill + tiles - 1) / tiles;
     const int64_t maxStages = std::max<int64_t>(1, (maxT + TILE_N - 1) / TILE_N);
     wantSplits = std::min<int64_t>(wantSplits, std::max<int64_t>(1, maxStages / 4));
+    // the 16-bit chunk counter inside the epilogue keys covers 2^22 train rows per split
+    wantSplits = std::max<int64_t>(wantSplits, (maxT + (1ll << 22) - 1) >> 22);
     int64_t splitRows = (std::max<int64_t>(maxT, 1) + wantSplits - 1) / wantSplits;
     splitRows = (splitRows + TILE_N - 1) / TILE_N * TILE_N;
     const int nSplits = (int)std::max<int64_t>(1, (maxT + splitRows - 1) / splitRows);
     if (nSplits > 65535) { set_error("train set too large for one launch"); return -1; }
-    const int nSlots = (ATILES == 2 ? 2 : 4) * nSplits;   // every epilogue warp of a lane quarter reports its own slot
+    const int nSlots = (4 / ATILES) * nSplits;   // one key slot per accumulator stage (epilogue warp group) and split
     if (ctx->ws[3].reserve((size_t)nSlots * totalQ * 16)) return -1;
     uint64_t* dSplitKeys = ctx->ws[3].as<uint64_t>();
 
