@@ -39,7 +39,8 @@
 namespace mcv {
 namespace {
 
-constexpr int EPI_WARPS = 16;      // four epilogue warps per TMEM lane quarter (latency hiding)
+constexpr int NBUF = 3;            // 128-column accumulator buffers in TMEM (columns 128..511)
+constexpr int EPI_WARPS = 4 * NBUF; // one group of four warps (one per TMEM lane quarter) per buffer
 constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
 using namespace tc;
 
@@ -75,6 +76,20 @@ expand_bits_kernel(const uint8_t* __restrict__ src, int srcBytes, int64_t nRows,
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
+#ifdef MCV_TC_PROF
+__device__ unsigned long long g_tc_prof[16];
+
+#define PROF_T0() const long long _pt = clock64()
+#if MCV_TC_PROF >= 2     // fine-grained wait / work counters (intrusive)
+#define PROF_ADD(i) atomicAdd(&g_tc_prof[i], (unsigned long long)(clock64() - _pt))
+#else
+#define PROF_ADD(i) (void)_pt
+#endif
+#else
+#define PROF_T0()
+#define PROF_ADD(i)
+#endif
+
 struct TcSmem {      // carved from dynamic shared memory (1024-byte aligned)
     static constexpr int BAR_BYTES = 256;
 };
@@ -162,32 +177,63 @@ __device__ __forceinline__ void mask_tail(uint32_t (&v)[64], int nv) {
     }
 }
 
+// 128 descriptor bits (16 bytes, zero-padded past descBytes) of one query row -> 32 words of
+// int8 +-1, written to 32 TMEM columns of this thread's lane: the A operand of the MMAs
+__device__ __forceinline__ void stage_query_chunk(const uint8_t* __restrict__ rowPtr, int descBytes, int kc,
+                                                  bool rowValid, uint32_t taddr) {
+    uint32_t src[4] = {0u, 0u, 0u, 0u};
+    if (rowValid) {
+        if (((descBytes | (int)(reinterpret_cast<uintptr_t>(rowPtr) & 3)) & 3) == 0) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                if (kc * 16 + w * 4 < descBytes) src[w] = __ldg(reinterpret_cast<const uint32_t*>(rowPtr) + kc * 4 + w);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (kc * 16 + i < descBytes) src[i >> 2] |= (uint32_t)__ldg(rowPtr + kc * 16 + i) << (8 * (i & 3));
+        }
+    }
+    uint32_t v[32];
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t nib = (src[w] >> (4 * q)) & 0xFu;
+            const uint32_t sp = (nib * 0x00204081u) & 0x01010101u;      // 4 bits -> 4 bytes of 0/1
+            v[w * 8 + q] = rowValid ? (0xFFFFFFFFu ^ (sp * 0xFEu)) : 0u;   // 1 -> +1, 0 -> -1
+        }
+    tc_st32(taddr, v);
+}
+
 template <int KC, int ATILES, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapT,
+hamming_tc_kernel(const uint8_t* __restrict__ query, int descBytes, const __grid_constant__ CUtensorMap mapT,
                   const int64_t* __restrict__ qOff, const int64_t* __restrict__ tOff,
                   const int* __restrict__ tileStart, int nPairs, int splitRows, int64_t totalQ,
                   uint64_t* __restrict__ splitKeys) {
     constexpr int QROWS = ATILES * TILE_M;
-    constexpr int A_BYTES = ATILES * KC * CHUNK_BYTES;
     constexpr int B_BYTES = KC * CHUNK_BYTES;
     constexpr int KBITS = KC * 128;
-    constexpr int NSTG = 4 / ATILES;                     // accumulator stages (4 TMEM buffers in all)
+    constexpr int A_COLS = KC * 32;                      // TMEM columns of one query tile (4 int8 per column)
+    constexpr int ACC_COL0 = 128;                        // accumulator buffers start here (ATILES * A_COLS <= 128)
+    static_assert(ATILES * A_COLS <= ACC_COL0, "query tiles must fit under the accumulators");
     constexpr int IDXB = KeyCfg<KC>::IDXB;
     constexpr int CH = KeyCfg<KC>::CH;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + STAGES * B_BYTES);
+    uint8_t* sB = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * B_BYTES);
     uint64_t* a_full = bars;                 // 1
     uint64_t* b_full = bars + 1;             // STAGES
     uint64_t* b_empty = b_full + STAGES;     // STAGES
-    uint64_t* acc_full = b_empty + STAGES;   // NSTG
-    uint64_t* acc_empty = acc_full + NSTG;   // NSTG
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NSTG);
+    uint64_t* acc_full = b_empty + STAGES;   // NBUF
+    uint64_t* acc_empty = acc_full + NBUF;   // NBUF
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NBUF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef MCV_TC_PROF
+    const long long _cta0 = clock64();
+#endif
 
     // locate pair / query tile / train split
     int lo = 0, hi = nPairs;
@@ -206,11 +252,12 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     const int t1 = min(tCount, t0 + splitRows);
     const int nT = t1 - t0;
     const int nStagesTotal = (nT + TILE_N - 1) / TILE_N;
+    const int nUnits = nStagesTotal * ATILES;            // unit n = stage * ATILES + query tile
 
     if (threadIdx.x == 0) {
-        mbar_init(a_full, 1);
+        mbar_init(a_full, ATILES * 128);
         for (int s = 0; s < STAGES; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < NSTG; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, ATILES * 128); }
+        for (int s = 0; s < NBUF; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -223,70 +270,91 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            mbar_expect_tx(a_full, A_BYTES);
-            for (int t = 0; t < ATILES; ++t)
-                for (int kc = 0; kc < KC; ++kc)
-                    tma_load_2d(sA + (t * KC + kc) * CHUNK_BYTES, &mapQ, kc * 128, (int)(qTile0 + t * TILE_M), a_full);
-            for (int j = 0; j < nStagesTotal; ++j) {
-                const int s = j % STAGES;
-                mbar_wait(b_empty + s, ((j / STAGES) & 1) ^ 1);
+        // ===== TMA producer (train stages only; the query tiles live in TMEM) =====
+        // the whole warp runs the loop (uniform control flow); one elected lane issues
+        for (int j = 0; j < nStagesTotal; ++j) {
+            const int s = j % STAGES;
+            mbar_wait(b_empty + s, ((j / STAGES) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(b_full + s, B_BYTES);
+#pragma unroll
                 for (int kc = 0; kc < KC; ++kc)
                     tma_load_2d(sB + s * B_BYTES + kc * CHUNK_BYTES, &mapT, kc * 128,
                                 (int)(tRow0 + t0 + (int64_t)j * TILE_N), b_full + s);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
         // instruction descriptor: D = s32, A = B = signed int8, K-major both, N = 128, M = 128
         constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-        if (lane == 0) {
-            mbar_wait(a_full, 0);
-            for (int j = 0; j < nStagesTotal; ++j) {
-                const int s = j % STAGES;
-                const int as = j % NSTG;
-                mbar_wait(b_full + s, (j / STAGES) & 1);
-                mbar_wait(acc_empty + as, ((j / NSTG) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t bBase = smem_u32(sB + s * B_BYTES);
+        mbar_wait(a_full, 0);
+        tc_fence_after();
+        int buf = 0, use = 0;                        // unit n -> buffer n % NBUF, use count n / NBUF
+        for (int j = 0; j < nStagesTotal; ++j) {
+            const int s = j % STAGES;
+            { PROF_T0(); mbar_wait(b_full + s, (j / STAGES) & 1); PROF_ADD(0); }
+            const uint32_t bBase = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-                for (int t = 0; t < ATILES; ++t) {
-                    const uint32_t aBase = smem_u32(sA + t * KC * CHUNK_BYTES);
-                    const uint32_t dcol = tmem_base + (uint32_t)((as * ATILES + t) * TILE_N);
+            for (int t = 0; t < ATILES; ++t) {
+                { PROF_T0(); mbar_wait(acc_empty + buf, (use & 1) ^ 1); PROF_ADD(1); }
+                tc_fence_after();
+                const uint32_t acol = tmem_base + (uint32_t)(t * A_COLS);
+                const uint32_t dcol = tmem_base + (uint32_t)(ACC_COL0 + buf * TILE_N);
+                PROF_T0();
+                if (elect_one()) {
 #pragma unroll
                     for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t da = umma_desc_sw128(aBase + kc * CHUNK_BYTES + k * 32);
                             const uint64_t db = umma_desc_sw128(bBase + kc * CHUNK_BYTES + k * 32);
-                            tc_mma_i8(dcol, da, db, idesc, (kc | k) ? 1u : 0u);
+                            tc_mma_i8_ts(dcol, acol + (uint32_t)((kc * 4 + k) * 8), db, idesc, (kc | k) ? 1u : 0u);
                         }
+                    tc_commit(acc_full + buf);       // this unit's accumulators are complete
+                    if (t == ATILES - 1) tc_commit(b_empty + s);   // frees the train stage once its MMAs retire
                 }
-                tc_commit(b_empty + s);      // frees the train stage once these MMAs retire
-                tc_commit(acc_full + as);    // accumulators of this stage are complete
+                __syncwarp();
+                PROF_ADD(7);
+                if (++buf == NBUF) { buf = 0; ++use; }
             }
         }
     } else {
-        // ===== epilogue: warps 2..17, TMEM lane quarter = warp % 4 =====
+        // ===== epilogue: warps 2..13, TMEM lane quarter = warp % 4 =====
         const int quarter = warp & 3;
-        const int grp = (warp - 2) >> 2;                 // 0 .. 3 = the accumulator buffer this warp owns
+        const int grp = (warp - 2) >> 2;                 // 0 .. 2 = the accumulator buffer this warp owns
         const int row = quarter * 32 + lane;             // accumulator row within an M tile
-        const int myTile = ATILES == 2 ? (grp & 1) : 0;
-        const int myAs = ATILES == 2 ? (grp >> 1) : grp; // stages j = myAs (mod NSTG)
-        int g1 = INT_MIN, g2 = INT_MIN;                  // running top-2 as (m, ctr, column) keys
-        const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((myAs * ATILES + myTile) * TILE_N);
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
-        for (int j = myAs; j < nStagesTotal; j += NSTG) {
-            mbar_wait(acc_full + myAs, (j / NSTG) & 1);
+        // stage the query tiles: group t expands the rows of tile t straight from the packed blob
+        if (grp < ATILES) {
+            const int64_t qRow = qTile0 + grp * TILE_M + row;
+            const bool rowValid = qRow < totalQ;
+            const uint8_t* rowPtr = query + (rowValid ? qRow : 0) * (int64_t)descBytes;
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc)
+                stage_query_chunk(rowPtr, descBytes, kc, rowValid, tlane + (uint32_t)(grp * A_COLS + kc * 32));
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(a_full);
+        }
+
+        // running top-2 as (m, ctr, column) keys; X = the tile of this group's first unit, Y = the other
+        int gx1 = INT_MIN, gx2 = INT_MIN, gy1 = INT_MIN, gy2 = INT_MIN;
+        const uint32_t tcol = tlane + (uint32_t)(ACC_COL0 + grp * TILE_N);
+        int use = 0;
+        auto unit = [&](int n, int& g1, int& g2) {
+            const int j = ATILES == 2 ? (n >> 1) : n;
+            { PROF_T0(); mbar_wait(acc_full + grp, use & 1); if (lane == 0 && warp == 2) PROF_ADD(2); }
+            ++use;
             tc_fence_after();
+            PROF_T0();
             uint32_t v[64];
             tc_ld32_pack16(tcol, v);                     // columns 0..63 of the buffer
             tc_ld32_pack16(tcol + 64, v + 32);           // columns 64..127
             tc_wait_ld();
             tc_fence_before();
-            mbar_arrive(acc_empty + myAs);               // the buffer can be overwritten now
+            mbar_arrive(acc_empty + grp);                // the buffer can be overwritten now
+            if (lane == 0 && warp == 2) PROF_ADD(3);
             const int valid = nT - j * TILE_N;           // train rows of this stage that exist
             if (valid < TILE_N) mask_tail(v, valid);
             if constexpr (CH == 128) {
@@ -295,27 +363,41 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 chunk_top2<IDXB, 32>(v, (uint32_t)(2 * j), g1, g2);
                 chunk_top2<IDXB, 32>(v + 32, (uint32_t)(2 * j + 1), g1, g2);
             }
+            if (lane == 0 && warp == 2) PROF_ADD(4);
+        };
+        for (int n = grp; n < nUnits; n += 2 * NBUF) {
+            unit(n, gx1, gx2);
+            if (n + NBUF < nUnits) {
+                if (ATILES == 2) unit(n + NBUF, gy1, gy2);      // NBUF is odd: the other query tile
+                else unit(n + NBUF, gx1, gx2);
+            }
         }
-        // emit packed keys (dist << 32) | pair-local train index
-        {
-            const int64_t qRow = qTile0 + myTile * TILE_M + row;
-            const int slot = split * NSTG + myAs;
+        // emit packed keys (dist << 32) | pair-local train index; one slot per (split, group)
+        auto decode = [&](int g) -> uint64_t {
+            const int m = g >> (16 + IDXB);                        // K/2 - hamming
+            const int dist = KBITS / 2 - m;
+            if (dist > KBITS) return ~0ull;                        // sentinel / masked column
+            const int chunkNo = 0xFFFF - ((g >> IDXB) & 0xFFFF);
+            const int col = (CH - 1) - (g & (CH - 1));
+            return ((uint64_t)(uint32_t)dist << 32) | (uint64_t)(uint32_t)(t0 + chunkNo * CH + col);
+        };
+        const int slot = split * NBUF + grp;
+#pragma unroll
+        for (int t = 0; t < ATILES; ++t) {
+            const int64_t qRow = qTile0 + t * TILE_M + row;
+            const bool isX = ATILES == 1 || t == (grp & 1);       // X belongs to tile grp % ATILES
+            const int k1 = isX ? gx1 : gy1, k2 = isX ? gx2 : gy2;
             if (qRow < qEnd) {
-                auto decode = [&](int g) -> uint64_t {
-                    const int m = g >> (16 + IDXB);                        // K/2 - hamming
-                    const int dist = KBITS / 2 - m;
-                    if (dist > KBITS) return ~0ull;                        // sentinel / masked column
-                    const int chunkNo = 0xFFFF - ((g >> IDXB) & 0xFFFF);
-                    const int col = (CH - 1) - (g & (CH - 1));
-                    return ((uint64_t)(uint32_t)dist << 32) | (uint64_t)(uint32_t)(t0 + chunkNo * CH + col);
-                };
                 uint64_t* o = splitKeys + ((int64_t)slot * totalQ + qRow) * 2;
-                reinterpret_cast<ulonglong2*>(o)[0] = make_ulonglong2(decode(g1), decode(g2));
+                reinterpret_cast<ulonglong2*>(o)[0] = make_ulonglong2(decode(k1), decode(k2));
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+#ifdef MCV_TC_PROF
+    if (threadIdx.x == 0) { atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - _cta0)); atomicAdd(&g_tc_prof[6], 1ull); }
+#endif
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -325,23 +407,32 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int KC, int ATILES, int STAGES>
-int launch_cfg(cudaStream_t stream, dim3 grid, const CUtensorMap& mq, const CUtensorMap& mt, const int64_t* qOff,
+int launch_cfg(cudaStream_t stream, dim3 grid, const uint8_t* query, int descBytes, const CUtensorMap& mt, const int64_t* qOff,
                const int64_t* tOff, const int* tileStart, int nPairs, int splitRows, int64_t totalQ,
                uint64_t* splitKeys) {
-    constexpr int SMEM = ATILES * KC * CHUNK_BYTES + STAGES * KC * CHUNK_BYTES + TcSmem::BAR_BYTES + 1024;
+    constexpr int SMEM = STAGES * KC * CHUNK_BYTES + TcSmem::BAR_BYTES + 1024;
     auto kern = hamming_tc_kernel<KC, ATILES, STAGES>;
     MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    kern<<<grid, TC_THREADS, SMEM, stream>>>(mq, mt, qOff, tOff, tileStart, nPairs, splitRows, totalQ, splitKeys);
+    kern<<<grid, TC_THREADS, SMEM, stream>>>(query, descBytes, mt, qOff, tOff, tileStart, nPairs, splitRows, totalQ, splitKeys);
     MCV_LAUNCH_CHECK();
     return 0;
 }
 
 }  // namespace
 
+#ifdef MCV_TC_PROF
+extern "C" __attribute__((visibility("default"))) void mcvDebugTcProf(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z)); }
+}
+
+#endif
+
 bool hamming_tc_supported(int descBytes) { return descBytes >= 1 && descBytes <= 64; }
 
 // Tensor-core engine.  Same contract as launch_hamming_knn2 (knn.cuh); uses ctx workspaces
-// 0 (control), 3 (split keys), 24 / 25 (expanded query / train rows).
+// 0 (control), 3 (split keys), 25 (expanded train rows).
 int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     if (a.nPairs <= 0) return 0;
     if (!hamming_tc_supported(a.descBytes)) { set_error("tensor-core matcher supports 1..64-byte descriptors"); return -1; }
@@ -380,24 +471,20 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
     const int64_t* dTOff = dQOff + n1;
     const int* dTile = reinterpret_cast<const int*>(dTOff + n1);
 
-    // expand bits -> int8 +-1
-    if (ctx->ws[24].reserve((size_t)totalQ * rowBytes + 1024) ||
-        ctx->ws[25].reserve((size_t)std::max<int64_t>(totalT, 1) * rowBytes + 1024))
-        return -1;
+    // expand the train bits -> int8 +-scale (the query rows are expanded inside the kernel, straight
+    // into TMEM)
+    if (ctx->ws[25].reserve((size_t)std::max<int64_t>(totalT, 1) * rowBytes + 1024)) return -1;
     {
-        const int64_t nq = totalQ * (rowBytes / 16), nt = totalT * (rowBytes / 16);
+        const int64_t nt = totalT * (rowBytes / 16);
         const uint32_t trainScale = KC == 4 ? KeyCfg<4>::SCALE : KeyCfg<2>::SCALE;
-        expand_bits_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(a.dQuery, a.descBytes, totalQ, rowBytes,
-                                                                             1u, ctx->ws[24].as<uint4>());
-        MCV_LAUNCH_CHECK();
         if (nt > 0) {
             expand_bits_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, stream>>>(a.dTrain, a.descBytes, totalT, rowBytes,
                                                                                  trainScale, ctx->ws[25].as<uint4>());
             MCV_LAUNCH_CHECK();
         }
     }
-    CUtensorMap mq, mt;
-    if (make_map(&mq, ctx->ws[24].p, totalQ, rowBytes) || make_map(&mt, ctx->ws[25].p, totalT, rowBytes)) return -1;
+    CUtensorMap mt;
+    if (make_map(&mt, ctx->ws[25].p, totalT, rowBytes)) return -1;
 
     // train splits: fill the machine when there are few query tiles
     int64_t wantSplits = 1;
@@ -411,15 +498,15 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
     splitRows = (splitRows + TILE_N - 1) / TILE_N * TILE_N;
     const int nSplits = (int)std::max<int64_t>(1, (maxT + splitRows - 1) / splitRows);
     if (nSplits > 65535) { set_error("train set too large for one launch"); return -1; }
-    const int nSlots = (4 / ATILES) * nSplits;   // one key slot per accumulator stage (epilogue warp group) and split
+    const int nSlots = NBUF * nSplits;   // one key slot per epilogue warp group and split
     if (ctx->ws[3].reserve((size_t)nSlots * totalQ * 16)) return -1;
     uint64_t* dSplitKeys = ctx->ws[3].as<uint64_t>();
 
     dim3 grid((unsigned)tiles, (unsigned)nSplits);
     int rc;
-    if (KC == 1) rc = launch_cfg<1, 2, 4>(stream, grid, mq, mt, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dSplitKeys);
-    else if (KC == 2) rc = launch_cfg<2, 2, 4>(stream, grid, mq, mt, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dSplitKeys);
-    else rc = launch_cfg<4, 1, 2>(stream, grid, mq, mt, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dSplitKeys);
+    if (KC == 1) rc = launch_cfg<1, 2, 8>(stream, grid, a.dQuery, a.descBytes, mt, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dSplitKeys);
+    else if (KC == 2) rc = launch_cfg<2, 2, 6>(stream, grid, a.dQuery, a.descBytes, mt, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dSplitKeys);
+    else rc = launch_cfg<4, 1, 3>(stream, grid, a.dQuery, a.descBytes, mt, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dSplitKeys);
     if (rc) return rc;
     return launch_knn2_finalize(stream, dSplitKeys, nSlots, totalQ, a);
 }
