@@ -76,6 +76,9 @@ expand_bits_kernel(const uint8_t* __restrict__ src, int srcBytes, int64_t nRows,
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
+#ifndef MCV_TC_ABLATE
+#define MCV_TC_ABLATE 0      // profiling builds only: 1 = epilogue without the top-2 math, 2 = also without tcgen05.ld, 3 = also without TMA after the pipeline fill
+#endif
 #ifdef MCV_TC_PROF
 __device__ unsigned long long g_tc_prof[16];
 
@@ -276,48 +279,66 @@ hamming_tc_kernel(const uint8_t* __restrict__ query, int descBytes, const __grid
             const int s = j % STAGES;
             mbar_wait(b_empty + s, ((j / STAGES) & 1) ^ 1);
             if (elect_one()) {
-                mbar_expect_tx(b_full + s, B_BYTES);
+#if MCV_TC_ABLATE >= 3
+                if (j >= STAGES) mbar_arrive(b_full + s);     // re-use the resident stages: no TMA traffic
+                else
+#endif
+                {
+                    mbar_expect_tx(b_full + s, B_BYTES);
 #pragma unroll
-                for (int kc = 0; kc < KC; ++kc)
-                    tma_load_2d(sB + s * B_BYTES + kc * CHUNK_BYTES, &mapT, kc * 128,
-                                (int)(tRow0 + t0 + (int64_t)j * TILE_N), b_full + s);
+                    for (int kc = 0; kc < KC; ++kc)
+                        tma_load_2d(sB + s * B_BYTES + kc * CHUNK_BYTES, &mapT, kc * 128,
+                                    (int)(tRow0 + t0 + (int64_t)j * TILE_N), b_full + s);
+                }
             }
             __syncwarp();
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
+        // ===== MMA issuer =====
+        // The tensor pipe queues only ~2-3 MMAs (tools/mma_bench.cu: an issuer that is away for more
+        // than ~150 cycles starves it), so the barrier waits of unit n+1 are taken in the middle of
+        // unit n, while its last MMAs are still queued.
         // instruction descriptor: D = s32, A = B = signed int8, K-major both, N = 128, M = 128
         constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-        mbar_wait(a_full, 0);
-        tc_fence_after();
-        int buf = 0, use = 0;                        // unit n -> buffer n % NBUF, use count n / NBUF
-        for (int j = 0; j < nStagesTotal; ++j) {
-            const int s = j % STAGES;
-            { PROF_T0(); mbar_wait(b_full + s, (j / STAGES) & 1); PROF_ADD(0); }
-            const uint32_t bBase = smem_u32(sB + s * B_BYTES);
-#pragma unroll
-            for (int t = 0; t < ATILES; ++t) {
-                { PROF_T0(); mbar_wait(acc_empty + buf, (use & 1) ^ 1); PROF_ADD(1); }
-                tc_fence_after();
+        constexpr int NMMA = KC * 4;                 // MMAs per unit
+        constexpr int TAIL = 2;                      // MMAs issued after the look-ahead waits
+        if (elect_one() && nUnits > 0) {
+            mbar_wait(a_full, 0);
+            mbar_wait(b_full, 0);
+            tc_fence_after();
+            int buf = 0, use = 0;                    // unit n -> buffer n % NBUF, use count n / NBUF
+            int j = 0, t = 0, s = 0, sphase = 0;     // stage, query tile, smem stage and its phase
+            for (int n = 0; n < nUnits; ++n) {
+                const uint32_t bBase = smem_u32(sB + s * B_BYTES);
                 const uint32_t acol = tmem_base + (uint32_t)(t * A_COLS);
                 const uint32_t dcol = tmem_base + (uint32_t)(ACC_COL0 + buf * TILE_N);
-                PROF_T0();
-                if (elect_one()) {
 #pragma unroll
-                    for (int kc = 0; kc < KC; ++kc)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t db = umma_desc_sw128(bBase + kc * CHUNK_BYTES + k * 32);
-                            tc_mma_i8_ts(dcol, acol + (uint32_t)((kc * 4 + k) * 8), db, idesc, (kc | k) ? 1u : 0u);
-                        }
-                    tc_commit(acc_full + buf);       // this unit's accumulators are complete
-                    if (t == ATILES - 1) tc_commit(b_empty + s);   // frees the train stage once its MMAs retire
+                for (int i = 0; i < NMMA - TAIL; ++i) {
+                    const uint64_t db = umma_desc_sw128(bBase + (i >> 2) * CHUNK_BYTES + (i & 3) * 32);
+                    tc_mma_i8_ts(dcol, acol + (uint32_t)(i * 8), db, idesc, i ? 1u : 0u);
                 }
-                __syncwarp();
-                PROF_ADD(7);
-                if (++buf == NBUF) { buf = 0; ++use; }
+                // look ahead: everything unit n+1 needs
+                int nbuf = buf + 1, nuse = use;
+                if (nbuf == NBUF) { nbuf = 0; ++nuse; }
+                const bool lastTile = t == ATILES - 1;
+                int ns = s, nsphase = sphase;
+                if (lastTile) { if (++ns == STAGES) { ns = 0; nsphase ^= 1; } }
+                if (n + 1 < nUnits) {
+                    if (lastTile) mbar_wait(b_full + ns, nsphase);
+                    mbar_wait(acc_empty + nbuf, (nuse & 1) ^ 1);
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int i = NMMA - TAIL; i < NMMA; ++i) {
+                    const uint64_t db = umma_desc_sw128(bBase + (i >> 2) * CHUNK_BYTES + (i & 3) * 32);
+                    tc_mma_i8_ts(dcol, acol + (uint32_t)(i * 8), db, idesc, 1u);
+                }
+                tc_commit(acc_full + buf);           // this unit's accumulators are complete
+                if (lastTile) { tc_commit(b_empty + s); ++j; t = 0; } else ++t;   // frees the train stage
+                buf = nbuf; use = nuse; s = ns; sphase = nsphase;
             }
         }
+        __syncwarp();
     } else {
         // ===== epilogue: warps 2..13, TMEM lane quarter = warp % 4 =====
         const int quarter = warp & 3;
@@ -349,14 +370,23 @@ hamming_tc_kernel(const uint8_t* __restrict__ query, int descBytes, const __grid
             tc_fence_after();
             PROF_T0();
             uint32_t v[64];
+#if MCV_TC_ABLATE >= 2
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = (uint32_t)(n + i);
+#else
             tc_ld32_pack16(tcol, v);                     // columns 0..63 of the buffer
             tc_ld32_pack16(tcol + 64, v + 32);           // columns 64..127
             tc_wait_ld();
+#endif
             tc_fence_before();
             mbar_arrive(acc_empty + grp);                // the buffer can be overwritten now
             if (lane == 0 && warp == 2) PROF_ADD(3);
             const int valid = nT - j * TILE_N;           // train rows of this stage that exist
             if (valid < TILE_N) mask_tail(v, valid);
+#if MCV_TC_ABLATE >= 1
+            g1 ^= (int)(v[0] ^ v[31] ^ v[32] ^ v[63]);
+            if (false)
+#endif
             if constexpr (CH == 128) {
                 chunk_top2<IDXB, 64>(v, (uint32_t)j, g1, g2);
             } else {
