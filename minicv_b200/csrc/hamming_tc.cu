@@ -76,6 +76,9 @@ expand_bits_kernel(const uint8_t* __restrict__ src, int srcBytes, int64_t nRows,
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
+#ifndef MCV_TC_WARP_ARRIVE
+#define MCV_TC_WARP_ARRIVE 0
+#endif
 #ifndef MCV_TC_ABLATE
 #define MCV_TC_ABLATE 0      // profiling builds only: 1 = epilogue without the top-2 math, 2 = also without tcgen05.ld, 3 = also without TMA after the pipeline fill
 #endif
@@ -92,6 +95,14 @@ __device__ unsigned long long g_tc_prof[16];
 #define PROF_T0()
 #define PROF_ADD(i)
 #endif
+
+struct alignas(16) TileDesc {   // work item of one CTA column: QROWS query rows of one pair against its train rows
+    int64_t qTile0;             // first query row (global row index in the packed batch)
+    int64_t qEnd;               // end of this pair's query rows
+    int64_t tRow0;              // first train row of the pair
+    int32_t tCount;             // train rows of the pair
+    int32_t pad;
+};
 
 struct TcSmem {      // carved from dynamic shared memory (1024-byte aligned)
     static constexpr int BAR_BYTES = 256;
@@ -211,10 +222,8 @@ __device__ __forceinline__ void stage_query_chunk(const uint8_t* __restrict__ ro
 template <int KC, int ATILES, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 hamming_tc_kernel(const uint8_t* __restrict__ query, int descBytes, const __grid_constant__ CUtensorMap mapT,
-                  const int64_t* __restrict__ qOff, const int64_t* __restrict__ tOff,
-                  const int* __restrict__ tileStart, int nPairs, int splitRows, int64_t totalQ,
+                  const TileDesc* __restrict__ tileDescs, int splitRows, int64_t totalQ,
                   uint64_t* __restrict__ splitKeys) {
-    constexpr int QROWS = ATILES * TILE_M;
     constexpr int B_BYTES = KC * CHUNK_BYTES;
     constexpr int KBITS = KC * 128;
     constexpr int A_COLS = KC * 32;                      // TMEM columns of one query tile (4 int8 per column)
@@ -238,18 +247,13 @@ hamming_tc_kernel(const uint8_t* __restrict__ query, int descBytes, const __grid
     const long long _cta0 = clock64();
 #endif
 
-    // locate pair / query tile / train split
-    int lo = 0, hi = nPairs;
-    const int tile = blockIdx.x;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (tileStart[mid] <= tile) lo = mid; else hi = mid;
-    }
-    const int p = lo;
-    const int64_t q0 = qOff[p], qEnd = qOff[p + 1];
-    const int64_t tRow0 = tOff[p];
-    const int tCount = (int)(tOff[p + 1] - tRow0);
-    const int64_t qTile0 = q0 + (int64_t)(tile - tileStart[p]) * QROWS;
+    // this CTA's query tile and train split
+    const int4 td0 = __ldg(reinterpret_cast<const int4*>(tileDescs + blockIdx.x));
+    const int4 td1 = __ldg(reinterpret_cast<const int4*>(tileDescs + blockIdx.x) + 1);
+    const int64_t qTile0 = ((int64_t)td0.y << 32) | (uint32_t)td0.x;
+    const int64_t qEnd = ((int64_t)td0.w << 32) | (uint32_t)td0.z;
+    const int64_t tRow0 = ((int64_t)td1.y << 32) | (uint32_t)td1.x;
+    const int tCount = td1.z;
     const int split = blockIdx.y;
     const int t0 = min(tCount, split * splitRows);
     const int t1 = min(tCount, t0 + splitRows);
@@ -258,9 +262,9 @@ hamming_tc_kernel(const uint8_t* __restrict__ query, int descBytes, const __grid
     const int nUnits = nStagesTotal * ATILES;            // unit n = stage * ATILES + query tile
 
     if (threadIdx.x == 0) {
-        mbar_init(a_full, ATILES * 128);
+        mbar_init(a_full, ATILES * 4);               // one arrival per staging warp
         for (int s = 0; s < STAGES; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < NBUF; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
+        for (int s = 0; s < NBUF; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, MCV_TC_WARP_ARRIVE ? 4 : 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -356,7 +360,8 @@ hamming_tc_kernel(const uint8_t* __restrict__ query, int descBytes, const __grid
                 stage_query_chunk(rowPtr, descBytes, kc, rowValid, tlane + (uint32_t)(grp * A_COLS + kc * 32));
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(a_full);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
         }
 
         // running top-2 as (m, ctr, column) keys; X = the tile of this group's first unit, Y = the other
@@ -379,7 +384,12 @@ hamming_tc_kernel(const uint8_t* __restrict__ query, int descBytes, const __grid
             tc_wait_ld();
 #endif
             tc_fence_before();
+#if MCV_TC_WARP_ARRIVE
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + grp); // the buffer can be overwritten now
+#else
             mbar_arrive(acc_empty + grp);                // the buffer can be overwritten now
+#endif
             if (lane == 0 && warp == 2) PROF_ADD(3);
             const int valid = nT - j * TILE_N;           // train rows of this stage that exist
             if (valid < TILE_N) mask_tail(v, valid);
@@ -437,13 +447,12 @@ hamming_tc_kernel(const uint8_t* __restrict__ query, int descBytes, const __grid
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int KC, int ATILES, int STAGES>
-int launch_cfg(cudaStream_t stream, dim3 grid, const uint8_t* query, int descBytes, const CUtensorMap& mt, const int64_t* qOff,
-               const int64_t* tOff, const int* tileStart, int nPairs, int splitRows, int64_t totalQ,
-               uint64_t* splitKeys) {
+int launch_cfg(cudaStream_t stream, dim3 grid, const uint8_t* query, int descBytes, const CUtensorMap& mt,
+               const TileDesc* tileDescs, int splitRows, int64_t totalQ, uint64_t* splitKeys) {
     constexpr int SMEM = STAGES * KC * CHUNK_BYTES + TcSmem::BAR_BYTES + 1024;
     auto kern = hamming_tc_kernel<KC, ATILES, STAGES>;
     MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    kern<<<grid, TC_THREADS, SMEM, stream>>>(query, descBytes, mt, qOff, tOff, tileStart, nPairs, splitRows, totalQ, splitKeys);
+    kern<<<grid, TC_THREADS, SMEM, stream>>>(query, descBytes, mt, tileDescs, splitRows, totalQ, splitKeys);
     MCV_LAUNCH_CHECK();
     return 0;
 }
@@ -474,32 +483,34 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
     if (a.hQOff[0] != 0 || a.hTOff[0] != 0) { set_error("offset arrays must start at 0"); return -1; }
     if (totalQ == 0) return 0;
 
-    // control arrays (same staging protocol as the integer-pipe engine)
-    const size_t n1 = (size_t)a.nPairs + 1;
-    const size_t ctlBytes = n1 * (8 + 8 + 4);
-    if (ctx->pin[0].reserve(ctlBytes) || ctx->ws[0].reserve(ctlBytes)) return -1;
-    MCV_CUDA_TRY(cudaEventSynchronize(ctx->ev[0]));
-    int64_t* hQ = ctx->pin[0].as<int64_t>();
-    int64_t* hT = hQ + n1;
-    int* hTile = reinterpret_cast<int*>(hT + n1);
+    // control array: one descriptor per query tile (a CTA finds its work with a single 32-byte load)
     int64_t tiles = 0, maxT = 0;
     for (int p = 0; p < a.nPairs; ++p) {
         const int64_t nq = a.hQOff[p + 1] - a.hQOff[p], nt = a.hTOff[p + 1] - a.hTOff[p];
         if (nq < 0 || nt < 0 || nt > 0x7FFFFFFFll) { set_error("bad offsets at pair %d", p); return -1; }
-        hQ[p] = a.hQOff[p]; hT[p] = a.hTOff[p]; hTile[p] = (int)tiles;
         tiles += (nq + QROWS - 1) / QROWS;
         maxT = std::max(maxT, nt);
     }
-    hQ[a.nPairs] = totalQ; hT[a.nPairs] = totalT; hTile[a.nPairs] = (int)tiles;
     if (tiles > 0x7FFFFFFFll || totalQ + 2 * QROWS > 0x7FFFFFFFll || totalT + 2 * TILE_N > 0x7FFFFFFFll) {
         set_error("batch too large for 32-bit TMA row coordinates");
         return -1;
     }
-    MCV_CUDA_TRY(cudaMemcpyAsync(ctx->ws[0].p, hQ, ctlBytes, cudaMemcpyHostToDevice, stream));
+    if (tiles == 0) return 0;
+    const size_t ctlBytes = (size_t)tiles * sizeof(TileDesc);
+    if (ctx->pin[0].reserve(ctlBytes) || ctx->ws[0].reserve(ctlBytes)) return -1;
+    MCV_CUDA_TRY(cudaEventSynchronize(ctx->ev[0]));
+    TileDesc* hTiles = ctx->pin[0].as<TileDesc>();
+    {
+        int64_t k = 0;
+        for (int p = 0; p < a.nPairs; ++p) {
+            const int64_t q0 = a.hQOff[p], q1 = a.hQOff[p + 1];
+            for (int64_t q = q0; q < q1; q += QROWS)
+                hTiles[k++] = TileDesc{q, q1, a.hTOff[p], (int)(a.hTOff[p + 1] - a.hTOff[p]), 0};
+        }
+    }
+    MCV_CUDA_TRY(cudaMemcpyAsync(ctx->ws[0].p, hTiles, ctlBytes, cudaMemcpyHostToDevice, stream));
     MCV_CUDA_TRY(cudaEventRecord(ctx->ev[0], stream));
-    const int64_t* dQOff = ctx->ws[0].as<int64_t>();
-    const int64_t* dTOff = dQOff + n1;
-    const int* dTile = reinterpret_cast<const int*>(dTOff + n1);
+    const TileDesc* dTiles = ctx->ws[0].as<TileDesc>();
 
     // expand the train bits -> int8 +-scale (the query rows are expanded inside the kernel, straight
     // into TMEM)
@@ -534,9 +545,9 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
 
     dim3 grid((unsigned)tiles, (unsigned)nSplits);
     int rc;
-    if (KC == 1) rc = launch_cfg<1, 2, 8>(stream, grid, a.dQuery, a.descBytes, mt, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dSplitKeys);
-    else if (KC == 2) rc = launch_cfg<2, 2, 6>(stream, grid, a.dQuery, a.descBytes, mt, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dSplitKeys);
-    else rc = launch_cfg<4, 1, 3>(stream, grid, a.dQuery, a.descBytes, mt, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dSplitKeys);
+    if (KC == 1) rc = launch_cfg<1, 2, 8>(stream, grid, a.dQuery, a.descBytes, mt, dTiles, (int)splitRows, totalQ, dSplitKeys);
+    else if (KC == 2) rc = launch_cfg<2, 2, 6>(stream, grid, a.dQuery, a.descBytes, mt, dTiles, (int)splitRows, totalQ, dSplitKeys);
+    else rc = launch_cfg<4, 1, 3>(stream, grid, a.dQuery, a.descBytes, mt, dTiles, (int)splitRows, totalQ, dSplitKeys);
     if (rc) return rc;
     return launch_knn2_finalize(stream, dSplitKeys, nSlots, totalQ, a);
 }
