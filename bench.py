@@ -547,7 +547,8 @@ def run_ours(args):
     lib = native.load()
     if lib.mcvDeviceCount() < 1:
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback): " + native.last_error())
-    numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     engine = {"auto": 0, "popc": 1, "tensor": 2, "packed": 3}[args.engine]
     mcv.set_hamming_engine(engine)
     use_tc = engine >= 2 or (engine == 0 and args.pairs * NQ * NT >= 64 * 1024 * 1024)
@@ -589,6 +590,8 @@ def run_ours(args):
         step_device()
     barrier()
     launches0 = lib.mcvKernelLaunchCount()
+    # CUDA events around the dominant kernel alone, recorded by the library on the launching stream
+    lib.mcvKernelTimingStart(local, args.steps + 1)
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -601,6 +604,9 @@ def run_ours(args):
     sampler.mark_end()
     launches = lib.mcvKernelLaunchCount() - launches0
     ms_total = e0.elapsed_time(e1)
+    kbuf = np.zeros(args.steps + 1, dtype=np.float32)
+    nk = lib.mcvKernelTimingStop(local, kbuf.ctypes.data, len(kbuf))
+    kern_ms = float(kbuf[:nk].mean()) if nk > 0 else None
     clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -654,23 +660,34 @@ def run_ours(args):
     int_pipe = {"achieved_gdist_s": gdist / world, "peak_gdist_s": pipe_peak, "frac": gdist / world / pipe_peak,
                 "model": f"{sms} SMs x 16 POPC/clk/SM x {sm_mhz:.0f} MHz / {popc_per_dist} POPC per distance"}
     if use_tc:
-        # tcgen05 int8 GEMM: 2*Q*T*K operations per pair; B200 runs int8 at twice the bf16 rate,
-        # so the denominator is 2 x the measured dense bf16 peak (MEASURED_PEAKS.json, burst figure)
+        # tcgen05 int8 GEMM: 2*Q*T*K operations per pair and launch, over the duration of the GEMM + top-2
+        # kernel alone (library-recorded CUDA events on the launching stream).  Denominator: the int8 rate
+        # of tcgen05.mma.kind::i8 measured on this pool's B200 by tools/mma_bench.cu (8185 MAC/clk/SM at the
+        # 1965 MHz this kernel runs at: profiles/r01_mma_bench.txt).  MEASURED_PEAKS.json carries no int8
+        # figure; its cuBLAS bf16 number (power-capped to ~1.3 GHz) x2 is quoted beside it.
         bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+        int8_peak = 2.0 * 8185.0 * sms * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
         ops = 2.0 * P * NQ * NT * (DESC_BYTES * 8)
-        ach = ops / kern_s / 1e12
+        k_s = (kern_ms if kern_ms else ms_step) / 1e3
+        ach = ops / k_s / 1e12
         traffic = None
         tj = ROOT / "profiles" / "r01_tc_traffic.json"
         if tj.exists() and P == 1024:
             traffic = json.loads(tj.read_text()).get("traffic_bytes_per_launch")
         roofline = {
-            "bound": "tensor", "achieved": ach, "peak": 2 * bf16_peak, "unit": "TFLOP/s", "frac": ach / (2 * bf16_peak),
-            "traffic": traffic, "peak_source": ("measured" if "bf16_tflops" in peaks else "fallback") + " bf16 x2 (int8 rate)",
-            "kernel": "hamming_tc_kernel<2,2,4> (tcgen05.mma.kind::i8 + top-2 epilogue)",
-            "note": "achieved = 2*Q*T*K int8 operations of one step / step time (bit-expansion + GEMM/top-2 + "
-                    "finalize kernels; the GEMM kernel is 93 % of it, profiles/r01_hamming_tc_ncu.md); the kernel "
-                    "is bound by TMEM accumulator read-out (~64 B/clk/SM), at ~97 % of that rate; traffic = DRAM "
-                    "bytes of the dominant kernel from the ncu capture of this same command",
+            "bound": "tensor", "achieved": ach, "peak": int8_peak, "unit": "TFLOP/s", "frac": ach / int8_peak,
+            "traffic": traffic,
+            "peak_source": "measured int8 tcgen05.mma issue rate, tools/mma_bench.cu (8185 MAC/clk/SM x SMs x sm_max_mhz)",
+            "kernel": "hamming_tc_kernel<2,2,6> (tcgen05.mma.kind::i8, A in TMEM + packed 16-bit top-2 epilogue)",
+            "kernel_ms": kern_ms, "kernel_share_of_step": (kern_ms / ms_step) if kern_ms else None,
+            "whole_step": {"achieved": ops / kern_s / 1e12, "frac": ops / kern_s / 1e12 / int8_peak},
+            "vs_2x_measured_bf16": ach / (2 * bf16_peak),
+            "note": "achieved = 2*Q*T*K int8 operations of one launch / mean duration of that launch (CUDA events "
+                    "recorded by the library around hamming_tc_kernel on the launching stream, inside the timed "
+                    "region); whole_step divides by the step time instead (train-bit expansion + this kernel + "
+                    "finalize); the kernel's steady state sits at the MMA issue floor (1024 clk per 128x256x256 "
+                    "stage), the rest is per-CTA fill/drain; traffic = DRAM bytes of this kernel from the ncu "
+                    "capture of this same command",
             "hbm": {"achieved_gbs": alg_bytes / kern_s / 1e9, "peak_gbs": hbm_peak},
             "vs_int_pipe_roof": gdist / world / pipe_peak,
         }
@@ -678,13 +695,14 @@ def run_ours(args):
         roofline = {
             "bound": "hbm", "achieved": alg_bytes / kern_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": alg_bytes / kern_s / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
-            "kernel": "hamming_knn2_kernel<8>",
+            "kernel": "hamming_knn2_kernel<8>", "kernel_ms": kern_ms,
             "note": "not HBM-bound by construction (~100 distances per byte moved); the binding roof is "
                     "the integer POPC pipe, reported in int_pipe",
             "int_pipe": int_pipe,
         }
 
     cpu = None
+    os.sched_setaffinity(0, all_cpus)      # the CPU baseline and the extras' CPU arms may use every core
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sample = max(1, min(args.cpu_sample_pairs, P))

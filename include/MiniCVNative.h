@@ -99,6 +99,13 @@ MCV_API const char* mcvLastError(void);
 MCV_API int mcvDeviceCount(void);
 /* Kernels launched by this library since load (all threads); used by bench.py. */
 MCV_API int64_t mcvKernelLaunchCount(void);
+/* CUDA-event timing of the dominant matcher kernel (the tcgen05 GEMM + top-2 kernel, or the
+ * XOR/POPC kernel) of every subsequent matcher launch of the calling thread on `device`: events
+ * are recorded on the launching stream around that kernel only.  Start allocates `capacity`
+ * event pairs; Stop synchronises, writes up to `capacity` durations in milliseconds (launch
+ * order) and returns how many.  Used by bench.py for the roofline figure. */
+MCV_API int mcvKernelTimingStart(int device, int capacity);
+MCV_API int mcvKernelTimingStop(int device, float* ms, int capacity);
 /* Hamming matcher engine: 0 = auto (default), 1 = integer pipe (XOR + POPC), 2 = tcgen05
  * tensor cores.  Both engines are bit-identical in their results; returns 0, or -1 if bad. */
 MCV_API int mcvSetHammingEngine(int engine);

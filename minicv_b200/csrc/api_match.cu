@@ -87,11 +87,9 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
     MCV_CUDA_TRY(cudaMemsetAsync(dCount, 0, sizeof(int), sK));
 
     // chunk the pair list so that copy-in, compute and copy-out overlap on three streams
-    const size_t chunkTarget = 48u << 20;
-    std::vector<int64_t> qo, to;
-    int p0 = 0;
-    int chunkNo = 0;
-    while (p0 < nPairs) {
+    const size_t chunkTarget = 32u << 20;
+    std::vector<int> bounds(1, 0);
+    for (int p0 = 0; p0 < nPairs;) {
         int p1 = p0;
         size_t bytes = 0;
         while (p1 < nPairs && (p1 == p0 || bytes < chunkTarget)) {
@@ -99,17 +97,27 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
                               trainOffsets[p1]) * rb;
             ++p1;
         }
+        bounds.push_back(p1);
+        p0 = p1;
+    }
+    const int nChunks = (int)bounds.size() - 1;
+    cudaEvent_t* ev = event_pool(ctx, 2 * nChunks);
+    if (!ev) { set_error("cvMatchKnn2Batch: cudaEventCreate failed"); return -1; }
+    std::vector<int64_t> qo, to;
+    for (int c = 0; c < nChunks; ++c) {
+        const int p0 = bounds[c], p1 = bounds[c + 1];
         const int64_t q0 = queryOffsets[p0], q1 = queryOffsets[p1];
         const int64_t t0 = trainOffsets[p0], t1 = trainOffsets[p1];
-        const int e = chunkNo & 1;
+        // copy-in of chunk c, then its (small) control copy right behind it: the copy engine serves
+        // its queue in submission order, so control copies must not sit behind later bulk copies
         if (q1 > q0)
             MCV_CUDA_TRY(cudaMemcpyAsync(dQ + q0 * rb, query + q0 * rb, (size_t)(q1 - q0) * rb,
                                          cudaMemcpyHostToDevice, sIn));
         if (t1 > t0)
             MCV_CUDA_TRY(cudaMemcpyAsync(dT + t0 * rb, train + t0 * rb, (size_t)(t1 - t0) * rb,
                                          cudaMemcpyHostToDevice, sIn));
-        MCV_CUDA_TRY(cudaEventRecord(ctx->ev[2 + e], sIn));
-        MCV_CUDA_TRY(cudaStreamWaitEvent(sK, ctx->ev[2 + e], 0));
+        MCV_CUDA_TRY(cudaEventRecord(ev[2 * c], sIn));
+        MCV_CUDA_TRY(cudaStreamWaitEvent(sK, ev[2 * c], 0));
         if (q1 > q0) {
             qo.resize(p1 - p0 + 1);
             to.resize(p1 - p0 + 1);
@@ -121,8 +129,8 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
             a.dTrainIdx = dIdx + 2 * q0; a.dDist = dDist + 2 * q0; a.dRatioPass = dPass + q0;
             a.dPassCount = dCount;
             if (dispatch(ctx, sK, normType, a)) return -1;
-            MCV_CUDA_TRY(cudaEventRecord(ctx->ev[4 + e], sK));
-            MCV_CUDA_TRY(cudaStreamWaitEvent(sOut, ctx->ev[4 + e], 0));
+            MCV_CUDA_TRY(cudaEventRecord(ev[2 * c + 1], sK));
+            MCV_CUDA_TRY(cudaStreamWaitEvent(sOut, ev[2 * c + 1], 0));
             MCV_CUDA_TRY(cudaMemcpyAsync(trainIdx + 2 * q0, dIdx + 2 * q0, (size_t)(q1 - q0) * 8,
                                          cudaMemcpyDeviceToHost, sOut));
             MCV_CUDA_TRY(cudaMemcpyAsync(dist + 2 * q0, dDist + 2 * q0, (size_t)(q1 - q0) * 8,
@@ -131,8 +139,6 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
                 MCV_CUDA_TRY(cudaMemcpyAsync(ratioPass + q0, dPass + q0, (size_t)(q1 - q0),
                                              cudaMemcpyDeviceToHost, sOut));
         }
-        p0 = p1;
-        ++chunkNo;
     }
     int count = 0;
     MCV_CUDA_TRY(cudaMemcpyAsync(&count, dCount, sizeof(int), cudaMemcpyDeviceToHost, sK));

@@ -72,7 +72,36 @@ struct Context {
     cudaEvent_t  ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf       ws[48];                 // numbered workspaces, meaning fixed per call site
     PinBuf       pin[4];
+    // tensor-core matcher control arrays, double-buffered so that the host can prepare launch k+1
+    // while the copy of launch k is still queued behind launch k-1
+    PinBuf       ctlPin[2];
+    DevBuf       ctlWs[2];
+    cudaEvent_t  ctlEv[2] = {nullptr, nullptr};
+    int          ctlTurn = 0;
+    // growable pool of (timing-disabled) events for the chunked host-buffer entry points
+    cudaEvent_t* evPool = nullptr;
+    int          evPoolSize = 0;
+    // optional CUDA-event timing of the dominant matcher kernel (mcvKernelTimingStart / Stop)
+    bool         kt_on = false;
+    int          kt_n = 0, kt_cap = 0;
+    cudaEvent_t* kt_ev = nullptr;        // 2 * kt_cap events
 };
+// n events from the pool (grown on demand); nullptr on failure
+inline cudaEvent_t* event_pool(Context* c, int n) {
+    if (n > c->evPoolSize) {
+        cudaEvent_t* ev = new cudaEvent_t[n];
+        for (int i = 0; i < c->evPoolSize; ++i) ev[i] = c->evPool[i];
+        for (int i = c->evPoolSize; i < n; ++i)
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { delete[] ev; return nullptr; }
+        delete[] c->evPool;
+        c->evPool = ev;
+        c->evPoolSize = n;
+    }
+    return c->evPool;
+}
+// Bracket the dominant kernel of a matcher call on its launching stream (no-ops unless enabled).
+inline void kt_begin(Context* c, cudaStream_t s) { if (c->kt_on && c->kt_n < c->kt_cap) cudaEventRecord(c->kt_ev[2 * c->kt_n], s); }
+inline void kt_end(Context* c, cudaStream_t s) { if (c->kt_on && c->kt_n < c->kt_cap) { cudaEventRecord(c->kt_ev[2 * c->kt_n + 1], s); ++c->kt_n; } }
 
 // Returns the calling thread's context for `device` (-1: cudaGetDevice()), creating it on
 // first use; nullptr (and an error string) when no CUDA device is usable -- there is no

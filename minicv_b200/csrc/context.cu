@@ -97,6 +97,7 @@ Context* get_context(int device) {
         return nullptr;
     }
     for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->ctlEv[i], cudaEventDisableTiming);
     Context* raw = c.get();
     t_ctx.by_device[device] = std::move(c);
     return raw;
@@ -115,6 +116,40 @@ MCV_API int mcvDeviceCount(void) {
 }
 
 MCV_API int64_t mcvKernelLaunchCount(void) { return mcv::g_launches.load(); }
+
+MCV_API int mcvKernelTimingStart(int device, int capacity) {
+    mcv::clear_error();
+    mcv::Context* c = mcv::get_context(device);
+    if (!c || capacity <= 0) return -1;
+    if (capacity > c->kt_cap) {
+        cudaEvent_t* ev = new cudaEvent_t[2 * (size_t)capacity];
+        for (int i = 0; i < 2 * capacity; ++i) cudaEventCreate(&ev[i]);
+        for (int i = 0; i < 2 * c->kt_cap; ++i) cudaEventDestroy(c->kt_ev[i]);
+        delete[] c->kt_ev;
+        c->kt_ev = ev;
+        c->kt_cap = capacity;
+    }
+    c->kt_n = 0;
+    c->kt_on = true;
+    return 0;
+}
+
+MCV_API int mcvKernelTimingStop(int device, float* ms, int capacity) {
+    mcv::clear_error();
+    mcv::Context* c = mcv::get_context(device);
+    if (!c) return -1;
+    c->kt_on = false;
+    int n = 0;
+    for (; n < c->kt_n && n < capacity; ++n) {
+        if (cudaEventSynchronize(c->kt_ev[2 * n + 1]) != cudaSuccess ||
+            cudaEventElapsedTime(&ms[n], c->kt_ev[2 * n], c->kt_ev[2 * n + 1]) != cudaSuccess) {
+            cudaGetLastError();
+            break;
+        }
+    }
+    c->kt_n = 0;
+    return n;
+}
 
 MCV_API int mcvSetHammingEngine(int engine) {
     if (engine < 0 || engine > 3) return -1;

@@ -377,6 +377,7 @@ int launch_hamming_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     rc = launch_kernel_w<WW>(stream, grid, q4, t4, dQOff, dTOff, dTile, a.nPairs,             \
                              (int)splitRows, nSplits, totalQ, a.ratio, a.dTrainIdx, a.dDist,  \
                              a.dRatioPass, a.dPassCount, dSplitKeys)
+    kt_begin(ctx, stream);
     switch (W) {
         case 4: MCV_W(4); break;
         case 8: MCV_W(8); break;
@@ -384,6 +385,7 @@ int launch_hamming_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
         default: MCV_W(32); break;
     }
 #undef MCV_W
+    kt_end(ctx, stream);
     if (rc) return rc;
     if (twoStage) return launch_knn2_finalize(stream, dSplitKeys, nSplits, totalQ, a);
     return 0;

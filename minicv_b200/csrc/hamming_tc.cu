@@ -103,6 +103,23 @@ struct alignas(16) TileDesc {   // work item of one CTA column: QROWS query rows
     int32_t tCount;             // train rows of the pair
     int32_t pad;
 };
+struct alignas(16) PairDesc {   // host-built, one per pair (pinned, read by build_tiles_kernel over PCIe)
+    int64_t q0, q1;             // query row range
+    int64_t t0;                 // first train row
+    int32_t tCount;             // train rows
+    int32_t tile0;              // first tile index of the pair
+};
+
+// one block per pair: writes the pair's tile descriptors into HBM
+__global__ void __launch_bounds__(128)
+build_tiles_kernel(const PairDesc* __restrict__ hostPairs, int qRows, TileDesc* __restrict__ tiles) {
+    __shared__ PairDesc pd;
+    if (threadIdx.x < 2) reinterpret_cast<uint4*>(&pd)[threadIdx.x] = reinterpret_cast<const uint4*>(hostPairs + blockIdx.x)[threadIdx.x];
+    __syncthreads();
+    const int n = (int)((pd.q1 - pd.q0 + qRows - 1) / qRows);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        tiles[pd.tile0 + i] = TileDesc{pd.q0 + (int64_t)i * qRows, pd.q1, pd.t0, pd.tCount, 0};
+}
 
 struct TcSmem {      // carved from dynamic shared memory (1024-byte aligned)
     static constexpr int BAR_BYTES = 256;
@@ -447,12 +464,14 @@ hamming_tc_kernel(const uint8_t* __restrict__ query, int descBytes, const __grid
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int KC, int ATILES, int STAGES>
-int launch_cfg(cudaStream_t stream, dim3 grid, const uint8_t* query, int descBytes, const CUtensorMap& mt,
+int launch_cfg(Context* ctx, cudaStream_t stream, dim3 grid, const uint8_t* query, int descBytes, const CUtensorMap& mt,
                const TileDesc* tileDescs, int splitRows, int64_t totalQ, uint64_t* splitKeys) {
     constexpr int SMEM = STAGES * KC * CHUNK_BYTES + TcSmem::BAR_BYTES + 1024;
     auto kern = hamming_tc_kernel<KC, ATILES, STAGES>;
     MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    kt_begin(ctx, stream);
     kern<<<grid, TC_THREADS, SMEM, stream>>>(query, descBytes, mt, tileDescs, splitRows, totalQ, splitKeys);
+    kt_end(ctx, stream);
     MCV_LAUNCH_CHECK();
     return 0;
 }
@@ -471,7 +490,7 @@ extern "C" __attribute__((visibility("default"))) void mcvDebugTcProf(unsigned l
 bool hamming_tc_supported(int descBytes) { return descBytes >= 1 && descBytes <= 64; }
 
 // Tensor-core engine.  Same contract as launch_hamming_knn2 (knn.cuh); uses ctx workspaces
-// 0 (control), 3 (split keys), 25 (expanded train rows).
+// 3 (split keys), 25 (expanded train rows) and the double-buffered control arrays.
 int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     if (a.nPairs <= 0) return 0;
     if (!hamming_tc_supported(a.descBytes)) { set_error("tensor-core matcher supports 1..64-byte descriptors"); return -1; }
@@ -496,21 +515,26 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
         return -1;
     }
     if (tiles == 0) return 0;
-    const size_t ctlBytes = (size_t)tiles * sizeof(TileDesc);
-    if (ctx->pin[0].reserve(ctlBytes) || ctx->ws[0].reserve(ctlBytes)) return -1;
-    MCV_CUDA_TRY(cudaEventSynchronize(ctx->ev[0]));
-    TileDesc* hTiles = ctx->pin[0].as<TileDesc>();
+    // per-pair control rows (q0, q1, t0, nT, first tile) go through a pinned buffer; a small kernel
+    // reads them over PCIe and writes one TileDesc per query tile.  Not cudaMemcpyAsync: a small copy
+    // queued on the compute stream would sit in the copy engine's in-order queue and hold back the
+    // bulk descriptor copies of the following chunks (cvMatchKnn2Batch) until this stream catches up.
+    const size_t pairBytes = (size_t)a.nPairs * sizeof(PairDesc);
+    const int turn = ctx->ctlTurn ^= 1;
+    if (ctx->ctlPin[turn].reserve(pairBytes) || ctx->ctlWs[turn].reserve((size_t)tiles * sizeof(TileDesc))) return -1;
+    MCV_CUDA_TRY(cudaEventSynchronize(ctx->ctlEv[turn]));     // the pinned buffer's use two launches ago
+    PairDesc* hPairs = ctx->ctlPin[turn].as<PairDesc>();
     {
         int64_t k = 0;
         for (int p = 0; p < a.nPairs; ++p) {
-            const int64_t q0 = a.hQOff[p], q1 = a.hQOff[p + 1];
-            for (int64_t q = q0; q < q1; q += QROWS)
-                hTiles[k++] = TileDesc{q, q1, a.hTOff[p], (int)(a.hTOff[p + 1] - a.hTOff[p]), 0};
+            hPairs[p] = PairDesc{a.hQOff[p], a.hQOff[p + 1], a.hTOff[p], (int)(a.hTOff[p + 1] - a.hTOff[p]), (int)k};
+            k += (a.hQOff[p + 1] - a.hQOff[p] + QROWS - 1) / QROWS;
         }
     }
-    MCV_CUDA_TRY(cudaMemcpyAsync(ctx->ws[0].p, hTiles, ctlBytes, cudaMemcpyHostToDevice, stream));
-    MCV_CUDA_TRY(cudaEventRecord(ctx->ev[0], stream));
-    const TileDesc* dTiles = ctx->ws[0].as<TileDesc>();
+    build_tiles_kernel<<<a.nPairs, 128, 0, stream>>>(hPairs, QROWS, ctx->ctlWs[turn].as<TileDesc>());
+    MCV_LAUNCH_CHECK();
+    MCV_CUDA_TRY(cudaEventRecord(ctx->ctlEv[turn], stream));
+    const TileDesc* dTiles = ctx->ctlWs[turn].as<TileDesc>();
 
     // expand the train bits -> int8 +-scale (the query rows are expanded inside the kernel, straight
     // into TMEM)
@@ -545,9 +569,9 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
 
     dim3 grid((unsigned)tiles, (unsigned)nSplits);
     int rc;
-    if (KC == 1) rc = launch_cfg<1, 2, 8>(stream, grid, a.dQuery, a.descBytes, mt, dTiles, (int)splitRows, totalQ, dSplitKeys);
-    else if (KC == 2) rc = launch_cfg<2, 2, 6>(stream, grid, a.dQuery, a.descBytes, mt, dTiles, (int)splitRows, totalQ, dSplitKeys);
-    else rc = launch_cfg<4, 1, 3>(stream, grid, a.dQuery, a.descBytes, mt, dTiles, (int)splitRows, totalQ, dSplitKeys);
+    if (KC == 1) rc = launch_cfg<1, 2, 8>(ctx, stream, grid, a.dQuery, a.descBytes, mt, dTiles, (int)splitRows, totalQ, dSplitKeys);
+    else if (KC == 2) rc = launch_cfg<2, 2, 6>(ctx, stream, grid, a.dQuery, a.descBytes, mt, dTiles, (int)splitRows, totalQ, dSplitKeys);
+    else rc = launch_cfg<4, 1, 3>(ctx, stream, grid, a.dQuery, a.descBytes, mt, dTiles, (int)splitRows, totalQ, dSplitKeys);
     if (rc) return rc;
     return launch_knn2_finalize(stream, dSplitKeys, nSlots, totalQ, a);
 }

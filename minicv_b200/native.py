@@ -68,6 +68,8 @@ SIGNATURES = {
     "mcvKernelLaunchCount": (_i64, []),
     "mcvBuildInfo": (C.c_char_p, []),
     "mcvSetHammingEngine": (_i, [_i]),
+    "mcvKernelTimingStart": (_i, [_i, _i]),
+    "mcvKernelTimingStop": (_i, [_i, _vp, _i]),
     "cvMatchKnn2": (_i, [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "cvMatchKnn2Batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i]),
     "cvMatchKnn2BatchDevice": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp]),
