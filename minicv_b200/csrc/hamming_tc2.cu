@@ -1,8 +1,9 @@
 // hamming_tc2.cu -- tensor-core Hamming kNN, packed-accumulator variant ("two distances per
 // TMEM word").
 //
-// hamming_tc.cu is bound by TMEM read-out: tcgen05.ld delivers ~16 accumulators/clk/SM while the
-// tensor pipe produces 32/clk/SM at K = 256.  This variant halves the read-out per distance.
+// Built when the first int8 engine was believed to be bound by TMEM read-out; this variant halves the
+// read-out per distance.  tools/tmem_bench.cu later measured tcgen05.ld at 1-4 KB/clk/SM -- the real limit
+// was the ALU pipe in the epilogue, which hamming_tc.cu now addresses with packed 16-bit keys.
 // Operands are FP8: queries e4m3 +-1, train rows e5m2, where the rows of the FIRST half of a
 // split carry +-1 ("lo" stream) and the rows of the SECOND half carry +-1024 ("hi" stream).
 // Two chained MMAs (kind::f8f6f4, fp32 accumulate) put both dot products into ONE accumulator:
