@@ -128,7 +128,7 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ C
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(a_full, A_BYTES);
             for (int kc = 0; kc < L2_CHUNKS; ++kc)
                 tma_load_2d(sA + kc * CHUNK_BYTES, &mapQ, kc * 128, (int)qTile0, a_full);
@@ -141,37 +141,42 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ C
                     tma_load_2d(sB + s * B_BYTES + kc * CHUNK_BYTES, &mapT, kc * 128, (int)r, b_full + s);
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        // D = f32, A = B = bf16, K-major, N = 128, M = 128
+        // D = f32, A = B = bf16, K-major, N = 128, M = 128.  One elected lane issues (uniform datapath,
+        // MMAs back to back); the waits of stage j+1 are taken before the last two MMAs of stage j
+        // because the tensor pipe queues only ~2-3 MMAs (tools/mma_bench.cu).
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-        if (lane == 0) {
+        if (elect_one() && nStagesTotal > 0) {
             mbar_wait(a_full, 0);
+            mbar_wait(b_full, 0);
+            tc_fence_after();
+            const uint32_t aBase = smem_u32(sA);
             for (int j = 0; j < nStagesTotal; ++j) {
                 const int s = j % STAGES;
                 const int as = j & 1;
-                mbar_wait(b_full + s, (j / STAGES) & 1);
-                mbar_wait(acc_empty + as, ((j >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB + s * B_BYTES);
+                const uint32_t bBase = smem_u32(sB + s * B_BYTES);
                 const uint32_t dcol = tmem_base + (uint32_t)(as * TILE_N);
                 // (A part, B part): hi.hi, hi.lo, lo.hi  -- part p occupies chunks 2p, 2p+1
-                const int pa[3] = {0, 0, 1}, pb[3] = {0, 1, 0};
-                bool first = true;
 #pragma unroll
-                for (int t = 0; t < 3; ++t)
-#pragma unroll
-                    for (int kc = 0; kc < 2; ++kc)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t da = umma_desc_sw128(aBase + (pa[t] * 2 + kc) * CHUNK_BYTES + k * 32);
-                            const uint64_t db = umma_desc_sw128(bBase + (pb[t] * 2 + kc) * CHUNK_BYTES + k * 32);
-                            tc_mma_f16(dcol, da, db, idesc, first ? 0u : 1u);
-                            first = false;
-                        }
+                for (int i = 0; i < 24; ++i) {
+                    const int t = i >> 3, kc = (i >> 2) & 1, k = i & 3;
+                    const int pa = t == 2 ? 1 : 0, pb = t == 1 ? 1 : 0;
+                    if (i == 22 && j + 1 < nStagesTotal) {
+                        const int jn = j + 1;
+                        mbar_wait(b_full + jn % STAGES, (jn / STAGES) & 1);
+                        mbar_wait(acc_empty + (jn & 1), ((jn >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                    }
+                    const uint64_t da = umma_desc_sw128(aBase + (pa * 2 + kc) * CHUNK_BYTES + k * 32);
+                    const uint64_t db = umma_desc_sw128(bBase + (pb * 2 + kc) * CHUNK_BYTES + k * 32);
+                    tc_mma_f16(dcol, da, db, idesc, i ? 1u : 0u);
+                }
                 tc_commit(b_empty + s);
                 tc_commit(acc_full + as);
             }
         }
+        __syncwarp();
     } else {
         // epilogue warps 2..9: quarter = warp % 4, column half = (warp - 2) / 4 (two 32-column chunks)
         const int quarter = warp & 3;
@@ -252,38 +257,84 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ C
     }
 }
 
-// exact re-scoring: the oracle's arithmetic on every candidate, best two by (distance, index)
+// exact re-scoring: the oracle's arithmetic (sequential fp32 sum over the dimensions) on every candidate.
+// One thread per (query, slot): its four candidates run as four independent dependency chains over
+// 128-bit loads; adjacent threads share the query row (broadcast loads).  Emits the slot's best two as
+// packed keys (float bits << 32) | index.
 __global__ void __launch_bounds__(128)
 l2_rescore_kernel(const float* __restrict__ query, const float* __restrict__ train,
                   const int64_t* __restrict__ qOff, const int64_t* __restrict__ tOff, int nPairs, int dim,
-                  const int4* __restrict__ cands, int nSlots, int64_t totalQ, float ratio,
-                  int* __restrict__ trainIdx, float* __restrict__ dist, uint8_t* __restrict__ ratioPass,
-                  int* __restrict__ passCount) {
+                  const int4* __restrict__ cands, int nSlots, int64_t totalQ, uint64_t* __restrict__ slotKeys) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= totalQ * nSlots) return;
+    const int64_t q = idx / nSlots;
+    const int s = (int)(idx - q * nSlots);
+    int lo = 0, hi = nPairs;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (qOff[mid] <= q) lo = mid; else hi = mid;
+    }
+    const int64_t tRow0 = tOff[lo];
+    const int4 c = cands[(int64_t)s * totalQ + q];
+    const int id[4] = {c.x, c.y, c.z, c.w};
+    const float* a = query + q * dim;
+    const float* b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b[k] = id[k] < 0 ? a : train + (tRow0 + id[k]) * dim;   // empty slot: any valid row
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(query) | reinterpret_cast<uintptr_t>(train)) & 15) == 0;   // rows are 16-byte aligned
+    if (vec) {
+        for (int d = 0; d < dim; d += 4) {
+            const float4 av = __ldg(reinterpret_cast<const float4*>(a + d));
+            float4 bv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bv[k] = __ldg(reinterpret_cast<const float4*>(b[k] + d));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float df = __fsub_rn(av.x, bv[k].x); acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
+                df = __fsub_rn(av.y, bv[k].y); acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
+                df = __fsub_rn(av.z, bv[k].z); acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
+                df = __fsub_rn(av.w, bv[k].w); acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
+            }
+        }
+    } else {
+        for (int d = 0; d < dim; ++d) {
+            const float av = a[d];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float df = __fsub_rn(av, b[k][d]);
+                acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
+            }
+        }
+    }
+    uint64_t m1 = ~0ull, m2 = ~0ull;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (id[k] < 0) continue;
+        const uint64_t key = ((uint64_t)__float_as_uint(__fsqrt_rn(acc[k])) << 32) | (uint32_t)id[k];
+        const uint64_t hi2 = m1 > key ? m1 : key;
+        m1 = m1 < key ? m1 : key;
+        m2 = m2 < hi2 ? m2 : hi2;
+    }
+    reinterpret_cast<ulonglong2*>(slotKeys + idx * 2)[0] = make_ulonglong2(m1, m2);
+}
+
+// best two over a query's slots by (distance, index), ratio test in fp32
+__global__ void __launch_bounds__(256)
+l2_merge_kernel(const uint64_t* __restrict__ slotKeys, int nSlots, int64_t totalQ, float ratio,
+                int* __restrict__ trainIdx, float* __restrict__ dist, uint8_t* __restrict__ ratioPass,
+                int* __restrict__ passCount) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool pass = false;
     if (q < totalQ) {
-        int lo = 0, hi = nPairs;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (qOff[mid] <= q) lo = mid; else hi = mid;
-        }
-        const int64_t tRow0 = tOff[lo];
-        const float* a = query + q * dim;
         uint64_t m1 = ~0ull, m2 = ~0ull;
         for (int s = 0; s < nSlots; ++s) {
-            const int4 c = cands[(int64_t)s * totalQ + q];
-            const int id[4] = {c.x, c.y, c.z, c.w};
-            for (int k = 0; k < 4; ++k) {
-                if (id[k] < 0) continue;
-                const float* bb = train + (tRow0 + id[k]) * dim;
-                float acc = 0.f;
-                for (int d = 0; d < dim; ++d) {
-                    const float df = __fsub_rn(a[d], bb[d]);
-                    acc = __fadd_rn(acc, __fmul_rn(df, df));
-                }
-                const uint64_t key = ((uint64_t)__float_as_uint(__fsqrt_rn(acc)) << 32) | (uint32_t)id[k];
-                const uint64_t hi2 = m1 > key ? m1 : key;
-                m1 = m1 < key ? m1 : key;
+            const ulonglong2 k = reinterpret_cast<const ulonglong2*>(slotKeys + (q * nSlots + s) * 2)[0];
+            const uint64_t keys[2] = {k.x, k.y};
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const uint64_t hi2 = m1 > keys[i] ? m1 : keys[i];
+                m1 = m1 < keys[i] ? m1 : keys[i];
                 m2 = m2 < hi2 ? m2 : hi2;
             }
         }
@@ -306,7 +357,7 @@ l2_rescore_kernel(const float* __restrict__ query, const float* __restrict__ tra
 
 bool l2_tc_supported(int descBytes) { return descBytes >= 4 && descBytes <= 512 && descBytes % 4 == 0; }
 
-// uses ctx workspaces 0 (control), 3 (candidates), 24 / 25 (bf16 rows), 26 (train norms)
+// uses ctx workspaces 0 (control), 3 (candidates), 24 / 25 (bf16 rows), 26 (train norms), 27 (slot keys)
 int launch_l2_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     if (a.nPairs <= 0) return 0;
     const int dim = a.descBytes / 4;
@@ -376,9 +427,14 @@ int launch_l2_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     dim3 grid((unsigned)tiles, (unsigned)nSplits);
     kern<<<grid, L2_THREADS, SMEM, stream>>>(mq, mt, dNorms, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dCands);
     MCV_LAUNCH_CHECK();
-    l2_rescore_kernel<<<(unsigned)((totalQ + 127) / 128), 128, 0, stream>>>(
+    if (ctx->ws[27].reserve((size_t)nSlots * totalQ * 16)) return -1;
+    uint64_t* dSlotKeys = ctx->ws[27].as<uint64_t>();
+    l2_rescore_kernel<<<(unsigned)((totalQ * nSlots + 127) / 128), 128, 0, stream>>>(
         reinterpret_cast<const float*>(a.dQuery), reinterpret_cast<const float*>(a.dTrain), dQOff, dTOff, a.nPairs,
-        dim, dCands, nSlots, totalQ, a.ratio, a.dTrainIdx, a.dDist, a.dRatioPass, a.dPassCount);
+        dim, dCands, nSlots, totalQ, dSlotKeys);
+    MCV_LAUNCH_CHECK();
+    l2_merge_kernel<<<(unsigned)((totalQ + 255) / 256), 256, 0, stream>>>(
+        dSlotKeys, nSlots, totalQ, a.ratio, a.dTrainIdx, a.dDist, a.dRatioPass, a.dPassCount);
     MCV_LAUNCH_CHECK();
     return 0;
 }
