@@ -81,6 +81,7 @@ struct Context {
     // growable pool of (timing-disabled) events for the chunked host-buffer entry points
     cudaEvent_t* evPool = nullptr;
     int          evPoolSize = 0;
+    bool         mwc_ready = false;      // ws[28] holds OpenCV's raw RNG stream (ransac.cu)
     // optional CUDA-event timing of the dominant matcher kernel (mcvKernelTimingStart / Stop)
     bool         kt_on = false;
     int          kt_n = 0, kt_cap = 0;

@@ -97,10 +97,11 @@ template <int MODEL>
 __global__ void __launch_bounds__(32)
 sample_mwc_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off, int nPairs,
                   int maxIters, int smemPoints, int* __restrict__ samples, int* __restrict__ nIter,
-                  int* __restrict__ flags) {
+                  int* __restrict__ flags, const uint8_t* __restrict__ needSeq) {
     constexpr int MP = MT<MODEL>::MP;
     extern __shared__ float4 sPts[];
     const int p = blockIdx.x;
+    if (needSeq && !needSeq[p]) return;      // the parallel sampler already did this pair
     const int64_t base = off[p];
     const int n = (int)(off[p + 1] - base);
     const bool staged = MODEL != RM_ESSENTIAL && n <= smemPoints;
@@ -138,6 +139,118 @@ sample_mwc_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off
     }
     nIter[p] = it;
     flags[p] = fl;
+}
+
+// The same stream, replayed in parallel.  OpenCV seeds RNG((uint64)-1) at the start of every call, so
+// the raw 32-bit draws are one fixed sequence (mwc_table_kernel, once per context); only `% n`, the
+// duplicate redraws and the degeneracy checks depend on the pair.  One CTA per pair:
+//   A  every thread simulates one *attempt* (draw MP distinct indices, check the subset) from every
+//      start position of a block of the stream: attempt length and outcome per position;
+//   B  one thread follows the chain position -> position + length, which is exactly the sequential
+//      loop (an iteration = attempts until one passes, at most 10 000);
+//   C  all threads copy the subsets of the iterations found to the sample list.
+// Pairs the table cannot serve (more than 65 536 points, > 64 draws in one attempt, stream longer than
+// the table) are flagged in needSeq and replayed by sample_mwc_kernel.
+constexpr int MWC_TABLE = 1 << 16;
+constexpr int MWC_BLOCK = 4096;
+constexpr int MWC_MAXDRAW = 64;
+
+__global__ void mwc_table_kernel(uint32_t* __restrict__ raw) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Mwc rng;
+    for (int i = 0; i < MWC_TABLE; ++i) raw[i] = rng.next();
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(256)
+sample_mwc_par_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off, int nPairs,
+                      int maxIters, int smemPoints, const uint32_t* __restrict__ raw,
+                      int* __restrict__ samples, int* __restrict__ nIter, int* __restrict__ flags,
+                      uint8_t* __restrict__ needSeq) {
+    constexpr int MP = MT<MODEL>::MP;
+    extern __shared__ float4 sDyn[];
+    const int p = blockIdx.x;
+    const int64_t base = off[p];
+    const int n = (int)(off[p + 1] - base);
+    int* out = samples + (int64_t)p * maxIters * MP;
+    if (n <= MP || n > 65536) {
+        if (threadIdx.x == 0) {
+            needSeq[p] = n > 65536 ? 1 : 0;
+            if (n < MP) { nIter[p] = 0; flags[p] = PAIR_FAIL; }
+            else if (n == MP) { for (int i = 0; i < MP; ++i) out[i] = i; nIter[p] = 1; flags[p] = PAIR_DIRECT; }
+        }
+        return;
+    }
+    const bool staged = MODEL != RM_ESSENTIAL && n <= smemPoints;
+    float4* sPts = sDyn;
+    uint32_t* sRaw = reinterpret_cast<uint32_t*>(sDyn + (MODEL == RM_ESSENTIAL ? 0 : smemPoints));
+    uint16_t* aIdx = reinterpret_cast<uint16_t*>(sRaw + MWC_BLOCK + MWC_MAXDRAW);
+    uint16_t* itPos = aIdx + MWC_BLOCK * MP;
+    uint8_t* aLen = reinterpret_cast<uint8_t*>(itPos + MWC_BLOCK / MP + 8);
+    __shared__ int sState[4];                 // found this round, stop code, next position, attempts
+    if (staged) for (int i = threadIdx.x; i < n; i += blockDim.x) sPts[i] = pf[base + i];
+    const float4* pts = staged ? sPts : (MODEL == RM_ESSENTIAL ? nullptr : pf + base);
+
+    int pos = 0, it = 0, attempts = 0, stop = 0;    // stop: 1 = out of hypotheses, 2 = hand over, 3 = no valid subset
+    while (it < maxIters && !stop) {
+        if (pos + MWC_BLOCK + MWC_MAXDRAW > MWC_TABLE) { stop = 2; break; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < MWC_BLOCK + MWC_MAXDRAW; i += blockDim.x) sRaw[i] = raw[pos + i];
+        __syncthreads();
+        // A: one attempt from every start position of the block
+        for (int q = threadIdx.x; q < MWC_BLOCK; q += blockDim.x) {
+            int idx[MP];
+            int c = 0;
+            bool over = false;
+#pragma unroll
+            for (int i = 0; i < MP; ++i) {
+                int v = 0;
+                bool dup;
+                do {
+                    if (c >= MWC_MAXDRAW) { over = true; break; }
+                    v = (int)(sRaw[q + c] % (uint32_t)n);
+                    ++c;
+                    dup = false;
+#pragma unroll
+                    for (int k = 0; k < MP; ++k) dup |= (k < i) && (idx[k] == v);
+                } while (dup);
+                idx[i] = v;
+            }
+            bool ok = false;
+            if (!over) ok = check_subset_pts<MODEL>(pts, idx);
+#pragma unroll
+            for (int i = 0; i < MP; ++i) aIdx[q * MP + i] = (uint16_t)idx[i];
+            aLen[q] = over ? 0xFF : (uint8_t)((ok ? 0x80 : 0) | c);
+        }
+        __syncthreads();
+        // B: follow the chain
+        if (threadIdx.x == 0) {
+            int q = 0, k = 0, st = 0, att = attempts;
+            while (q < MWC_BLOCK && it + k < maxIters) {
+                const int len = aLen[q];
+                if (len == 0xFF) { st = 2; break; }
+                if (len & 0x80) { itPos[k++] = (uint16_t)q; att = 0; }
+                else if (++att >= 10000) { st = 3; break; }
+                q += len & 0x7F;
+            }
+            sState[0] = k; sState[1] = st; sState[2] = pos + q; sState[3] = att;
+        }
+        __syncthreads();
+        const int k = sState[0];
+        stop = sState[1]; pos = sState[2]; attempts = sState[3];
+        // C: subsets of the iterations found in this round
+        for (int i = threadIdx.x; i < k * MP; i += blockDim.x)
+            out[(int64_t)it * MP + i] = aIdx[itPos[i / MP] * MP + (i % MP)];
+        it += k;
+    }
+    if (threadIdx.x == 0) {
+        if (stop == 2) { needSeq[p] = 1; }
+        else {
+            needSeq[p] = 0;
+            nIter[p] = it;
+            flags[p] = (stop == 3 && it == 0) ? PAIR_FAIL : 0;
+        }
+    }
 }
 
 // Native mode: hypothesis (pair, it) draws from its own counter-based stream -- no sequential
@@ -906,12 +1019,32 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
                                                             dSamples, dNIter, dFlags);
             MCV_LAUNCH_CHECK();
         } else {
+            // OpenCV's stream, replayed in parallel from the precomputed raw draws ...
+            if (ctx->ws[28].reserve((size_t)MWC_TABLE * 4) || ctx->ws[29].reserve((size_t)np)) return -1;
+            uint32_t* dRaw = ctx->ws[28].as<uint32_t>();
+            uint8_t* dNeedSeq = ctx->ws[29].as<uint8_t>();
+            if (!ctx->mwc_ready) {
+                mwc_table_kernel<<<1, 32, 0, st>>>(dRaw);
+                MCV_LAUNCH_CHECK();
+                ctx->mwc_ready = true;
+            }
+            {
+                const int smemPts = MODEL == RM_ESSENTIAL ? 0 : (int)std::min<int64_t>(maxN, 8192);   // 128 KB of float4 points
+                auto kern = sample_mwc_par_kernel<MODEL>;
+                const size_t smemBytes = (size_t)smemPts * 16 + (MWC_BLOCK + MWC_MAXDRAW) * 4 + (size_t)MWC_BLOCK * MP * 2 +
+                                         (MWC_BLOCK / MP + 8) * 2 + MWC_BLOCK + 64;
+                if (smemBytes > 48 * 1024)
+                    MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+                kern<<<np, 256, smemBytes, st>>>(pf, off, np, maxIters, smemPts, dRaw, dSamples, dNIter, dFlags, dNeedSeq);
+                MCV_LAUNCH_CHECK();
+            }
+            // ... and sequentially for the pairs the table cannot serve
             const int smemPts = (int)std::min<int64_t>(maxN, 12288);       // up to 192 KB of float4 points
             auto kern = sample_mwc_kernel<MODEL>;
             const size_t smemBytes = MODEL == RM_ESSENTIAL ? 0 : (size_t)smemPts * 16;
             if (smemBytes > 48 * 1024)
                 MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-            kern<<<np, 32, smemBytes, st>>>(pf, off, np, maxIters, smemPts, dSamples, dNIter, dFlags);
+            kern<<<np, 32, smemBytes, st>>>(pf, off, np, maxIters, smemPts, dSamples, dNIter, dFlags, dNeedSeq);
             MCV_LAUNCH_CHECK();
         }
         // ---- solve
