@@ -675,7 +675,7 @@ def run_ours(args):
         traffic = None
         tj = ROOT / "profiles" / "r01_tc_traffic.json"
         if tj.exists() and P == 1024:
-            traffic = json.loads(tj.read_text()).get("traffic_bytes_per_launch")
+            traffic = json.loads(tj.read_text()).get("traffic_bytes_per_step")
         roofline = {
             "bound": "tensor", "achieved": ach, "peak": int8_peak, "unit": "TFLOP/s", "frac": ach / int8_peak,
             "traffic": traffic,
