@@ -142,3 +142,26 @@ def descriptor_pair_geo(seed: int, n_query: int = 8192, n_train: int = 8192, des
     ph = np.concatenate([kq[m], np.ones((int(m.sum()), 1))], axis=1) @ H.T
     kt[gt[m]] = ph[:, :2] / ph[:, 2:3] + rng.normal(0, noise, (int(m.sum()), 2))
     return q, t, gt, np.ascontiguousarray(kq), np.ascontiguousarray(kt), H
+
+
+def pnp_scene(rng, n: int, inlier_frac: float = 0.4, noise: float = 0.5, K=None):
+    """PnP problem: 3-D points in [-2,2]^2 x [4,8] seen by a camera rotated by a random Rodrigues
+    vector (sigma 0.3 rad) and shifted by N(0, 0.5); pixel noise sigma; the first n - round(n*inlier_frac)
+    observations are replaced by uniform outliers in the 640x480 image.  ``rng`` is a numpy Generator
+    (or a seed).  Returns (world [n,3], image [n,2], rvec, tvec)."""
+    if not isinstance(rng, np.random.Generator):
+        rng = np.random.default_rng(5000 + int(rng))
+    if K is None:
+        K = np.array([[800.0, 0, 320.0], [0, 800.0, 240.0], [0, 0, 1.0]])
+    X = np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n), rng.uniform(4, 8, n)], axis=1)
+    rvec = rng.normal(size=3) * 0.3
+    tvec = rng.normal(size=3) * 0.5
+    ang = float(np.linalg.norm(rvec))
+    R = rodrigues(rvec, ang) if ang > 0 else np.eye(3)
+    Xc = X @ R.T + tvec
+    uv = Xc[:, :2] / Xc[:, 2:3] * np.array([K[0, 0], K[1, 1]]) + np.array([K[0, 2], K[1, 2]])
+    uv = uv + rng.normal(0, noise, (n, 2)) if noise > 0 else uv
+    n_out = n - int(round(n * inlier_frac))
+    if n_out > 0:
+        uv[:n_out] = np.stack([rng.uniform(0, 640, n_out), rng.uniform(0, 480, n_out)], axis=1)
+    return np.ascontiguousarray(X), np.ascontiguousarray(uv), rvec, tvec
