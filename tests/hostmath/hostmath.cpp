@@ -48,3 +48,47 @@ void hm_mwc(int n, unsigned* out) { Mwc r; for (int i = 0; i < n; ++i) out[i] = 
 int hm_real_roots10(const double* c, double* out) { return real_roots10(c, out); }
 
 }
+
+// ---- PnP row (pnpmath.cuh) ------------------------------------------------------------------------
+#include "../../minicv_b200/csrc/pnpmath.cuh"
+extern "C" {
+// the reference's solveAp3p (ap3p.cpp:282): img [3][2], obj [3][3]
+int hm_ap3p(const double* img, const double* obj, double inv_fx, double inv_fy, double cx_fx, double cy_fy, double* Rs,
+            double* ts) {
+    double b[3][3];
+    for (int i = 0; i < 3; ++i) ap3p_bearing(img[2 * i], img[2 * i + 1], inv_fx, inv_fy, cx_fx, cy_fy, b[i], nullptr);
+    return ap3p_poses(b[0], b[1], b[2], obj, obj + 3, obj + 6, false, nullptr, nullptr, Rs, ts);
+}
+int hm_pnp_solve4(const double* cam, const float* obj, const float* img, double* rvec, double* tvec) {
+    PnpCamera c{cam[0], cam[1], cam[2], cam[3], cam[4], cam[5], cam[6], cam[7]};
+    return pnp_solve4(c, obj, img, rvec, tvec) ? 1 : 0;
+}
+void hm_rodrigues_v2m(const double* r, double* R) { rodrigues_v2m(r, R); }
+void hm_rodrigues_m2v(const double* R, double* r) { rodrigues_m2v(R, r); }
+void hm_undistort(const double* cam, const float* uv, int n, float* out) {
+    PnpCamera c{cam[0], cam[1], cam[2], cam[3], cam[4], cam[5], cam[6], cam[7]};
+    for (int i = 0; i < n; ++i) {
+        double x, y;
+        undistort_point(c, (double)uv[2 * i], (double)uv[2 * i + 1], &x, &y);
+        out[2 * i] = (float)x; out[2 * i + 1] = (float)y;
+    }
+}
+void hm_project_error(const double* cam, const double* rvec, const double* tvec, const float* obj, const float* img, int n,
+                      float* err) {
+    PnpCamera c{cam[0], cam[1], cam[2], cam[3], cam[4], cam[5], cam[6], cam[7]};
+    double R[9];
+    rodrigues_v2m(rvec, R);
+    for (int i = 0; i < n; ++i)
+        err[i] = project_error(R, tvec, c, c.distorted(), obj[3 * i], obj[3 * i + 1], obj[3 * i + 2], img[2 * i], img[2 * i + 1]);
+}
+// cv::solvePnP(SOLVEPNP_EPNP) on float64 points: undistort, EPnP, Rodrigues
+void hm_epnp(const double* cam, const double* obj, const double* img, int n, double* rvec, double* tvec) {
+    PnpCamera c{cam[0], cam[1], cam[2], cam[3], cam[4], cam[5], cam[6], cam[7]};
+    double* und = new double[2 * n];
+    for (int i = 0; i < n; ++i) undistort_point(c, img[2 * i], img[2 * i + 1], und + 2 * i, und + 2 * i + 1);
+    double R[9];
+    epnp_sequential(n, obj, und, c.fx, c.fy, c.cx, c.cy, R, tvec);
+    rodrigues_m2v(R, rvec);
+    delete[] und;
+}
+}

@@ -158,3 +158,64 @@ def test_symmetric_solvers(hm):
             assert np.abs(x2 - ref).max() / np.abs(ref).max() < 1e-6
         else:   # ill-conditioned: the Cholesky guard must hand over to the eigen-solve
             np.testing.assert_array_equal(x1, x2)
+
+
+# ---- PnP row: pnpmath.cuh against the oracle and the cv2 / compiled-reference goldens ----------------
+def _cam(K, dist):
+    return np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2], dist[0], dist[1], dist[2], dist[3]], np.float64)
+
+
+def test_pnp_ap3p_reference_export(hm):
+    """ap3p_poses (reference mode) == the reference's solveAp3p compiled from ap3p.cpp (frozen golden)."""
+    g = np.load(GOLDEN / "pnp.npz")
+    K = g["K"]
+    hm.hm_ap3p.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    for i in range(len(g["ap3p_n"])):
+        Rs = np.zeros((4, 9)); ts = np.zeros((4, 3))
+        img = np.ascontiguousarray(g["ap3p_img"][i]); obj = np.ascontiguousarray(g["ap3p_obj"][i])
+        n = hm.hm_ap3p(p(img), p(obj), 1 / K[0, 0], 1 / K[1, 1], K[0, 2] / K[0, 0], K[1, 2] / K[1, 1], p(Rs), p(ts))
+        assert n == int(g["ap3p_n"][i])
+        np.testing.assert_allclose(Rs[:n], g["ap3p_R"][i, :n], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(ts[:n], g["ap3p_t"][i, :n], rtol=0, atol=1e-8)
+
+
+@pytest.mark.parametrize("dk", ["d0", "d1"])
+def test_pnp_building_blocks(hm, dk):
+    g = np.load(GOLDEN / "pnp.npz")
+    cam = _cam(g["K"], g[f"dist_{dk}"])
+    # Rodrigues both ways
+    for rv, R in zip(g["rod_rvec"], g["rod_R"]):
+        out = np.zeros(9)
+        hm.hm_rodrigues_v2m(p(np.ascontiguousarray(rv)), p(out))
+        assert np.array_equal(out.reshape(3, 3), R)
+    for Rin, rv in zip(g["rod_Rin"], g["rod_rvec_back"]):
+        out = np.zeros(3)
+        hm.hm_rodrigues_m2v(p(np.ascontiguousarray(Rin)), p(out))
+        np.testing.assert_allclose(out, rv, rtol=0, atol=1e-12)
+    # undistortPoints, float32 in / out: bit-exact
+    uv = np.ascontiguousarray(g[f"und_{dk}_in"]); out = np.zeros_like(uv)
+    hm.hm_undistort(p(cam), p(uv), len(uv), p(out))
+    assert np.array_equal(out, g[f"und_{dk}_out"])
+    # projectPoints + squared float32 residual: bit-exact vs cv2's float32 projection
+    obj = np.ascontiguousarray(g[f"proj_{dk}_obj"]); rvec = g[f"proj_{dk}_rvec"].copy(); tvec = g[f"proj_{dk}_tvec"].copy()
+    img = np.ascontiguousarray((g[f"proj_{dk}_f32"] + np.float32(1.25)).astype(np.float32))
+    err = np.zeros(len(obj), np.float32)
+    hm.hm_project_error(p(cam), p(rvec), p(tvec), p(obj), p(img), len(obj), p(err))
+    d = img - g[f"proj_{dk}_f32"]
+    assert np.array_equal(err, d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
+    # solvePnP(AP3P) on four float32 points
+    close = 0
+    n4 = len(g[f"p4_{dk}_ok"])
+    for i in range(n4):
+        rv = np.zeros(3); tv = np.zeros(3)
+        ok = hm.hm_pnp_solve4(p(cam), p(np.ascontiguousarray(g[f"p4_{dk}_obj"][i])), p(np.ascontiguousarray(g[f"p4_{dk}_img"][i])), p(rv), p(tv))
+        assert bool(ok) == bool(g[f"p4_{dk}_ok"][i])
+        if ok:
+            close += max(np.abs(rv - g[f"p4_{dk}_rvec"][i]).max(), np.abs(tv - g[f"p4_{dk}_tvec"][i]).max()) < 1e-6
+    assert close >= n4 - 2
+    # EPnP
+    for n in (6, 40, 300):
+        rv = np.zeros(3); tv = np.zeros(3)
+        hm.hm_epnp(p(cam), p(np.ascontiguousarray(g[f"epnp_{dk}_{n}_obj"])), p(np.ascontiguousarray(g[f"epnp_{dk}_{n}_img"])), n, p(rv), p(tv))
+        np.testing.assert_allclose(rv, g[f"epnp_{dk}_{n}_rvec"], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(tv, g[f"epnp_{dk}_{n}_tvec"], rtol=0, atol=1e-8)
