@@ -205,6 +205,10 @@ def _cpu_ransac_task(task):
         cv2.findHomography(a, b, cv2.RANSAC, 3.0, maxIters=4096, confidence=0.995)
     elif kind == "F":
         cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, 3.0, 0.99, 4096)
+    elif kind == "P":          # a = world points, b = image points
+        K = np.array([[800.0, 0, 320.0], [0, 800.0, 240.0], [0, 0, 1.0]])
+        cv2.solvePnPRansac(a, b, K, np.zeros(4), iterationsCount=1000, reprojectionError=2.0, confidence=0.999,
+                           flags=cv2.SOLVEPNP_AP3P)
     else:
         E, m = cv2.findEssentialMat(a, b, 800.0, (320.0, 240.0), cv2.RANSAC, 0.999, 1.0)
         cv2.recoverPose(E, a, b, focal=800.0, pp=(320.0, 240.0), mask=m)
@@ -426,6 +430,33 @@ def extra_ransac(local, with_cpu=True):
                         "mode": "OpenCV MWC sampling + adaptive stop (cvRecoverPose semantics)"}
     if with_cpu:
         out["C4_E_pose"]["cpu"] = cpu_ransac_pairs_per_s("E", [(A[p * N:(p + 1) * N], B[p * N:(p + 1) * N]) for p in range(cores)], cores)
+    del dA, dB
+    # ---- PnP RANSAC: cvSolvePnPRansac(AP3P) semantics, 2000 correspondences, 30 % inliers
+    P, N = 1024, 2000
+    off = np.arange(P + 1, dtype=np.int64) * N
+    X = np.empty((P * N, 3)); U = np.empty((P * N, 2))
+    Kc = np.array([[800.0, 0, 320.0], [0, 800.0, 240.0], [0, 0, 1.0]])
+    for p in range(P):
+        X[p * N:(p + 1) * N], U[p * N:(p + 1) * N], _, _ = synth.pnp_scene(p, N, 0.3, noise=0.5, K=Kc)
+    dX = torch.from_numpy(X).to(dev); dU = torch.from_numpy(U).to(dev)
+    dC = torch.from_numpy(est.camera_rows(Kc, None, P)).to(dev)
+    dRv = torch.empty((P, 3), dtype=torch.float64, device=dev); dTv = torch.empty((P, 3), dtype=torch.float64, device=dev)
+    dMk = torch.empty(P * N, dtype=torch.uint8, device=dev)
+    dCn = torch.empty(P, dtype=torch.int32, device=dev); dOk2 = torch.empty(P, dtype=torch.uint8, device=dev)
+    for name, sm, stp, mode in (("PnP_AP3P_opencv_semantics", est.SAMPLE_MWC, est.STOP_ADAPTIVE,
+                                 "OpenCV MWC sampling + adaptive stop + EPnP refit (cvSolvePnPRansac semantics)"),
+                                ("PnP_AP3P_fixed_1000", est.SAMPLE_COUNTER, est.STOP_FIXED,
+                                 "counter-based sampling, 1000 hypotheses scored per problem, EPnP refit")):
+        def run_p():
+            est.solve_pnp_ransac_batch_device(dX, dU, off, dC, 2.0, 1000, 0.999, dRv, dTv, dMk, dCn, dOk2, sample_mode=sm,
+                                              stop_mode=stp, seed=3, device=local, stream=stream.cuda_stream)
+        t = timed(run_p, reps=2)
+        out[name] = {"problems_per_s": P / t, "ms_per_batch": t * 1e3, "problems": P, "correspondences": N,
+                     "max_iters": 1000, "ok": int(dOk2.sum().item()), "mean_inliers": float(dCn.float().mean().item()),
+                     "ghyp_x_corr_per_s": P * N * 1000 / t / 1e9 if stp == est.STOP_FIXED else None, "mode": mode}
+    if with_cpu:
+        out["PnP_AP3P_opencv_semantics"]["cpu"] = cpu_ransac_pairs_per_s(
+            "P", [(X[p * N:(p + 1) * N], U[p * N:(p + 1) * N]) for p in range(cores)], cores)
     return out
 
 

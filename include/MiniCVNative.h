@@ -267,20 +267,72 @@ MCV_API int cvFivePointBatch(const McvPoint2d* pa, const McvPoint2d* pb, int nSe
                              McvMatx33d* Es, int32_t* counts);
 
 
-/* ---- (3) reference exports that are not on the path: forwarded, not implemented -----------
- * Signatures are the reference's (src/MiniCVNative/MiniCVNative.cpp:48,93,140,152,221,347,384,
- * 439,504; ap3p.cpp:282).  Each call is forwarded to a side-by-side build of the original shim
- * ($MINICV_ORIGINAL_NATIVE, default "libMiniCVNativeCv.so"); without it the reference's failure
- * value is returned.  See INTEGRATION.md section 3. */
+/* ---- (2b) PnP RANSAC --------------------------------------------
+ * cvSolvePnPRansac and solveAp3p keep the reference's signatures and are re-implemented on the GPU. */
 typedef struct { double X, Y, Z; } McvPoint3d;
-MCV_API bool cvSolvePnP(const McvPoint2d* imgPoints, const McvPoint3d* worldPoints, const int N,
-                        const McvMatx33d K, const double* distortionCoeffs, const int solverKind,
-                        McvVec3d* tVec, McvVec3d* rVec);
+
+/* Reference: src/MiniCVNative/MiniCVNative.cpp:93-139 -> cv::solvePnPRansac(world, image, K, dist(4), rvec,
+ * tvec, false, iterationsCount, reprojectionError, confidence, inliers, kind).  Native for solverKind 5
+ * (SOLVEPNP_AP3P): 4-point AP3P hypotheses from OpenCV's sampling stream, reprojection-error scoring,
+ * adaptive stop, final pose = EPnP over the inliers; outInliers (room for N) receives the ascending
+ * indices of the best minimal model's inliers.  Every other solverKind is forwarded to the original shim
+ * (section 3).  Returns false with *inlierCount = 0 and tVec / rVec untouched on failure. */
 MCV_API bool cvSolvePnPRansac(const McvPoint2d* imgPoints, const McvPoint3d* worldPoints, const int N,
                               const McvMatx33d K, const double* distortionCoeffs, const int solverKind,
                               const int iterationsCount, const float reprojectionError,
                               const double confidence, McvVec3d* tVec, McvVec3d* rVec,
                               int* inlierCount, int* outInliers);
+
+/* Reference: src/MiniCVNative/ap3p.cpp:282-317.  Up to four poses through three correspondences;
+ * R (room for 4) in the reference's layout (camera point = R^T X + t), returns the count. */
+MCV_API int solveAp3p(McvMatx33d* R, McvVec3d* t, double mu0, double mv0, double X0, double Y0, double Z0,
+                      double mu1, double mv1, double X1, double Y1, double Z1, double mu2, double mv2,
+                      double X2, double Y2, double Z2, double inv_fx, double inv_fy, double cx_fx, double cy_fy);
+/* Batched solveAp3p: img [n][3], obj [n][3], cam4 [n][4] = inv_fx, inv_fy, cx_fx, cy_fy ->
+ * Rs [n][4], ts [n][4], counts [n].  Returns 0, or -1 on error. */
+MCV_API int cvSolveAp3pBatch(const McvPoint2d* img, const McvPoint3d* obj, const double* cam4, int n,
+                             McvMatx33d* Rs, McvVec3d* ts, int32_t* counts);
+
+typedef struct {
+    int32_t  sampleMode;   /* MCV_SAMPLE_*                                                          */
+    int32_t  stopMode;     /* MCV_STOP_*                                                            */
+    int32_t  maxIters;     /* iterationsCount                                                       */
+    int32_t  refine;       /* 1 = final pose is EPnP over the inliers (cv::solvePnPRansac); 0 = the
+                              best minimal model                                                    */
+    double   threshold;    /* reprojectionError in pixels                                           */
+    double   confidence;   /* (0,1) exclusive                                                       */
+    uint64_t seed;         /* MCV_SAMPLE_COUNTER only                                               */
+} McvPnpParams;
+
+/* Batched form over packed correspondences: problem p owns rows [offsets[p], offsets[p+1]) of obj / img
+ * and the camera cams[8 p ..] = fx, fy, cx, cy, k1, k2, p1, p2.  Also the test-only *WithHypotheses form:
+ *   injSamples : [nProblems][maxIters][4] sample indices (MCV_SAMPLE_INJECTED) or NULL
+ *   injModels  : [nProblems][maxIters][6] (rvec, tvec) scored as given (skips the solver) or NULL
+ * Outputs (host; all but rvecs / tvecs / masks / ok optional): rvecs, tvecs [nProblems]; masks [total rows]
+ * (RANSAC mask of the best minimal model); inlierCounts, ok, itersRun, bestIter [nProblems]; minimal
+ * [nProblems][6] (the winning minimal model); parity taps dbgCounts [nProblems][maxIters] (-1 = no pose),
+ * dbgModels [nProblems][maxIters][6], dbgSamples [nProblems][maxIters][4].
+ * Returns the number of problems with ok = 1, or -1. */
+MCV_API int cvSolvePnPRansacBatch(const McvPnpParams* prm, const McvPoint3d* obj, const McvPoint2d* img,
+                                  const int64_t* offsets, int nProblems, const double* cams,
+                                  const int32_t* injSamples, const double* injModels, McvVec3d* rvecs,
+                                  McvVec3d* tvecs, uint8_t* masks, int32_t* inlierCounts, uint8_t* ok,
+                                  int32_t* itersRun, int32_t* bestIter, double* minimal, int32_t* dbgCounts,
+                                  double* dbgModels, int32_t* dbgSamples, int device);
+/* Device-resident form (offsets on the host, everything else in device memory; asynchronous). */
+MCV_API int cvSolvePnPRansacBatchDevice(const McvPnpParams* prm, const double* dObj, const double* dImg,
+                                        const int64_t* offsets, int nProblems, const double* dCams,
+                                        double* dRvecs, double* dTvecs, uint8_t* dMasks,
+                                        int32_t* dInlierCounts, uint8_t* dOk, int device, void* stream);
+
+/* ---- (3) reference exports that are not on the path: forwarded, not implemented -----------
+ * Signatures are the reference's (src/MiniCVNative/MiniCVNative.cpp:48,140,152,221,347,384,
+ * 439,504; cvSolvePnPRansac for solver kinds other than AP3P).  Each call is forwarded to a side-by-side build of the original shim
+ * ($MINICV_ORIGINAL_NATIVE, default "libMiniCVNativeCv.so"); without it the reference's failure
+ * value is returned.  See INTEGRATION.md section 3. */
+MCV_API bool cvSolvePnP(const McvPoint2d* imgPoints, const McvPoint3d* worldPoints, const int N,
+                        const McvMatx33d K, const double* distortionCoeffs, const int solverKind,
+                        McvVec3d* tVec, McvVec3d* rVec);
 MCV_API void cvRefinePnPLM(const McvPoint2d* imgPoints, const McvPoint3d* worldPoints, const int N,
                            const McvMatx33d K, const double* distortionCoeffs, McvVec3d* tVec, McvVec3d* rVec);
 MCV_API void cvRefinePnPVVS(const McvPoint2d* imgPoints, const McvPoint3d* worldPoints, const int N,
@@ -290,10 +342,6 @@ MCV_API void cvFreeFeatures(McvDetectorResult* res);
 MCV_API bool cvDetectQRCode(char* data, int width, int height, int channels, int* positions, int* count);
 MCV_API bool cvDetectArucoMarkers(char* data, int width, int height, int channels, int* infoCount, void* infos);
 MCV_API void cvTest(void);
-MCV_API int solveAp3p(McvMatx33d* R, McvVec3d* t, double mu0, double mv0, double X0, double Y0, double Z0,
-                      double mu1, double mv1, double X1, double Y1, double Z1, double mu2, double mv2,
-                      double X2, double Y2, double Z2, double inv_fx, double inv_fy, double cx_fx, double cy_fy);
-
 #ifdef __cplusplus
 }
 #endif

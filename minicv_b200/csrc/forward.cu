@@ -1,5 +1,5 @@
-// forward.cu -- the ten reference exports that are NOT on the match / two-view path
-// (PnP, AP3P, detectors, fiducials, cvTest: reference src/MiniCVNative/MiniCVNative.cpp:48,93,
+// forward.cu -- the reference exports that are NOT on the match / two-view / PnP-RANSAC path
+// (plain PnP and its refiners, detectors, fiducials, cvTest: reference src/MiniCVNative/MiniCVNative.cpp:48,93,
 // 140,152,221,347,384,439,504 and ap3p.cpp:282).  They are out of scope for acceleration and need
 // the OpenCV C++ SDK, so this library does not implement them; it keeps every F# DllImport
 // (src/MiniCV/OpenCV.fs:343-382) resolving by forwarding to a side-by-side build of the original
@@ -44,7 +44,11 @@ MCV_API bool cvSolvePnP(const McvPoint2d* img, const McvPoint3d* world, const in
     return f ? f(img, world, N, K, dist, solverKind, tVec, rVec) : false;
 }
 
-MCV_API bool cvSolvePnPRansac(const McvPoint2d* img, const McvPoint3d* world, const int N, const McvMatx33d K,
+}  // extern "C"
+
+// cvSolvePnPRansac is native for solverKind 5 (AP3P) -- api_pnp.cu; every other kind lands here.
+namespace mcv {
+bool forward_solve_pnp_ransac(const McvPoint2d* img, const McvPoint3d* world, const int N, const McvMatx33d K,
                               const double* dist, const int solverKind, const int iterationsCount,
                               const float reprojectionError, const double confidence, McvVec3d* tVec,
                               McvVec3d* rVec, int* inlierCount, int* outInliers) {
@@ -55,6 +59,9 @@ MCV_API bool cvSolvePnPRansac(const McvPoint2d* img, const McvPoint3d* world, co
                  inlierCount, outInliers)
              : false;
 }
+}  // namespace mcv
+
+extern "C" {
 
 MCV_API void cvRefinePnPLM(const McvPoint2d* img, const McvPoint3d* world, const int N, const McvMatx33d K,
                            const double* dist, McvVec3d* tVec, McvVec3d* rVec) {
@@ -95,15 +102,6 @@ MCV_API bool cvDetectArucoMarkers(char* data, int width, int height, int channel
 MCV_API void cvTest(void) {
     using Fn = void (*)();
     if (Fn f = resolve<Fn>("cvTest")) f();
-}
-
-MCV_API int solveAp3p(McvMatx33d* R, McvVec3d* t, double mu0, double mv0, double X0, double Y0, double Z0,
-                      double mu1, double mv1, double X1, double Y1, double Z1, double mu2, double mv2,
-                      double X2, double Y2, double Z2, double inv_fx, double inv_fy, double cx_fx, double cy_fy) {
-    using Fn = int (*)(McvMatx33d*, McvVec3d*, double, double, double, double, double, double, double, double,
-                       double, double, double, double, double, double, double, double, double, double, double);
-    Fn f = resolve<Fn>("solveAp3p");
-    return f ? f(R, t, mu0, mv0, X0, Y0, Z0, mu1, mv1, X1, Y1, Z1, mu2, mv2, X2, Y2, Z2, inv_fx, inv_fy, cx_fx, cy_fy) : 0;
 }
 
 }  // extern "C"

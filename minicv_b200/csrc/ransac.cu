@@ -33,8 +33,6 @@ template <> struct MT<RM_HOMOGRAPHY>  { static constexpr int MP = 4, MAXM = 1; }
 template <> struct MT<RM_FUNDAMENTAL> { static constexpr int MP = 7, MAXM = 3; };
 template <> struct MT<RM_ESSENTIAL>   { static constexpr int MP = 5, MAXM = 10; };
 
-constexpr int PAIR_FAIL = 1;     // sampling failed at iteration 0 / N < modelPoints
-constexpr int PAIR_DIRECT = 2;   // N == modelPoints: kernel on all points, mask all ones
 
 // ---------------------------------------------------------------------------------------------
 // prep: double (x,y) pairs -> working layout
@@ -1115,6 +1113,23 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
 }
 
 }  // namespace
+
+// The model-independent stages, shared with the PnP engine (pnp.cu).
+int ransac_compact(cudaStream_t st, int np, const uint8_t* dNModels, const int* dNIter, int maxIters, int maxm,
+                   int* dIterStart, int* dSlotList, int* dNTotal) {
+    compact_kernel<<<np, 256, 0, st>>>(dNModels, dNIter, maxIters, maxm, dIterStart, dSlotList, dNTotal);
+    MCV_LAUNCH_CHECK();
+    return 0;
+}
+
+int ransac_select(cudaStream_t st, const int64_t* dOff, int np, int maxIters, int maxm, int mp, bool adaptive,
+                  double confidence, const int* dNIter, const int* dFlags, const int* dIterStart,
+                  const int* dSlotList, const int* dCounts, int* dBest) {
+    select_kernel<<<(np + 3) / 4, 128, 0, st>>>(dOff, np, maxIters, maxm, mp, adaptive ? 1 : 0, confidence, dNIter,
+                                                dFlags, dIterStart, dSlotList, dCounts, dBest);
+    MCV_LAUNCH_CHECK();
+    return 0;
+}
 
 int ransac_batch_device(Context* ctx, cudaStream_t stream, const RansacParams& prm, const RansacIO& io) {
     if (io.nPairs <= 0) return 0;

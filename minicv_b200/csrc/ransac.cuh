@@ -41,6 +41,21 @@ struct RansacIO {
     int*     dDbgSamples = nullptr;        // [nPairs][maxIters][MP]
 };
 
+// per-problem flags written by the samplers and read by select / finalize
+constexpr int PAIR_FAIL = 1;     // sampling failed at iteration 0 / N < modelPoints
+constexpr int PAIR_DIRECT = 2;   // N == modelPoints: kernel on all points, mask all ones
+
+// Model-independent stages (ransac.cu), shared with the PnP engine (pnp.cu):
+//   compact: nModels [np][maxIters] -> iterStart [np][maxIters+1], slotList [np][maxIters*maxm] (dense list of
+//            iteration*maxm+model in OpenCV's evaluation order), nTotal [np]
+//   select : replays OpenCV's accept rule and RANSACUpdateNumIters over counts [np][maxIters*maxm] (compacted
+//            order); best [np][4] = compacted index, inlier count, iterations run, slot
+int ransac_compact(cudaStream_t st, int np, const uint8_t* dNModels, const int* dNIter, int maxIters, int maxm,
+                   int* dIterStart, int* dSlotList, int* dNTotal);
+int ransac_select(cudaStream_t st, const int64_t* dOff, int np, int maxIters, int maxm, int mp, bool adaptive,
+                  double confidence, const int* dNIter, const int* dFlags, const int* dIterStart,
+                  const int* dSlotList, const int* dCounts, int* dBest);
+
 // Asynchronous on `stream`.  Uses ctx workspaces 10..21 and pinned buffer 1.
 int ransac_batch_device(Context* ctx, cudaStream_t stream, const RansacParams& prm, const RansacIO& io);
 
@@ -67,5 +82,49 @@ int recover_pose_batch_device(Context* ctx, cudaStream_t stream, const PoseIO& i
 // cvFivePoint on the device: 5 correspondences -> <= 10 essential matrices.
 int five_point_device(Context* ctx, cudaStream_t stream, const double* dA, const double* dB,
                       int nSets, double* dEs /*[nSets][10][9]*/, int* dCounts /*[nSets]*/);
+
+}  // namespace mcv
+
+namespace mcv {
+
+// ---- PnP RANSAC (pnp.cu): cv::solvePnPRansac(SOLVEPNP_AP3P) semantics, batched ------------------------
+struct PnpParams {
+    int      sampleMode = MCV_SAMPLE_OPENCV_MWC;
+    int      stopMode = MCV_STOP_ADAPTIVE;
+    int      maxIters = 100;
+    double   threshold = 8.0;      // reprojectionError (pixels)
+    double   confidence = 0.99;
+    uint64_t seed = 0;
+    int      refine = 1;           // final pose = EPnP over the inliers (what solvePnPRansac returns)
+};
+
+struct PnpIO {
+    const double* dObj = nullptr;          // [total][3] world points
+    const double* dImg = nullptr;          // [total][2] image points (pixels)
+    const int64_t* hOff = nullptr;         // host, nProblems+1
+    int nProblems = 0;
+    const double* dCam = nullptr;          // [nProblems][8]: fx, fy, cx, cy, k1, k2, p1, p2
+    const int* dInjSamples = nullptr;      // [nProblems][maxIters][4]
+    const double* dInjModels = nullptr;    // [nProblems][maxIters][6] (rvec, tvec), scored as given
+    double*  dRvec = nullptr;              // [nProblems][3]
+    double*  dTvec = nullptr;              // [nProblems][3]
+    uint8_t* dMasks = nullptr;             // [total] RANSAC mask of the best minimal model
+    int*     dInlierIdx = nullptr;         // [total]: problem p's inlier indices, ascending, from hOff[p] (optional)
+    int*     dInlierCounts = nullptr;      // [nProblems]
+    uint8_t* dOk = nullptr;                // [nProblems]
+    int*     dItersRun = nullptr;          // [nProblems] (optional)
+    int*     dBestIter = nullptr;          // [nProblems] iteration of the winner (optional)
+    double*  dMinimal = nullptr;           // [nProblems][6] the winning minimal model (optional)
+    int*     dDbgCounts = nullptr;         // [nProblems][maxIters], -1 where the solver returned no pose
+    double*  dDbgModels = nullptr;         // [nProblems][maxIters][6]
+    int*     dDbgSamples = nullptr;        // [nProblems][maxIters][4]
+};
+// Asynchronous on `stream`.  Uses ctx workspaces 48..61 and pinned buffer 1.
+int pnp_ransac_batch_device(Context* ctx, cudaStream_t stream, const PnpParams& prm, const PnpIO& io);
+
+// The reference's solveAp3p (ap3p.cpp:282) for a batch: img [n][3][2] pixels, obj [n][3][3], cam4 [n][4] =
+// inv_fx, inv_fy, cx_fx, cy_fy -> Rs [n][4][9], ts [n][4][3], counts [n].  All device pointers.
+int ap3p_batch_device(Context* ctx, cudaStream_t stream, const double* dImg, const double* dObj, const double* dCam4,
+                      int n, double* dRs, double* dTs, int* dCounts);
 
 }  // namespace mcv

@@ -248,3 +248,152 @@ def recover_pose_batch_device(cfg: RecoverPoseConfig, d_a, d_b, offsets, d_E, d_
                                               sample_mode, maxIters, _dp(d_E), _dp(d_R), _dp(d_t), _dp(d_ms),
                                               _dp(d_good), _dp(d_ok), device, stream),
                  "cvRecoverPoseBatchDevice")
+
+
+# ------------------------------------------------------------------------------------------
+# PnP RANSAC -- mirror of ``OpenCV.solvePnPRansac`` / ``OpenCV.solveAp3p`` (reference
+# ``src/MiniCV/OpenCV.fs:383-432, 956-1052``); SURVEY.md section 8f rank 3
+# ------------------------------------------------------------------------------------------
+class SolverKind:
+    """Reference ``SolverKind`` (``OpenCV.fs:956-961``) with the native codes of ``solvePnPInternal``."""
+    Iterative, EPNP, P3P, AP3P, SQPNP = 0, 1, 2, 5, 6
+
+
+@dataclass
+class PnPRansacParams:
+    """Reference ``RansacParams`` (``OpenCV.fs:962-974``)."""
+    reprojectionError: float = 8.0
+    iterationsCount: int = 100
+    confidence: float = 0.99
+
+    @staticmethod
+    def MaxReprojError(e: float) -> "PnPRansacParams":
+        return PnPRansacParams(float(np.float32(e)), 100, 0.99)
+
+
+def solvePnPRansac(solver: int, cfg: PnPRansacParams, imgPoints, worldPoints, intern, distortionCoeffs):
+    """``OpenCV.solvePnPRansac`` up to the native call (``OpenCV.fs:976-1000``): returns
+    ``(rvec, tvec, inliers)`` or ``None`` when the lengths differ or the estimator fails.
+    The Rot3d / Euclidean3d conversion that follows in the reference is Aardvark-side."""
+    lib = native.load()
+    img = _pts(imgPoints)
+    world = np.ascontiguousarray(worldPoints, dtype=np.float64).reshape(-1, 3)
+    if img.shape[0] != world.shape[0]:
+        return None
+    K = native.Matx33d()
+    Kf = np.asarray(intern, np.float64).reshape(9)
+    for i in range(9):
+        K.M[i] = Kf[i]
+    dist = np.zeros(4)
+    d = np.asarray(distortionCoeffs, np.float64).ravel()
+    dist[:min(4, d.size)] = d[:4]
+    t = np.zeros(3)
+    r = np.zeros(3)
+    icnt = C.c_int(0)
+    inliers = np.zeros(max(img.shape[0], 1), np.int32)
+    ok = lib.cvSolvePnPRansac(_p(img), _p(world), img.shape[0], K, _p(dist), int(solver), int(cfg.iterationsCount),
+                              float(cfg.reprojectionError), float(cfg.confidence), _p(t), _p(r), C.addressof(icnt),
+                              _p(inliers))
+    if not ok:
+        return None
+    return r, t, inliers[:icnt.value].copy()
+
+
+def solveAp3p(img, world, inv_fx, inv_fy, cx_fx, cy_fy):
+    """``Native.solveAp3p`` (``OpenCV.fs:373-374``, reference ``ap3p.cpp:282``): up to four (R, t) through
+    three correspondences, R in the reference's layout (camera point = R^T X + t)."""
+    lib = native.load()
+    img = _pts(img)
+    world = np.ascontiguousarray(world, dtype=np.float64).reshape(-1, 3)
+    Rs = np.zeros((4, 9))
+    ts = np.zeros((4, 3))
+    args = []
+    for i in range(3):
+        args += [img[i, 0], img[i, 1], world[i, 0], world[i, 1], world[i, 2]]
+    n = lib.solveAp3p(_p(Rs), _p(ts), *[float(v) for v in args], float(inv_fx), float(inv_fy), float(cx_fx), float(cy_fy))
+    return Rs[:n].reshape(n, 3, 3).copy(), ts[:n].copy()
+
+
+def solve_ap3p_batch(img, world, cam4):
+    """Batched ``solveAp3p``: img [n,3,2], world [n,3,3], cam4 [n,4] -> (Rs [n,4,3,3], ts [n,4,3], counts)."""
+    lib = native.load()
+    img = np.ascontiguousarray(img, np.float64).reshape(-1, 3, 2)
+    world = np.ascontiguousarray(world, np.float64).reshape(-1, 3, 3)
+    cam4 = np.ascontiguousarray(cam4, np.float64).reshape(-1, 4)
+    n = img.shape[0]
+    Rs = np.zeros((n, 4, 9))
+    ts = np.zeros((n, 4, 3))
+    counts = np.zeros(n, np.int32)
+    native.check(lib.cvSolveAp3pBatch(_p(img), _p(world), _p(cam4), n, _p(Rs), _p(ts), _p(counts)), "cvSolveAp3pBatch")
+    return Rs.reshape(n, 4, 3, 3), ts, counts
+
+
+@dataclass
+class PnpBatchResult:
+    rvecs: np.ndarray
+    tvecs: np.ndarray
+    masks: np.ndarray
+    inlier_counts: np.ndarray
+    ok: np.ndarray
+    iters_run: np.ndarray
+    best_iter: np.ndarray
+    minimal: np.ndarray
+    dbg_counts: np.ndarray | None = None
+    dbg_models: np.ndarray | None = None
+    dbg_samples: np.ndarray | None = None
+    n_ok: int = 0
+
+
+def camera_rows(K, dist=None, n: int = 1) -> np.ndarray:
+    """[n, 8] camera rows (fx, fy, cx, cy, k1, k2, p1, p2) from a 3x3 K and up to four coefficients."""
+    K = np.asarray(K, np.float64).reshape(3, 3)
+    row = np.zeros(8)
+    row[:4] = (K[0, 0], K[1, 1], K[0, 2], K[1, 2])
+    if dist is not None:
+        d = np.asarray(dist, np.float64).ravel()
+        row[4:4 + min(4, d.size)] = d[:4]
+    return np.tile(row, (n, 1))
+
+
+def solve_pnp_ransac_batch(world, img, offsets, cams, thr: float = 8.0, maxIters: int = 100, confidence: float = 0.99,
+                           sample_mode: int = SAMPLE_MWC, stop_mode: int = STOP_ADAPTIVE, seed: int = 0,
+                           refine: bool = True, inj_samples=None, inj_models=None, debug: bool = False,
+                           device: int = -1) -> PnpBatchResult:
+    """``cvSolvePnPRansacBatch``: problem p owns rows [offsets[p], offsets[p+1])."""
+    lib = native.load()
+    world = np.ascontiguousarray(world, np.float64).reshape(-1, 3)
+    img = _pts(img)
+    off = np.ascontiguousarray(offsets, np.int64)
+    n = off.size - 1
+    cams = np.ascontiguousarray(cams, np.float64).reshape(-1, 8)
+    assert cams.shape[0] == n
+    prm = native.PnpParams(sample_mode if inj_samples is None else SAMPLE_INJECTED, stop_mode, maxIters, 1 if refine else 0,
+                           thr, confidence, seed)
+    total = int(off[-1])
+    rv = np.zeros((n, 3)); tv = np.zeros((n, 3))
+    masks = np.zeros(total, np.uint8)
+    cnt = np.zeros(n, np.int32); ok = np.zeros(n, np.uint8)
+    iters = np.zeros(n, np.int32); best = np.zeros(n, np.int32); minimal = np.zeros((n, 6))
+    js = np.ascontiguousarray(inj_samples, np.int32) if inj_samples is not None else None
+    jm = np.ascontiguousarray(inj_models, np.float64) if inj_models is not None else None
+    mi = max(maxIters, 1)
+    dc = np.zeros((n, mi), np.int32) if debug else None
+    dm = np.zeros((n, mi, 6)) if debug else None
+    ds = np.zeros((n, mi, 4), np.int32) if debug else None
+    rc = lib.cvSolvePnPRansacBatch(C.addressof(prm), _p(world), _p(img), _p(off), n, _p(cams), _p(js), _p(jm), _p(rv), _p(tv),
+                                   _p(masks), _p(cnt), _p(ok), _p(iters), _p(best), _p(minimal), _p(dc), _p(dm), _p(ds),
+                                   device)
+    native.check(rc, "cvSolvePnPRansacBatch")
+    return PnpBatchResult(rv, tv, masks, cnt, ok, iters, best, minimal, dc, dm, ds, rc)
+
+
+def solve_pnp_ransac_batch_device(d_world, d_img, offsets, d_cams, thr, maxIters, confidence, d_rvecs, d_tvecs, d_masks,
+                                  d_counts, d_ok, sample_mode: int = SAMPLE_MWC, stop_mode: int = STOP_ADAPTIVE,
+                                  seed: int = 0, refine: bool = True, device: int = -1, stream: int = 0):
+    """``cvSolvePnPRansacBatchDevice``: torch tensors (or raw device pointers), asynchronous."""
+    lib = native.load()
+    off = np.ascontiguousarray(offsets, np.int64)
+    prm = native.PnpParams(sample_mode, stop_mode, maxIters, 1 if refine else 0, thr, confidence, seed)
+    rc = lib.cvSolvePnPRansacBatchDevice(C.addressof(prm), _dp(d_world), _dp(d_img), _p(off), off.size - 1, _dp(d_cams),
+                                         _dp(d_rvecs), _dp(d_tvecs), _dp(d_masks), _dp(d_counts), _dp(d_ok), device, stream)
+    native.check(rc, "cvSolvePnPRansacBatchDevice")

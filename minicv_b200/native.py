@@ -91,7 +91,6 @@ SIGNATURES = {
     "cvFivePointBatch": (_i, [_vp, _vp, _i, _vp, _vp]),
     # group (3): forwarded to the original shim when present
     "cvSolvePnP": (C.c_bool, [_vp, _vp, _i, Matx33d, _vp, _i, _vp, _vp]),
-    "cvSolvePnPRansac": (C.c_bool, [_vp, _vp, _i, Matx33d, _vp, _i, _i, _f, _d, _vp, _vp, _vp, _vp]),
     "cvRefinePnPLM": (None, [_vp, _vp, _i, Matx33d, _vp, _vp, _vp]),
     "cvRefinePnPVVS": (None, [_vp, _vp, _i, Matx33d, _vp, _vp, _vp]),
     "cvDetectFeatures": (_vp, [_vp, _i, _i, _i, _i, _vp]),
@@ -99,8 +98,16 @@ SIGNATURES = {
     "cvDetectQRCode": (C.c_bool, [_vp, _i, _i, _i, _vp, _vp]),
     "cvDetectArucoMarkers": (C.c_bool, [_vp, _i, _i, _i, _vp, _vp]),
     "cvTest": (None, []),
-    "solveAp3p": (_i, [_vp, _vp] + [_d] * 19),
 }
+# group (2b): PnP RANSAC (AP3P solver kind native; other kinds of cvSolvePnPRansac are forwarded)
+SIGNATURES.update({
+    "cvSolvePnPRansac": (C.c_bool, [_vp, _vp, _i, Matx33d, _vp, _i, _i, _f, _d, _vp, _vp, _vp, _vp]),
+    "solveAp3p": (_i, [_vp, _vp] + [_d] * 19),
+    "cvSolveAp3pBatch": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "cvSolvePnPRansacBatch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _vp, _vp, _i]),
+    "cvSolvePnPRansacBatchDevice": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+})
 
 
 class RansacParams(C.Structure):
@@ -109,6 +116,14 @@ class RansacParams(C.Structure):
                 ("maxIters", C.c_int32), ("threshold", C.c_double), ("confidence", C.c_double),
                 ("seed", C.c_uint64), ("focal", C.c_double), ("ppx", C.c_double), ("ppy", C.c_double),
                 ("refine", C.c_int32), ("reserved", C.c_int32)]
+
+
+
+class PnpParams(C.Structure):
+    """``McvPnpParams`` of include/MiniCVNative.h."""
+    _fields_ = [("sampleMode", C.c_int32), ("stopMode", C.c_int32), ("maxIters", C.c_int32), ("refine", C.c_int32),
+                ("threshold", C.c_double), ("confidence", C.c_double), ("seed", C.c_uint64)]
+
 
 _lib = None
 
