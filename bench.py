@@ -457,6 +457,40 @@ def extra_ransac(local, with_cpu=True):
     if with_cpu:
         out["PnP_AP3P_opencv_semantics"]["cpu"] = cpu_ransac_pairs_per_s(
             "P", [(X[p * N:(p + 1) * N], U[p * N:(p + 1) * N]) for p in range(cores)], cores)
+    del dX, dU
+    # ---- scale search: CameraPose.findScaled, 2000 observations -> 4000 candidate scales x
+    #      2000 projections per problem
+    from minicv_b200 import camera_pose as mcp
+    P, N = 256, 2000
+    off = np.arange(P + 1, dtype=np.int64) * N
+    rows = np.empty((P, 14)); Rs = np.empty((P, 9)); Ts = np.empty((P, 3)); W = np.empty((P * N, 3)); O = np.empty((P * N, 2))
+    planted = np.empty(P)
+    for p in range(P):
+        rows[p], R, Ts[p], W[p * N:(p + 1) * N], O[p * N:(p + 1) * N], planted[p] = synth.scale_scene(p, N)
+        Rs[p] = R.ravel()
+    dCam = torch.from_numpy(rows).to(dev); dRot = torch.from_numpy(Rs).to(dev); dTr = torch.from_numpy(Ts).to(dev)
+    dW = torch.from_numpy(W).to(dev); dO = torch.from_numpy(O).to(dev)
+    dCost = torch.empty(P, dtype=torch.float64, device=dev); dSc = torch.empty(P, dtype=torch.float64, device=dev)
+    dST = torch.empty((P, 3), dtype=torch.float64, device=dev); dSg = torch.empty(P, dtype=torch.int32, device=dev)
+
+    def run_s():
+        mcp.find_scaled_batch_device(dCam, dRot, dTr, dW, dO, off, dCost, dSc, dST, dSg, device=local, stream=stream.cuda_stream)
+    t = timed(run_s, reps=3)
+    rel = np.abs(dSc.cpu().numpy() - planted) / planted
+    out["findScaled"] = {"problems_per_s": P / t, "ms_per_batch": t * 1e3, "problems": P, "observations": N,
+                         "candidates_per_problem": 2 * N, "geval_per_s": P * 2 * N * N / t / 1e9,
+                         "planted_scale_recovered": int((rel < 0.01).sum()),
+                         "mode": "CameraPose.findScaled semantics (every candidate costed against every observation, sums in order)"}
+    if with_cpu:
+        # no F# runtime and no OpenCV counterpart: the CPU figure is the numpy port (oracle/camera_pose.py), one core, one problem
+        from oracle import camera_pose as ocp
+        cam = ocp.Camera(rows[0, 0:3], rows[0, 3:6], rows[0, 6:9], rows[0, 9:12], rows[0, 12:14])
+        pose = ocp.CameraPose(0, 1, Rs[0].reshape(3, 3), Ts[0], False)
+        t0 = time.perf_counter()
+        oc, osc = ocp.find_scaled_fast(cam, W[:N], O[:N], pose)[:2]
+        dt = time.perf_counter() - t0
+        out["findScaled"]["cpu"] = {"problems_per_s": 1.0 / dt, "cores": 1, "kind": "port (numpy restatement, vectorised)",
+                                    "sample": "problem 0", "bit_identical_to_gpu": bool(oc == float(dCost[0].item()) and osc == float(dSc[0].item()))}
     return out
 
 

@@ -325,6 +325,55 @@ MCV_API int cvSolvePnPRansacBatchDevice(const McvPnpParams* prm, const double* d
                                         double* dRvecs, double* dTvecs, uint8_t* dMasks,
                                         int32_t* dInlierCounts, uint8_t* dOk, int device, void* stream);
 
+/* ---- (2c) scale search -------------------------------------------
+ * CameraPose.findScaled (managed code in the reference: src/MiniCV/CameraPose.fs:39-134, with
+ * Camera.transformedView / project1, src/MiniCV/Camera.fs:61-84) moved behind the native boundary: every
+ * observation proposes two candidate scales for the pose's unit translation and every candidate is costed
+ * against all observations -- O(2 n^2) projections, one candidate per GPU thread, sums in the reference's
+ * order.  New exports (the reference has no native counterpart); blittable mirrors of the F# types: */
+typedef struct {               /* F# record Camera (Camera.fs:7-14), field order kept */
+    double location[3];
+    double forward[3];
+    double up[3];
+    double right[3];
+    double focal[2];
+} McvCamera;                   /* 112 bytes */
+typedef struct {               /* F# struct CameraPose (CameraPose.fs:7-16), sequential layout */
+    int32_t RotationIndex;
+    int32_t ScaleSign;
+    double  Rotation[9];       /* M33d, row-major */
+    double  Translation[3];
+    int32_t IsInverse;         /* bool marshalled as a 4-byte BOOL */
+    int32_t _pad;
+} McvCameraPose;               /* 112 bytes */
+
+/* == CameraPose.findScaled inlierThreshold srcCam worldObservations pose: returns the cost and writes
+ * CameraPose.scale bestScale pose to *scaled.  n = 0 -> +inf and an all-zero pose (CameraPose.fs:42);
+ * NaN on error (outputs untouched).  inlierThreshold is accepted and unused, as in the reference. */
+MCV_API double cvFindScaled(double inlierThreshold, const McvCamera* srcCam, const McvPoint3d* world,
+                            const McvPoint2d* obs, int n, const McvCameraPose* pose, McvCameraPose* scaled);
+/* Batched form: problem p owns rows [offsets[p], offsets[p+1]) of world / obs, camera srcCams[p] and pose
+ * poses[p].  Outputs (host): costs, scaled [nProblems]; optional bestScales [nProblems] and parity taps over
+ * candidate c = 2 i + {0: x-equation, 1: y-equation} of observation i: candidates, candOk (0 where the
+ * reference's Fun.IsTiny test rejects the observation), candCosts (+inf where rejected) [2 * total rows].
+ * Returns 0, or -1 on error. */
+MCV_API int cvFindScaledBatch(const McvCamera* srcCams, const McvCameraPose* poses, const McvPoint3d* world,
+                              const McvPoint2d* obs, const int64_t* offsets, int nProblems, double* costs,
+                              McvCameraPose* scaled, double* bestScales, double* candidates, uint8_t* candOk,
+                              double* candCosts, int device);
+/* Device-resident form (offsets on the host; asynchronous on `stream`): dCams [nProblems][14], dRot
+ * [nProblems][9], dTrans [nProblems][3], dWorld [total][3], dObs [total][2] -> dCosts, dBestScales
+ * [nProblems], dScaledT [nProblems][3], dSigns [nProblems] (sign of the best scale). */
+MCV_API int cvFindScaledBatchDevice(const double* dCams, const double* dRot, const double* dTrans,
+                                    const double* dWorld, const double* dObs, const int64_t* offsets,
+                                    int nProblems, double* dCosts, double* dBestScales, double* dScaledT,
+                                    int32_t* dSigns, int device, void* stream);
+/* == avgReprojectionError s (CameraPose.fs:75-90) for nScales given scales of one problem (parity tap for
+ * injected scales): costs[k] = mean squared reprojection error under scale scales[k], +inf when no
+ * observation projects.  Returns 0, or -1. */
+MCV_API int cvScaleCosts(const McvCamera* srcCam, const McvCameraPose* pose, const McvPoint3d* world,
+                         const McvPoint2d* obs, int n, const double* scales, int nScales, double* costs);
+
 /* ---- (3) reference exports that are not on the path: forwarded, not implemented -----------
  * Signatures are the reference's (src/MiniCVNative/MiniCVNative.cpp:48,140,152,221,347,384,
  * 439,504; cvSolvePnPRansac for solver kinds other than AP3P).  Each call is forwarded to a side-by-side build of the original shim

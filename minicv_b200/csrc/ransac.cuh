@@ -128,3 +128,33 @@ int ap3p_batch_device(Context* ctx, cudaStream_t stream, const double* dImg, con
                       int n, double* dRs, double* dTs, int* dCounts);
 
 }  // namespace mcv
+
+namespace mcv {
+
+// ---- scale search (scale_search.cu): CameraPose.findScaled (src/MiniCV/CameraPose.fs:39-134), batched ----
+struct ScaleIO {
+    const double* dCams = nullptr;         // [nProblems][14]: location, forward, up, right, focal (Camera.fs:7-14)
+    const double* dRot = nullptr;          // [nProblems][9]  pose.Rotation, row-major
+    const double* dTrans = nullptr;        // [nProblems][3]  pose.Translation
+    const double* dWorld = nullptr;        // [total][3]
+    const double* dObs = nullptr;          // [total][2]
+    const int64_t* hOff = nullptr;         // host, nProblems+1
+    int nProblems = 0;
+    double* dCost = nullptr;               // [nProblems] best cost (+inf when no candidate projects anything)
+    double* dBestScale = nullptr;          // [nProblems]
+    double* dScaledT = nullptr;            // [nProblems][3] bestScale * Translation
+    int*    dSign = nullptr;               // [nProblems] sign(bestScale)
+    // parity taps (device, optional): candidate c = 2 i + {0: from x, 1: from y} of observation i
+    double*  dCand = nullptr;              // [2 total]
+    uint8_t* dCandOk = nullptr;            // [2 total] 0 where Fun.IsTiny rejected the observation
+    double*  dCandCost = nullptr;          // [2 total] (+inf where rejected)
+};
+// Asynchronous on `stream`.  Uses ctx workspaces 64..65, pinned buffer 4, event 5.
+int find_scaled_batch_device(Context* ctx, cudaStream_t stream, const ScaleIO& io);
+// avgReprojectionError (CameraPose.fs:75-90) of given scales: problem p owns scales [dScaleOff[p], dScaleOff[p+1]).
+int scale_costs_device(Context* ctx, cudaStream_t st, const double* dCams, const double* dRot, const double* dTrans,
+                       const double* dWorld, const double* dObs, const int64_t* dOff, int nProblems,
+                       const double* dScales, const uint8_t* dScaleOk, const int64_t* dScaleOff, int64_t maxScales,
+                       double* dCosts);
+
+}  // namespace mcv

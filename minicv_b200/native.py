@@ -108,6 +108,28 @@ SIGNATURES.update({
                                    _vp, _vp, _vp, _i]),
     "cvSolvePnPRansacBatchDevice": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
 })
+# group (2c): scale search (CameraPose.findScaled moved behind the native boundary)
+SIGNATURES.update({
+    "cvFindScaled": (_d, [_d, _vp, _vp, _vp, _i, _vp, _vp]),
+    "cvFindScaledBatch": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "cvFindScaledBatchDevice": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "cvScaleCosts": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+})
+
+
+class Camera(C.Structure):
+    """``McvCamera``: blittable mirror of the F# record ``Camera`` (``src/MiniCV/Camera.fs:7-14``)."""
+    _fields_ = [("location", C.c_double * 3), ("forward", C.c_double * 3), ("up", C.c_double * 3),
+                ("right", C.c_double * 3), ("focal", C.c_double * 2)]
+
+
+class CameraPose(C.Structure):
+    """``McvCameraPose``: the F# struct ``CameraPose`` (``src/MiniCV/CameraPose.fs:7-16``)."""
+    _fields_ = [("RotationIndex", C.c_int32), ("ScaleSign", C.c_int32), ("Rotation", C.c_double * 9),
+                ("Translation", C.c_double * 3), ("IsInverse", C.c_int32), ("_pad", C.c_int32)]
+
+
+assert C.sizeof(Camera) == 112 and C.sizeof(CameraPose) == 112
 
 
 class RansacParams(C.Structure):

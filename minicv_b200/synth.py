@@ -165,3 +165,38 @@ def pnp_scene(rng, n: int, inlier_frac: float = 0.4, noise: float = 0.5, K=None)
     if n_out > 0:
         uv[:n_out] = np.stack([rng.uniform(0, 640, n_out), rng.uniform(0, 480, n_out)], axis=1)
     return np.ascontiguousarray(X), np.ascontiguousarray(uv), rvec, tvec
+
+
+def scale_scene(seed: int, n: int = 2000, noise: float = 1e-3, outlier_frac: float = 0.0):
+    """Scale-search problem (``CameraPose.findScaled``): a source camera, a unit-translation
+    pose (R, T) as ``recoverPoses2`` returns it, a planted scale, and ``n`` (world point, observation) pairs seen by
+    the camera that pose and scale produce; ``outlier_frac`` of the observations are uniform in the image.
+    Observations are in the reference's normalised image units (|x|,|y| <= 1) with focal = (-1,-1): the candidate
+    equations of ``findScaled`` (``CameraPose.fs:104-113``) agree with ``Camera.project1`` only for that sign.
+    Returns (cam_row [14], R [3,3], T [3], world [n,3], obs [n,2], planted_scale)."""
+    rng = np.random.default_rng(5000 + seed)
+    eye = np.array([0.3, -4.0, 1.2]) + rng.normal(0, 0.2, 3)
+    fw = np.array([0.0, 0.0, 0.5]) - eye
+    fw /= np.linalg.norm(fw)
+    right = np.cross(fw, [0.0, 0.0, 1.0]); right /= np.linalg.norm(right)
+    up = np.cross(right, fw); up /= np.linalg.norm(up)
+    focal = np.array([-1.0, -1.0])
+    axis = rng.normal(0, 1, 3)
+    R = rodrigues(axis, rng.uniform(0.05, 0.25))
+    T = rng.normal(0, 1, 3); T /= np.linalg.norm(T)
+    s = float(rng.uniform(0.2, 0.8))
+    basis = np.stack([right, up, -fw], axis=1)                    # columns: camera axes in the world
+    loc2 = eye + basis @ (R @ (s * T))
+    axes2 = basis @ R                                             # columns: right, up, -forward of the moved camera
+    # points in front of the moved camera, inside its field of view
+    depth = rng.uniform(2.5, 6.0, n)
+    xy = rng.uniform(-0.9, 0.9, (n, 2))
+    pc = np.stack([xy[:, 0] * depth / focal[0], xy[:, 1] * depth / focal[1], depth], axis=1)   # (right, up, forward)
+    world = loc2 + pc[:, 0:1] * axes2[:, 0] + pc[:, 1:2] * axes2[:, 1] - pc[:, 2:3] * axes2[:, 2]
+    obs = xy + rng.normal(0, noise, (n, 2))
+    n_out = int(n * outlier_frac)
+    if n_out:
+        idx = rng.permutation(n)[:n_out]
+        obs[idx] = rng.uniform(-1, 1, (n_out, 2))
+    cam_row = np.concatenate([eye, fw, up, right, focal])
+    return cam_row, R, T, world, obs, s

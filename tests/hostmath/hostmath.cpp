@@ -92,3 +92,60 @@ void hm_epnp(const double* cam, const double* obj, const double* img, int n, dou
     delete[] und;
 }
 }
+
+// ---- scale-search row (scalemath.cuh) ---------------------------------------------------------------
+#include "../../minicv_b200/csrc/scalemath.cuh"
+
+extern "C" {
+using namespace mcv::scm;
+
+static Cam cam_from_row(const double* c) {
+    Cam cam;
+    for (int i = 0; i < 3; ++i) { cam.loc[i] = c[i]; cam.fwd[i] = c[3 + i]; cam.up[i] = c[6 + i]; cam.right[i] = c[9 + i]; }
+    cam.focal[0] = c[12]; cam.focal[1] = c[13];
+    return cam;
+}
+int hm_lu_inverse4(const double* A, double* inv) { return lu_inverse4(A, inv) ? 1 : 0; }
+// camera (14 doubles, McvCamera order) that scale s produces
+void hm_camera_for_scale(const double* camRow, const double* R, const double* T, double s, double* outRow) {
+    const Cam src = cam_from_row(camRow);
+    double basis[16];
+    camera_basis(src, basis);
+    Cam out;
+    camera_for_scale(basis, src.focal, R, T, s, out);
+    for (int i = 0; i < 3; ++i) { outRow[i] = out.loc[i]; outRow[3 + i] = out.fwd[i]; outRow[6 + i] = out.up[i]; outRow[9 + i] = out.right[i]; }
+    outRow[12] = out.focal[0]; outRow[13] = out.focal[1];
+}
+// candidates [n][2], ok [n]
+void hm_candidate_scales(const double* camRow, const double* R, const double* T, const double* world, const double* obs,
+                         int n, double* cand, unsigned char* ok) {
+    ScaleSetup S;
+    scale_setup(cam_from_row(camRow), R, T, S);
+    for (int i = 0; i < n; ++i) {
+        double sx = 0, sy = 0;
+        ok[i] = candidate_scales(S, world + 3 * i, obs + 2 * i, sx, sy) ? 1 : 0;
+        cand[2 * i] = sx; cand[2 * i + 1] = sy;
+    }
+}
+// avgReprojectionError for each scale
+void hm_scale_costs(const double* camRow, const double* R, const double* T, const double* world, const double* obs, int n,
+                    const double* scales, int ns, double* costs) {
+    const Cam src = cam_from_row(camRow);
+    double basis[16];
+    camera_basis(src, basis);
+    for (int k = 0; k < ns; ++k) {
+        Cam cam;
+        camera_for_scale(basis, src.focal, R, T, scales[k], cam);
+        double sum = 0.0;
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) {
+            double term;
+            if (project_term(cam, world[3 * i], world[3 * i + 1], world[3 * i + 2], obs[2 * i], obs[2 * i + 1], term)) {
+                sum = dadd(sum, term);
+                ++cnt;
+            }
+        }
+        costs[k] = cnt ? ddiv(sum, (double)cnt) : INFINITY;
+    }
+}
+}
