@@ -81,7 +81,8 @@ def _native_cam(cam: Camera) -> native.Camera:
 
 def _split(worldObservations):
     """``list<V3d * V2d>`` -> packed world [n,3] and observation [n,2] arrays."""
-    if isinstance(worldObservations, tuple) and len(worldObservations) == 2 and np.ndim(worldObservations[0]) == 2:
+    if isinstance(worldObservations, tuple) and len(worldObservations) == 2 and (
+            np.ndim(worldObservations[0]) == 2 or np.size(worldObservations[0]) == 0):
         w, o = worldObservations
     else:
         w = [wo[0] for wo in worldObservations]

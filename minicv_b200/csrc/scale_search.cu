@@ -106,13 +106,32 @@ scale_cost_kernel(const double* __restrict__ cams, const double* __restrict__ ro
         }
         __syncthreads();
         if (active) {
-#pragma unroll 4
-            for (int i = 0; i < tn; ++i) {
-                const double2 a = *reinterpret_cast<const double2*>(&tile[6 * i]);
-                const double2 b = *reinterpret_cast<const double2*>(&tile[6 * i + 2]);
-                const double oy = tile[6 * i + 4];
+            // four observations at a time: the fast-path chains are independent and interleave; the generic
+            // division (denormal / huge quotients) is decided once per group and is rare
+            int i = 0;
+            for (; i + 4 <= tn; i += 4) {
+                double term[4];
+                bool ok[4];
+                bool exact = true;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double2 a = *reinterpret_cast<const double2*>(&tile[6 * (i + k)]);
+                    const double2 b = *reinterpret_cast<const double2*>(&tile[6 * (i + k) + 2]);
+                    exact &= project_term_t<true>(cam, a.x, a.y, b.x, b.y, tile[6 * (i + k) + 4], term[k], ok[k]);
+                }
+                if (!exact) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ok[k] = project_term(cam, tile[6 * (i + k)], tile[6 * (i + k) + 1], tile[6 * (i + k) + 2],
+                                             tile[6 * (i + k) + 3], tile[6 * (i + k) + 4], term[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (ok[k]) { sum = dadd(sum, term[k]); ++cnt; }
+            }
+            for (; i < tn; ++i) {
                 double term;
-                if (project_term(cam, a.x, a.y, b.x, b.y, oy, term)) {
+                if (project_term(cam, tile[6 * i], tile[6 * i + 1], tile[6 * i + 2], tile[6 * i + 3], tile[6 * i + 4], term)) {
                     sum = dadd(sum, term);
                     ++cnt;
                 }
