@@ -378,6 +378,60 @@ MCV_HD bool f_inlier(const double* F, double x1, double y1, double x2, double y2
     return (float)((e1 < e2) ? e2 : e1) <= thr;
 }
 
+// ---- fp32 filter in front of f_inlier ------------------------------------------------------------
+// Almost every (model, correspondence) pair of a RANSAC batch is an outlier by a wide margin, and the exact test
+// above costs ~52 FP64-pipe instructions.  The filter evaluates ONE of the two point-line distances (the line F x1
+// in image 2) in fp32 with FMAs, together with a running bound of its own rounding error, and answers "certainly an
+// outlier" only when the distance exceeds the threshold by more than every error that could have been made; the
+// caller runs the exact test on everything else, so the result is f_inlier's, bit for bit.
+//
+// Error budget (u = 2^-24; points are exact fp32, F_i are converted with relative error u; filter is switched off
+// for a model with a non-finite entry or a non-zero entry below 1e-30, so conversions never underflow):
+//   a~ = fma(F0,x1, fma(F1,y1,F2)):  |a~ - a| <= 4u A,  A = |F0||x1| + |F1||y1| + |F2|   (same for b, c)
+//   d~ = fma(x2,a~, fma(y2,b~,c~)):  |d~ - d| <= 7u D,  D = |x2| A + |y2| B + C
+//   A, B, C, D are themselves computed in fp32 (sums of non-negative terms: relative error <= 6u) and carry an
+//   absolute slack (FILTER_TINY inside A, B, C) that dominates any underflow (2^-149 per operation).
+// With EPS_A = 8u and EPS_D = 16u:  L = |d~| - EPS_D D  <=  |d|,   N = (|a~| + EPS_A A)^2 + (|b~| + EPS_A B)^2 >= (a^2 + b^2)(1 - 2u),
+// so L > 0 and L^2 > thr (1 + 2^-10) N (with N >= 1e-30: no underflow in the squares) implies d^2 / (a^2 + b^2) >
+// thr (1 + 2^-11): the fp64 value e2 of f_error exceeds thr by far more than its own rounding, (float)max(e1, e2) >
+// thr, and f_inlier returns false on every one of its paths.
+struct FFilter {
+    float f[9];
+    bool on;
+};
+constexpr float FILTER_TINY = 1e-30f;
+constexpr float FILTER_EPS_A = 4.76837158203125e-07f;     // 8 * 2^-24
+constexpr float FILTER_EPS_D = 9.5367431640625e-07f;      // 16 * 2^-24
+constexpr float FILTER_MARGIN = 1.0009765625f;            // 1 + 2^-10
+
+MCV_HD void f_filter_init(const double* F, FFilter& ff) {
+    bool on = true;
+    for (int i = 0; i < 9; ++i) {
+        const double v = fabs(F[i]);
+        if (!(v <= 1e30) || (v != 0.0 && v < 1e-30)) on = false;     // also catches NaN
+        ff.f[i] = (float)F[i];
+    }
+    ff.on = on;
+}
+
+// thrM = thr * FILTER_MARGIN, precomputed by the caller
+MCV_HD bool f_certain_outlier(const FFilter& ff, float x1, float y1, float x2, float y2, float thrM) {
+    const float ax1 = fabsf(x1), ay1 = fabsf(y1);
+    const float a = fmaf(ff.f[0], x1, fmaf(ff.f[1], y1, ff.f[2]));
+    const float A = fmaf(fabsf(ff.f[0]), ax1, fmaf(fabsf(ff.f[1]), ay1, fabsf(ff.f[2]) + FILTER_TINY));
+    const float b = fmaf(ff.f[3], x1, fmaf(ff.f[4], y1, ff.f[5]));
+    const float B = fmaf(fabsf(ff.f[3]), ax1, fmaf(fabsf(ff.f[4]), ay1, fabsf(ff.f[5]) + FILTER_TINY));
+    const float c = fmaf(ff.f[6], x1, fmaf(ff.f[7], y1, ff.f[8]));
+    const float C = fmaf(fabsf(ff.f[6]), ax1, fmaf(fabsf(ff.f[7]), ay1, fabsf(ff.f[8]) + FILTER_TINY));
+    const float d = fmaf(x2, a, fmaf(y2, b, c));
+    const float D = fmaf(fabsf(x2), A, fmaf(fabsf(y2), B, C));
+    const float L = fmaf(-FILTER_EPS_D, D, fabsf(d));
+    const float ah = fmaf(FILTER_EPS_A, A, fabsf(a));
+    const float bh = fmaf(FILTER_EPS_A, B, fabsf(b));
+    const float N = fmaf(ah, ah, bh * bh);
+    return ff.on && L > 0.0f && N >= 1e-30f && L * L > thrM * N;      // any NaN / inf makes a comparison fail
+}
+
 MCV_HD bool e_inlier(const double* E, double x1, double y1, double x2, double y2, float thr) {
     const double t = (double)thr, tl = t * (1.0 - 2e-7), th = t * (1.0 + 2e-7);
     const double Ex0 = dadd(dadd(dmul(E[0], x1), dmul(E[1], y1)), E[2]);

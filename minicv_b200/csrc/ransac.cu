@@ -436,6 +436,9 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) Hf[j] = (float)m[j];
+    FFilter ffil;
+    const float thrM = thr2 * FILTER_MARGIN;
+    if (MODEL == RM_FUNDAMENTAL) f_filter_init(m, ffil);
 
     int cnt = 0;
     for (int s0 = i0; s0 < i1; s0 += TP) {
@@ -458,11 +461,34 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
                 cnt += (h_error(Hf, q.x, q.y, q.z, q.w) <= thr2) ? 1 : 0;
             }
         } else if (MODEL == RM_FUNDAMENTAL) {
+            // filtered exact scoring: 64 correspondences through the fp32 filter (cvmath.cuh, f_certain_outlier),
+            // the survivors -- about 1 % for a wrong model -- collected in a bit mask and given the exact fp64 test
+            // afterwards, so the FP64 work of a warp is the longest survivor list of its 32 models, not 64
             const float4* sp = reinterpret_cast<const float4*>(sraw);
-#pragma unroll 2
-            for (int j = 0; j < rows; ++j) {
-                const float4 q = sp[j];
-                cnt += f_inlier(m, (double)q.x, (double)q.y, (double)q.z, (double)q.w, thr2) ? 1 : 0;
+            for (int j0 = 0; j0 < rows; j0 += 64) {
+                const int jn = min(64, rows - j0);
+                unsigned long long pending = 0;
+                if (jn == 64) {
+#pragma unroll 8
+                    for (int j = 0; j < 64; ++j) {
+                        const float4 q = sp[j0 + j];
+                        if (!f_certain_outlier(ffil, q.x, q.y, q.z, q.w, thrM)) pending |= 1ull << j;
+                    }
+                } else {
+                    for (int j = 0; j < jn; ++j) {
+                        const float4 q = sp[j0 + j];
+                        if (!f_certain_outlier(ffil, q.x, q.y, q.z, q.w, thrM)) pending |= 1ull << j;
+                    }
+                }
+                if (!active) pending = 0;
+                while (__any_sync(0xFFFFFFFFu, pending != 0)) {
+                    if (pending) {
+                        const int j = __ffsll((long long)pending) - 1;
+                        pending &= pending - 1;
+                        const float4 q = sp[j0 + j];
+                        cnt += f_inlier(m, (double)q.x, (double)q.y, (double)q.z, (double)q.w, thr2) ? 1 : 0;
+                    }
+                }
             }
         } else {
             const double4* sp = reinterpret_cast<const double4*>(sraw);

@@ -149,3 +149,20 @@ void hm_scale_costs(const double* camRow, const double* R, const double* T, cons
     }
 }
 }
+
+// ---- fp32 filter in front of f_inlier (cvmath.cuh) ---------------------------------------------------
+extern "C" {
+// For n (model, point) pairs: filt[i] = filter says "certainly outlier", exact[i] = f_inlier.
+void hm_f_filter(const double* F, int nModels, const float* a, const float* b, int n, float thr, unsigned char* filt,
+                 unsigned char* exact) {
+    for (int k = 0; k < nModels; ++k) {
+        FFilter ff;
+        f_filter_init(F + 9 * k, ff);
+        const float thrM = thr * FILTER_MARGIN;
+        for (int i = 0; i < n; ++i) {
+            filt[(size_t)k * n + i] = f_certain_outlier(ff, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], thrM) ? 1 : 0;
+            exact[(size_t)k * n + i] = f_inlier(F + 9 * k, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], thr) ? 1 : 0;
+        }
+    }
+}
+}

@@ -219,3 +219,56 @@ def test_pnp_building_blocks(hm, dk):
         hm.hm_epnp(p(cam), p(np.ascontiguousarray(g[f"epnp_{dk}_{n}_obj"])), p(np.ascontiguousarray(g[f"epnp_{dk}_{n}_img"])), n, p(rv), p(tv))
         np.testing.assert_allclose(rv, g[f"epnp_{dk}_{n}_rvec"], rtol=0, atol=1e-8)
         np.testing.assert_allclose(tv, g[f"epnp_{dk}_{n}_tvec"], rtol=0, atol=1e-8)
+
+
+# ---- fp32 filter in front of the exact fundamental-matrix inlier test --------------------------------
+def test_f_filter_is_conservative(hm):
+    """f_certain_outlier may only fire where f_inlier is false -- on realistic models, on models that almost fit
+    (where the decision is within rounding of the threshold), and on badly scaled / degenerate / non-finite ones --
+    and it must remove most of the work on a wrong model."""
+    rng = np.random.default_rng(7)
+    a, b, gt, R, t = synth.two_view_pair(2, 4000)
+    af, bf = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    g = np.load(GOLDEN / "ransac_hf.npz")
+    Fgood = g["f2_F"].ravel()
+    models = []
+    # 7-point models from random samples of this very pair (what RANSAC scores)
+    F7 = np.zeros(27)
+    for _ in range(300):
+        idx = rng.permutation(len(af))[:7]
+        n = hm.hm_f_solve7(p(np.ascontiguousarray(af[idx])), p(np.ascontiguousarray(bf[idx])), p(F7))
+        for k in range(n):
+            models.append(F7[9 * k:9 * k + 9].copy())
+    # the same with inlier-only samples (near-perfect models: many decisions close to the threshold)
+    inl = np.flatnonzero(gt)
+    for _ in range(100):
+        idx = rng.choice(inl, 7, replace=False)
+        n = hm.hm_f_solve7(p(np.ascontiguousarray(af[idx])), p(np.ascontiguousarray(bf[idx])), p(F7))
+        for k in range(n):
+            models.append(F7[9 * k:9 * k + 9].copy())
+    base = models[0]
+    # scalings over the whole exponent range, degenerate rows, non-finite entries
+    for sc in (1e-40, 1e-33, 1e-20, 1e-6, 1e6, 1e20, 1e29, 1e35, 1e300):
+        models.append(base * sc)
+    z = base.copy(); z[:6] = 0; models.append(z)
+    z = base.copy(); z[:6] *= 1e-25; models.append(z)
+    z = base.copy(); z[6:] = 0; models.append(z)
+    z = base.copy(); z[4] = np.nan; models.append(z)
+    z = base.copy(); z[8] = np.inf; models.append(z)
+    models.append(np.zeros(9))
+    models.append(rng.normal(0, 1, 9))
+    M = np.ascontiguousarray(np.stack(models))
+    n = len(af)
+    for thr in (9.0, 1.0, 1e-4):
+        filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
+        hm.hm_f_filter(p(M), len(M), p(af), p(bf), n, C.c_float(thr), p(filt), p(exact))
+        assert not (filt & exact).any(), "filter rejected an inlier"
+        if thr == 9.0:
+            wrong = exact[:300].sum(axis=1) < 0.05 * n          # wrong models among the first random-sample ones
+            assert filt[:300][wrong].mean() > 0.95              # >95 % of their evaluations never reach fp64
+    # points far outside the image, tiny and huge coordinates
+    af2 = (af * rng.choice([1e-20, 1e-3, 1.0, 1e3, 1e15], size=(n, 1))).astype(np.float32)
+    bf2 = (bf * rng.choice([1e-20, 1e-3, 1.0, 1e3, 1e15], size=(n, 1))).astype(np.float32)
+    filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
+    hm.hm_f_filter(p(M), len(M), p(af2), p(bf2), n, C.c_float(9.0), p(filt), p(exact))
+    assert not (filt & exact).any()
