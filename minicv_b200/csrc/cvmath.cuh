@@ -414,22 +414,37 @@ MCV_HD void f_filter_init(const double* F, FFilter& ff) {
     ff.on = on;
 }
 
-// thrM = thr * FILTER_MARGIN, precomputed by the caller
-MCV_HD bool f_certain_outlier(const FFilter& ff, float x1, float y1, float x2, float y2, float thrM) {
-    const float ax1 = fabsf(x1), ay1 = fabsf(y1);
+// The error terms for a whole tile of correspondences at once: with X1 >= |x1|, Y1 >= |y1|, X2 >= |x2|, Y2 >= |y2|
+// for every correspondence of the tile, A <= Amax = |F0| X1 + |F1| Y1 + |F2| (same for B, C) and D <= X2 Amax + Y2 Bmax
+// + Cmax, so the three bounds the filter subtracts / adds are constants of (model, tile):
+//   eA = EPS_A Amax, eB = EPS_A Bmax, eD = EPS_D Dmax.   A NaN / inf bound (NaN coordinate in the tile, huge model)
+// makes every comparison of the filter fail, i.e. sends everything to the exact test.
+struct FFilterTile {
+    float eA, eB, eD;
+};
+MCV_HD void f_filter_tile(const FFilter& ff, float X1, float Y1, float X2, float Y2, FFilterTile& t) {
+    const float A = fmaf(fabsf(ff.f[0]), X1, fmaf(fabsf(ff.f[1]), Y1, fabsf(ff.f[2]) + FILTER_TINY));
+    const float B = fmaf(fabsf(ff.f[3]), X1, fmaf(fabsf(ff.f[4]), Y1, fabsf(ff.f[5]) + FILTER_TINY));
+    const float Cc = fmaf(fabsf(ff.f[6]), X1, fmaf(fabsf(ff.f[7]), Y1, fabsf(ff.f[8]) + FILTER_TINY));
+    const float D = fmaf(X2, A, fmaf(Y2, B, Cc));
+    t.eA = FILTER_EPS_A * A;
+    t.eB = FILTER_EPS_A * B;
+    t.eD = ff.on ? FILTER_EPS_D * D : INFINITY;                  // filter off: L = -inf, nothing is ever rejected
+}
+
+// thrM = thr * FILTER_MARGIN, precomputed by the caller.  Written so that it costs one compare: L is clamped at 0
+// (a non-positive lower bound proves nothing: 0 > thrM N is false) and N is raised to 1e-30 (still an upper bound of
+// a^2 + b^2, and above the range where the squares could have underflowed); a NaN anywhere fails the comparison.
+MCV_HD bool f_certain_outlier(const FFilter& ff, const FFilterTile& t, float x1, float y1, float x2, float y2, float thrM) {
     const float a = fmaf(ff.f[0], x1, fmaf(ff.f[1], y1, ff.f[2]));
-    const float A = fmaf(fabsf(ff.f[0]), ax1, fmaf(fabsf(ff.f[1]), ay1, fabsf(ff.f[2]) + FILTER_TINY));
     const float b = fmaf(ff.f[3], x1, fmaf(ff.f[4], y1, ff.f[5]));
-    const float B = fmaf(fabsf(ff.f[3]), ax1, fmaf(fabsf(ff.f[4]), ay1, fabsf(ff.f[5]) + FILTER_TINY));
     const float c = fmaf(ff.f[6], x1, fmaf(ff.f[7], y1, ff.f[8]));
-    const float C = fmaf(fabsf(ff.f[6]), ax1, fmaf(fabsf(ff.f[7]), ay1, fabsf(ff.f[8]) + FILTER_TINY));
     const float d = fmaf(x2, a, fmaf(y2, b, c));
-    const float D = fmaf(fabsf(x2), A, fmaf(fabsf(y2), B, C));
-    const float L = fmaf(-FILTER_EPS_D, D, fabsf(d));
-    const float ah = fmaf(FILTER_EPS_A, A, fabsf(a));
-    const float bh = fmaf(FILTER_EPS_A, B, fabsf(b));
-    const float N = fmaf(ah, ah, bh * bh);
-    return ff.on && L > 0.0f && N >= 1e-30f && L * L > thrM * N;      // any NaN / inf makes a comparison fail
+    const float L = fmaxf(fabsf(d) - t.eD, 0.0f);
+    const float ah = fabsf(a) + t.eA;
+    const float bh = fabsf(b) + t.eB;
+    const float N = fmaxf(fmaf(ah, ah, bh * bh), 1e-30f);
+    return L * L > thrM * N;
 }
 
 MCV_HD bool e_inlier(const double* E, double x1, double y1, double x2, double y2, float thr) {

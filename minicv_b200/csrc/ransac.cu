@@ -413,6 +413,7 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
              float thr2, int chunkPts, int* __restrict__ counts) {
     constexpr int TP = (MODEL == RM_ESSENTIAL) ? 512 : 1024;   // 16 KB per stage
     __shared__ __align__(16) unsigned char sraw[16384];
+    __shared__ int smax[4];
     const int p = blockIdx.y;
     const int total = nTotal[p];
     const int k = blockIdx.x * 128 + threadIdx.x;
@@ -447,6 +448,25 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
             double4* sp = reinterpret_cast<double4*>(sraw);
             const double4* g = reinterpret_cast<const double4*>(pd) + base + s0;
             for (int j = threadIdx.x; j < rows; j += 128) sp[j] = g[j];
+        } else if (MODEL == RM_FUNDAMENTAL) {
+            // also the largest |x1|, |y1|, |x2|, |y2| of the tile (bit patterns of non-negative floats order like
+            // integers, and a NaN sorts above everything, which switches the filter off for the tile)
+            if (threadIdx.x < 4) smax[threadIdx.x] = 0;
+            __syncthreads();
+            float4* sp = reinterpret_cast<float4*>(sraw);
+            const float4* g = pf + base + s0;
+            int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+            for (int j = threadIdx.x; j < rows; j += 128) {
+                const float4 q = g[j];
+                sp[j] = q;
+                m0 = max(m0, __float_as_int(fabsf(q.x))); m1 = max(m1, __float_as_int(fabsf(q.y)));
+                m2 = max(m2, __float_as_int(fabsf(q.z))); m3 = max(m3, __float_as_int(fabsf(q.w)));
+            }
+            m0 = __reduce_max_sync(0xFFFFFFFFu, m0); m1 = __reduce_max_sync(0xFFFFFFFFu, m1);
+            m2 = __reduce_max_sync(0xFFFFFFFFu, m2); m3 = __reduce_max_sync(0xFFFFFFFFu, m3);
+            if ((threadIdx.x & 31) == 0) {
+                atomicMax(&smax[0], m0); atomicMax(&smax[1], m1); atomicMax(&smax[2], m2); atomicMax(&smax[3], m3);
+            }
         } else {
             float4* sp = reinterpret_cast<float4*>(sraw);
             const float4* g = pf + base + s0;
@@ -465,22 +485,32 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
             // the survivors -- about 1 % for a wrong model -- collected in a bit mask and given the exact fp64 test
             // afterwards, so the FP64 work of a warp is the longest survivor list of its 32 models, not 64
             const float4* sp = reinterpret_cast<const float4*>(sraw);
+            FFilterTile ft;
+            f_filter_tile(ffil, __int_as_float(smax[0]), __int_as_float(smax[1]), __int_as_float(smax[2]),
+                          __int_as_float(smax[3]), ft);
             for (int j0 = 0; j0 < rows; j0 += 64) {
                 const int jn = min(64, rows - j0);
-                unsigned long long pending = 0;
+                unsigned lo = 0, hi = 0;
                 if (jn == 64) {
-#pragma unroll 8
-                    for (int j = 0; j < 64; ++j) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
                         const float4 q = sp[j0 + j];
-                        if (!f_certain_outlier(ffil, q.x, q.y, q.z, q.w, thrM)) pending |= 1ull << j;
+                        if (!f_certain_outlier(ffil, ft, q.x, q.y, q.z, q.w, thrM)) lo |= 1u << j;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float4 q = sp[j0 + 32 + j];
+                        if (!f_certain_outlier(ffil, ft, q.x, q.y, q.z, q.w, thrM)) hi |= 1u << j;
                     }
                 } else {
                     for (int j = 0; j < jn; ++j) {
                         const float4 q = sp[j0 + j];
-                        if (!f_certain_outlier(ffil, q.x, q.y, q.z, q.w, thrM)) pending |= 1ull << j;
+                        if (!f_certain_outlier(ffil, ft, q.x, q.y, q.z, q.w, thrM)) {
+                            if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
+                        }
                     }
                 }
-                if (!active) pending = 0;
+                unsigned long long pending = active ? (((unsigned long long)hi << 32) | lo) : 0ull;
                 while (__any_sync(0xFFFFFFFFu, pending != 0)) {
                     if (pending) {
                         const int j = __ffsll((long long)pending) - 1;

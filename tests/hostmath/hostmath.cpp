@@ -155,13 +155,24 @@ extern "C" {
 // For n (model, point) pairs: filt[i] = filter says "certainly outlier", exact[i] = f_inlier.
 void hm_f_filter(const double* F, int nModels, const float* a, const float* b, int n, float thr, unsigned char* filt,
                  unsigned char* exact) {
+    const int TILE = 1024;                                       // as in score_kernel: bounds per tile of correspondences
     for (int k = 0; k < nModels; ++k) {
         FFilter ff;
         f_filter_init(F + 9 * k, ff);
         const float thrM = thr * FILTER_MARGIN;
-        for (int i = 0; i < n; ++i) {
-            filt[(size_t)k * n + i] = f_certain_outlier(ff, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], thrM) ? 1 : 0;
-            exact[(size_t)k * n + i] = f_inlier(F + 9 * k, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], thr) ? 1 : 0;
+        for (int i0 = 0; i0 < n; i0 += TILE) {
+            const int i1 = i0 + TILE < n ? i0 + TILE : n;
+            float mx[4] = {0, 0, 0, 0};
+            for (int i = i0; i < i1; ++i) {
+                const float v[4] = {fabsf(a[2 * i]), fabsf(a[2 * i + 1]), fabsf(b[2 * i]), fabsf(b[2 * i + 1])};
+                for (int c = 0; c < 4; ++c) if (!(v[c] <= mx[c])) mx[c] = v[c];        // NaN sticks
+            }
+            FFilterTile t;
+            f_filter_tile(ff, mx[0], mx[1], mx[2], mx[3], t);
+            for (int i = i0; i < i1; ++i) {
+                filt[(size_t)k * n + i] = f_certain_outlier(ff, t, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], thrM) ? 1 : 0;
+                exact[(size_t)k * n + i] = f_inlier(F + 9 * k, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], thr) ? 1 : 0;
+            }
         }
     }
 }
