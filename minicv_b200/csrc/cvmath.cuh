@@ -464,6 +464,42 @@ MCV_HD bool e_inlier(const double* E, double x1, double y1, double x2, double y2
     return (float)ddiv(q, den) <= thr;
 }
 
+// ---- fp32 filter in front of e_inlier ------------------------------------------------------------
+// Same construction as the fundamental-matrix filter, for the Sampson error q / den with q = (x2' E x1)^2 and
+// den = (E x1)_0^2 + (E x1)_1^2 + (E' x2)_0^2 + (E' x2)_1^2.  The correspondences are fp64 here (normalised
+// coordinates), so the filter works on their fp32 roundings (one more relative error u per coordinate; the budget
+// above -- 4u per row, 8u for the residual -- still holds and EPS_A = 8u, EPS_D = 16u keep their factor-of-two
+// slack).  L <= |x2' E x1|, N >= den (1 - 4u): L^2 > thr (1 + 2^-10) N implies q / den > thr (1 + 2^-11), and e_inlier
+// returns false on each of its paths (den = 0 included: q / 0 = inf).
+struct EFilterTile {
+    float eA, eB, eD, eT0, eT1;
+};
+MCV_HD void e_filter_tile(const FFilter& ff, float X1, float Y1, float X2, float Y2, EFilterTile& t) {
+    const float A = fmaf(fabsf(ff.f[0]), X1, fmaf(fabsf(ff.f[1]), Y1, fabsf(ff.f[2]) + FILTER_TINY));
+    const float B = fmaf(fabsf(ff.f[3]), X1, fmaf(fabsf(ff.f[4]), Y1, fabsf(ff.f[5]) + FILTER_TINY));
+    const float Cc = fmaf(fabsf(ff.f[6]), X1, fmaf(fabsf(ff.f[7]), Y1, fabsf(ff.f[8]) + FILTER_TINY));
+    const float D = fmaf(X2, A, fmaf(Y2, B, Cc));
+    const float T0 = fmaf(fabsf(ff.f[0]), X2, fmaf(fabsf(ff.f[3]), Y2, fabsf(ff.f[6]) + FILTER_TINY));
+    const float T1 = fmaf(fabsf(ff.f[1]), X2, fmaf(fabsf(ff.f[4]), Y2, fabsf(ff.f[7]) + FILTER_TINY));
+    t.eA = FILTER_EPS_A * A;
+    t.eB = FILTER_EPS_A * B;
+    t.eT0 = FILTER_EPS_A * T0;
+    t.eT1 = FILTER_EPS_A * T1;
+    t.eD = ff.on ? FILTER_EPS_D * D : INFINITY;
+}
+MCV_HD bool e_certain_outlier(const FFilter& ff, const EFilterTile& t, float x1, float y1, float x2, float y2, float thrM) {
+    const float a = fmaf(ff.f[0], x1, fmaf(ff.f[1], y1, ff.f[2]));
+    const float b = fmaf(ff.f[3], x1, fmaf(ff.f[4], y1, ff.f[5]));
+    const float c = fmaf(ff.f[6], x1, fmaf(ff.f[7], y1, ff.f[8]));
+    const float d = fmaf(x2, a, fmaf(y2, b, c));
+    const float t0 = fmaf(ff.f[0], x2, fmaf(ff.f[3], y2, ff.f[6]));
+    const float t1 = fmaf(ff.f[1], x2, fmaf(ff.f[4], y2, ff.f[7]));
+    const float L = fmaxf(fabsf(d) - t.eD, 0.0f);
+    const float ah = fabsf(a) + t.eA, bh = fabsf(b) + t.eB, t0h = fabsf(t0) + t.eT0, t1h = fabsf(t1) + t.eT1;
+    const float N = fmaxf(fmaf(ah, ah, fmaf(bh, bh, fmaf(t0h, t0h, t1h * t1h))), 1e-30f);
+    return L * L > thrM * N;
+}
+
 // ---- subset checks ----------------------------------------------------------------------------
 // haveCollinearPoints: last point against every earlier pair; pts as float (x,y) pairs.
 MCV_HDN inline bool have_collinear(const float* pts, int count) {

@@ -414,6 +414,7 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
     constexpr int TP = (MODEL == RM_ESSENTIAL) ? 512 : 1024;   // 16 KB per stage
     __shared__ __align__(16) unsigned char sraw[16384];
     __shared__ int smax[4];
+    __shared__ __align__(16) float4 sfl[(MODEL == RM_ESSENTIAL) ? 512 : 1];
     const int p = blockIdx.y;
     const int total = nTotal[p];
     const int k = blockIdx.x * 128 + threadIdx.x;
@@ -439,15 +440,31 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
     for (int j = 0; j < 8; ++j) Hf[j] = (float)m[j];
     FFilter ffil;
     const float thrM = thr2 * FILTER_MARGIN;
-    if (MODEL == RM_FUNDAMENTAL) f_filter_init(m, ffil);
+    if (MODEL != RM_HOMOGRAPHY) f_filter_init(m, ffil);
 
     int cnt = 0;
     for (int s0 = i0; s0 < i1; s0 += TP) {
         const int rows = min(TP, i1 - s0);
         if (MODEL == RM_ESSENTIAL) {
+            // fp64 tile for the exact test, its fp32 rounding for the filter, and the tile's coordinate maxima
+            if (threadIdx.x < 4) smax[threadIdx.x] = 0;
+            __syncthreads();
             double4* sp = reinterpret_cast<double4*>(sraw);
             const double4* g = reinterpret_cast<const double4*>(pd) + base + s0;
-            for (int j = threadIdx.x; j < rows; j += 128) sp[j] = g[j];
+            int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+            for (int j = threadIdx.x; j < rows; j += 128) {
+                const double4 q = g[j];
+                sp[j] = q;
+                const float4 qf = make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
+                sfl[j] = qf;
+                m0 = max(m0, __float_as_int(fabsf(qf.x))); m1 = max(m1, __float_as_int(fabsf(qf.y)));
+                m2 = max(m2, __float_as_int(fabsf(qf.z))); m3 = max(m3, __float_as_int(fabsf(qf.w)));
+            }
+            m0 = __reduce_max_sync(0xFFFFFFFFu, m0); m1 = __reduce_max_sync(0xFFFFFFFFu, m1);
+            m2 = __reduce_max_sync(0xFFFFFFFFu, m2); m3 = __reduce_max_sync(0xFFFFFFFFu, m3);
+            if ((threadIdx.x & 31) == 0) {
+                atomicMax(&smax[0], m0); atomicMax(&smax[1], m1); atomicMax(&smax[2], m2); atomicMax(&smax[3], m3);
+            }
         } else if (MODEL == RM_FUNDAMENTAL) {
             // also the largest |x1|, |y1|, |x2|, |y2| of the tile (bit patterns of non-negative floats order like
             // integers, and a NaN sorts above everything, which switches the filter off for the tile)
@@ -521,11 +538,43 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
                 }
             }
         } else {
+            // filtered exact scoring, as for the fundamental matrix (fp32 filter on the rounded tile, exact fp64
+            // Sampson test on the survivors)
             const double4* sp = reinterpret_cast<const double4*>(sraw);
-#pragma unroll 2
-            for (int j = 0; j < rows; ++j) {
-                const double4 q = sp[j];
-                cnt += e_inlier(m, q.x, q.y, q.z, q.w, thr2) ? 1 : 0;
+            EFilterTile et;
+            e_filter_tile(ffil, __int_as_float(smax[0]), __int_as_float(smax[1]), __int_as_float(smax[2]),
+                          __int_as_float(smax[3]), et);
+            for (int j0 = 0; j0 < rows; j0 += 64) {
+                const int jn = min(64, rows - j0);
+                unsigned lo = 0, hi = 0;
+                if (jn == 64) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float4 q = sfl[j0 + j];
+                        if (!e_certain_outlier(ffil, et, q.x, q.y, q.z, q.w, thrM)) lo |= 1u << j;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float4 q = sfl[j0 + 32 + j];
+                        if (!e_certain_outlier(ffil, et, q.x, q.y, q.z, q.w, thrM)) hi |= 1u << j;
+                    }
+                } else {
+                    for (int j = 0; j < jn; ++j) {
+                        const float4 q = sfl[j0 + j];
+                        if (!e_certain_outlier(ffil, et, q.x, q.y, q.z, q.w, thrM)) {
+                            if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
+                        }
+                    }
+                }
+                unsigned long long pending = active ? (((unsigned long long)hi << 32) | lo) : 0ull;
+                while (__any_sync(0xFFFFFFFFu, pending != 0)) {
+                    if (pending) {
+                        const int j = __ffsll((long long)pending) - 1;
+                        pending &= pending - 1;
+                        const double4 q = sp[j0 + j];
+                        cnt += e_inlier(m, q.x, q.y, q.z, q.w, thr2) ? 1 : 0;
+                    }
+                }
             }
         }
         __syncthreads();

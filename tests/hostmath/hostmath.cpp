@@ -177,3 +177,31 @@ void hm_f_filter(const double* F, int nModels, const float* a, const float* b, i
     }
 }
 }
+
+extern "C" {
+// The same for e_inlier: points are fp64 (normalised coordinates), the filter sees their fp32 roundings.
+void hm_e_filter(const double* E, int nModels, const double* a, const double* b, int n, float thr, unsigned char* filt,
+                 unsigned char* exact) {
+    const int TILE = 512;
+    for (int k = 0; k < nModels; ++k) {
+        FFilter ff;
+        f_filter_init(E + 9 * k, ff);
+        const float thrM = thr * FILTER_MARGIN;
+        for (int i0 = 0; i0 < n; i0 += TILE) {
+            const int i1 = i0 + TILE < n ? i0 + TILE : n;
+            float mx[4] = {0, 0, 0, 0};
+            for (int i = i0; i < i1; ++i) {
+                const float v[4] = {fabsf((float)a[2 * i]), fabsf((float)a[2 * i + 1]), fabsf((float)b[2 * i]), fabsf((float)b[2 * i + 1])};
+                for (int c = 0; c < 4; ++c) if (!(v[c] <= mx[c])) mx[c] = v[c];
+            }
+            EFilterTile t;
+            e_filter_tile(ff, mx[0], mx[1], mx[2], mx[3], t);
+            for (int i = i0; i < i1; ++i) {
+                filt[(size_t)k * n + i] = e_certain_outlier(ff, t, (float)a[2 * i], (float)a[2 * i + 1], (float)b[2 * i],
+                                                            (float)b[2 * i + 1], thrM) ? 1 : 0;
+                exact[(size_t)k * n + i] = e_inlier(E + 9 * k, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], thr) ? 1 : 0;
+            }
+        }
+    }
+}
+}

@@ -272,3 +272,43 @@ def test_f_filter_is_conservative(hm):
     filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
     hm.hm_f_filter(p(M), len(M), p(af2), p(bf2), n, C.c_float(9.0), p(filt), p(exact))
     assert not (filt & exact).any()
+
+
+def test_e_filter_is_conservative(hm):
+    """e_certain_outlier may only fire where e_inlier is false (5-point models of random and of inlier-only samples,
+    rescaled / degenerate / non-finite models, tiny and huge coordinates) and removes most of the work."""
+    rng = np.random.default_rng(11)
+    a, b, gt, R, t = synth.two_view_pair(3, 5000)
+    x1 = np.ascontiguousarray(essential.normalize_points(a, 800.0, (320.0, 240.0)))
+    x2 = np.ascontiguousarray(essential.normalize_points(b, 800.0, (320.0, 240.0)))
+    models = []
+    Es = np.zeros(90)
+    inl = np.flatnonzero(gt)
+    for it in range(160):
+        idx = rng.permutation(len(x1))[:5] if it < 120 else rng.choice(inl, 5, replace=False)
+        n = hm.hm_e_solve5(p(np.ascontiguousarray(x1[idx])), p(np.ascontiguousarray(x2[idx])), p(Es))
+        for k in range(n):
+            models.append(Es[9 * k:9 * k + 9].copy())
+    n_random = len(models)
+    base = models[0]
+    for sc in (1e-40, 1e-33, 1e-20, 1e-6, 1e6, 1e20, 1e29, 1e35, 1e300):
+        models.append(base * sc)
+    z = base.copy(); z[:6] = 0; models.append(z)
+    z = base.copy(); z[[0, 1, 3, 4]] = 0; models.append(z)
+    z = base.copy(); z[4] = np.nan; models.append(z)
+    z = base.copy(); z[8] = -np.inf; models.append(z)
+    models.append(np.zeros(9))
+    M = np.ascontiguousarray(np.stack(models))
+    n = len(x1)
+    for thr in ((1.0 / 800) ** 2, 0.005 ** 2, 1e-12):
+        filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
+        hm.hm_e_filter(p(M), len(M), p(x1), p(x2), n, C.c_float(thr), p(filt), p(exact))
+        assert not (filt & exact).any(), "filter rejected an inlier"
+        if thr == (1.0 / 800) ** 2:
+            wrong = exact[:n_random].sum(axis=1) < 0.05 * n
+            assert filt[:n_random][wrong].mean() > 0.9
+    sc = rng.choice([1e-20, 1e-3, 1.0, 1e3, 1e15], size=(n, 1))
+    y1, y2 = np.ascontiguousarray(x1 * sc), np.ascontiguousarray(x2 * sc[::-1])
+    filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
+    hm.hm_e_filter(p(M), len(M), p(y1), p(y2), n, C.c_float((1.0 / 800) ** 2), p(filt), p(exact))
+    assert not (filt & exact).any()
