@@ -381,20 +381,26 @@ MCV_HD bool f_inlier(const double* F, double x1, double y1, double x2, double y2
 // ---- fp32 filter in front of f_inlier ------------------------------------------------------------
 // Almost every (model, correspondence) pair of a RANSAC batch is an outlier by a wide margin, and the exact test
 // above costs ~52 FP64-pipe instructions.  The filter evaluates ONE of the two point-line distances (the line F x1
-// in image 2) in fp32 with FMAs, together with a running bound of its own rounding error, and answers "certainly an
-// outlier" only when the distance exceeds the threshold by more than every error that could have been made; the
-// caller runs the exact test on everything else, so the result is f_inlier's, bit for bit.
+// in image 2) in fp32 with FMAs, carries a bound of its own rounding error, and answers "certainly an outlier" only
+// when the distance exceeds the threshold by more than every error that could have been made; the caller runs the
+// exact test on everything else, so the result is f_inlier's, bit for bit.
 //
-// Error budget (u = 2^-24; points are exact fp32, F_i are converted with relative error u; filter is switched off
-// for a model with a non-finite entry or a non-zero entry below 1e-30, so conversions never underflow):
+// Error budget (u = 2^-24; points are exact fp32, F_i are converted with relative error u; the filter is switched
+// off for a model with a non-finite entry or a non-zero entry below 1e-30, so conversions never underflow):
 //   a~ = fma(F0,x1, fma(F1,y1,F2)):  |a~ - a| <= 4u A,  A = |F0||x1| + |F1||y1| + |F2|   (same for b, c)
 //   d~ = fma(x2,a~, fma(y2,b~,c~)):  |d~ - d| <= 7u D,  D = |x2| A + |y2| B + C
-//   A, B, C, D are themselves computed in fp32 (sums of non-negative terms: relative error <= 6u) and carry an
-//   absolute slack (FILTER_TINY inside A, B, C) that dominates any underflow (2^-149 per operation).
-// With EPS_A = 8u and EPS_D = 16u:  L = |d~| - EPS_D D  <=  |d|,   N = (|a~| + EPS_A A)^2 + (|b~| + EPS_A B)^2 >= (a^2 + b^2)(1 - 2u),
-// so L > 0 and L^2 > thr (1 + 2^-10) N (with N >= 1e-30: no underflow in the squares) implies d^2 / (a^2 + b^2) >
-// thr (1 + 2^-11): the fp64 value e2 of f_error exceeds thr by far more than its own rounding, (float)max(e1, e2) >
-// thr, and f_inlier returns false on every one of its paths.
+// The bounds are taken per TILE of correspondences: with X1 >= |x1|, Y1 >= |y1|, X2 >= |x2|, Y2 >= |y2| over the tile,
+// A <= Amax = |F0| X1 + |F1| Y1 + |F2| etc., so eA = 8u Amax >= |a~ - a|, eB, eD = 16u Dmax >= |d~ - d| (factor two
+// of slack; Amax .. Dmax carry an absolute 1e-30 that dominates any underflow) are constants of (model, tile).
+// To need neither |.| nor a square root per evaluation, both bounds are applied through (p + q)^2 <= (1 + mu) p^2 +
+// (1 + 1/mu) q^2 with mu = 2^-12:
+//   a^2 + b^2 <= (|a~| + eA)^2 + (|b~| + eB)^2 <= (1 + mu)(a~^2 + b~^2) + K,   K  = (1 + 1/mu)(eA^2 + eB^2) + 1e-30
+//   (sqrt(T) + eD)^2 <= (1 + mu) T + KD,                                       KD = (1 + 1/mu) eD^2 + 1e-30
+// so  d~^2 > thr (1 + 2^-9)(1 + mu) [(1 + mu)(a~^2 + b~^2) + K] + KD  implies |d| >= |d~| - eD > sqrt(thr (1 + 2^-9)(a^2 + b^2)):
+// the true ratio exceeds thr by 2^-9 relative -- far more than the rounding of this test (a few u) and of the exact
+// fp64 path -- so (float)max(e1, e2) > thr and f_inlier returns false on every one of its paths (a^2 + b^2 = 0 and
+// NaN included).  The 1e-30 terms also cover the squares' own underflow.  Any NaN / inf (NaN coordinate in the tile,
+// huge model, filter off: KD = inf) makes the single comparison fail, i.e. sends the evaluation to the exact test.
 struct FFilter {
     float f[9];
     bool on;
@@ -402,7 +408,9 @@ struct FFilter {
 constexpr float FILTER_TINY = 1e-30f;
 constexpr float FILTER_EPS_A = 4.76837158203125e-07f;     // 8 * 2^-24
 constexpr float FILTER_EPS_D = 9.5367431640625e-07f;      // 16 * 2^-24
-constexpr float FILTER_MARGIN = 1.0009765625f;            // 1 + 2^-10
+constexpr float FILTER_MU1 = 1.000244140625f;             // 1 + mu, mu = 2^-12
+constexpr float FILTER_SQ = 64.02f;                       // sqrt(1 + 1/mu) = 64.0078.., rounded up
+constexpr float FILTER_MARGIN = 1.001953125f * 1.000244140625f;   // (1 + 2^-9)(1 + mu)
 
 MCV_HD void f_filter_init(const double* F, FFilter& ff) {
     bool on = true;
@@ -414,37 +422,27 @@ MCV_HD void f_filter_init(const double* F, FFilter& ff) {
     ff.on = on;
 }
 
-// The error terms for a whole tile of correspondences at once: with X1 >= |x1|, Y1 >= |y1|, X2 >= |x2|, Y2 >= |y2|
-// for every correspondence of the tile, A <= Amax = |F0| X1 + |F1| Y1 + |F2| (same for B, C) and D <= X2 Amax + Y2 Bmax
-// + Cmax, so the three bounds the filter subtracts / adds are constants of (model, tile):
-//   eA = EPS_A Amax, eB = EPS_A Bmax, eD = EPS_D Dmax.   A NaN / inf bound (NaN coordinate in the tile, huge model)
-// makes every comparison of the filter fail, i.e. sends everything to the exact test.
 struct FFilterTile {
-    float eA, eB, eD;
+    float K, KD;
 };
 MCV_HD void f_filter_tile(const FFilter& ff, float X1, float Y1, float X2, float Y2, FFilterTile& t) {
     const float A = fmaf(fabsf(ff.f[0]), X1, fmaf(fabsf(ff.f[1]), Y1, fabsf(ff.f[2]) + FILTER_TINY));
     const float B = fmaf(fabsf(ff.f[3]), X1, fmaf(fabsf(ff.f[4]), Y1, fabsf(ff.f[5]) + FILTER_TINY));
     const float Cc = fmaf(fabsf(ff.f[6]), X1, fmaf(fabsf(ff.f[7]), Y1, fabsf(ff.f[8]) + FILTER_TINY));
     const float D = fmaf(X2, A, fmaf(Y2, B, Cc));
-    t.eA = FILTER_EPS_A * A;
-    t.eB = FILTER_EPS_A * B;
-    t.eD = ff.on ? FILTER_EPS_D * D : INFINITY;                  // filter off: L = -inf, nothing is ever rejected
+    const float sA = FILTER_SQ * FILTER_EPS_A * A, sB = FILTER_SQ * FILTER_EPS_A * B, sD = FILTER_SQ * FILTER_EPS_D * D;
+    t.K = fmaf(sA, sA, fmaf(sB, sB, 1e-30f));
+    t.KD = ff.on ? fmaf(sD, sD, 1e-30f) : INFINITY;
 }
 
-// thrM = thr * FILTER_MARGIN, precomputed by the caller.  Written so that it costs one compare: L is clamped at 0
-// (a non-positive lower bound proves nothing: 0 > thrM N is false) and N is raised to 1e-30 (still an upper bound of
-// a^2 + b^2, and above the range where the squares could have underflowed); a NaN anywhere fails the comparison.
+// thrM = thr * FILTER_MARGIN, precomputed by the caller
 MCV_HD bool f_certain_outlier(const FFilter& ff, const FFilterTile& t, float x1, float y1, float x2, float y2, float thrM) {
     const float a = fmaf(ff.f[0], x1, fmaf(ff.f[1], y1, ff.f[2]));
     const float b = fmaf(ff.f[3], x1, fmaf(ff.f[4], y1, ff.f[5]));
     const float c = fmaf(ff.f[6], x1, fmaf(ff.f[7], y1, ff.f[8]));
     const float d = fmaf(x2, a, fmaf(y2, b, c));
-    const float L = fmaxf(fabsf(d) - t.eD, 0.0f);
-    const float ah = fabsf(a) + t.eA;
-    const float bh = fabsf(b) + t.eB;
-    const float N = fmaxf(fmaf(ah, ah, bh * bh), 1e-30f);
-    return L * L > thrM * N;
+    const float N = fmaf(fmaf(a, a, b * b), FILTER_MU1, t.K);
+    return d * d > fmaf(thrM, N, t.KD);
 }
 
 MCV_HD bool e_inlier(const double* E, double x1, double y1, double x2, double y2, float thr) {
@@ -465,40 +463,93 @@ MCV_HD bool e_inlier(const double* E, double x1, double y1, double x2, double y2
 }
 
 // ---- fp32 filter in front of e_inlier ------------------------------------------------------------
-// Same construction as the fundamental-matrix filter, for the Sampson error q / den with q = (x2' E x1)^2 and
-// den = (E x1)_0^2 + (E x1)_1^2 + (E' x2)_0^2 + (E' x2)_1^2.  The correspondences are fp64 here (normalised
-// coordinates), so the filter works on their fp32 roundings (one more relative error u per coordinate; the budget
-// above -- 4u per row, 8u for the residual -- still holds and EPS_A = 8u, EPS_D = 16u keep their factor-of-two
-// slack).  L <= |x2' E x1|, N >= den (1 - 4u): L^2 > thr (1 + 2^-10) N implies q / den > thr (1 + 2^-11), and e_inlier
-// returns false on each of its paths (den = 0 included: q / 0 = inf).
-struct EFilterTile {
-    float eA, eB, eD, eT0, eT1;
-};
-MCV_HD void e_filter_tile(const FFilter& ff, float X1, float Y1, float X2, float Y2, EFilterTile& t) {
+// Same construction for the Sampson error q / den with q = (x2' E x1)^2 and den = (E x1)_0^2 + (E x1)_1^2 +
+// (E' x2)_0^2 + (E' x2)_1^2.  The correspondences are fp64 here (normalised coordinates), so the filter works on
+// their fp32 roundings (one more relative error u per coordinate; the budget above -- 4u per row, 8u for the
+// residual -- still holds and EPS_A = 8u, EPS_D = 16u keep their slack).  The rejection implies q / den >
+// thr (1 + 2^-9), and e_inlier returns false on each of its paths (den = 0 included: q / 0 = inf).
+MCV_HD void e_filter_tile(const FFilter& ff, float X1, float Y1, float X2, float Y2, FFilterTile& t) {
     const float A = fmaf(fabsf(ff.f[0]), X1, fmaf(fabsf(ff.f[1]), Y1, fabsf(ff.f[2]) + FILTER_TINY));
     const float B = fmaf(fabsf(ff.f[3]), X1, fmaf(fabsf(ff.f[4]), Y1, fabsf(ff.f[5]) + FILTER_TINY));
     const float Cc = fmaf(fabsf(ff.f[6]), X1, fmaf(fabsf(ff.f[7]), Y1, fabsf(ff.f[8]) + FILTER_TINY));
     const float D = fmaf(X2, A, fmaf(Y2, B, Cc));
     const float T0 = fmaf(fabsf(ff.f[0]), X2, fmaf(fabsf(ff.f[3]), Y2, fabsf(ff.f[6]) + FILTER_TINY));
     const float T1 = fmaf(fabsf(ff.f[1]), X2, fmaf(fabsf(ff.f[4]), Y2, fabsf(ff.f[7]) + FILTER_TINY));
-    t.eA = FILTER_EPS_A * A;
-    t.eB = FILTER_EPS_A * B;
-    t.eT0 = FILTER_EPS_A * T0;
-    t.eT1 = FILTER_EPS_A * T1;
-    t.eD = ff.on ? FILTER_EPS_D * D : INFINITY;
+    const float sA = FILTER_SQ * FILTER_EPS_A * A, sB = FILTER_SQ * FILTER_EPS_A * B, sD = FILTER_SQ * FILTER_EPS_D * D;
+    const float s0 = FILTER_SQ * FILTER_EPS_A * T0, s1 = FILTER_SQ * FILTER_EPS_A * T1;
+    t.K = fmaf(sA, sA, fmaf(sB, sB, fmaf(s0, s0, fmaf(s1, s1, 1e-30f))));
+    t.KD = ff.on ? fmaf(sD, sD, 1e-30f) : INFINITY;
 }
-MCV_HD bool e_certain_outlier(const FFilter& ff, const EFilterTile& t, float x1, float y1, float x2, float y2, float thrM) {
+MCV_HD bool e_certain_outlier(const FFilter& ff, const FFilterTile& t, float x1, float y1, float x2, float y2, float thrM) {
     const float a = fmaf(ff.f[0], x1, fmaf(ff.f[1], y1, ff.f[2]));
     const float b = fmaf(ff.f[3], x1, fmaf(ff.f[4], y1, ff.f[5]));
     const float c = fmaf(ff.f[6], x1, fmaf(ff.f[7], y1, ff.f[8]));
     const float d = fmaf(x2, a, fmaf(y2, b, c));
     const float t0 = fmaf(ff.f[0], x2, fmaf(ff.f[3], y2, ff.f[6]));
     const float t1 = fmaf(ff.f[1], x2, fmaf(ff.f[4], y2, ff.f[7]));
-    const float L = fmaxf(fabsf(d) - t.eD, 0.0f);
-    const float ah = fabsf(a) + t.eA, bh = fabsf(b) + t.eB, t0h = fabsf(t0) + t.eT0, t1h = fabsf(t1) + t.eT1;
-    const float N = fmaxf(fmaf(ah, ah, fmaf(bh, bh, fmaf(t0h, t0h, t1h * t1h))), 1e-30f);
-    return L * L > thrM * N;
+    const float N = fmaf(fmaf(a, a, fmaf(b, b, fmaf(t0, t0, t1 * t1))), FILTER_MU1, t.K);
+    return d * d > fmaf(thrM, N, t.KD);
 }
+
+#if defined(__CUDACC__)
+// ---- the two filters on Blackwell's packed fp32 pipe: two correspondences per instruction ------------------------
+// fma.rn.f32x2 / mul.rn.f32x2 (sm_100+, SASS FFMA2) operate on a register pair; the filter is bound by instruction
+// issue, so evaluating two correspondences per instruction halves its cost.  Same formulas, same constants as the
+// scalar forms above (every packed operation rounds exactly like its scalar counterpart).
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 f2_make(float lo, float hi) {
+    F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ F2 f2_bcast(float x) { return f2_make(x, x); }
+__device__ __forceinline__ void f2_split(F2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+    F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+    F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r;
+}
+struct FFilter2 {          // coefficients and per-tile constants broadcast to both halves
+    F2 f[9], K, KD, mu1, thrM;
+};
+__device__ __forceinline__ void filter2_init(const FFilter& ff, FFilter2& p, float thrM) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) p.f[i] = f2_bcast(ff.f[i]);
+    p.mu1 = f2_bcast(FILTER_MU1);
+    p.thrM = f2_bcast(thrM);
+}
+__device__ __forceinline__ void filter2_tile(FFilter2& p, const FFilterTile& t) { p.K = f2_bcast(t.K); p.KD = f2_bcast(t.KD); }
+// X1 = (x1 of point 0, x1 of point 1) etc.; r0 / r1 = "certainly an outlier" for the two points
+__device__ __forceinline__ void f_certain_outlier2(const FFilter2& p, F2 X1, F2 Y1, F2 X2, F2 Y2, bool& r0, bool& r1) {
+    const F2 a = f2_fma(p.f[0], X1, f2_fma(p.f[1], Y1, p.f[2]));
+    const F2 b = f2_fma(p.f[3], X1, f2_fma(p.f[4], Y1, p.f[5]));
+    const F2 c = f2_fma(p.f[6], X1, f2_fma(p.f[7], Y1, p.f[8]));
+    const F2 d = f2_fma(X2, a, f2_fma(Y2, b, c));
+    const F2 N = f2_fma(f2_fma(a, a, f2_mul(b, b)), p.mu1, p.K);
+    const F2 rhs = f2_fma(p.thrM, N, p.KD);
+    const F2 lhs = f2_mul(d, d);
+    float l0, l1, h0, h1;
+    f2_split(lhs, l0, l1);
+    f2_split(rhs, h0, h1);
+    r0 = l0 > h0;
+    r1 = l1 > h1;
+}
+__device__ __forceinline__ void e_certain_outlier2(const FFilter2& p, F2 X1, F2 Y1, F2 X2, F2 Y2, bool& r0, bool& r1) {
+    const F2 a = f2_fma(p.f[0], X1, f2_fma(p.f[1], Y1, p.f[2]));
+    const F2 b = f2_fma(p.f[3], X1, f2_fma(p.f[4], Y1, p.f[5]));
+    const F2 c = f2_fma(p.f[6], X1, f2_fma(p.f[7], Y1, p.f[8]));
+    const F2 d = f2_fma(X2, a, f2_fma(Y2, b, c));
+    const F2 t0 = f2_fma(p.f[0], X2, f2_fma(p.f[3], Y2, p.f[6]));
+    const F2 t1 = f2_fma(p.f[1], X2, f2_fma(p.f[4], Y2, p.f[7]));
+    const F2 N = f2_fma(f2_fma(a, a, f2_fma(b, b, f2_fma(t0, t0, f2_mul(t1, t1)))), p.mu1, p.K);
+    const F2 rhs = f2_fma(p.thrM, N, p.KD);
+    const F2 lhs = f2_mul(d, d);
+    float l0, l1, h0, h1;
+    f2_split(lhs, l0, l1);
+    f2_split(rhs, h0, h1);
+    r0 = l0 > h0;
+    r1 = l1 > h1;
+}
+#endif
 
 // ---- subset checks ----------------------------------------------------------------------------
 // haveCollinearPoints: last point against every earlier pair; pts as float (x,y) pairs.

@@ -402,6 +402,50 @@ compact_kernel(const uint8_t* __restrict__ nModels, const int* __restrict__ nIte
     if (tid == 0) { is[maxIters] = sBase; nTotal[p] = sBase; }
 }
 
+// Filter tile layout: correspondences in pairs, 8 floats per pair = x1 x1' | y1 y1' | x2 x2' | y2 y2', so that two
+// 128-bit shared-memory loads deliver the four packed (f32x2) operands of two correspondences.
+__device__ __forceinline__ void store_pair_slot(float* spair, int j, const float4& q) {
+    float* d = spair + 8 * (j >> 1) + (j & 1);
+    d[0] = q.x; d[2] = q.y; d[4] = q.z; d[6] = q.w;
+}
+// 64 correspondences (jn of them valid) through the packed filter; bit j of the result = "needs the exact test"
+template <int MODEL>
+__device__ __forceinline__ unsigned long long filter_block64(const FFilter2& p, const float* blk, int jn) {
+    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(blk);
+    unsigned lo = 0, hi = 0;
+    if (jn == 64) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const ulonglong2 u = b2[2 * q], v = b2[2 * q + 1];
+            bool r0, r1;
+            if (MODEL == RM_FUNDAMENTAL) f_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
+            else e_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
+            if (!r0) lo |= 1u << (2 * q);
+            if (!r1) lo |= 2u << (2 * q);
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const ulonglong2 u = b2[32 + 2 * q], v = b2[32 + 2 * q + 1];
+            bool r0, r1;
+            if (MODEL == RM_FUNDAMENTAL) f_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
+            else e_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
+            if (!r0) hi |= 1u << (2 * q);
+            if (!r1) hi |= 2u << (2 * q);
+        }
+        return ((unsigned long long)hi << 32) | lo;
+    }
+    unsigned long long pend = 0;
+    for (int q = 0; 2 * q < jn; ++q) {
+        const ulonglong2 u = b2[2 * q], v = b2[2 * q + 1];
+        bool r0, r1;
+        if (MODEL == RM_FUNDAMENTAL) f_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
+        else e_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
+        if (!r0) pend |= 1ull << (2 * q);
+        if (!r1 && 2 * q + 1 < jn) pend |= 2ull << (2 * q);
+    }
+    return pend;
+}
+
 // ---------------------------------------------------------------------------------------------
 // score: one model per thread, correspondences through shared memory
 // ---------------------------------------------------------------------------------------------
@@ -414,7 +458,8 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
     constexpr int TP = (MODEL == RM_ESSENTIAL) ? 512 : 1024;   // 16 KB per stage
     __shared__ __align__(16) unsigned char sraw[16384];
     __shared__ int smax[4];
-    __shared__ __align__(16) float4 sfl[(MODEL == RM_ESSENTIAL) ? 512 : 1];
+    __shared__ __align__(16) float spair_e[(MODEL == RM_ESSENTIAL) ? 4 * 512 : 4];    // essential: fp32 rounding of the tile
+    float* const spair = spair_e;
     const int p = blockIdx.y;
     const int total = nTotal[p];
     const int k = blockIdx.x * 128 + threadIdx.x;
@@ -440,7 +485,8 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
     for (int j = 0; j < 8; ++j) Hf[j] = (float)m[j];
     FFilter ffil;
     const float thrM = thr2 * FILTER_MARGIN;
-    if (MODEL != RM_HOMOGRAPHY) f_filter_init(m, ffil);
+    FFilter2 ffil2;
+    if (MODEL != RM_HOMOGRAPHY) { f_filter_init(m, ffil); filter2_init(ffil, ffil2, thrM); }
 
     int cnt = 0;
     for (int s0 = i0; s0 < i1; s0 += TP) {
@@ -456,7 +502,8 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
                 const double4 q = g[j];
                 sp[j] = q;
                 const float4 qf = make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
-                sfl[j] = qf;
+                store_pair_slot(spair, j, qf);
+                if (j == rows - 1 && !(j & 1)) store_pair_slot(spair, j + 1, qf);     // odd tail: duplicate, masked off later
                 m0 = max(m0, __float_as_int(fabsf(qf.x))); m1 = max(m1, __float_as_int(fabsf(qf.y)));
                 m2 = max(m2, __float_as_int(fabsf(qf.z))); m3 = max(m3, __float_as_int(fabsf(qf.w)));
             }
@@ -470,12 +517,13 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
             // integers, and a NaN sorts above everything, which switches the filter off for the tile)
             if (threadIdx.x < 4) smax[threadIdx.x] = 0;
             __syncthreads();
-            float4* sp = reinterpret_cast<float4*>(sraw);
+            float* spair = reinterpret_cast<float*>(sraw);
             const float4* g = pf + base + s0;
             int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
             for (int j = threadIdx.x; j < rows; j += 128) {
                 const float4 q = g[j];
-                sp[j] = q;
+                store_pair_slot(spair, j, q);
+                if (j == rows - 1 && !(j & 1)) store_pair_slot(spair, j + 1, q);       // odd tail: duplicate, masked off later
                 m0 = max(m0, __float_as_int(fabsf(q.x))); m1 = max(m1, __float_as_int(fabsf(q.y)));
                 m2 = max(m2, __float_as_int(fabsf(q.z))); m3 = max(m3, __float_as_int(fabsf(q.w)));
             }
@@ -498,42 +546,24 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
                 cnt += (h_error(Hf, q.x, q.y, q.z, q.w) <= thr2) ? 1 : 0;
             }
         } else if (MODEL == RM_FUNDAMENTAL) {
-            // filtered exact scoring: 64 correspondences through the fp32 filter (cvmath.cuh, f_certain_outlier),
-            // the survivors -- about 1 % for a wrong model -- collected in a bit mask and given the exact fp64 test
-            // afterwards, so the FP64 work of a warp is the longest survivor list of its 32 models, not 64
-            const float4* sp = reinterpret_cast<const float4*>(sraw);
+            // filtered exact scoring: 64 correspondences through the fp32 filter (cvmath.cuh, two per packed
+            // instruction), the survivors -- about 1.5 % for a wrong model -- collected in a bit mask and given the
+            // exact fp64 test afterwards, so the FP64 work of a warp is the longest survivor list of its 32 models
+            const float* spair = reinterpret_cast<const float*>(sraw);
             FFilterTile ft;
             f_filter_tile(ffil, __int_as_float(smax[0]), __int_as_float(smax[1]), __int_as_float(smax[2]),
                           __int_as_float(smax[3]), ft);
+            filter2_tile(ffil2, ft);
             for (int j0 = 0; j0 < rows; j0 += 64) {
                 const int jn = min(64, rows - j0);
-                unsigned lo = 0, hi = 0;
-                if (jn == 64) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float4 q = sp[j0 + j];
-                        if (!f_certain_outlier(ffil, ft, q.x, q.y, q.z, q.w, thrM)) lo |= 1u << j;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float4 q = sp[j0 + 32 + j];
-                        if (!f_certain_outlier(ffil, ft, q.x, q.y, q.z, q.w, thrM)) hi |= 1u << j;
-                    }
-                } else {
-                    for (int j = 0; j < jn; ++j) {
-                        const float4 q = sp[j0 + j];
-                        if (!f_certain_outlier(ffil, ft, q.x, q.y, q.z, q.w, thrM)) {
-                            if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
-                        }
-                    }
-                }
-                unsigned long long pending = active ? (((unsigned long long)hi << 32) | lo) : 0ull;
+                unsigned long long pending = filter_block64<RM_FUNDAMENTAL>(ffil2, spair + 4 * j0, jn);
+                if (!active) pending = 0;
                 while (__any_sync(0xFFFFFFFFu, pending != 0)) {
                     if (pending) {
-                        const int j = __ffsll((long long)pending) - 1;
+                        const int j = j0 + __ffsll((long long)pending) - 1;
                         pending &= pending - 1;
-                        const float4 q = sp[j0 + j];
-                        cnt += f_inlier(m, (double)q.x, (double)q.y, (double)q.z, (double)q.w, thr2) ? 1 : 0;
+                        const float* q = spair + 8 * (j >> 1) + (j & 1);
+                        cnt += f_inlier(m, (double)q[0], (double)q[2], (double)q[4], (double)q[6], thr2) ? 1 : 0;
                     }
                 }
             }
@@ -541,32 +571,14 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
             // filtered exact scoring, as for the fundamental matrix (fp32 filter on the rounded tile, exact fp64
             // Sampson test on the survivors)
             const double4* sp = reinterpret_cast<const double4*>(sraw);
-            EFilterTile et;
+            FFilterTile et;
             e_filter_tile(ffil, __int_as_float(smax[0]), __int_as_float(smax[1]), __int_as_float(smax[2]),
                           __int_as_float(smax[3]), et);
+            filter2_tile(ffil2, et);
             for (int j0 = 0; j0 < rows; j0 += 64) {
                 const int jn = min(64, rows - j0);
-                unsigned lo = 0, hi = 0;
-                if (jn == 64) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float4 q = sfl[j0 + j];
-                        if (!e_certain_outlier(ffil, et, q.x, q.y, q.z, q.w, thrM)) lo |= 1u << j;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float4 q = sfl[j0 + 32 + j];
-                        if (!e_certain_outlier(ffil, et, q.x, q.y, q.z, q.w, thrM)) hi |= 1u << j;
-                    }
-                } else {
-                    for (int j = 0; j < jn; ++j) {
-                        const float4 q = sfl[j0 + j];
-                        if (!e_certain_outlier(ffil, et, q.x, q.y, q.z, q.w, thrM)) {
-                            if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
-                        }
-                    }
-                }
-                unsigned long long pending = active ? (((unsigned long long)hi << 32) | lo) : 0ull;
+                unsigned long long pending = filter_block64<RM_ESSENTIAL>(ffil2, spair + 4 * j0, jn);
+                if (!active) pending = 0;
                 while (__any_sync(0xFFFFFFFFu, pending != 0)) {
                     if (pending) {
                         const int j = __ffsll((long long)pending) - 1;

@@ -194,7 +194,7 @@ void hm_e_filter(const double* E, int nModels, const double* a, const double* b,
                 const float v[4] = {fabsf((float)a[2 * i]), fabsf((float)a[2 * i + 1]), fabsf((float)b[2 * i]), fabsf((float)b[2 * i + 1])};
                 for (int c = 0; c < 4; ++c) if (!(v[c] <= mx[c])) mx[c] = v[c];
             }
-            EFilterTile t;
+            FFilterTile t;
             e_filter_tile(ff, mx[0], mx[1], mx[2], mx[3], t);
             for (int i = i0; i < i1; ++i) {
                 filt[(size_t)k * n + i] = e_certain_outlier(ff, t, (float)a[2 * i], (float)a[2 * i + 1], (float)b[2 * i],
