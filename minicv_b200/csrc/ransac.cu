@@ -412,27 +412,25 @@ __device__ __forceinline__ void store_pair_slot(float* spair, int j, const float
 template <int MODEL>
 __device__ __forceinline__ unsigned long long filter_block64(const FFilter2& p, const float* blk, int jn) {
     const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(blk);
-    unsigned lo = 0, hi = 0;
     if (jn == 64) {
+        // 8 pairs (16 correspondences) per fully unrolled step: mask bits are immediates, and the live state stays
+        // small enough for 5 blocks per SM
+        unsigned long long pend = 0;
+#pragma unroll 1
+        for (int o = 0; o < 4; ++o) {
+            unsigned w = 0;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const ulonglong2 u = b2[2 * q], v = b2[2 * q + 1];
-            bool r0, r1;
-            if (MODEL == RM_FUNDAMENTAL) f_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
-            else e_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
-            if (!r0) lo |= 1u << (2 * q);
-            if (!r1) lo |= 2u << (2 * q);
+            for (int q = 0; q < 8; ++q) {
+                const ulonglong2 u = b2[16 * o + 2 * q], v = b2[16 * o + 2 * q + 1];
+                bool r0, r1;
+                if (MODEL == RM_FUNDAMENTAL) f_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
+                else e_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
+                if (!r0) w |= 1u << (2 * q);
+                if (!r1) w |= 2u << (2 * q);
+            }
+            pend |= (unsigned long long)w << (16 * o);
         }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const ulonglong2 u = b2[32 + 2 * q], v = b2[32 + 2 * q + 1];
-            bool r0, r1;
-            if (MODEL == RM_FUNDAMENTAL) f_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
-            else e_certain_outlier2(p, F2{u.x}, F2{u.y}, F2{v.x}, F2{v.y}, r0, r1);
-            if (!r0) hi |= 1u << (2 * q);
-            if (!r1) hi |= 2u << (2 * q);
-        }
-        return ((unsigned long long)hi << 32) | lo;
+        return pend;
     }
     unsigned long long pend = 0;
     for (int q = 0; 2 * q < jn; ++q) {
