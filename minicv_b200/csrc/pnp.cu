@@ -183,6 +183,8 @@ pnp_score_kernel(const float4* __restrict__ of, const float2* __restrict__ imf, 
                  int chunkPts, int* __restrict__ counts) {
     __shared__ float4 sO[SCORE_TP];
     __shared__ float2 sI[SCORE_TP];
+    __shared__ float2 sC[SCORE_TP];      // (u - cx, v - cy) in float32, for the filter
+    __shared__ int smax[7];
     const int p = blockIdx.y;
     const int total = nTotal[p];
     const int k = blockIdx.x * 128 + threadIdx.x;
@@ -206,16 +208,71 @@ pnp_score_kernel(const float4* __restrict__ of, const float2* __restrict__ imf, 
 #pragma unroll
         for (int j = 0; j < 9; ++j) R[j] = 0;
     }
+    PnpFilter pfil;
+    pnp_filter_init(R, t, cam, dist, pfil);
     int cnt = 0;
     for (int s0 = i0; s0 < i1; s0 += SCORE_TP) {
         const int rows = min(SCORE_TP, i1 - s0);
-        for (int j = threadIdx.x; j < rows; j += 128) { sO[j] = of[base + s0 + j]; sI[j] = imf[base + s0 + j]; }
+        // tile + the maxima the filter's error bounds need (bit patterns of non-negative floats order like integers;
+        // a NaN sorts above everything and switches the filter off for the tile)
+        if (threadIdx.x < 7) smax[threadIdx.x] = 0;
         __syncthreads();
-#pragma unroll 2
-        for (int j = 0; j < rows; ++j) {
-            const float4 q = sO[j];
-            const float2 m = sI[j];
-            cnt += (project_error(R, t, cam, dist, q.x, q.y, q.z, m.x, m.y) <= thr2) ? 1 : 0;
+        {
+            int mx[7] = {0, 0, 0, 0, 0, 0, 0};
+            for (int j = threadIdx.x; j < rows; j += 128) {
+                const float4 q = of[base + s0 + j];
+                const float2 m = imf[base + s0 + j];
+                const float2 c = make_float2((float)((double)m.x - cam.cx), (float)((double)m.y - cam.cy));
+                sO[j] = q; sI[j] = m; sC[j] = c;
+                const float v[7] = {q.x, q.y, q.z, c.x, c.y, m.x, m.y};
+#pragma unroll
+                for (int e = 0; e < 7; ++e) mx[e] = max(mx[e], __float_as_int(fabsf(v[e])));
+            }
+#pragma unroll
+            for (int e = 0; e < 7; ++e) {
+                const int r = __reduce_max_sync(0xFFFFFFFFu, mx[e]);
+                if ((threadIdx.x & 31) == 0) atomicMax(&smax[e], r);
+            }
+        }
+        __syncthreads();
+        // filtered exact scoring: fp32 filter over 64 correspondences (pnpmath.cuh, pnp_certain_outlier), the survivors
+        // collected in a bit mask and given the exact fp64 projection afterwards
+        PnpFilterTile ft;
+        pnp_filter_tile(pfil, __int_as_float(smax[0]), __int_as_float(smax[1]), __int_as_float(smax[2]),
+                        __int_as_float(smax[3]), __int_as_float(smax[4]), __int_as_float(smax[5]),
+                        __int_as_float(smax[6]), thr2, ft);
+        for (int j0 = 0; j0 < rows; j0 += 64) {
+            const int jn = min(64, rows - j0);
+            unsigned long long pending = 0;
+            if (jn == 64) {
+#pragma unroll 1
+                for (int o = 0; o < 4; ++o) {
+                    unsigned w = 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 q = sO[j0 + 16 * o + j];
+                        const float2 c = sC[j0 + 16 * o + j];
+                        if (!pnp_certain_outlier(pfil, ft, q.x, q.y, q.z, c.x, c.y)) w |= 1u << j;
+                    }
+                    pending |= (unsigned long long)w << (16 * o);
+                }
+            } else {
+                for (int j = 0; j < jn; ++j) {
+                    const float4 q = sO[j0 + j];
+                    const float2 c = sC[j0 + j];
+                    if (!pnp_certain_outlier(pfil, ft, q.x, q.y, q.z, c.x, c.y)) pending |= 1ull << j;
+                }
+            }
+            if (!active) pending = 0;
+            while (__any_sync(0xFFFFFFFFu, pending != 0)) {
+                if (pending) {
+                    const int j = j0 + __ffsll((long long)pending) - 1;
+                    pending &= pending - 1;
+                    const float4 q = sO[j];
+                    const float2 m = sI[j];
+                    cnt += (project_error(R, t, cam, dist, q.x, q.y, q.z, m.x, m.y) <= thr2) ? 1 : 0;
+                }
+            }
         }
         __syncthreads();
     }

@@ -324,6 +324,69 @@ MCV_HD float project_error(const double* R, const double* t, const PnpCamera& c,
     return fadd(fmul(dx, dx), fmul(dy, dy));
 }
 
+// ---- fp32 filter in front of project_error <= thr (cameras without distortion) -----------------------------------
+// Same idea as the fundamental / essential filters of cvmath.cuh: most (pose, correspondence) pairs of a RANSAC batch
+// are outliers by a wide margin, and the exact test above costs ~30 FP64-pipe instructions, a division and five
+// conversions.  In fp32, with rows 0 / 1 of [R | t] pre-multiplied by fx / fy:
+//     x' = fx (R0 . X + t0),  y' = fy (R1 . X + t1),  z = R2 . X + t2,   u - pu = (uc z - x') / z,  uc = u - cx
+// so with g = (uc z - x', vc z - y') the squared reprojection error is |g|^2 / z^2 -- no division needed to compare it
+// with the threshold.  Error budget per tile of correspondences (u = 2^-24; Xm >= |X| etc. over the tile):
+//     |x~' - x'| <= 5u Xb,  Xb = |r0| Xm + |r1| Ym + |r2| Zm + |t0'|   (same for y', z);   eZ = 8u Zb >= |z~ - z|
+//     |g~x - gx| <= 8u (UCm Zb + Xb)                                  -> 16u (..) used
+//   and the exact path's own float32 roundings (pu = (float)(..), dx = u - pu) move its |dx| by at most
+//   u (|u| + 2 |dx|): a further 2.1u Um Zb on the g scale; the relative part goes into the threshold margin.
+// With ex, ey those bounds, zh = |z~| + eZ >= |z| and (p + q)^2 <= (1 + mu) p^2 + (1 + 1/mu) q^2 (mu = 2^-12) applied to
+// both sides, the single comparison
+//     g~x^2 + g~y^2 > thr (1 + 2^-9)(1 + mu)^2 z~^2 + K,   K = thr 1.003 (64.02 eZ)^2 + (64.02 ex)^2 + (64.02 ey)^2 + 1e-30
+// together with |z~| > eZ (z certainly non-zero: project_error special-cases z = 0) implies that the float32 error the
+// exact path computes exceeds thr.  Filter off (K = inf) for distorted cameras and non-finite / extreme poses.
+struct PnpFilter {
+    float r[9], t[3];
+    bool on;
+};
+struct PnpFilterTile {
+    float K, eZ, thrMM;
+};
+MCV_HD void pnp_filter_init(const double* R, const double* t, const PnpCamera& c, bool dist, PnpFilter& pf) {
+    const double sc[3] = {c.fx, c.fy, 1.0};
+    bool on = !dist;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 4; ++j) {
+            const double v = sc[i] * (j < 3 ? R[3 * i + j] : t[i]);
+            const double av = fabs(v);
+            if (!(av <= 1e30) || (av != 0.0 && av < 1e-30)) on = false;
+            if (j < 3) pf.r[3 * i + j] = (float)v; else pf.t[i] = (float)v;
+        }
+    }
+    pf.on = on;
+}
+// maxima over the tile: |X|, |Y|, |Z| of the world points, |u - cx|, |v - cy|, |u|, |v| of the image points
+MCV_HD void pnp_filter_tile(const PnpFilter& pf, float Xm, float Ym, float Zm, float UCm, float VCm, float Um, float Vm,
+                            float thr, PnpFilterTile& ft) {
+    using cvm::FILTER_EPS_A; using cvm::FILTER_EPS_D; using cvm::FILTER_SQ; using cvm::FILTER_TINY;
+    const float Xb = fmaf(fabsf(pf.r[0]), Xm, fmaf(fabsf(pf.r[1]), Ym, fmaf(fabsf(pf.r[2]), Zm, fabsf(pf.t[0]) + FILTER_TINY)));
+    const float Yb = fmaf(fabsf(pf.r[3]), Xm, fmaf(fabsf(pf.r[4]), Ym, fmaf(fabsf(pf.r[5]), Zm, fabsf(pf.t[1]) + FILTER_TINY)));
+    const float Zb = fmaf(fabsf(pf.r[6]), Xm, fmaf(fabsf(pf.r[7]), Ym, fmaf(fabsf(pf.r[8]), Zm, fabsf(pf.t[2]) + FILTER_TINY)));
+    const float u21 = 1.2516975402832031e-07f;                   // 2.1 * 2^-24
+    const float eZ = FILTER_EPS_A * Zb;
+    const float ex = fmaf(FILTER_EPS_D, fmaf(UCm, Zb, Xb), u21 * Um * Zb);
+    const float ey = fmaf(FILTER_EPS_D, fmaf(VCm, Zb, Yb), u21 * Vm * Zb);
+    const float sZ = FILTER_SQ * eZ, sx = FILTER_SQ * ex, sy = FILTER_SQ * ey;
+    ft.eZ = eZ;
+    ft.thrMM = thr * (1.001953125f * 1.000244140625f * 1.000244140625f * 1.0001f);
+    ft.K = pf.on ? fmaf(thr * 1.003f, sZ * sZ, fmaf(sx, sx, fmaf(sy, sy, 1e-30f))) : INFINITY;
+}
+// uc = (float)(u - cx), vc = (float)(v - cy)
+MCV_HD bool pnp_certain_outlier(const PnpFilter& pf, const PnpFilterTile& ft, float X, float Y, float Z, float uc, float vc) {
+    const float x = fmaf(pf.r[0], X, fmaf(pf.r[1], Y, fmaf(pf.r[2], Z, pf.t[0])));
+    const float y = fmaf(pf.r[3], X, fmaf(pf.r[4], Y, fmaf(pf.r[5], Z, pf.t[1])));
+    const float z = fmaf(pf.r[6], X, fmaf(pf.r[7], Y, fmaf(pf.r[8], Z, pf.t[2])));
+    const float gx = fmaf(uc, z, -x), gy = fmaf(vc, z, -y);
+    const float lhs = fmaf(gx, gx, gy * gy);
+    const float rhs = fmaf(ft.thrMM, z * z, ft.K);
+    return lhs > rhs && fabsf(z) > ft.eZ;
+}
+
 // cv::solvePnP(SOLVEPNP_AP3P) on four float32 correspondences, as PnPRansacCallback::runKernel calls it:
 // undistort (float32 result), AP3P on the first three, fourth point picks the pose, Rodrigues.
 // obj [4][3], img [4][2]; model = rvec[3], tvec[3].

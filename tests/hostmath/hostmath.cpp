@@ -205,3 +205,38 @@ void hm_e_filter(const double* E, int nModels, const double* a, const double* b,
     }
 }
 }
+
+extern "C" {
+// PnP filter vs the exact reprojection test: nModels (rvec, tvec) x n correspondences; cam = fx, fy, cx, cy (no distortion).
+void hm_pnp_filter(const double* models, int nModels, const float* obj, const float* img, int n, const double* cam4,
+                   float thr, unsigned char* filt, unsigned char* exact) {
+    PnpCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    cam.k1 = cam.k2 = cam.p1 = cam.p2 = 0;
+    const int TILE = 512;
+    for (int k = 0; k < nModels; ++k) {
+        double R[9];
+        rodrigues_v2m(models + 6 * k, R);
+        const double* t = models + 6 * k + 3;
+        PnpFilter pf;
+        pnp_filter_init(R, t, cam, false, pf);
+        for (int i0 = 0; i0 < n; i0 += TILE) {
+            const int i1 = i0 + TILE < n ? i0 + TILE : n;
+            float mx[7] = {0, 0, 0, 0, 0, 0, 0};
+            for (int i = i0; i < i1; ++i) {
+                const float v[7] = {obj[3 * i], obj[3 * i + 1], obj[3 * i + 2], (float)((double)img[2 * i] - cam.cx),
+                                    (float)((double)img[2 * i + 1] - cam.cy), img[2 * i], img[2 * i + 1]};
+                for (int c = 0; c < 7; ++c) if (!(fabsf(v[c]) <= mx[c])) mx[c] = fabsf(v[c]);
+            }
+            PnpFilterTile ft;
+            pnp_filter_tile(pf, mx[0], mx[1], mx[2], mx[3], mx[4], mx[5], mx[6], thr, ft);
+            for (int i = i0; i < i1; ++i) {
+                const float uc = (float)((double)img[2 * i] - cam.cx), vc = (float)((double)img[2 * i + 1] - cam.cy);
+                filt[(size_t)k * n + i] = pnp_certain_outlier(pf, ft, obj[3 * i], obj[3 * i + 1], obj[3 * i + 2], uc, vc) ? 1 : 0;
+                exact[(size_t)k * n + i] =
+                    project_error(R, t, cam, false, obj[3 * i], obj[3 * i + 1], obj[3 * i + 2], img[2 * i], img[2 * i + 1]) <= thr ? 1 : 0;
+            }
+        }
+    }
+}
+}

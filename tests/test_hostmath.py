@@ -312,3 +312,39 @@ def test_e_filter_is_conservative(hm):
     filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
     hm.hm_e_filter(p(M), len(M), p(y1), p(y2), n, C.c_float((1.0 / 800) ** 2), p(filt), p(exact))
     assert not (filt & exact).any()
+
+
+def test_pnp_filter_is_conservative(hm):
+    """pnp_certain_outlier may only fire where the exact reprojection test says outlier: true pose, perturbed poses
+    (decisions near the threshold), random poses, points behind / on the camera plane, extreme scalings."""
+    rng = np.random.default_rng(5)
+    K = np.array([[800.0, 0, 320.0], [0, 810.0, 240.0], [0, 0, 1.0]])
+    X, uv, rv_gt, tv_gt = synth.pnp_scene(4, 3000, 0.5, noise=0.7, K=K)
+    Xf, uf = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(uv, np.float32)
+    cam4 = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]])
+    models = [np.concatenate([rv_gt, tv_gt])]
+    for s in (1e-6, 1e-4, 1e-3, 1e-2, 0.1):
+        for _ in range(20):
+            models.append(models[0] + rng.normal(0, s, 6))
+    for _ in range(100):
+        models.append(np.concatenate([rng.normal(0, 1.0, 3), rng.normal(0, 3.0, 3)]))
+    z = models[0].copy(); z[3:] *= 1e20; models.append(z)
+    z = models[0].copy(); z[3:] *= 1e-20; models.append(z)
+    z = models[0].copy(); z[3:] = 0; models.append(z)
+    z = models[0].copy(); z[5] = -float(np.mean(X[:, 2])); models.append(z)     # camera plane through the scene
+    z = models[0].copy(); z[2] = np.nan; models.append(z)
+    z = models[0].copy(); z[4] = np.inf; models.append(z)
+    M = np.ascontiguousarray(np.stack(models))
+    n = len(Xf)
+    for thr in (4.0, 64.0, 1e-3):
+        filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
+        hm.hm_pnp_filter(p(M), len(M), p(Xf), p(uf), n, p(cam4), C.c_float(thr), p(filt), p(exact))
+        assert not (filt & exact).any(), "filter rejected an inlier"
+        if thr == 4.0:
+            assert exact[0].mean() > 0.3                                        # the true pose has its inliers
+            assert filt[101:201].mean() > 0.95                                  # random poses: almost nothing survives
+    # a point exactly on the camera plane (z = 0 is special-cased by the exact path) and huge coordinates
+    Xb = Xf.copy(); Xb[::7] *= 1e12; Xb[1::7] *= 1e-12
+    filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
+    hm.hm_pnp_filter(p(M), len(M), p(Xb), p(uf), n, p(cam4), C.c_float(4.0), p(filt), p(exact))
+    assert not (filt & exact).any()
