@@ -491,6 +491,48 @@ MCV_HD bool e_certain_outlier(const FFilter& ff, const FFilterTile& t, float x1,
     return d * d > fmaf(thrM, N, t.KD);
 }
 
+// ---- fp32 filter in front of h_error <= thr ------------------------------------------------------
+// The exact homography test is already float32, but it must round every operation separately and divide (about 28
+// instructions); the filter is the division-free FMA form:  with w = h6 x + h7 y + 1, X = h0 x + h1 y + h2, Y likewise and
+// g = (X - u w, Y - v w), the squared error is |g|^2 / w^2.  Both paths start from the same float32 coefficients.
+// Budget (u = 2^-24, per tile maxima Xm >= |x| etc.): the exact path's X, w and the filter's X~, w~ each differ from the
+// real values by <= 3u Xb resp. 3u Wb (Xb = |h0| Xm + |h1| Ym + |h2|, Wb = |h6| Xm + |h7| Ym + 1), so with g_e = X - u w
+// formed from the exact path's values |g_e - g~| <= 6u (Xb + Um Wb), and the exact path's own division / product /
+// subtraction roundings give |dx_f| >= |g_e / w| (1 - 4.1u) - 3.1u Um.  With eW = 8u Wb >= |w - w~| and ex = 24u (Xb + Um Wb)
+// >= 6u (Xb + Um Wb) + 3.2u Um Wb (1 + 5u), the relative factors inside the 2^-9 threshold margin, the comparison
+//     g~x^2 + g~y^2 > thr (1 + 2^-9)(1 + mu)^2 w~^2 + K,  K = thr 1.003 (64.02 eW)^2 + (64.02 ex)^2 + (64.02 ey)^2 + 1e-30
+// together with |w~| > eW implies that the error h_error computes exceeds thr (an exact-path overflow or w = 0 gives
+// inf / NaN there, which is an outlier as well).
+struct HFilterTile {
+    float K, eW, thrMM;
+};
+MCV_HD void h_filter_tile(const float* Hf, float Xm, float Ym, float Um, float Vm, float thr, HFilterTile& t) {
+    const float Xb = fmaf(fabsf(Hf[0]), Xm, fmaf(fabsf(Hf[1]), Ym, fabsf(Hf[2]) + FILTER_TINY));
+    const float Yb = fmaf(fabsf(Hf[3]), Xm, fmaf(fabsf(Hf[4]), Ym, fabsf(Hf[5]) + FILTER_TINY));
+    const float Wb = fmaf(fabsf(Hf[6]), Xm, fmaf(fabsf(Hf[7]), Ym, 1.0f));
+    const float u24 = 1.430511474609375e-06f;                    // 24 * 2^-24
+    const float eW = FILTER_EPS_A * Wb;
+    const float ex = u24 * fmaf(Um, Wb, Xb), ey = u24 * fmaf(Vm, Wb, Yb);
+    const float sW = FILTER_SQ * eW, sx = FILTER_SQ * ex, sy = FILTER_SQ * ey;
+    bool on = true;
+    for (int i = 0; i < 8; ++i) {
+        const float v = fabsf(Hf[i]);
+        if (!(v <= 1e30f) || (v != 0.0f && v < 1e-30f)) on = false;
+    }
+    t.eW = eW;
+    t.thrMM = thr * (1.001953125f * 1.000244140625f * 1.000244140625f * 1.0001f);
+    t.K = on ? fmaf(thr * 1.003f, sW * sW, fmaf(sx, sx, fmaf(sy, sy, 1e-30f))) : INFINITY;
+}
+MCV_HD bool h_certain_outlier(const float* Hf, const HFilterTile& t, float x, float y, float u, float v) {
+    const float w = fmaf(Hf[6], x, fmaf(Hf[7], y, 1.0f));
+    const float X = fmaf(Hf[0], x, fmaf(Hf[1], y, Hf[2]));
+    const float Y = fmaf(Hf[3], x, fmaf(Hf[4], y, Hf[5]));
+    const float gx = fmaf(-u, w, X), gy = fmaf(-v, w, Y);
+    const float lhs = fmaf(gx, gx, gy * gy);
+    const float rhs = fmaf(t.thrMM, w * w, t.K);
+    return lhs > rhs && fabsf(w) > t.eW;
+}
+
 #if defined(__CUDACC__)
 // ---- the two filters on Blackwell's packed fp32 pipe: two correspondences per instruction ------------------------
 // fma.rn.f32x2 / mul.rn.f32x2 (sm_100+, SASS FFMA2) operate on a register pair; the filter is bound by instruction

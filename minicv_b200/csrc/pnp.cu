@@ -17,6 +17,7 @@
 //   finalize  one CTA per problem: mask + ordered inlier list of the winner, then EPnP over the inliers
 //             (block-wide reductions for the sums over points, thread 0 for the small dense algebra)
 #include "ransac.cuh"
+#include "filter_pass.cuh"
 #include "pnpmath.cuh"
 
 #include <algorithm>
@@ -241,8 +242,33 @@ pnp_score_kernel(const float4* __restrict__ of, const float2* __restrict__ imf, 
         pnp_filter_tile(pfil, __int_as_float(smax[0]), __int_as_float(smax[1]), __int_as_float(smax[2]),
                         __int_as_float(smax[3]), __int_as_float(smax[4]), __int_as_float(smax[5]),
                         __int_as_float(smax[6]), thr2, ft);
+        struct MP { double R[9], t[3]; };
+        MP mine;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) mine.R[j] = R[j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) mine.t[j] = t[j];
+        auto shfl = [](const MP& a, int src) {
+            MP r;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) r.R[j] = __shfl_sync(0xFFFFFFFFu, a.R[j], src);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) r.t[j] = __shfl_sync(0xFFFFFFFFu, a.t[j], src);
+            return r;
+        };
+        bool skipFilter = false;
         for (int j0 = 0; j0 < rows; j0 += 64) {
             const int jn = min(64, rows - j0);
+            auto test = [&](const MP& mm, int j) {
+                const float4 q = sO[j0 + j];
+                const float2 m = sI[j0 + j];
+                return project_error(mm.R, mm.t, cam, dist, q.x, q.y, q.z, m.x, m.y) <= thr2;
+            };
+            if (skipFilter) {
+#pragma unroll 2
+                for (int j = 0; j < jn; ++j) cnt += test(mine, j) ? 1 : 0;
+                continue;
+            }
             unsigned long long pending = 0;
             if (jn == 64) {
 #pragma unroll 1
@@ -264,15 +290,7 @@ pnp_score_kernel(const float4* __restrict__ of, const float2* __restrict__ imf, 
                 }
             }
             if (!active) pending = 0;
-            while (__any_sync(0xFFFFFFFFu, pending != 0)) {
-                if (pending) {
-                    const int j = j0 + __ffsll((long long)pending) - 1;
-                    pending &= pending - 1;
-                    const float4 q = sO[j];
-                    const float2 m = sI[j];
-                    cnt += (project_error(R, t, cam, dist, q.x, q.y, q.z, m.x, m.y) <= thr2) ? 1 : 0;
-                }
-            }
+            cnt += resolve_pending(pending, mine, shfl, test, &skipFilter);
         }
         __syncthreads();
     }

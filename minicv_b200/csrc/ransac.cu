@@ -18,6 +18,7 @@
 //   finalize  inlier mask of the winner; homography: refit on inliers (normalised DLT) +
 //             10 Levenberg-Marquardt iterations + mask from the refined H (findHomography)
 #include "ransac.cuh"
+#include "filter_pass.cuh"
 #include "cvmath.cuh"
 
 #include <algorithm>
@@ -531,60 +532,115 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
                 atomicMax(&smax[0], m0); atomicMax(&smax[1], m1); atomicMax(&smax[2], m2); atomicMax(&smax[3], m3);
             }
         } else {
+            if (threadIdx.x < 4) smax[threadIdx.x] = 0;
+            __syncthreads();
             float4* sp = reinterpret_cast<float4*>(sraw);
             const float4* g = pf + base + s0;
-            for (int j = threadIdx.x; j < rows; j += 128) sp[j] = g[j];
+            int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+            for (int j = threadIdx.x; j < rows; j += 128) {
+                const float4 q = g[j];
+                sp[j] = q;
+                m0 = max(m0, __float_as_int(fabsf(q.x))); m1 = max(m1, __float_as_int(fabsf(q.y)));
+                m2 = max(m2, __float_as_int(fabsf(q.z))); m3 = max(m3, __float_as_int(fabsf(q.w)));
+            }
+            m0 = __reduce_max_sync(0xFFFFFFFFu, m0); m1 = __reduce_max_sync(0xFFFFFFFFu, m1);
+            m2 = __reduce_max_sync(0xFFFFFFFFu, m2); m3 = __reduce_max_sync(0xFFFFFFFFu, m3);
+            if ((threadIdx.x & 31) == 0) {
+                atomicMax(&smax[0], m0); atomicMax(&smax[1], m1); atomicMax(&smax[2], m2); atomicMax(&smax[3], m3);
+            }
         }
         __syncthreads();
+        // ---- filtered exact scoring (filters: cvmath.cuh; resolution of the survivors: filter_pass.cuh) ----
+        // 64 correspondences at a time go through the fp32 filter; what it cannot reject is given the reference's
+        // exact test.  skipFilter: every model of the warp fits (see filter_pass.cuh) -> plain loop for this tile.
+        bool skipFilter = false;
         if (MODEL == RM_HOMOGRAPHY) {
             const float4* sp = reinterpret_cast<const float4*>(sraw);
+            HFilterTile ht;
+            h_filter_tile(Hf, __int_as_float(smax[0]), __int_as_float(smax[1]), __int_as_float(smax[2]),
+                          __int_as_float(smax[3]), thr2, ht);
+            struct MH { float h[8]; };
+            MH mine;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mine.h[j] = Hf[j];
+            auto shfl = [](const MH& a, int src) {
+                MH r;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r.h[j] = __shfl_sync(0xFFFFFFFFu, a.h[j], src);
+                return r;
+            };
+            for (int j0 = 0; j0 < rows; j0 += 64) {
+                const int jn = min(64, rows - j0);
+                auto test = [&](const MH& mm, int j) {
+                    const float4 q = sp[j0 + j];
+                    return h_error(mm.h, q.x, q.y, q.z, q.w) <= thr2;
+                };
+                if (skipFilter) {
 #pragma unroll 4
-            for (int j = 0; j < rows; ++j) {
-                const float4 q = sp[j];
-                cnt += (h_error(Hf, q.x, q.y, q.z, q.w) <= thr2) ? 1 : 0;
+                    for (int j = 0; j < jn; ++j) cnt += test(mine, j) ? 1 : 0;
+                    continue;
+                }
+                unsigned long long pending = 0;
+                if (jn == 64) {
+#pragma unroll 1
+                    for (int o = 0; o < 4; ++o) {
+                        unsigned w = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float4 q = sp[j0 + 16 * o + j];
+                            if (!h_certain_outlier(Hf, ht, q.x, q.y, q.z, q.w)) w |= 1u << j;
+                        }
+                        pending |= (unsigned long long)w << (16 * o);
+                    }
+                } else {
+                    for (int j = 0; j < jn; ++j) {
+                        const float4 q = sp[j0 + j];
+                        if (!h_certain_outlier(Hf, ht, q.x, q.y, q.z, q.w)) pending |= 1ull << j;
+                    }
+                }
+                if (!active) pending = 0;
+                cnt += resolve_pending(pending, mine, shfl, test, &skipFilter);
             }
-        } else if (MODEL == RM_FUNDAMENTAL) {
-            // filtered exact scoring: 64 correspondences through the fp32 filter (cvmath.cuh, two per packed
-            // instruction), the survivors -- about 1.5 % for a wrong model -- collected in a bit mask and given the
-            // exact fp64 test afterwards, so the FP64 work of a warp is the longest survivor list of its 32 models
-            const float* spair = reinterpret_cast<const float*>(sraw);
+        } else {
+            struct MD { double m[9]; };
+            MD mine;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) mine.m[j] = m[j];
+            auto shfl = [](const MD& a, int src) {
+                MD r;
+#pragma unroll
+                for (int j = 0; j < 9; ++j) r.m[j] = __shfl_sync(0xFFFFFFFFu, a.m[j], src);
+                return r;
+            };
+            const float* sfilt = (MODEL == RM_FUNDAMENTAL) ? reinterpret_cast<const float*>(sraw) : spair;
+            const double4* spd = reinterpret_cast<const double4*>(sraw);
             FFilterTile ft;
-            f_filter_tile(ffil, __int_as_float(smax[0]), __int_as_float(smax[1]), __int_as_float(smax[2]),
-                          __int_as_float(smax[3]), ft);
+            if (MODEL == RM_FUNDAMENTAL)
+                f_filter_tile(ffil, __int_as_float(smax[0]), __int_as_float(smax[1]), __int_as_float(smax[2]),
+                              __int_as_float(smax[3]), ft);
+            else
+                e_filter_tile(ffil, __int_as_float(smax[0]), __int_as_float(smax[1]), __int_as_float(smax[2]),
+                              __int_as_float(smax[3]), ft);
             filter2_tile(ffil2, ft);
             for (int j0 = 0; j0 < rows; j0 += 64) {
                 const int jn = min(64, rows - j0);
-                unsigned long long pending = filter_block64<RM_FUNDAMENTAL>(ffil2, spair + 4 * j0, jn);
-                if (!active) pending = 0;
-                while (__any_sync(0xFFFFFFFFu, pending != 0)) {
-                    if (pending) {
-                        const int j = j0 + __ffsll((long long)pending) - 1;
-                        pending &= pending - 1;
-                        const float* q = spair + 8 * (j >> 1) + (j & 1);
-                        cnt += f_inlier(m, (double)q[0], (double)q[2], (double)q[4], (double)q[6], thr2) ? 1 : 0;
+                auto test = [&](const MD& mm, int j) {
+                    if (MODEL == RM_FUNDAMENTAL) {
+                        const float* q = sfilt + 8 * ((j0 + j) >> 1) + ((j0 + j) & 1);
+                        return f_inlier(mm.m, (double)q[0], (double)q[2], (double)q[4], (double)q[6], thr2);
+                    } else {
+                        const double4 q = spd[j0 + j];
+                        return e_inlier(mm.m, q.x, q.y, q.z, q.w, thr2);
                     }
+                };
+                if (skipFilter) {
+#pragma unroll 2
+                    for (int j = 0; j < jn; ++j) cnt += test(mine, j) ? 1 : 0;
+                    continue;
                 }
-            }
-        } else {
-            // filtered exact scoring, as for the fundamental matrix (fp32 filter on the rounded tile, exact fp64
-            // Sampson test on the survivors)
-            const double4* sp = reinterpret_cast<const double4*>(sraw);
-            FFilterTile et;
-            e_filter_tile(ffil, __int_as_float(smax[0]), __int_as_float(smax[1]), __int_as_float(smax[2]),
-                          __int_as_float(smax[3]), et);
-            filter2_tile(ffil2, et);
-            for (int j0 = 0; j0 < rows; j0 += 64) {
-                const int jn = min(64, rows - j0);
-                unsigned long long pending = filter_block64<RM_ESSENTIAL>(ffil2, spair + 4 * j0, jn);
+                unsigned long long pending = filter_block64<MODEL>(ffil2, sfilt + 4 * j0, jn);
                 if (!active) pending = 0;
-                while (__any_sync(0xFFFFFFFFu, pending != 0)) {
-                    if (pending) {
-                        const int j = __ffsll((long long)pending) - 1;
-                        pending &= pending - 1;
-                        const double4 q = sp[j0 + j];
-                        cnt += e_inlier(m, q.x, q.y, q.z, q.w, thr2) ? 1 : 0;
-                    }
-                }
+                cnt += resolve_pending(pending, mine, shfl, test, &skipFilter);
             }
         }
         __syncthreads();

@@ -240,3 +240,29 @@ void hm_pnp_filter(const double* models, int nModels, const float* obj, const fl
     }
 }
 }
+
+extern "C" {
+// Homography filter vs the exact float32 test.  H: nModels x 9 doubles (h33 = 1 normalisation as the kernels use).
+void hm_h_filter(const double* H, int nModels, const float* a, const float* b, int n, float thr, unsigned char* filt,
+                 unsigned char* exact) {
+    const int TILE = 1024;
+    for (int k = 0; k < nModels; ++k) {
+        float Hf[8];
+        for (int i = 0; i < 8; ++i) Hf[i] = (float)H[9 * k + i];
+        for (int i0 = 0; i0 < n; i0 += TILE) {
+            const int i1 = i0 + TILE < n ? i0 + TILE : n;
+            float mx[4] = {0, 0, 0, 0};
+            for (int i = i0; i < i1; ++i) {
+                const float v[4] = {fabsf(a[2 * i]), fabsf(a[2 * i + 1]), fabsf(b[2 * i]), fabsf(b[2 * i + 1])};
+                for (int c = 0; c < 4; ++c) if (!(v[c] <= mx[c])) mx[c] = v[c];
+            }
+            HFilterTile t;
+            h_filter_tile(Hf, mx[0], mx[1], mx[2], mx[3], thr, t);
+            for (int i = i0; i < i1; ++i) {
+                filt[(size_t)k * n + i] = h_certain_outlier(Hf, t, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]) ? 1 : 0;
+                exact[(size_t)k * n + i] = h_error(Hf, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]) <= thr ? 1 : 0;
+            }
+        }
+    }
+}
+}

@@ -348,3 +348,43 @@ def test_pnp_filter_is_conservative(hm):
     filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
     hm.hm_pnp_filter(p(M), len(M), p(Xb), p(uf), n, p(cam4), C.c_float(4.0), p(filt), p(exact))
     assert not (filt & exact).any()
+
+
+def test_h_filter_is_conservative(hm):
+    """h_certain_outlier may only fire where the exact float32 homography test says outlier."""
+    rng = np.random.default_rng(3)
+    a, b, gt, Hgt = synth.homography_pair(2, 4000)
+    af, bf = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    models = [(Hgt / Hgt[2, 2]).ravel()]
+    Hh = np.zeros(9)
+    inl = np.flatnonzero(gt)
+    for it in range(300):
+        idx = rng.permutation(len(af))[:4] if it < 200 else rng.choice(inl, 4, replace=False)
+        if hm.hm_h_solve4(p(np.ascontiguousarray(af[idx])), p(np.ascontiguousarray(bf[idx])), p(Hh)):
+            models.append(Hh.copy())
+    base = models[0]
+    for s in (1e-7, 1e-5, 1e-3):
+        for _ in range(20):
+            z = base * (1 + rng.normal(0, s, 9)); z[8] = 1; models.append(z)
+    for sc in (1e-35, 1e-20, 1e-6, 1e6, 1e20, 1e35):
+        z = base * sc; z[8] = 1; models.append(z)
+    z = base.copy(); z[6] = -1.0 / 500; z[7] = 0; models.append(z)      # line at infinity through the image (w = 0 at x = 500)
+    z = base.copy(); z[3] = np.nan; models.append(z)
+    z = base.copy(); z[7] = np.inf; models.append(z)
+    models.append(np.array([0, 0, 0, 0, 0, 0, 0, 0, 1.0]))
+    M = np.ascontiguousarray(np.stack(models))
+    n = len(af)
+    for thr in (9.0, 0.25, 1e-4):
+        filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
+        hm.hm_h_filter(p(M), len(M), p(af), p(bf), n, C.c_float(thr), p(filt), p(exact))
+        assert not (filt & exact).any(), "filter rejected an inlier"
+        if thr == 9.0:
+            assert exact[0].mean() > 0.25
+            wrong = exact[1:201].sum(axis=1) < 0.05 * n
+            assert filt[1:201][wrong].mean() > 0.98
+    af2 = np.ascontiguousarray(af.copy()); af2[::5, 0] = 500.0               # exactly on the w = 0 line of that model
+    af3 = (af * rng.choice([1e-20, 1.0, 1e12], size=(n, 1))).astype(np.float32)
+    for A_ in (af2, af3):
+        filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
+        hm.hm_h_filter(p(M), len(M), p(A_), p(bf), n, C.c_float(9.0), p(filt), p(exact))
+        assert not (filt & exact).any()
