@@ -5,8 +5,8 @@
 //   * a lane with at least DENSE_MIN survivors is resolved by the whole warp: its model is broadcast with shuffles and
 //     lane k tests correspondences k and k + 32;
 //   * the remaining sparse masks are resolved lane-serially (a handful of iterations);
-//   * a warp with many dense lanes (every model fits: e.g. scoring after a ratio-tested match) reports that back, and
-//     the caller skips the filter for the rest of the tile and runs the plain broadcast loop.
+//   * a warp with many dense lanes (every model fits: e.g. scoring after a ratio-tested match) stops filtering for the
+//     rest of the launch and runs the plain broadcast loop (warp_too_dense).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -15,16 +15,20 @@ namespace mcv {
 constexpr int FP_DENSE_MIN = 6;         // survivors (of 64) from which a lane is resolved cooperatively
 constexpr int FP_DENSE_LANES = 8;       // dense lanes (of 32) from which the warp gives up filtering for the tile
 
+// Warp-uniform: at least FP_DENSE_LANES lanes of the warp have dense masks -> the caller should stop filtering (the models
+// do not change, so it stays that way for the rest of the launch) and run the plain broadcast loop, this block included.
+__device__ __forceinline__ bool warp_too_dense(unsigned long long pending) {
+    return __popc(__ballot_sync(0xFFFFFFFFu, __popcll(pending) >= FP_DENSE_MIN)) >= FP_DENSE_LANES;
+}
+
 // Model: trivially copyable register struct; shfl(model, srcLane) -> Model; test(model, j) -> bool (exact inlier test
-// of correspondence j of the block).  Returns this lane's inlier count; *manyDense = the warp had >= FP_DENSE_LANES dense lanes.
+// of correspondence j of the block).  Returns this lane's inlier count.
 template <class Model, class Shfl, class Test>
-__device__ __forceinline__ int resolve_pending(unsigned long long pending, const Model& mine, Shfl shfl, Test test,
-                                               bool* manyDense) {
+__device__ __forceinline__ int resolve_pending(unsigned long long pending, const Model& mine, Shfl shfl, Test test) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     int cnt = 0;
     unsigned dense = __ballot_sync(FULL, __popcll(pending) >= FP_DENSE_MIN);
-    *manyDense = __popc(dense) >= FP_DENSE_LANES;
     while (dense) {
         const int m = __ffs(dense) - 1;
         dense &= dense - 1;

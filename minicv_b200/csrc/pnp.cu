@@ -212,6 +212,7 @@ pnp_score_kernel(const float4* __restrict__ of, const float2* __restrict__ imf, 
     PnpFilter pfil;
     pnp_filter_init(R, t, cam, dist, pfil);
     int cnt = 0;
+    bool skipFilter = false;
     for (int s0 = i0; s0 < i1; s0 += SCORE_TP) {
         const int rows = min(SCORE_TP, i1 - s0);
         // tile + the maxima the filter's error bounds need (bit patterns of non-negative floats order like integers;
@@ -256,7 +257,6 @@ pnp_score_kernel(const float4* __restrict__ of, const float2* __restrict__ imf, 
             for (int j = 0; j < 3; ++j) r.t[j] = __shfl_sync(0xFFFFFFFFu, a.t[j], src);
             return r;
         };
-        bool skipFilter = false;
         for (int j0 = 0; j0 < rows; j0 += 64) {
             const int jn = min(64, rows - j0);
             auto test = [&](const MP& mm, int j) {
@@ -264,13 +264,9 @@ pnp_score_kernel(const float4* __restrict__ of, const float2* __restrict__ imf, 
                 const float2 m = sI[j0 + j];
                 return project_error(mm.R, mm.t, cam, dist, q.x, q.y, q.z, m.x, m.y) <= thr2;
             };
-            if (skipFilter) {
-#pragma unroll 2
-                for (int j = 0; j < jn; ++j) cnt += test(mine, j) ? 1 : 0;
-                continue;
-            }
             unsigned long long pending = 0;
-            if (jn == 64) {
+            if (skipFilter) {
+            } else if (jn == 64) {
 #pragma unroll 1
                 for (int o = 0; o < 4; ++o) {
                     unsigned w = 0;
@@ -290,7 +286,13 @@ pnp_score_kernel(const float4* __restrict__ of, const float2* __restrict__ imf, 
                 }
             }
             if (!active) pending = 0;
-            cnt += resolve_pending(pending, mine, shfl, test, &skipFilter);
+            if (!skipFilter) skipFilter = warp_too_dense(pending);
+            if (skipFilter) {
+#pragma unroll 2
+                for (int j = 0; j < jn; ++j) cnt += test(mine, j) ? 1 : 0;
+            } else {
+                cnt += resolve_pending(pending, mine, shfl, test);
+            }
         }
         __syncthreads();
     }

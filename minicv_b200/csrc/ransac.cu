@@ -488,6 +488,7 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
     if (MODEL != RM_HOMOGRAPHY) { f_filter_init(m, ffil); filter2_init(ffil, ffil2, thrM); }
 
     int cnt = 0;
+    bool skipFilter = false;
     for (int s0 = i0; s0 < i1; s0 += TP) {
         const int rows = min(TP, i1 - s0);
         if (MODEL == RM_ESSENTIAL) {
@@ -552,8 +553,7 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
         __syncthreads();
         // ---- filtered exact scoring (filters: cvmath.cuh; resolution of the survivors: filter_pass.cuh) ----
         // 64 correspondences at a time go through the fp32 filter; what it cannot reject is given the reference's
-        // exact test.  skipFilter: every model of the warp fits (see filter_pass.cuh) -> plain loop for this tile.
-        bool skipFilter = false;
+        // exact test.  skipFilter (sticky for the launch): every model of the warp fits (see filter_pass.cuh) -> plain loop.
         if (MODEL == RM_HOMOGRAPHY) {
             const float4* sp = reinterpret_cast<const float4*>(sraw);
             HFilterTile ht;
@@ -575,13 +575,9 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
                     const float4 q = sp[j0 + j];
                     return h_error(mm.h, q.x, q.y, q.z, q.w) <= thr2;
                 };
-                if (skipFilter) {
-#pragma unroll 4
-                    for (int j = 0; j < jn; ++j) cnt += test(mine, j) ? 1 : 0;
-                    continue;
-                }
                 unsigned long long pending = 0;
-                if (jn == 64) {
+                if (skipFilter) {
+                } else if (jn == 64) {
 #pragma unroll 1
                     for (int o = 0; o < 4; ++o) {
                         unsigned w = 0;
@@ -599,7 +595,13 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
                     }
                 }
                 if (!active) pending = 0;
-                cnt += resolve_pending(pending, mine, shfl, test, &skipFilter);
+                if (!skipFilter) skipFilter = warp_too_dense(pending);
+                if (skipFilter) {
+#pragma unroll 4
+                    for (int j = 0; j < jn; ++j) cnt += test(mine, j) ? 1 : 0;
+                } else {
+                    cnt += resolve_pending(pending, mine, shfl, test);
+                }
             }
         } else {
             struct MD { double m[9]; };
@@ -633,14 +635,18 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
                         return e_inlier(mm.m, q.x, q.y, q.z, q.w, thr2);
                     }
                 };
+                unsigned long long pending = 0;
+                if (!skipFilter) {
+                    pending = filter_block64<MODEL>(ffil2, sfilt + 4 * j0, jn);
+                    if (!active) pending = 0;
+                    skipFilter = warp_too_dense(pending);
+                }
                 if (skipFilter) {
 #pragma unroll 2
                     for (int j = 0; j < jn; ++j) cnt += test(mine, j) ? 1 : 0;
-                    continue;
+                } else {
+                    cnt += resolve_pending(pending, mine, shfl, test);
                 }
-                unsigned long long pending = filter_block64<MODEL>(ffil2, sfilt + 4 * j0, jn);
-                if (!active) pending = 0;
-                cnt += resolve_pending(pending, mine, shfl, test, &skipFilter);
             }
         }
         __syncthreads();
