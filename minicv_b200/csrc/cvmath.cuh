@@ -88,12 +88,13 @@ MCV_HDN inline int update_num_iters(double p, double ep, int modelPoints, int ma
 // to orthogonalise.  On return rows 0..N1-1 are unit "left" vectors (rows >= N fabricated by
 // OpenCV's fixed pseudo-random completion), W[N] the singular values (descending), Vt (N x N)
 // the accumulated rotations.  WANT_V = false skips Vt.
-template <int M, int N, int N1, bool WANT_V>
+// S = element stride of At (1 = a plain array; blockDim for a thread-interleaved shared-memory matrix, see solve_kernel).
+template <int M, int N, int N1, bool WANT_V, int S = 1>
 MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
     const double eps = DBL_EPSILON * 10, minval = DBL_MIN;
     for (int i = 0; i < N; ++i) {
         double sd = 0;
-        for (int k = 0; k < M; ++k) sd += At[i * M + k] * At[i * M + k];
+        for (int k = 0; k < M; ++k) sd += At[(i * M + k) * S] * At[(i * M + k) * S];
         W[i] = sd;
         if (WANT_V) {
             for (int k = 0; k < N; ++k) Vt[i * N + k] = 0;
@@ -105,10 +106,10 @@ MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
         bool changed = false;
         for (int i = 0; i < N - 1; ++i)
             for (int j = i + 1; j < N; ++j) {
-                double* Ai = At + i * M;
-                double* Aj = At + j * M;
+                double* Ai = At + i * M * S;
+                double* Aj = At + j * M * S;
                 double a = W[i], p = 0, b = W[j];
-                for (int k = 0; k < M; ++k) p += Ai[k] * Aj[k];
+                for (int k = 0; k < M; ++k) p += Ai[k * S] * Aj[k * S];
                 if (fabs(p) <= eps * sqrt(a * b)) continue;
                 p *= 2;
                 double beta = a - b, gamma = hypot(p, beta), c, s;
@@ -122,9 +123,9 @@ MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
                 }
                 a = b = 0;
                 for (int k = 0; k < M; ++k) {
-                    double t0 = c * Ai[k] + s * Aj[k];
-                    double t1 = -s * Ai[k] + c * Aj[k];
-                    Ai[k] = t0; Aj[k] = t1;
+                    double t0 = c * Ai[k * S] + s * Aj[k * S];
+                    double t1 = -s * Ai[k * S] + c * Aj[k * S];
+                    Ai[k * S] = t0; Aj[k * S] = t1;
                     a += t0 * t0; b += t1 * t1;
                 }
                 W[i] = a; W[j] = b;
@@ -143,7 +144,7 @@ MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
     }
     for (int i = 0; i < N; ++i) {
         double sd = 0;
-        for (int k = 0; k < M; ++k) sd += At[i * M + k] * At[i * M + k];
+        for (int k = 0; k < M; ++k) sd += At[(i * M + k) * S] * At[(i * M + k) * S];
         W[i] = sqrt(sd);
     }
     for (int i = 0; i < N - 1; ++i) {
@@ -152,7 +153,7 @@ MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
             if (W[j] < W[k]) j = k;
         if (i != j) {
             double t = W[i]; W[i] = W[j]; W[j] = t;
-            for (int k = 0; k < M; ++k) { t = At[i * M + k]; At[i * M + k] = At[j * M + k]; At[j * M + k] = t; }
+            for (int k = 0; k < M; ++k) { t = At[(i * M + k) * S]; At[(i * M + k) * S] = At[(j * M + k) * S]; At[(j * M + k) * S] = t; }
             if (WANT_V)
                 for (int k = 0; k < N; ++k) { t = Vt[i * N + k]; Vt[i * N + k] = Vt[j * N + k]; Vt[j * N + k] = t; }
         }
@@ -162,26 +163,26 @@ MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
         double sd = i < N ? W[i] : 0;
         for (int ii = 0; ii < 100 && sd <= minval; ++ii) {
             const double val0 = 1. / M;
-            for (int k = 0; k < M; ++k) At[i * M + k] = (rng.next() & 256) != 0 ? val0 : -val0;
+            for (int k = 0; k < M; ++k) At[(i * M + k) * S] = (rng.next() & 256) != 0 ? val0 : -val0;
             for (int it = 0; it < 2; ++it)
                 for (int j = 0; j < i; ++j) {
                     sd = 0;
-                    for (int k = 0; k < M; ++k) sd += At[i * M + k] * At[j * M + k];
+                    for (int k = 0; k < M; ++k) sd += At[(i * M + k) * S] * At[(j * M + k) * S];
                     double asum = 0;
                     for (int k = 0; k < M; ++k) {
-                        double t = At[i * M + k] - sd * At[j * M + k];
-                        At[i * M + k] = t;
+                        double t = At[(i * M + k) * S] - sd * At[(j * M + k) * S];
+                        At[(i * M + k) * S] = t;
                         asum += fabs(t);
                     }
                     asum = asum > eps * 100 ? 1 / asum : 0;
-                    for (int k = 0; k < M; ++k) At[i * M + k] *= asum;
+                    for (int k = 0; k < M; ++k) At[(i * M + k) * S] *= asum;
                 }
             sd = 0;
-            for (int k = 0; k < M; ++k) sd += At[i * M + k] * At[i * M + k];
+            for (int k = 0; k < M; ++k) sd += At[(i * M + k) * S] * At[(i * M + k) * S];
             sd = sqrt(sd);
         }
         const double s = sd > minval ? 1 / sd : 0.;
-        for (int k = 0; k < M; ++k) At[i * M + k] *= s;
+        for (int k = 0; k < M; ++k) At[(i * M + k) * S] *= s;
     }
 }
 
@@ -751,20 +752,20 @@ MCV_HDN inline int solve_cubic(const double* cf, double* roots) {
 
 // ---- 7-point fundamental matrix (run7Point) ----------------------------------------------------
 // m1/m2: 7 (x,y) float pairs.  F: up to 3 matrices (9 doubles each).  Returns the count.
-MCV_HDN inline int f_solve7(const float* m1, const float* m2, double* Fout) {
-    double At[9 * 9];
+// At: 81 doubles of scratch with element stride S (the 9 x 9 design matrix / null-space basis)
+template <int S>
+MCV_HDN inline int f_solve7_at(const float* m1, const float* m2, double* Fout, double* At) {
     for (int i = 0; i < 7; ++i) {
         const double x0 = m1[2 * i], y0 = m1[2 * i + 1], x1 = m2[2 * i], y1 = m2[2 * i + 1];
-        double* a = At + i * 9;
-        a[0] = x1 * x0; a[1] = x1 * y0; a[2] = x1; a[3] = y1 * x0; a[4] = y1 * y0; a[5] = y1;
-        a[6] = x0; a[7] = y0; a[8] = 1;
+        double* a = At + i * 9 * S;
+        a[0] = x1 * x0; a[1 * S] = x1 * y0; a[2 * S] = x1; a[3 * S] = y1 * x0; a[4 * S] = y1 * y0; a[5 * S] = y1;
+        a[6 * S] = x0; a[7 * S] = y0; a[8 * S] = 1;
     }
-    for (int k = 63; k < 81; ++k) At[k] = 0;
+    for (int k = 63; k < 81; ++k) At[k * S] = 0;
     double W[7];
-    jacobi_svd_rows<9, 7, 9, false>(At, W, nullptr);   // rows 7, 8 = null-space basis (Vt rows)
-    double* f1 = At + 7 * 9;
-    double* f2 = At + 8 * 9;
-    for (int i = 0; i < 9; ++i) f1[i] -= f2[i];
+    jacobi_svd_rows<9, 7, 9, false, S>(At, W, nullptr);   // rows 7, 8 = null-space basis (Vt rows)
+    double f1[9], f2[9];
+    for (int i = 0; i < 9; ++i) { f2[i] = At[(8 * 9 + i) * S]; f1[i] = At[(7 * 9 + i) * S] - f2[i]; }
     double c[4], r[3] = {0, 0, 0};
     const double t0 = f2[4] * f2[8] - f2[5] * f2[7];
     const double t1 = f2[3] * f2[8] - f2[5] * f2[6];
@@ -793,6 +794,10 @@ MCV_HDN inline int f_solve7(const float* m1, const float* m2, double* Fout) {
         for (int i = 0; i < 8; ++i) F[i] = f1[i] * lambda + f2[i] * mu;
     }
     return n;
+}
+MCV_HDN inline int f_solve7(const float* m1, const float* m2, double* Fout) {
+    double At[9 * 9];
+    return f_solve7_at<1>(m1, m2, Fout, At);
 }
 
 // ---- 5-point essential matrix ------------------------------------------------------------------
