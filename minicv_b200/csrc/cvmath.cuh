@@ -633,7 +633,9 @@ MCV_HDN inline bool h_check_subset(const float* src, const float* dst) {
 // is obtained from the 8x9 DLT system by elimination with complete pivoting (OpenCV takes the
 // smallest eigenvector of the 9x9 normal matrix -- same H up to rounding for a minimal set).
 // src/dst: 4 (x,y) float pairs.  H: 9 doubles, scaled so H[8] = 1.  Returns false if degenerate.
-MCV_HDN inline bool h_solve4(const float* src, const float* dst, double* H) {
+// Ab: 72 doubles of scratch with element stride S (the 8 x 9 system; 1 = plain array, blockDim = thread-interleaved smem)
+template <int S>
+MCV_HDN inline bool h_solve4_at(const float* src, const float* dst, double* H, double* Ab) {
     double cMx = 0, cMy = 0, cmx = 0, cmy = 0;
     for (int i = 0; i < 4; ++i) { cmx += dst[2 * i]; cmy += dst[2 * i + 1]; cMx += src[2 * i]; cMy += src[2 * i + 1]; }
     cmx /= 4; cmy /= 4; cMx /= 4; cMy /= 4;
@@ -645,14 +647,13 @@ MCV_HDN inline bool h_solve4(const float* src, const float* dst, double* H) {
     if (fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON)
         return false;
     smx = 4 / smx; smy = 4 / smy; sMx = 4 / sMx; sMy = 4 / sMy;
-    double A[8][9];
     for (int i = 0; i < 4; ++i) {
         const double x = (dst[2 * i] - cmx) * smx, y = (dst[2 * i + 1] - cmy) * smy;
         const double X = (src[2 * i] - cMx) * sMx, Y = (src[2 * i + 1] - cMy) * sMy;
-        double* r0 = A[2 * i];
-        double* r1 = A[2 * i + 1];
-        r0[0] = X; r0[1] = Y; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -x * X; r0[7] = -x * Y; r0[8] = -x;
-        r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = X; r1[4] = Y; r1[5] = 1; r1[6] = -y * X; r1[7] = -y * Y; r1[8] = -y;
+        double* r0 = Ab + (2 * i) * 9 * S;
+        double* r1 = Ab + (2 * i + 1) * 9 * S;
+        r0[0 * S] = X; r0[1 * S] = Y; r0[2 * S] = 1; r0[3 * S] = 0; r0[4 * S] = 0; r0[5 * S] = 0; r0[6 * S] = -x * X; r0[7 * S] = -x * Y; r0[8 * S] = -x;
+        r1[0 * S] = 0; r1[1 * S] = 0; r1[2 * S] = 0; r1[3 * S] = X; r1[4 * S] = Y; r1[5 * S] = 1; r1[6 * S] = -y * X; r1[7 * S] = -y * Y; r1[8 * S] = -y;
     }
     int perm[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
     for (int c = 0; c < 8; ++c) {
@@ -660,27 +661,27 @@ MCV_HDN inline bool h_solve4(const float* src, const float* dst, double* H) {
         double best = -1;
         for (int r = c; r < 8; ++r)
             for (int k = c; k < 9; ++k) {
-                const double v = fabs(A[r][k]);
+                const double v = fabs(Ab[((r) * 9 + (k)) * S]);
                 if (v > best) { best = v; pr = r; pc = k; }
             }
         if (!(best > 1e-14)) return false;
-        if (pr != c) for (int k = 0; k < 9; ++k) { double t = A[c][k]; A[c][k] = A[pr][k]; A[pr][k] = t; }
+        if (pr != c) for (int k = 0; k < 9; ++k) { double t = Ab[((c) * 9 + (k)) * S]; Ab[((c) * 9 + (k)) * S] = Ab[((pr) * 9 + (k)) * S]; Ab[((pr) * 9 + (k)) * S] = t; }
         if (pc != c) {
-            for (int r = 0; r < 8; ++r) { double t = A[r][c]; A[r][c] = A[r][pc]; A[r][pc] = t; }
+            for (int r = 0; r < 8; ++r) { double t = Ab[((r) * 9 + (c)) * S]; Ab[((r) * 9 + (c)) * S] = Ab[((r) * 9 + (pc)) * S]; Ab[((r) * 9 + (pc)) * S] = t; }
             int t = perm[c]; perm[c] = perm[pc]; perm[pc] = t;
         }
-        const double inv = 1 / A[c][c];
+        const double inv = 1 / Ab[((c) * 9 + (c)) * S];
         for (int r = c + 1; r < 8; ++r) {
-            const double f = A[r][c] * inv;
-            if (f != 0) for (int k = c; k < 9; ++k) A[r][k] -= f * A[c][k];
+            const double f = Ab[((r) * 9 + (c)) * S] * inv;
+            if (f != 0) for (int k = c; k < 9; ++k) Ab[((r) * 9 + (k)) * S] -= f * Ab[((c) * 9 + (k)) * S];
         }
     }
     double h[9], sol[9];
     sol[8] = 1;
     for (int c = 7; c >= 0; --c) {
         double s = 0;
-        for (int k = c + 1; k < 9; ++k) s += A[c][k] * sol[k];
-        sol[c] = -s / A[c][c];
+        for (int k = c + 1; k < 9; ++k) s += Ab[((c) * 9 + (k)) * S] * sol[k];
+        sol[c] = -s / Ab[((c) * 9 + (c)) * S];
     }
     for (int k = 0; k < 9; ++k) h[perm[k]] = sol[k];
     // H = invHnorm * h0 * Hnorm2
@@ -696,6 +697,11 @@ MCV_HDN inline bool h_solve4(const float* src, const float* dst, double* H) {
     for (int k = 0; k < 9; ++k) H[k] *= sc;
     for (int k = 0; k < 9; ++k) if (!(fabs(H[k]) < 1e300)) return false;
     return true;
+}
+
+MCV_HDN inline bool h_solve4(const float* src, const float* dst, double* H) {
+    double A[8 * 9];
+    return h_solve4_at<1>(src, dst, H, A);
 }
 
 // ---- cv::solveCubic (closed form); coeffs c[0] x^3 + c[1] x^2 + c[2] x + c[3] -----------------

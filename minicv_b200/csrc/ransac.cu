@@ -340,8 +340,11 @@ solve_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
             s[2 * i] = q.x; s[2 * i + 1] = q.y; d[2 * i] = q.z; d[2 * i + 1] = q.w;
         }
         if (MODEL == RM_HOMOGRAPHY) {
+            // 8 x 9 elimination matrix in thread-interleaved shared memory (as a local array it was the kernel's
+            // whole cost: 11.5 GB of local-memory write-back per launch)
+            __shared__ double sAb[(MODEL == RM_HOMOGRAPHY) ? 72 * 64 : 1];
             double H[9];
-            cnt = h_solve4(s, d, H) ? 1 : 0;
+            cnt = h_solve4_at<64>(s, d, H, sAb + threadIdx.x) ? 1 : 0;
             if (cnt) for (int k = 0; k < 9; ++k) out[k] = H[k];
         } else {
             // the 9 x 9 design matrix of the Jacobi SVD lives in shared memory, interleaved by thread (element e of
