@@ -97,8 +97,8 @@ MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
         for (int k = 0; k < M; ++k) sd += At[(i * M + k) * S] * At[(i * M + k) * S];
         W[i] = sd;
         if (WANT_V) {
-            for (int k = 0; k < N; ++k) Vt[i * N + k] = 0;
-            Vt[i * N + i] = 1;
+            for (int k = 0; k < N; ++k) Vt[(i * N + k) * S] = 0;
+            Vt[(i * N + i) * S] = 1;
         }
     }
     const int max_iter = M > 30 ? M : 30;
@@ -131,12 +131,12 @@ MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
                 W[i] = a; W[j] = b;
                 changed = true;
                 if (WANT_V) {
-                    double* Vi = Vt + i * N;
-                    double* Vj = Vt + j * N;
+                    double* Vi = Vt + i * N * S;
+                    double* Vj = Vt + j * N * S;
                     for (int k = 0; k < N; ++k) {
-                        double t0 = c * Vi[k] + s * Vj[k];
-                        double t1 = -s * Vi[k] + c * Vj[k];
-                        Vi[k] = t0; Vj[k] = t1;
+                        double t0 = c * Vi[k * S] + s * Vj[k * S];
+                        double t1 = -s * Vi[k * S] + c * Vj[k * S];
+                        Vi[k * S] = t0; Vj[k * S] = t1;
                     }
                 }
             }
@@ -155,7 +155,7 @@ MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
             double t = W[i]; W[i] = W[j]; W[j] = t;
             for (int k = 0; k < M; ++k) { t = At[(i * M + k) * S]; At[(i * M + k) * S] = At[(j * M + k) * S]; At[(j * M + k) * S] = t; }
             if (WANT_V)
-                for (int k = 0; k < N; ++k) { t = Vt[i * N + k]; Vt[i * N + k] = Vt[j * N + k]; Vt[j * N + k] = t; }
+                for (int k = 0; k < N; ++k) { t = Vt[(i * N + k) * S]; Vt[(i * N + k) * S] = Vt[(j * N + k) * S]; Vt[(j * N + k) * S] = t; }
         }
     }
     Mwc rng(0x12345678ull);
@@ -1116,8 +1116,11 @@ MCV_HDN inline void decompose_essential(const double* E, double* R1, double* R2,
 // ---- recoverPose cheirality test for one correspondence and one candidate (R, t) ---------------
 // DLT triangulation (cv::triangulatePoints): 4x4 system, right singular vector of the smallest
 // singular value; then z*w > 0, z/w < dist, 0 < z2 < dist in the second camera.
-MCV_HDN inline bool cheirality_ok(const double* R, const double* t, double x1, double y1, double x2,
-                                  double y2, double dist) {
+// scr: 32 doubles of scratch with element stride S (the transposed 4 x 4 system and the accumulated rotations of its
+// Jacobi SVD; 1 = plain array, blockDim = thread-interleaved shared memory).  Only the last right singular vector is used.
+template <int S>
+MCV_HDN inline bool cheirality_ok_at(const double* R, const double* t, double x1, double y1, double x2, double y2,
+                                     double dist, double* scr) {
     double A[16];
     // P0 = [I | 0], P1 = [R | t]
     A[0] = x1 * 0 - 1; A[1] = x1 * 0 - 0; A[2] = x1 * 1 - 0; A[3] = x1 * 0 - 0;
@@ -1128,15 +1131,24 @@ MCV_HDN inline bool cheirality_ok(const double* R, const double* t, double x1, d
     }
     A[11] = x2 * t[2] - t[0];
     A[15] = y2 * t[2] - t[1];
-    double w[4], U[16], Vt[16];
-    svd_square<4>(A, w, U, Vt);
-    double Q0 = Vt[12], Q1 = Vt[13], Q2 = Vt[14], Q3 = Vt[15];
+    double* At = scr;
+    double* Vt = scr + 16 * S;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) At[(i * 4 + j) * S] = A[j * 4 + i];   // rows of At = columns of A (svd_square)
+    double w[4];
+    jacobi_svd_rows<4, 4, 4, true, S>(At, w, Vt);
+    double Q0 = Vt[12 * S], Q1 = Vt[13 * S], Q2 = Vt[14 * S], Q3 = Vt[15 * S];
     bool ok = (Q2 * Q3) > 0;
     Q0 /= Q3; Q1 /= Q3; Q2 /= Q3; Q3 /= Q3;
     ok = ok && (Q2 < dist);
     const double z2 = R[6] * Q0 + R[7] * Q1 + R[8] * Q2 + t[2] * Q3;
     ok = ok && (z2 > 0) && (z2 < dist);
     return ok;
+}
+MCV_HDN inline bool cheirality_ok(const double* R, const double* t, double x1, double y1, double x2,
+                                  double y2, double dist) {
+    double scr[32];
+    return cheirality_ok_at<1>(R, t, x1, y1, x2, y2, dist, scr);
 }
 
 }  // namespace cvm

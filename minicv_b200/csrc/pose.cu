@@ -59,14 +59,18 @@ cheirality_kernel(const double* __restrict__ pd, const int64_t* __restrict__ off
     if (threadIdx.x < 9) { sR[threadIdx.x] = R1[9 * p + threadIdx.x]; sR[9 + threadIdx.x] = R2[9 * p + threadIdx.x]; }
     if (threadIdx.x < 3) sT[threadIdx.x] = T[3 * p + threadIdx.x];
     __syncthreads();
+    // scratch of the 4 x 4 Jacobi SVDs in thread-interleaved shared memory (as local arrays the resident threads'
+    // frames exceed L2 and are written back to DRAM)
+    __shared__ double sScr[32 * 128];
+    double* scr = sScr + threadIdx.x;
     unsigned bits = 0;
     if (i < n && (!maskIn || maskIn[base + i])) {
         const double* q = pd + 4 * (base + i);
         const double tp[3] = {sT[0], sT[1], sT[2]}, tn[3] = {-sT[0], -sT[1], -sT[2]};
-        if (cheirality_ok(sR, tp, q[0], q[1], q[2], q[3], 50.0)) bits |= 1;
-        if (cheirality_ok(sR + 9, tp, q[0], q[1], q[2], q[3], 50.0)) bits |= 2;
-        if (cheirality_ok(sR, tn, q[0], q[1], q[2], q[3], 50.0)) bits |= 4;
-        if (cheirality_ok(sR + 9, tn, q[0], q[1], q[2], q[3], 50.0)) bits |= 8;
+        if (cheirality_ok_at<128>(sR, tp, q[0], q[1], q[2], q[3], 50.0, scr)) bits |= 1;
+        if (cheirality_ok_at<128>(sR + 9, tp, q[0], q[1], q[2], q[3], 50.0, scr)) bits |= 2;
+        if (cheirality_ok_at<128>(sR, tn, q[0], q[1], q[2], q[3], 50.0, scr)) bits |= 4;
+        if (cheirality_ok_at<128>(sR + 9, tn, q[0], q[1], q[2], q[3], 50.0, scr)) bits |= 8;
     }
     if (i < n) cand[base + i] = (uint8_t)bits;
     for (int k = 0; k < 4; ++k) {
