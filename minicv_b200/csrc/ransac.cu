@@ -304,8 +304,11 @@ injected_setup_kernel(const int64_t* __restrict__ off, int nPairs, int maxIters,
 // ---------------------------------------------------------------------------------------------
 // solve: one hypothesis per thread
 // ---------------------------------------------------------------------------------------------
+#ifndef SOLVE_E_MIN_BLOCKS
+#define SOLVE_E_MIN_BLOCKS 8
+#endif
 template <int MODEL>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, (MODEL == RM_ESSENTIAL) ? SOLVE_E_MIN_BLOCKS : 1)
 solve_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
              const int64_t* __restrict__ off, int maxIters, const int* __restrict__ samples,
              const int* __restrict__ nIter, double* __restrict__ models,
