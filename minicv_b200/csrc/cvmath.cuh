@@ -967,7 +967,11 @@ MCV_HDN inline int real_roots10(const double* c, double* out) {
 // Es: up to 10 matrices, 9 doubles each, row-major, unit Frobenius norm.  Returns the count.
 // Follows the reference's runFivepoint (src/MiniCVNative/fivepoint.cpp:233-339); the
 // generated coefficient table of getCoeffMat (:10-231) is replaced by polynomial arithmetic.
-MCV_HDN inline int e_solve5(const double* pa, const double* pb, double* Es) {
+// The solver in three stages, so that the GPU can run them as separate kernels (one thread per hypothesis for the
+// first two, one thread per root for the last); e_solve5 below is their composition.
+// Stage 1: null-space basis EE (4 x 9), the three rows of B(z) (b: 3 x 13) and det B(z) (coef: degree 10, descending).
+MCV_HDN inline bool e5_stage1(const double* pa, const double* pb, double* EEout /*[36]*/, double* bout /*[39]*/,
+                              double* coef /*[11]*/) {
     // 1. null space of the 5x9 system: rows 5..8 of Vt (OpenCV basis, incl. its completion)
     double At[9 * 9];
     for (int i = 0; i < 5; ++i) {
@@ -1021,7 +1025,7 @@ MCV_HDN inline int e_solve5(const double* pa, const double* pb, double* Es) {
         double best = fabs(A[c][c]);
         for (int r = c + 1; r < 10; ++r)
             if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); pr = r; }
-        if (!(best > 0)) return 0;
+        if (!(best > 0)) return false;
         if (pr != c) for (int k = 0; k < 20; ++k) { double t = A[c][k]; A[c][k] = A[pr][k]; A[pr][k] = t; }
         const double inv = 1 / A[c][c];
         for (int k = c; k < 20; ++k) A[c][k] *= inv;
@@ -1047,7 +1051,6 @@ MCV_HDN inline int e_solve5(const double* pa, const double* pb, double* Es) {
         for (int k = 0; k < 13; ++k) b[i][k] = row1[k] - row2[k];
     }
     // det B(z): degree 10, descending coefficients
-    double coef[11];
     for (int k = 0; k < 11; ++k) coef[k] = 0;
     {
         const int perm[6][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 0}};
@@ -1060,35 +1063,47 @@ MCV_HDN inline int e_solve5(const double* pa, const double* pb, double* Es) {
             for (int k = 0; k < 11; ++k) coef[k] += sgn * full[k];
         }
     }
+    for (int k = 0; k < 36; ++k) EEout[k] = EE[k];
+    for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 13; ++k) bout[13 * i + k] = b[i][k];
+    return true;
+}
+
+// Stage 3: one real root z of det B(z) -> the essential matrix (unit Frobenius norm); false when the root is rejected.
+MCV_HDN inline bool e5_root_to_E(const double* EE /*[36]*/, const double* b /*[39]*/, double z1, double* E) {
+    const double z2 = z1 * z1, z3 = z2 * z1, z4 = z3 * z1;
+    double bz[9];
+    for (int j = 0; j < 3; ++j) {
+        const double* br = b + 13 * j;
+        bz[j * 3 + 0] = br[0] * z3 + br[1] * z2 + br[2] * z1 + br[3];
+        bz[j * 3 + 1] = br[4] * z3 + br[5] * z2 + br[6] * z1 + br[7];
+        bz[j * 3 + 2] = br[8] * z4 + br[9] * z3 + br[10] * z2 + br[11] * z1 + br[12];
+    }
+    // SVD::solveZ(Bz): right singular vector of the smallest singular value
+    double w3[3], u3[9], vt3[9];
+    svd_square<3>(bz, w3, u3, vt3);
+    const double vx = vt3[6], vy = vt3[7], vw = vt3[8];
+    if (fabs(vw) < 1e-10) return false;
+    const double xs = vx / vw, ys = vy / vw;
+    double nrm = 0;
+    for (int k = 0; k < 9; ++k) {
+        E[k] = EE[k] * xs + EE[9 + k] * ys + EE[18 + k] * z1 + EE[27 + k];
+        nrm += E[k] * E[k];
+    }
+    nrm = sqrt(nrm);
+    if (!(nrm > 0)) return false;
+    for (int k = 0; k < 9; ++k) E[k] /= nrm;
+    return true;
+}
+
+MCV_HDN inline int e_solve5(const double* pa, const double* pb, double* Es) {
+    double EE[36], b[39], coef[11];
+    if (!e5_stage1(pa, pb, EE, b, coef)) return 0;
     double roots[10];
     const int nr = real_roots10(coef, roots);
     int count = 0;
-    for (int ri = 0; ri < nr; ++ri) {
-        const double z1 = roots[ri], z2 = z1 * z1, z3 = z2 * z1, z4 = z3 * z1;
-        double bz[9];
-        for (int j = 0; j < 3; ++j) {
-            const double* br = b[j];
-            bz[j * 3 + 0] = br[0] * z3 + br[1] * z2 + br[2] * z1 + br[3];
-            bz[j * 3 + 1] = br[4] * z3 + br[5] * z2 + br[6] * z1 + br[7];
-            bz[j * 3 + 2] = br[8] * z4 + br[9] * z3 + br[10] * z2 + br[11] * z1 + br[12];
-        }
-        // SVD::solveZ(Bz): right singular vector of the smallest singular value
-        double w3[3], u3[9], vt3[9];
-        svd_square<3>(bz, w3, u3, vt3);
-        const double vx = vt3[6], vy = vt3[7], vw = vt3[8];
-        if (fabs(vw) < 1e-10) continue;
-        const double xs = vx / vw, ys = vy / vw;
-        double* E = Es + 9 * count;
-        double nrm = 0;
-        for (int k = 0; k < 9; ++k) {
-            E[k] = EE[k] * xs + EE[9 + k] * ys + EE[18 + k] * z1 + EE[27 + k];
-            nrm += E[k] * E[k];
-        }
-        nrm = sqrt(nrm);
-        if (!(nrm > 0)) continue;
-        for (int k = 0; k < 9; ++k) E[k] /= nrm;
-        ++count;
-    }
+    for (int ri = 0; ri < nr; ++ri)
+        if (e5_root_to_E(EE, b, roots[ri], Es + 9 * count)) ++count;
     return count;
 }
 

@@ -362,6 +362,84 @@ solve_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
     *nm = (uint8_t)cnt;
 }
 
+// 5-point solver as three kernels (cvmath.cuh: e5_stage1 / real_roots10 / e5_root_to_E).  As one kernel it needed 255
+// registers (8 warps per SM) and ran with 18.7 of 32 lanes active: the number of real roots and the Laguerre iteration
+// counts differ per hypothesis, and every root carries a 3x3 Jacobi SVD.  Split: (1) null space, elimination and
+// det B(z) per hypothesis; (2) root finding per hypothesis; (3) one thread per (hypothesis, root), the valid roots
+// compacted in root order inside a 16-lane group, so the models land exactly where the single kernel put them.
+constexpr int E5_SCR = 96;          // doubles per hypothesis: EE 36 | b 39 | coef 11 | roots 10
+
+__global__ void __launch_bounds__(64)
+solve_e_stage1_kernel(const double* __restrict__ pd, const int64_t* __restrict__ off, int maxIters,
+                      const int* __restrict__ samples, const int* __restrict__ nIter, double* __restrict__ scr,
+                      int* __restrict__ nRoots) {
+    constexpr int MP = 5;
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y;
+    if (it >= maxIters) return;
+    const int64_t h = (int64_t)p * maxIters + it;
+    nRoots[h] = -1;                                          // -1: no system (skipped iteration / bad sample / singular)
+    if (it >= nIter[p]) return;
+    const int64_t base = off[p];
+    const int n = (int)(off[p + 1] - base);
+    const int* idx = samples + h * MP;
+    bool bad = false;
+    for (int i = 0; i < MP; ++i) bad |= (idx[i] < 0 || idx[i] >= n);
+    if (bad) return;
+    double a[2 * MP], b[2 * MP];
+    for (int i = 0; i < MP; ++i) {
+        const double* q = pd + 4 * (base + idx[i]);
+        a[2 * i] = q[0]; a[2 * i + 1] = q[1]; b[2 * i] = q[2]; b[2 * i + 1] = q[3];
+    }
+    double EE[36], bb[39], coef[11];
+    if (!e5_stage1(a, b, EE, bb, coef)) return;
+    double* o = scr + h * E5_SCR;
+    for (int k = 0; k < 36; ++k) o[k] = EE[k];
+    for (int k = 0; k < 39; ++k) o[36 + k] = bb[k];
+    for (int k = 0; k < 11; ++k) o[75 + k] = coef[k];
+    nRoots[h] = 0;
+}
+
+__global__ void __launch_bounds__(128)
+solve_e_roots_kernel(int64_t nHyp, double* __restrict__ scr, int* __restrict__ nRoots) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nHyp || nRoots[h] < 0) return;
+    double coef[11], roots[10];
+    const double* c = scr + h * E5_SCR + 75;
+    for (int k = 0; k < 11; ++k) coef[k] = c[k];
+    const int nr = real_roots10(coef, roots);
+    double* o = scr + h * E5_SCR + 86;
+    for (int k = 0; k < nr; ++k) o[k] = roots[k];
+    nRoots[h] = nr;
+}
+
+__global__ void __launch_bounds__(128)
+solve_e_models_kernel(int64_t nHyp, const double* __restrict__ scr, const int* __restrict__ nRoots,
+                      double* __restrict__ models, uint8_t* __restrict__ nModels) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t h = t >> 4;                                // 16 lanes per hypothesis, lane r = root r
+    const int r = (int)(t & 15);
+    const bool live = h < nHyp;
+    const int nr = live ? nRoots[h] : -1;
+    double E[9];
+    bool valid = false;
+    if (r < nr) {
+        const double* s = scr + h * E5_SCR;
+        double EE[36], bb[39];
+        for (int k = 0; k < 36; ++k) EE[k] = s[k];
+        for (int k = 0; k < 39; ++k) bb[k] = s[36 + k];
+        valid = e5_root_to_E(EE, bb, s[86 + r], E);
+    }
+    const unsigned all = __ballot_sync(0xFFFFFFFFu, valid);
+    const unsigned grp = (all >> (threadIdx.x & 16)) & 0xFFFFu;
+    if (valid) {
+        const int slot = __popc(grp & ((1u << r) - 1u));
+        double* o = models + (h * 10 + slot) * 9;
+        for (int k = 0; k < 9; ++k) o[k] = E[k];
+    }
+    if (live && r == 0) nModels[h] = (uint8_t)__popc(grp);
+}
+
 // injected models: one model per iteration, copied into slot 0
 __global__ void __launch_bounds__(256)
 inject_models_kernel(const double* __restrict__ inj, int64_t nHyp, int maxm,
@@ -1180,6 +1258,13 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
     int* dCounts = ctx->ws[18].as<int>();
     int* dNTotal = ctx->ws[19].as<int>();
     int* dBest = ctx->ws[20].as<int>();
+    double* dE5Scr = nullptr;
+    int* dE5Roots = nullptr;
+    if (MODEL == RM_ESSENTIAL && !io.dInjModels) {
+        if (ctx->ws[68].reserve((size_t)chunk * maxIters * E5_SCR * 8) || ctx->ws[69].reserve((size_t)chunk * maxIters * 4)) return -1;
+        dE5Scr = ctx->ws[68].as<double>();
+        dE5Roots = ctx->ws[69].as<int>();
+    }
 
     for (int p0 = 0; p0 < nPairs; p0 += chunk) {
         const int np = std::min(chunk, nPairs - p0);
@@ -1236,6 +1321,15 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             const int64_t nh = (int64_t)np * maxIters;
             inject_models_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(
                 io.dInjModels + (size_t)p0 * maxIters * 9, nh, MAXM, dModels, dNModels);
+            MCV_LAUNCH_CHECK();
+        } else if (MODEL == RM_ESSENTIAL) {
+            const int64_t nh = (int64_t)np * maxIters;
+            dim3 g((maxIters + 63) / 64, np);
+            solve_e_stage1_kernel<<<g, 64, 0, st>>>(pd, off, maxIters, dSamples, dNIter, dE5Scr, dE5Roots);
+            MCV_LAUNCH_CHECK();
+            solve_e_roots_kernel<<<(unsigned)((nh + 127) / 128), 128, 0, st>>>(nh, dE5Scr, dE5Roots);
+            MCV_LAUNCH_CHECK();
+            solve_e_models_kernel<<<(unsigned)((nh * 16 + 127) / 128), 128, 0, st>>>(nh, dE5Scr, dE5Roots, dModels, dNModels);
             MCV_LAUNCH_CHECK();
         } else {
             dim3 g((maxIters + 63) / 64, np);
