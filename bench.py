@@ -241,15 +241,20 @@ def extra_ransac(local, with_cpu=True):
     out = {}
 
     def timed(fn, reps=3):
-        fn()
+        """Seconds per call: two warm-up calls, then the median of `reps` (>= 3) individually event-timed calls -- the
+        extras with host synchronisation inside a call (gather -> offsets) showed 4x outliers on a freshly leased box."""
+        fn(); fn()
         torch.cuda.synchronize()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        reps = max(reps, 3)
+        ts = []
         for _ in range(reps):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
             fn()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps / 1e3
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts)) / 1e3
 
     # ---- C3: homography 4-pt and fundamental 7-pt, 2000 correspondences, 4096 hypotheses, 1024 pairs
     P, N, HYP = 1024, 2000, 4096

@@ -113,18 +113,6 @@ pose_mask_kernel(const int64_t* __restrict__ off, const int* __restrict__ choice
     maskOut[base + i] = (k >= 0 && ((cand[base + i] >> k) & 1)) ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(64)
-five_point_kernel(const double* __restrict__ a, const double* __restrict__ b, int nSets,
-                  double* __restrict__ Es, int* __restrict__ counts) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nSets) return;
-    double pa[10], pb[10], E[90];
-    for (int k = 0; k < 10; ++k) { pa[k] = a[10 * s + k]; pb[k] = b[10 * s + k]; }
-    const int c = e_solve5(pa, pb, E);
-    for (int k = 0; k < c * 9; ++k) Es[90 * (int64_t)s + k] = E[k];
-    counts[s] = c;
-}
-
 }  // namespace
 
 int recover_pose_batch_device(Context* ctx, cudaStream_t st, const PoseIO& io) {
@@ -181,13 +169,6 @@ int recover_pose_batch_device(Context* ctx, cudaStream_t st, const PoseIO& io) {
     return 0;
 }
 
-int five_point_device(Context* ctx, cudaStream_t st, const double* dA, const double* dB, int nSets,
-                      double* dEs, int* dCounts) {
-    (void)ctx;
-    if (nSets <= 0) return 0;
-    five_point_kernel<<<(nSets + 63) / 64, 64, 0, st>>>(dA, dB, nSets, dEs, dCounts);
-    MCV_LAUNCH_CHECK();
-    return 0;
-}
+// five_point_device: ransac.cu (the 5-point solver runs as the three stage kernels there)
 
 }  // namespace mcv

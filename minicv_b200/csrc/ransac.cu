@@ -304,11 +304,8 @@ injected_setup_kernel(const int64_t* __restrict__ off, int nPairs, int maxIters,
 // ---------------------------------------------------------------------------------------------
 // solve: one hypothesis per thread
 // ---------------------------------------------------------------------------------------------
-#ifndef SOLVE_E_MIN_BLOCKS
-#define SOLVE_E_MIN_BLOCKS 8
-#endif
 template <int MODEL>
-__global__ void __launch_bounds__(64, (MODEL == RM_ESSENTIAL) ? SOLVE_E_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(64)
 solve_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
              const int64_t* __restrict__ off, int maxIters, const int* __restrict__ samples,
              const int* __restrict__ nIter, double* __restrict__ models,
@@ -327,16 +324,11 @@ solve_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
     bool bad = false;
     for (int i = 0; i < MP; ++i) bad |= (idx[i] < 0 || idx[i] >= n);
     if (bad) { *nm = 0; return; }
-    if (MODEL == RM_ESSENTIAL) {
-        double a[2 * MP], b[2 * MP];
-        for (int i = 0; i < MP; ++i) {
-            const double* q = pd + 4 * (base + idx[i]);
-            a[2 * i] = q[0]; a[2 * i + 1] = q[1]; b[2 * i] = q[2]; b[2 * i + 1] = q[3];
-        }
-        double Es[MAXM * 9];
-        cnt = e_solve5(a, b, Es);
-        for (int k = 0; k < cnt * 9; ++k) out[k] = Es[k];
-    } else {
+    // (the 5-point solver does not run here: as one kernel it needed 255 registers and ran at 18.7 of 32 active lanes,
+    // and the single-function composition e_solve5, compiled for the device, missed cv2 on 40 of 184 golden roots by > 1e-6
+    // while the same stages as separate kernels match -- see solve_e_*_kernel below)
+    static_assert(MODEL != RM_ESSENTIAL, "essential matrices are solved by the three solve_e_* kernels");
+    {
         float s[2 * MP], d[2 * MP];
         for (int i = 0; i < MP; ++i) {
             const float4 q = pf[base + idx[i]];
@@ -438,6 +430,29 @@ solve_e_models_kernel(int64_t nHyp, const double* __restrict__ scr, const int* _
         for (int k = 0; k < 9; ++k) o[k] = E[k];
     }
     if (live && r == 0) nModels[h] = (uint8_t)__popc(grp);
+}
+
+// cvFivePoint / cvFivePointBatch: the same three stages over explicit 5-point sets (a, b: [nSets][5][2]).
+__global__ void __launch_bounds__(64)
+five_point_stage1_kernel(const double* __restrict__ a, const double* __restrict__ b, int nSets,
+                         double* __restrict__ scr, int* __restrict__ nRoots) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nSets) return;
+    nRoots[h] = -1;
+    double pa[10], pb[10];
+    for (int k = 0; k < 10; ++k) { pa[k] = a[10 * (int64_t)h + k]; pb[k] = b[10 * (int64_t)h + k]; }
+    double EE[36], bb[39], coef[11];
+    if (!e5_stage1(pa, pb, EE, bb, coef)) return;
+    double* o = scr + (int64_t)h * E5_SCR;
+    for (int k = 0; k < 36; ++k) o[k] = EE[k];
+    for (int k = 0; k < 39; ++k) o[36 + k] = bb[k];
+    for (int k = 0; k < 11; ++k) o[75 + k] = coef[k];
+    nRoots[h] = 0;
+}
+__global__ void __launch_bounds__(256)
+widen_counts_kernel(const uint8_t* __restrict__ in, int n, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
 }
 
 // injected models: one model per iteration, copied into slot 0
@@ -1322,7 +1337,7 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             inject_models_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(
                 io.dInjModels + (size_t)p0 * maxIters * 9, nh, MAXM, dModels, dNModels);
             MCV_LAUNCH_CHECK();
-        } else if (MODEL == RM_ESSENTIAL) {
+        } else if constexpr (MODEL == RM_ESSENTIAL) {
             const int64_t nh = (int64_t)np * maxIters;
             dim3 g((maxIters + 63) / 64, np);
             solve_e_stage1_kernel<<<g, 64, 0, st>>>(pd, off, maxIters, dSamples, dNIter, dE5Scr, dE5Roots);
@@ -1407,6 +1422,25 @@ int ransac_select(cudaStream_t st, const int64_t* dOff, int np, int maxIters, in
                   const int* dSlotList, const int* dCounts, int* dBest) {
     select_kernel<<<(np + 3) / 4, 128, 0, st>>>(dOff, np, maxIters, maxm, mp, adaptive ? 1 : 0, confidence, dNIter,
                                                 dFlags, dIterStart, dSlotList, dCounts, dBest);
+    MCV_LAUNCH_CHECK();
+    return 0;
+}
+
+int five_point_device(Context* ctx, cudaStream_t st, const double* dA, const double* dB, int nSets, double* dEs,
+                      int* dCounts) {
+    if (nSets <= 0) return 0;
+    const size_t n = (size_t)nSets;
+    if (ctx->ws[68].reserve(n * E5_SCR * 8) || ctx->ws[69].reserve(n * 4 + n + 64)) return -1;
+    double* scr = ctx->ws[68].as<double>();
+    int* nRoots = ctx->ws[69].as<int>();
+    uint8_t* nModels = reinterpret_cast<uint8_t*>(nRoots + n);
+    five_point_stage1_kernel<<<(nSets + 63) / 64, 64, 0, st>>>(dA, dB, nSets, scr, nRoots);
+    MCV_LAUNCH_CHECK();
+    solve_e_roots_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((int64_t)n, scr, nRoots);
+    MCV_LAUNCH_CHECK();
+    solve_e_models_kernel<<<(unsigned)((n * 16 + 127) / 128), 128, 0, st>>>((int64_t)n, scr, nRoots, dEs, nModels);
+    MCV_LAUNCH_CHECK();
+    widen_counts_kernel<<<(nSets + 255) / 256, 256, 0, st>>>(nModels, nSets, dCounts);
     MCV_LAUNCH_CHECK();
     return 0;
 }
