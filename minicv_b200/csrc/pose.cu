@@ -62,20 +62,37 @@ cheirality_kernel(const double* __restrict__ pd, const int64_t* __restrict__ off
     // scratch of the 4 x 4 Jacobi SVDs in thread-interleaved shared memory (as local arrays the resident threads'
     // frames exceed L2 and are written back to DRAM)
     __shared__ double sScr[32 * 128];
+    __shared__ int sIdx[128];
+    __shared__ int sWarpCnt[4];
     double* scr = sScr + threadIdx.x;
+    // Only the points of the input mask (the RANSAC inliers, typically a quarter) are triangulated.  They are
+    // compacted inside the block first, so the SVDs run on full warps instead of on 8 of 32 lanes.
+    const bool want = i < n && (!maskIn || maskIn[base + i]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned wb = __ballot_sync(0xFFFFFFFFu, want);
+    if (lane == 0) sWarpCnt[warp] = __popc(wb);
+    if (i < n && !want) cand[base + i] = 0;
+    __syncthreads();
+    int before = 0, cnt = 0;
+    for (int w = 0; w < 4; ++w) { if (w < warp) before += sWarpCnt[w]; cnt += sWarpCnt[w]; }
+    if (want) sIdx[before + __popc(wb & ((1u << lane) - 1u))] = i;
+    __syncthreads();
     unsigned bits = 0;
-    if (i < n && (!maskIn || maskIn[base + i])) {
-        const double* q = pd + 4 * (base + i);
+    if ((int)threadIdx.x < cnt) {
+        const int j = sIdx[threadIdx.x];
+        const double* q = pd + 4 * (base + j);
         const double tp[3] = {sT[0], sT[1], sT[2]}, tn[3] = {-sT[0], -sT[1], -sT[2]};
         if (cheirality_ok_at<128>(sR, tp, q[0], q[1], q[2], q[3], 50.0, scr)) bits |= 1;
         if (cheirality_ok_at<128>(sR + 9, tp, q[0], q[1], q[2], q[3], 50.0, scr)) bits |= 2;
         if (cheirality_ok_at<128>(sR, tn, q[0], q[1], q[2], q[3], 50.0, scr)) bits |= 4;
         if (cheirality_ok_at<128>(sR + 9, tn, q[0], q[1], q[2], q[3], 50.0, scr)) bits |= 8;
+        cand[base + j] = (uint8_t)bits;
     }
-    if (i < n) cand[base + i] = (uint8_t)bits;
-    for (int k = 0; k < 4; ++k) {
-        const unsigned b = __ballot_sync(0xFFFFFFFFu, (bits >> k) & 1);
-        if ((threadIdx.x & 31) == 0 && b) atomicAdd(good4 + 4 * p + k, __popc(b));
+    if (warp * 32 < cnt) {                                   // warp-uniform: this warp holds compacted points
+        for (int k = 0; k < 4; ++k) {
+            const unsigned b = __ballot_sync(0xFFFFFFFFu, (bits >> k) & 1);
+            if (lane == 0 && b) atomicAdd(good4 + 4 * p + k, __popc(b));
+        }
     }
 }
 
