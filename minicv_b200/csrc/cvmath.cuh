@@ -89,8 +89,10 @@ MCV_HDN inline int update_num_iters(double p, double ep, int modelPoints, int ma
 // OpenCV's fixed pseudo-random completion), W[N] the singular values (descending), Vt (N x N)
 // the accumulated rotations.  WANT_V = false skips Vt.
 // S = element stride of At (1 = a plain array; blockDim for a thread-interleaved shared-memory matrix, see solve_kernel).
-template <int M, int N, int N1, bool WANT_V, int S = 1>
-MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
+// EXT: the fabricated rows N .. N1-1 live in Ext ((N1 - N) x M, stride 1) instead of At, so that a strided (shared-memory)
+// At only has to hold the N data rows.
+template <int M, int N, int N1, bool WANT_V, int S = 1, bool EXT = false>
+MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt, double* Ext = nullptr) {
     const double eps = DBL_EPSILON * 10, minval = DBL_MIN;
     for (int i = 0; i < N; ++i) {
         double sd = 0;
@@ -160,29 +162,33 @@ MCV_HDN inline void jacobi_svd_rows(double* At, double* W, double* Vt) {
     }
     Mwc rng(0x12345678ull);
     for (int i = 0; i < N1; ++i) {
+        double* Ri = (EXT && i >= N) ? Ext + (i - N) * M : At + i * M * S;
+        const int si = (EXT && i >= N) ? 1 : S;
         double sd = i < N ? W[i] : 0;
         for (int ii = 0; ii < 100 && sd <= minval; ++ii) {
             const double val0 = 1. / M;
-            for (int k = 0; k < M; ++k) At[(i * M + k) * S] = (rng.next() & 256) != 0 ? val0 : -val0;
+            for (int k = 0; k < M; ++k) Ri[k * si] = (rng.next() & 256) != 0 ? val0 : -val0;
             for (int it = 0; it < 2; ++it)
                 for (int j = 0; j < i; ++j) {
+                    const double* Rj = (EXT && j >= N) ? Ext + (j - N) * M : At + j * M * S;
+                    const int sj = (EXT && j >= N) ? 1 : S;
                     sd = 0;
-                    for (int k = 0; k < M; ++k) sd += At[(i * M + k) * S] * At[(j * M + k) * S];
+                    for (int k = 0; k < M; ++k) sd += Ri[k * si] * Rj[k * sj];
                     double asum = 0;
                     for (int k = 0; k < M; ++k) {
-                        double t = At[(i * M + k) * S] - sd * At[(j * M + k) * S];
-                        At[(i * M + k) * S] = t;
+                        double t = Ri[k * si] - sd * Rj[k * sj];
+                        Ri[k * si] = t;
                         asum += fabs(t);
                     }
                     asum = asum > eps * 100 ? 1 / asum : 0;
-                    for (int k = 0; k < M; ++k) At[(i * M + k) * S] *= asum;
+                    for (int k = 0; k < M; ++k) Ri[k * si] *= asum;
                 }
             sd = 0;
-            for (int k = 0; k < M; ++k) sd += At[(i * M + k) * S] * At[(i * M + k) * S];
+            for (int k = 0; k < M; ++k) sd += Ri[k * si] * Ri[k * si];
             sd = sqrt(sd);
         }
         const double s = sd > minval ? 1 / sd : 0.;
-        for (int k = 0; k < M; ++k) At[(i * M + k) * S] *= s;
+        for (int k = 0; k < M; ++k) Ri[k * si] *= s;
     }
 }
 
@@ -758,7 +764,7 @@ MCV_HDN inline int solve_cubic(const double* cf, double* roots) {
 
 // ---- 7-point fundamental matrix (run7Point) ----------------------------------------------------
 // m1/m2: 7 (x,y) float pairs.  F: up to 3 matrices (9 doubles each).  Returns the count.
-// At: 81 doubles of scratch with element stride S (the 9 x 9 design matrix / null-space basis)
+// At: 63 doubles of scratch with element stride S (the 7 x 9 design matrix)
 template <int S>
 MCV_HDN inline int f_solve7_at(const float* m1, const float* m2, double* Fout, double* At) {
     for (int i = 0; i < 7; ++i) {
@@ -767,11 +773,11 @@ MCV_HDN inline int f_solve7_at(const float* m1, const float* m2, double* Fout, d
         a[0] = x1 * x0; a[1 * S] = x1 * y0; a[2 * S] = x1; a[3 * S] = y1 * x0; a[4 * S] = y1 * y0; a[5 * S] = y1;
         a[6 * S] = x0; a[7 * S] = y0; a[8 * S] = 1;
     }
-    for (int k = 63; k < 81; ++k) At[k * S] = 0;
-    double W[7];
-    jacobi_svd_rows<9, 7, 9, false, S>(At, W, nullptr);   // rows 7, 8 = null-space basis (Vt rows)
+    double W[7], ext[18];
+    for (int k = 0; k < 18; ++k) ext[k] = 0;
+    jacobi_svd_rows<9, 7, 9, false, S, true>(At, W, nullptr, ext);   // ext = rows 7, 8 = null-space basis (Vt rows)
     double f1[9], f2[9];
-    for (int i = 0; i < 9; ++i) { f2[i] = At[(8 * 9 + i) * S]; f1[i] = At[(7 * 9 + i) * S] - f2[i]; }
+    for (int i = 0; i < 9; ++i) { f2[i] = ext[9 + i]; f1[i] = ext[i] - f2[i]; }
     double c[4], r[3] = {0, 0, 0};
     const double t0 = f2[4] * f2[8] - f2[5] * f2[7];
     const double t1 = f2[3] * f2[8] - f2[5] * f2[6];
@@ -802,7 +808,7 @@ MCV_HDN inline int f_solve7_at(const float* m1, const float* m2, double* Fout, d
     return n;
 }
 MCV_HDN inline int f_solve7(const float* m1, const float* m2, double* Fout) {
-    double At[9 * 9];
+    double At[7 * 9];
     return f_solve7_at<1>(m1, m2, Fout, At);
 }
 

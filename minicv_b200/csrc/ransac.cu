@@ -342,9 +342,9 @@ solve_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
             cnt = h_solve4_at<64>(s, d, H, sAb + threadIdx.x) ? 1 : 0;
             if (cnt) for (int k = 0; k < 9; ++k) out[k] = H[k];
         } else {
-            // the 9 x 9 design matrix of the Jacobi SVD lives in shared memory, interleaved by thread (element e of
+            // the 7 x 9 design matrix of the Jacobi SVD lives in shared memory, interleaved by thread (element e of
             // thread t at [e * 64 + t]: conflict-free); as a local array it thrashed L1 and was written back to DRAM
-            __shared__ double sAt[(MODEL == RM_FUNDAMENTAL) ? 81 * 64 : 1];
+            __shared__ double sAt[(MODEL == RM_FUNDAMENTAL) ? 63 * 64 : 1];
             double F[27];
             cnt = f_solve7_at<64>(s, d, F, sAt + threadIdx.x);
             if (cnt < 0 || cnt > 3) cnt = 0;
