@@ -377,7 +377,7 @@ MCV_HD bool f_inlier(const double* F, double x1, double y1, double x2, double y2
     const double n1 = dadd(dmul(a, a), dmul(b, b));
     const double d1 = dadd(dadd(dmul(x1, a), dmul(y1, b)), c);
     const double q1 = dmul(d1, d1), q2 = dmul(d2, d2);
-    if (n1 > 0 && n2 > 0) {
+    if (n1 > 0 && n2 > 0 && n1 <= DBL_MAX && n2 <= DBL_MAX) {   // finite: inf <= inf would pass where inf / inf = NaN fails
         if (q1 <= tl * n1 && q2 <= tl * n2) return true;
         if (q1 > th * n1 || q2 > th * n2) return false;
     }
@@ -462,7 +462,7 @@ MCV_HD bool e_inlier(const double* E, double x1, double y1, double x2, double y2
     const double xe = dadd(dadd(dmul(x2, Ex0), dmul(y2, Ex1)), Ex2);
     const double den = dadd(dadd(dadd(dmul(Ex0, Ex0), dmul(Ex1, Ex1)), dmul(Et0, Et0)), dmul(Et1, Et1));
     const double q = dmul(xe, xe);
-    if (den > 0) {
+    if (den > 0 && den <= DBL_MAX) {                            // finite: inf <= inf would pass where inf / inf = NaN fails
         if (q <= tl * den) return true;
         if (q > th * den) return false;
     }
