@@ -154,3 +154,34 @@ def test_error_convention():
     assert math.isnan(lib.cvFindScaled(0.01, None, None, None, 3, None, None))
     assert lib.cvFindScaledBatch(None, None, None, None, None, 2, None, None, None, None, None, None, -1) == -1
     assert lib.cvScaleCosts(None, None, None, None, 1, None, 1, None) == -1
+
+
+def test_non_finite_and_extreme_inputs_bit_exact():
+    """NaN / inf / huge / tiny world points and observations: the shared-reciprocal division falls back to the generic one
+    exactly where ptxas' own sequence would, so candidates and costs still equal the oracle's bit for bit (variant 0: only
+    world-side specials, which project1 rejects -> finite costs; variant 1: observation-side specials as well, which
+    poison the sums with inf / NaN exactly as the reference's `sum <- sum + d` would)."""
+    cam, ocam, pose, opose, world0, obs0, s = scene(8, 200)
+    for variant in (0, 1):
+        world, obs = world0.copy(), obs0.copy()
+        world[3] = [np.nan, 0.0, 1.0]
+        world[10] *= 1e200
+        world[11] *= 1e-200
+        world[12] = [np.inf, 1.0, -np.inf]
+        world[30] = ocam.location            # pc = 0: 0 / 0
+        obs[21] = [1e-310, -1e-310]          # denormals
+        if variant:
+            obs[20] = [np.inf, 0.1]
+            obs[22] = [np.nan, np.nan]
+        with np.errstate(all="ignore"):
+            res = mcp.find_scaled_batch([cam], [pose], world, obs, [0, 200], taps=True)
+            ocost, oscale, ocand, ook, ocosts = cp.find_scaled_fast(ocam, world, obs, opose)
+            np.testing.assert_array_equal(res.cand_ok, ook)
+            np.testing.assert_array_equal(res.candidates[ook], ocand[ook])
+            np.testing.assert_array_equal(res.cand_costs, ocosts)
+            assert (res.costs[0] == ocost or (np.isnan(res.costs[0]) and np.isnan(ocost))) and res.scales[0] == oscale
+            if not variant:
+                assert np.isfinite(ocosts[ook]).mean() > 0.5
+            scales = np.array([0.0, s, 1e300, -1e300, 1e-300, np.inf, -np.inf, np.nan])
+            np.testing.assert_array_equal(mcp.avgReprojectionError(scales, cam, (world, obs), pose),
+                                          cp.avg_reprojection_errors(scales, ocam, world, obs, opose))
