@@ -42,6 +42,8 @@ def point_variants(a, b, rng):
     """The pair as it is; all inliers of the true model only (every model near it fits: plain-loop mode); coordinates
     scaled far out of range on a few rows; a NaN coordinate in one tile."""
     yield "plain", a, b
+    yield "odd count (pair-interleaved tile with a half-filled last pair)", a[:-1], b[:-1]
+    yield "tiny", a[:9], b[:9]
     a2, b2 = a.copy(), b.copy()
     rows = rng.permutation(len(a))[:40]
     a2[rows[:20]] *= 1e7; b2[rows[20:]] *= 1e-7
