@@ -12,7 +12,10 @@
 
 namespace mcv {
 
-constexpr int FP_DENSE_MIN = 6;         // survivors (of 64) from which a lane is resolved cooperatively
+#ifndef FP_DENSE_MIN_V
+#define FP_DENSE_MIN_V 6
+#endif
+constexpr int FP_DENSE_MIN = FP_DENSE_MIN_V;   // survivors (of 64) from which a lane is resolved cooperatively
 constexpr int FP_DENSE_LANES = 8;       // dense lanes (of 32) from which the warp gives up filtering for the tile
 
 // Warp-uniform: at least FP_DENSE_LANES lanes of the warp have dense masks -> the caller should stop filtering (the models
