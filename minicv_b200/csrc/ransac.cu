@@ -833,6 +833,8 @@ select_kernel(const int64_t* __restrict__ off, int nPairs, int maxIters, int max
 // finalize
 // ---------------------------------------------------------------------------------------------
 constexpr int FB = 128;   // finalize block size (several blocks per SM overlap the serial thread-0 phases)
+// The homography refit also runs with 64-thread blocks (large batches: all pairs resident at once, 7 blocks per SM), so its
+// loops and reductions use blockDim.x; shared arrays are sized for FB.
 
 template <int K>
 __device__ __forceinline__ void block_sum(double (&v)[K], double* sred /*[K * 8]*/, double* sout /*[K]*/) {
@@ -847,7 +849,7 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* sred /*[K * 8]
     __syncthreads();
     if (threadIdx.x < K) {
         double s = 0;
-        for (int w = 0; w < FB / 32; ++w) s += sred[w * K + threadIdx.x];
+        for (int w = 0; w < (int)blockDim.x / 32; ++w) s += sred[w * K + threadIdx.x];
         sout[threadIdx.x] = s;
     }
     __syncthreads();
@@ -860,7 +862,7 @@ __device__ __forceinline__ double block_max(double x, double* sred) {
     if (lane == 0) sred[warp] = x;
     __syncthreads();
     double r = sred[0];
-    for (int w = 1; w < FB / 32; ++w) r = fmax(r, sred[w]);
+    for (int w = 1; w < (int)blockDim.x / 32; ++w) r = fmax(r, sred[w]);
     __syncthreads();
     return r;
 }
@@ -926,24 +928,72 @@ finalize_plain_kernel(const float4* __restrict__ pf, const double* __restrict__ 
 
 // Thread-0 helpers of the homography refit, kept out of line so the kernel's register and
 // stack footprint stay small.
-__device__ __noinline__ void h_from_ltl(const double* ltl45, double cmx, double cmy, double cMx, double cMy,
-                                        double smx, double smy, double sMx, double sMy, double* H) {
-    double L[81], w[9], V[81];
-    int k = 0;
-    for (int r = 0; r < 9; ++r)
-        for (int c = r; c < 9; ++c) { L[r * 9 + c] = ltl45[k]; L[c * 9 + r] = ltl45[k]; ++k; }
-    jacobi_eigen_sym<9>(L, w, V);
-    int mi = 0;
-    for (int i = 1; i < 9; ++i) if (w[i] < w[mi]) mi = i;
-    const double* h = V + 9 * mi;
-    const double iH[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
-    const double N2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
-    double T[9], Hn[9];
-    mat3mul(iH, h, T);
-    mat3mul(T, N2, Hn);
-    if (Hn[8] != 0) {
-        const double sc = 1. / Hn[8];
-        for (int j = 0; j < 9; ++j) H[j] = Hn[j] * sc;
+// H from the 45 upper-triangle sums of L'L (runKernel of the refit), executed by one warp: the symmetric 9 x 9
+// eigen-decomposition (cvmath.cuh, jacobi_eigen_sym: same operations) is the longest serial stretch of the refit,
+// and inside a Jacobi rotation every element update is independent, so lanes 0-8 take the column / row updates of L
+// and lanes 16-24 the eigenvector rows.  No sum changes its order (the rotation angle and the convergence sums are
+// computed redundantly by every lane, in the serial order), so H is bit-identical to the single-thread form's.
+__device__ __noinline__ void h_from_ltl_warp(const double* ltl45, double cmx, double cmy, double cMx, double cMy,
+                                             double smx, double smy, double sMx, double sMy, double* H,
+                                             double* L /*smem [81]*/, double* V /*smem [81]*/) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        int k = 0;
+        for (int r = 0; r < 9; ++r)
+            for (int c = r; c < 9; ++c) { L[r * 9 + c] = ltl45[k]; L[c * 9 + r] = ltl45[k]; ++k; }
+    }
+    for (int idx = lane; idx < 81; idx += 32) V[idx] = (idx / 9 == idx % 9) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0, diag = 0;
+        for (int i = 0; i < 9; ++i) {
+            diag += L[i * 9 + i] * L[i * 9 + i];
+            for (int j = i + 1; j < 9; ++j) off += L[i * 9 + j] * L[i * 9 + j];
+        }
+        if (off <= 1e-32 * diag || off == 0) break;
+        for (int p = 0; p < 8; ++p)
+            for (int q = p + 1; q < 9; ++q) {
+                const double apq = L[p * 9 + q];
+                if (apq == 0) continue;
+                const double app = L[p * 9 + p], aqq = L[q * 9 + q];
+                const double theta = (aqq - app) / (2 * apq);
+                const double t = (theta >= 0 ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1));
+                const double c = 1 / sqrt(t * t + 1), sn = t * c;
+                __syncwarp();                                   // everyone has read app, aqq, apq
+                if (lane < 9) {
+                    const int k = lane;
+                    const double akp = L[k * 9 + p], akq = L[k * 9 + q];
+                    L[k * 9 + p] = c * akp - sn * akq;
+                    L[k * 9 + q] = sn * akp + c * akq;
+                } else if (lane >= 16 && lane < 25) {
+                    const int k = lane - 16;
+                    const double vp = V[p * 9 + k], vq = V[q * 9 + k];
+                    V[p * 9 + k] = c * vp - sn * vq;
+                    V[q * 9 + k] = sn * vp + c * vq;
+                }
+                __syncwarp();
+                if (lane < 9) {
+                    const int k = lane;
+                    const double apk = L[p * 9 + k], aqk = L[q * 9 + k];
+                    L[p * 9 + k] = c * apk - sn * aqk;
+                    L[q * 9 + k] = sn * apk + c * aqk;
+                }
+                __syncwarp();
+            }
+    }
+    if (lane == 0) {
+        int mi = 0;
+        for (int i = 1; i < 9; ++i) if (L[i * 9 + i] < L[mi * 9 + mi]) mi = i;
+        const double* h = V + 9 * mi;
+        const double iH[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
+        const double N2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
+        double T[9], Hn[9];
+        mat3mul(iH, h, T);
+        mat3mul(T, N2, Hn);
+        if (Hn[8] != 0) {
+            const double sc = 1. / Hn[8];
+            for (int j = 0; j < 9; ++j) H[j] = Hn[j] * sc;
+        }
     }
 }
 
@@ -965,7 +1015,7 @@ __device__ __noinline__ double lm_reseed(const double* A) {
 
 // Homography with OpenCV's post-processing: runKernel on the inliers, LMSolver(10), mask
 // recomputed from the refined H, H /= h33 (cv::findHomography, calib3d/src/fundam.cpp).
-__global__ void __launch_bounds__(FB)
+__global__ void __launch_bounds__(FB, 4)
 finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off,
                            const double* __restrict__ models, int maxSlots,
                            const int* __restrict__ best, const int* __restrict__ flags, float thr2,
@@ -988,7 +1038,7 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
         if (bestOut) { bestOut[2 * p] = slot; bestOut[2 * p + 1] = slot < 0 ? -1 : 0; }
     }
     if (slot < 0) {
-        for (int i = tid; i < n; i += FB) masks[base + i] = 0;
+        for (int i = tid; i < n; i += (int)blockDim.x) masks[base + i] = 0;
         if (tid == 0) { ok[p] = 0; if (inlierCounts) inlierCounts[p] = 0; }
         return;
     }
@@ -1001,7 +1051,7 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
     for (int j = 0; j < 8; ++j) Hf[j] = (float)sH[j];
 
     // RANSAC mask of the winner
-    for (int i = tid; i < n; i += FB) {
+    for (int i = tid; i < n; i += (int)blockDim.x) {
         const float4 q = pf[base + i];
         masks[base + i] = (direct || h_error(Hf, q.x, q.y, q.z, q.w) <= thr2) ? 1 : 0;
     }
@@ -1018,7 +1068,7 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
     // ---- runKernel on the inliers: centroids, mean absolute deviations, LtL ----
     {
         double v[5] = {0, 0, 0, 0, 0};
-        for (int i = tid; i < n; i += FB)
+        for (int i = tid; i < n; i += (int)blockDim.x)
             if (masks[base + i]) {
                 const float4 q = pf[base + i];
                 v[0] += q.z; v[1] += q.w; v[2] += q.x; v[3] += q.y; v[4] += 1;
@@ -1030,7 +1080,7 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
     __syncthreads();
     {
         double v[4] = {0, 0, 0, 0};
-        for (int i = tid; i < n; i += FB)
+        for (int i = tid; i < n; i += (int)blockDim.x)
             if (masks[base + i]) {
                 const float4 q = pf[base + i];
                 v[0] += fabs(q.z - cmx); v[1] += fabs(q.w - cmy);
@@ -1047,7 +1097,7 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
         double v[45];
 #pragma unroll
         for (int k = 0; k < 45; ++k) v[k] = 0;
-        for (int i = tid; i < n; i += FB)
+        for (int i = tid; i < n; i += (int)blockDim.x)
             if (masks[base + i]) {
                 const float4 q = pf[base + i];
                 const double x = (q.z - cmx) * smx, y = (q.w - cmy) * smy;
@@ -1061,7 +1111,8 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
                     for (int c = r; c < 9; ++c) { v[k] += Lx[r] * Lx[c] + Ly[r] * Ly[c]; ++k; }
             }
         block_sum<45>(v, sred, sout);
-        if (tid == 0) h_from_ltl(sout, cmx, cmy, cMx, cMy, smx, smy, sMx, sMy, sH);
+        __shared__ double sL[81], sV[81];
+        if (tid < 32) h_from_ltl_warp(sout, cmx, cmy, cMx, cMy, smx, smy, sMx, sMy, sH, sL, sV);
         __syncthreads();
     }
 
@@ -1073,7 +1124,7 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
 #pragma unroll
         for (int k = 0; k < 45; ++k) v[k] = 0;
         double rmax = 0;
-        for (int i = tid; i < n; i += FB)
+        for (int i = tid; i < n; i += (int)blockDim.x)
             if (masks[base + i]) {
                 const float4 q = pf[base + i];
                 const double Mx = q.x, My = q.y;
@@ -1108,7 +1159,7 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
     };
     auto residual_sq = [&](const double* x) -> double {   // Sd at trial parameters
         double v[1] = {0};
-        for (int i = tid; i < n; i += FB)
+        for (int i = tid; i < n; i += (int)blockDim.x)
             if (masks[base + i]) {
                 const float4 q = pf[base + i];
                 const double Mx = q.x, My = q.y;
@@ -1182,7 +1233,7 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j) Hf[j] = (float)sH[j];
     int c2 = 0;
-    for (int i = tid; i < n; i += FB) {
+    for (int i = tid; i < n; i += (int)blockDim.x) {
         const float4 q = pf[base + i];
         const bool in = h_error(Hf, q.x, q.y, q.z, q.w) <= thr2;
         masks[base + i] = in ? 1 : 0;
@@ -1383,7 +1434,10 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
         int* oIt = io.dItersRun ? io.dItersRun + p0 : nullptr;
         int* oBest = io.dBest ? io.dBest + 2 * (size_t)p0 : nullptr;
         if (MODEL == RM_HOMOGRAPHY && prm.refine) {
-            finalize_homography_kernel<<<np, FB, 0, st>>>(pf, off, dModels, (int)slots, dBest, dFlags, thr2,
+            // small blocks once there are enough pairs to fill the machine with them: 7 x 64 threads per SM keep every
+            // pair of a 1024-pair batch resident, so the serial warp-0 phases of all refits overlap (one wave instead of three)
+            const int fb = np >= 4 * ctx->sm_count ? 64 : FB;
+            finalize_homography_kernel<<<np, fb, 0, st>>>(pf, off, dModels, (int)slots, dBest, dFlags, thr2,
                                                           oM, io.dMasks, oCnt, oOk, oIt, oBest);
         } else {
             finalize_plain_kernel<MODEL><<<np, FB, 0, st>>>(pf, pd, off, dModels, (int)slots, dBest, dFlags,
