@@ -305,7 +305,7 @@ pnp_score_kernel(const float4* __restrict__ of, const float2* __restrict__ imf, 
 // ---------------------------------------------------------------------------------------------
 // finalize
 // ---------------------------------------------------------------------------------------------
-constexpr int FB = 128;
+constexpr int FB = 64;      // finalize block size: small blocks keep more problems resident (the serial thread-0 phases of EPnP dominate)
 
 template <int K>
 __device__ __forceinline__ void block_sum(double (&v)[K], double* sred /*[K * FB/32]*/, double* sout /*[K]*/) {
@@ -326,7 +326,7 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* sred /*[K * FB
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(FB)
+__global__ void __launch_bounds__(FB, 7)
 pnp_finalize_kernel(const float4* __restrict__ of, const float2* __restrict__ imf, const int64_t* __restrict__ off,
                     const double* __restrict__ cams, const double* __restrict__ models, int maxSlots,
                     const int* __restrict__ best, const int* __restrict__ flags, float thr2, int refine,
