@@ -374,12 +374,12 @@ def extra_ransac(local, with_cpu=True):
     dol = torch.empty(Pl * nl, dtype=torch.uint8, device=dev)
     l2 = {}
     for ename, eng in (("fp32_cuda_core", 1), ("tcgen05_bf16_split_rescore", 2)):
-        mcv.set_hamming_engine(eng)
+        mcv.set_l2_engine(eng)
         tl2 = timed(lambda: mcv.match_knn2_batch_device(dql, lo_, dtl, lo_, dl * 4, RATIO, dil, ddl, dol, norm=mcv.NORM_L2,
                                                         device=local, stream=stream.cuda_stream))
         l2[ename] = {"pairs_per_s": Pl / tl2, "ms_per_batch": tl2 * 1e3, "gdist_per_s": Pl * nl * nl / tl2 / 1e9,
                      "planted_found": int((dil[::2, 0] == torch.arange(0, Pl * nl, 2, device=dev) % nl).sum().item())}
-    mcv.set_hamming_engine(0)
+    mcv.set_l2_engine(0)
     l2["pairs"] = Pl; l2["shape"] = f"{nl} x {nl} x {dl} f32"
     l2["pairs_per_s"] = max(l2["fp32_cuda_core"]["pairs_per_s"], l2["tcgen05_bf16_split_rescore"]["pairs_per_s"])
     l2["ms_per_batch"] = min(l2["fp32_cuda_core"]["ms_per_batch"], l2["tcgen05_bf16_split_rescore"]["ms_per_batch"])

@@ -8,7 +8,10 @@
  * everything else hidden.  All buffers are caller-allocated and caller-owned; the
  * callee reads inputs during the call and writes outputs before it returns; no
  * pointer is retained.  No export throws; failure is 0 / -1 with outputs untouched
- * (the reference's convention).
+ * (the reference's convention).  Every export may be called from any
+ * number of host threads at once, leaves the caller's current CUDA device as it found it, and
+ * the asynchronous *Device exports may be issued on any streams in any order: scratch memory is
+ * leased per call and ordered on the device behind its previous user (common.cuh).
  *
  * Three groups of exports:
  *   (1) EXISTING exports on the hot path, re-implemented on the GPU with their
@@ -100,7 +103,7 @@ MCV_API int mcvDeviceCount(void);
 /* Kernels launched by this library since load (all threads); used by bench.py. */
 MCV_API int64_t mcvKernelLaunchCount(void);
 /* CUDA-event timing of the dominant matcher kernel (the tcgen05 GEMM + top-2 kernel, or the
- * XOR/POPC kernel) of every subsequent matcher launch of the calling thread on `device`: events
+ * XOR/POPC kernel) of every subsequent matcher launch on `device` (any thread): events
  * are recorded on the launching stream around that kernel only.  Start allocates `capacity`
  * event pairs; Stop synchronises, writes up to `capacity` durations in milliseconds (launch
  * order) and returns how many.  Used by bench.py for the roofline figure. */
@@ -109,6 +112,36 @@ MCV_API int mcvKernelTimingStop(int device, float* ms, int capacity);
 /* Hamming matcher engine: 0 = auto (default), 1 = integer pipe (XOR + POPC), 2 = tcgen05
  * tensor cores.  Both engines are bit-identical in their results; returns 0, or -1 if bad. */
 MCV_API int mcvSetHammingEngine(int engine);
+/* L2 matcher engine: 0 = auto (default), 1 = fp32 CUDA cores, 2 = tcgen05 bf16-split GEMM + exact re-scoring. */
+MCV_API int mcvSetL2Engine(int engine);
+/* Contexts (stream set + grow-only workspaces) live in a per-device pool and are leased per call, so device
+ * memory scales with the number of concurrent calls (at most $MINICV_MAX_CONTEXTS per device, default 8), not
+ * with the number of host threads.  mcvTrim frees the workspaces and staging buffers of every idle context and
+ * returns how many it trimmed; mcvWorkspaceBytes reports the device (kind 0) or pinned-host (kind 1) bytes
+ * currently held; mcvSetWorkspaceLimit makes every call free its context's workspaces on return when they
+ * exceed `bytesPerContext` (< 0: keep them, the default); mcvContextCount = contexts created on `device`. */
+MCV_API int mcvTrim(void);
+MCV_API int64_t mcvWorkspaceBytes(int kind);
+MCV_API int mcvSetWorkspaceLimit(int64_t bytesPerContext);
+MCV_API int mcvContextCount(int device);
+
+/* ---- host buffers ----------------------------------------------------------------------------
+ * The host-pointer exports accept any host memory.  CUDA-pinned or registered buffers are copied by DMA directly;
+ * pageable buffers (what a P/Invoke caller's `fixed` arrays are) go through a library-owned ring of pinned slots
+ * filled by a small pool of copy threads ($MINICV_COPY_THREADS).  A caller that wants the direct path can take
+ * its buffers from mcvAllocPinned or register long-lived arrays once with mcvHostRegister. */
+MCV_API void* mcvAllocPinned(int64_t bytes);
+MCV_API void mcvFreePinned(void* p);
+MCV_API int mcvHostRegister(void* p, int64_t bytes);
+MCV_API int mcvHostUnregister(void* p);
+/* 0 = stage pageable buffers through the pinned ring (default), 1 = plain cudaMemcpyAsync for everything. */
+MCV_API int mcvSetStagingMode(int mode);
+MCV_API int mcvCopyThreads(void);
+/* Host<->device copy rate of `device` in GB/s: `reps` timed copies of `bytes` (CUDA events, private stream, one
+ * untimed copy first).  direction 0 = host->device, 1 = device->host, 2 = both at once (sum).  hostKind 0 = pinned,
+ * 1 = pageable through the staging ring, 2 = pageable through plain cudaMemcpyAsync.  < 0 on error.  bench.py runs
+ * it on every rank at once to measure the box's aggregate ceiling. */
+MCV_API double mcvMeasureCopyBandwidth(int device, int64_t bytes, int reps, int direction, int hostKind);
 /* Library build tag: "minicv_b200 sm_100a <date>". */
 MCV_API const char* mcvBuildInfo(void);
 
@@ -147,6 +180,15 @@ MCV_API int cvMatchKnn2BatchDevice(const uint8_t* dQuery, const int64_t* queryOf
                                    int* dTrainIdx, float* dDist, uint8_t* dRatioPass,
                                    int device, void* stream);
 
+/* Multi-GPU form (SURVEY.md section 8b "optional deviceMask", 8e): the pair list is cut into contiguous blocks of
+ * equal work, one per device whose bit is set in deviceMask (bit d = CUDA ordinal d; 0 = every visible device);
+ * one host thread and one stream set per device, disjoint output slices, no collective.  Host pointers as in
+ * cvMatchKnn2Batch.  Returns the total number of ratio-passing queries or -1. */
+MCV_API int cvMatchKnn2BatchMulti(const uint8_t* query, const int64_t* queryOffsets,
+                                  const uint8_t* train, const int64_t* trainOffsets,
+                                  int nPairs, int descBytes, int normType, float ratio,
+                                  int* trainIdx, float* dist, uint8_t* ratioPass, uint32_t deviceMask);
+
 /* Matcher over two detector results in the reference's own container
  * (src/MiniCVNative/MiniCVNative.h:23-29) -- SURVEY.md section 8f next-1. */
 MCV_API int cvMatchFeatures(const McvDetectorResult* query, const McvDetectorResult* train,
@@ -178,6 +220,28 @@ MCV_API int cvMatchKnn2ShardKeysDevice(const uint8_t* dQuery, int nQuery,
 MCV_API int cvMergeShardKeysDevice(const uint64_t* dKeys, int nShards, int nQuery, float ratio,
                                    int64_t* dTrainIdx64, float* dDist, uint8_t* dRatioPass,
                                    int device, void* stream);
+
+/* Large-database matching with the collective inside the library (config C5).
+ * (i) In-process: the train set is sharded by contiguous index range over the devices of deviceMask and stays
+ * resident; cvLargeDbMatch replicates the queries, takes every shard's local top-2, all-gathers the packed keys with
+ * NCCL (loaded at run time: libnccl.so.2, $MINICV_NCCL_LIB; peer copies to the first device when NCCL cannot be
+ * loaded or $MINICV_SHARD_TRANSPORT=p2p) and merges them.  trainIdx64 [2 nQuery] are GLOBAL train indices (-1 if
+ * absent), dist / ratioPass as in cvMatchKnn2.  Returns the number of ratio-passing queries or -1. */
+MCV_API void* cvLargeDbCreate(const uint8_t* train, int64_t nTrain, int descBytes, uint32_t deviceMask);
+MCV_API int cvLargeDbMatch(void* db, const uint8_t* query, int nQuery, float ratio, int64_t* trainIdx64,
+                           float* dist, uint8_t* ratioPass);
+MCV_API int cvLargeDbInfo(void* db, int* nShards, int* usesNccl, int64_t* nTrain);
+MCV_API void cvLargeDbDestroy(void* db);
+/* (ii) One process per GPU: rank 0 obtains a 128-byte id (mcvShardCommUniqueId) and distributes it by any means;
+ * every rank calls mcvShardCommInit (collective), then cvMatchKnn2ShardedDevice = local keys -> ncclAllGather ->
+ * merge, asynchronous on `stream`, device pointers, every rank receives the global result. */
+MCV_API int mcvNcclVersion(void);
+MCV_API int mcvShardCommUniqueId(uint8_t* id128);
+MCV_API void* mcvShardCommInit(const uint8_t* id128, int nRanks, int rank, int device);
+MCV_API void mcvShardCommDestroy(void* comm);
+MCV_API int cvMatchKnn2ShardedDevice(void* comm, const uint8_t* dQuery, int nQuery, const uint8_t* dTrainShard,
+                                     int64_t nTrainShard, int64_t globalIdxBase, int descBytes, float ratio,
+                                     int64_t* dTrainIdx64, float* dDist, uint8_t* dRatioPass, void* stream);
 
 
 /* ---- (1) existing hot-path exports, re-implemented on the GPU -------------------------
@@ -213,7 +277,8 @@ typedef struct {
     uint64_t seed;         /* MCV_SAMPLE_COUNTER only                                             */
     double   focal, ppx, ppy; /* essential only (findEssentialMat(focal, pp) overload)            */
     int32_t  refine;       /* homography: 1 = findHomography's refit + 10 LM iterations + re-mask */
-    int32_t  reserved;
+    int32_t  pairIndexBase;/* MCV_SAMPLE_COUNTER: global index of pair 0 (the multi-GPU forms set it per block,
+                              so a pair draws the same stream whichever device it lands on); else 0         */
 } McvRansacParams;
 
 /* == cv2.findHomography(a, b, RANSAC, thr, maxIters=, confidence=): H (h33 = 1) and mask.
@@ -237,6 +302,10 @@ MCV_API int cvRansacBatch(const McvRansacParams* prm, const McvPoint2d* a, const
                           const double* injModels, McvMatx33d* models, uint8_t* masks,
                           int32_t* inlierCounts, uint8_t* ok, int32_t* itersRun, int32_t* best,
                           int32_t* dbgCounts, double* dbgModels, int32_t* dbgSamples, int device);
+/* Multi-GPU form (see cvMatchKnn2BatchMulti): no injected hypotheses / parity taps. */
+MCV_API int cvRansacBatchMulti(const McvRansacParams* prm, const McvPoint2d* a, const McvPoint2d* b,
+                               const int64_t* offsets, int nPairs, McvMatx33d* models, uint8_t* masks,
+                               int32_t* inlierCounts, uint8_t* ok, int32_t* itersRun, uint32_t deviceMask);
 /* Device-resident form (offsets on the host, everything else in device memory; asynchronous). */
 MCV_API int cvRansacBatchDevice(const McvRansacParams* prm, const double* dA, const double* dB,
                                 const int64_t* offsets, int nPairs, double* dModels, uint8_t* dMasks,
@@ -249,6 +318,10 @@ MCV_API int cvRecoverPoseBatch(const RecoverPoseConfig* config, const McvPoint2d
                                const McvPoint2d* b, const int64_t* offsets, int nPairs,
                                int sampleMode, int maxIters, McvMatx33d* R, McvVec3d* t,
                                uint8_t* ms, int32_t* good, uint8_t* ok, int device);
+MCV_API int cvRecoverPoseBatchMulti(const RecoverPoseConfig* config, const McvPoint2d* a,
+                                    const McvPoint2d* b, const int64_t* offsets, int nPairs,
+                                    int sampleMode, int maxIters, McvMatx33d* R, McvVec3d* t,
+                                    uint8_t* ms, int32_t* good, uint8_t* ok, uint32_t deviceMask);
 MCV_API int cvRecoverPoseBatchDevice(const RecoverPoseConfig* config, const double* dA,
                                      const double* dB, const int64_t* offsets, int nPairs,
                                      int sampleMode, int maxIters, double* dE, double* dR, double* dT,
@@ -302,6 +375,7 @@ typedef struct {
     double   threshold;    /* reprojectionError in pixels                                           */
     double   confidence;   /* (0,1) exclusive                                                       */
     uint64_t seed;         /* MCV_SAMPLE_COUNTER only                                               */
+    int64_t  problemIndexBase; /* MCV_SAMPLE_COUNTER: global index of problem 0 (see McvRansacParams)       */
 } McvPnpParams;
 
 /* Batched form over packed correspondences: problem p owns rows [offsets[p], offsets[p+1]) of obj / img
@@ -319,6 +393,11 @@ MCV_API int cvSolvePnPRansacBatch(const McvPnpParams* prm, const McvPoint3d* obj
                                   McvVec3d* tvecs, uint8_t* masks, int32_t* inlierCounts, uint8_t* ok,
                                   int32_t* itersRun, int32_t* bestIter, double* minimal, int32_t* dbgCounts,
                                   double* dbgModels, int32_t* dbgSamples, int device);
+/* Multi-GPU form (see cvMatchKnn2BatchMulti). */
+MCV_API int cvSolvePnPRansacBatchMulti(const McvPnpParams* prm, const McvPoint3d* obj, const McvPoint2d* img,
+                                       const int64_t* offsets, int nProblems, const double* cams, McvVec3d* rvecs,
+                                       McvVec3d* tvecs, uint8_t* masks, int32_t* inlierCounts, uint8_t* ok,
+                                       int32_t* itersRun, uint32_t deviceMask);
 /* Device-resident form (offsets on the host, everything else in device memory; asynchronous). */
 MCV_API int cvSolvePnPRansacBatchDevice(const McvPnpParams* prm, const double* dObj, const double* dImg,
                                         const int64_t* offsets, int nProblems, const double* dCams,

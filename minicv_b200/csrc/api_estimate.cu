@@ -4,6 +4,7 @@
 //   group (2): findHomography / findFundamentalMat and the batched + injected forms
 // Thin host layer over ransac.cu / pose.cu: stages buffers, never computes on the CPU.
 #include "ransac.cuh"
+#include "staging.cuh"
 
 #include <vector>
 #include <string.h>
@@ -25,6 +26,7 @@ RansacParams to_params(const McvRansacParams* p) {
     r.model = p->model; r.sampleMode = p->sampleMode; r.stopMode = p->stopMode;
     r.maxIters = p->maxIters; r.threshold = p->threshold; r.confidence = p->confidence;
     r.seed = p->seed; r.focal = p->focal; r.ppx = p->ppx; r.ppy = p->ppy; r.refine = p->refine;
+    r.pairIndexBase = p->pairIndexBase;
     return r;
 }
 
@@ -40,8 +42,10 @@ int stage_points(Staged& s, const McvPoint2d* a, const McvPoint2d* b, int64_t to
     s.dCnt = c->ws[34].as<int>(); s.dOk = c->ws[35].as<uint8_t>();
     s.dIters = c->ws[36].as<int>(); s.dBest = c->ws[37].as<int>();
     if (total > 0) {
-        MCV_CUDA_TRY(cudaMemcpyAsync(s.dA, a, (size_t)total * 16, cudaMemcpyHostToDevice, s.st));
-        MCV_CUDA_TRY(cudaMemcpyAsync(s.dB, b, (size_t)total * 16, cudaMemcpyHostToDevice, s.st));
+        // pageable caller arrays (P/Invoke) go through the pinned ring, pinned ones are copied directly
+        if (h2d_copy(c, s.dA, a, (size_t)total * 16, s.st, host_is_pageable(a)) ||
+            h2d_copy(c, s.dB, b, (size_t)total * 16, s.st, host_is_pageable(b)))
+            return -1;
     }
     return 0;
 }
@@ -92,7 +96,7 @@ extern "C" {
 
 MCV_API int cvFindHomography(const McvPoint2d* a, const McvPoint2d* b, int N, double thr, int maxIters,
                              double conf, McvMatx33d* H, uint8_t* mask) {
-    clear_error();
+    MCV_API_ENTER();
     RansacParams prm;
     prm.model = RM_HOMOGRAPHY; prm.threshold = thr; prm.maxIters = maxIters; prm.confidence = conf;
     prm.refine = 1;
@@ -102,7 +106,7 @@ MCV_API int cvFindHomography(const McvPoint2d* a, const McvPoint2d* b, int N, do
 
 MCV_API int cvFindFundamentalMat(const McvPoint2d* a, const McvPoint2d* b, int N, double thr, double conf,
                                  int maxIters, McvMatx33d* F, uint8_t* mask) {
-    clear_error();
+    MCV_API_ENTER();
     RansacParams prm;
     prm.model = RM_FUNDAMENTAL; prm.threshold = thr; prm.maxIters = maxIters; prm.confidence = conf;
     const int rc = single_ransac(prm, a, b, N, F, mask, nullptr);
@@ -112,10 +116,10 @@ MCV_API int cvFindFundamentalMat(const McvPoint2d* a, const McvPoint2d* b, int N
 MCV_API int cvRansacBatchDevice(const McvRansacParams* p, const double* dA, const double* dB,
                                 const int64_t* offsets, int nPairs, double* dModels, uint8_t* dMasks,
                                 int32_t* dInlierCounts, uint8_t* dOk, int device, void* stream) {
-    clear_error();
+    MCV_API_ENTER();
     if (!p || check_batch_args(dA, dB, offsets, nPairs)) return -1;
     if (nPairs == 0) return 0;
-    Context* ctx = get_context(device);
+    Context* ctx = get_context_async(device, static_cast<cudaStream_t>(stream));
     if (!ctx) return -1;
     RansacIO io;
     io.dA = dA; io.dB = dB; io.hOff = offsets; io.nPairs = nPairs;
@@ -128,7 +132,7 @@ MCV_API int cvRansacBatch(const McvRansacParams* p, const McvPoint2d* a, const M
                           const double* injModels, McvMatx33d* models, uint8_t* masks,
                           int32_t* inlierCounts, uint8_t* ok, int32_t* itersRun, int32_t* best,
                           int32_t* dbgCounts, double* dbgModels, int32_t* dbgSamples, int device) {
-    clear_error();
+    MCV_API_ENTER();
     if (!p || check_batch_args(a, b, offsets, nPairs)) return -1;
     if (nPairs == 0) return 0;
     if (!models || !ok) { set_error("cvRansacBatch: null outputs"); return -1; }
@@ -179,11 +183,11 @@ MCV_API int cvRecoverPoseBatchDevice(const RecoverPoseConfig* cfg, const double*
                                      const int64_t* offsets, int nPairs, int sampleMode, int maxIters,
                                      double* dE, double* dR, double* dT, uint8_t* dMs, int32_t* dGood,
                                      uint8_t* dOk, int device, void* stream) {
-    clear_error();
+    MCV_API_ENTER();
     if (!cfg || check_batch_args(dA, dB, offsets, nPairs)) return -1;
     if (nPairs == 0) return 0;
     if (!dE || !dMs || !dOk) { set_error("cvRecoverPoseBatchDevice: null outputs"); return -1; }
-    Context* ctx = get_context(device);
+    Context* ctx = get_context_async(device, static_cast<cudaStream_t>(stream));
     if (!ctx) return -1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     RansacParams prm;
@@ -206,7 +210,7 @@ MCV_API int cvRecoverPoseBatch(const RecoverPoseConfig* cfg, const McvPoint2d* a
                                const int64_t* offsets, int nPairs, int sampleMode, int maxIters,
                                McvMatx33d* R, McvVec3d* t, uint8_t* ms, int32_t* good, uint8_t* ok,
                                int device) {
-    clear_error();
+    MCV_API_ENTER();
     if (!cfg || check_batch_args(a, b, offsets, nPairs)) return -1;
     if (nPairs == 0) return 0;
     if (!R || !t || !ok) { set_error("cvRecoverPoseBatch: null outputs"); return -1; }
@@ -235,7 +239,7 @@ MCV_API int cvRecoverPoseBatch(const RecoverPoseConfig* cfg, const McvPoint2d* a
 
 MCV_API int cvRecoverPose(const RecoverPoseConfig* cfg, int N, const McvPoint2d* pa, const McvPoint2d* pb,
                           McvMatx33d* rMat, McvVec3d* tVec, uint8_t* ms) {
-    clear_error();
+    MCV_API_ENTER();
     if (!cfg || !pa || !pb || !rMat || !tVec || N < 5) {
         // the reference asserts inside OpenCV for N < 5 (process abort); we return 0 instead
         set_error("cvRecoverPose: bad arguments or N < 5");
@@ -254,7 +258,7 @@ MCV_API int cvRecoverPose(const RecoverPoseConfig* cfg, int N, const McvPoint2d*
 
 MCV_API int32_t cvRecoverPoses(const RecoverPoseConfig* cfg, int N, const McvPoint2d* pa, const McvPoint2d* pb,
                                McvMatx33d* rMat1, McvMatx33d* rMat2, McvVec3d* tVec, uint8_t* ms) {
-    clear_error();
+    MCV_API_ENTER();
     if (N < 5) return 0;   // reference: `if (N < 5) return false;` (MiniCVNative.cpp:167)
     if (!cfg || !pa || !pb || !rMat1 || !rMat2 || !tVec) { set_error("cvRecoverPoses: null arguments"); return 0; }
     Context* ctx = get_context(-1);
@@ -294,7 +298,7 @@ MCV_API int32_t cvRecoverPoses(const RecoverPoseConfig* cfg, int N, const McvPoi
 
 MCV_API int cvFivePointBatch(const McvPoint2d* pa, const McvPoint2d* pb, int nSets, McvMatx33d* Es,
                              int32_t* counts) {
-    clear_error();
+    MCV_API_ENTER();
     if (nSets < 0 || (nSets > 0 && (!pa || !pb || !Es || !counts))) { set_error("cvFivePointBatch: bad arguments"); return -1; }
     if (nSets == 0) return 0;
     Context* ctx = get_context(-1);
@@ -331,7 +335,7 @@ MCV_API int cvFivePoint(const McvPoint2d* pa, const McvPoint2d* pb, McvMatx33d* 
 }
 
 MCV_API int cvDecomposeEssentialMat(const McvMatx33d* E, McvMatx33d* R1, McvMatx33d* R2, McvVec3d* t) {
-    clear_error();
+    MCV_API_ENTER();
     if (!E || !R1 || !R2 || !t) { set_error("cvDecomposeEssentialMat: null arguments"); return 0; }
     Context* ctx = get_context(-1);
     if (!ctx) return 0;
@@ -353,7 +357,7 @@ MCV_API int cvDecomposeEssentialMat(const McvMatx33d* E, McvMatx33d* R1, McvMatx
 MCV_API int cvRecoverPoseFromE(const McvMatx33d* E, const McvPoint2d* a, const McvPoint2d* b, int N,
                                double focal, double ppx, double ppy, uint8_t* mask, McvMatx33d* R,
                                McvVec3d* t, int32_t* good4) {
-    clear_error();
+    MCV_API_ENTER();
     if (!E || !a || !b || N <= 0 || !R || !t) { set_error("cvRecoverPoseFromE: bad arguments"); return -1; }
     Context* ctx = get_context(-1);
     if (!ctx) return -1;

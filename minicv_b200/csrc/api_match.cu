@@ -2,6 +2,7 @@
 // has no matcher, see include/MiniCVNative.h group (2)).  Thin host layer: stages buffers,
 // drives the kernels in hamming_knn.cu / l2_knn.cu, never computes on the CPU.
 #include "knn.cuh"
+#include "staging.cuh"
 
 #include <algorithm>
 #include <vector>
@@ -32,14 +33,14 @@ MCV_API int cvMatchKnn2BatchDevice(const uint8_t* dQuery, const int64_t* queryOf
                                    const uint8_t* dTrain, const int64_t* trainOffsets, int nPairs,
                                    int descBytes, int normType, float ratio, int* dTrainIdx,
                                    float* dDist, uint8_t* dRatioPass, int device, void* stream) {
-    clear_error();
+    MCV_API_ENTER();
     if (nPairs < 0 || !queryOffsets || !trainOffsets || !dTrainIdx || !dDist) {
         set_error("cvMatchKnn2BatchDevice: bad arguments");
         return -1;
     }
     if (nPairs == 0) return 0;
     if (check_norm(normType, descBytes)) return -1;
-    Context* ctx = get_context(device);
+    Context* ctx = get_context_async(device, static_cast<cudaStream_t>(stream));
     if (!ctx) return -1;
     KnnArgs a;
     a.dQuery = dQuery; a.dTrain = dTrain;
@@ -53,7 +54,7 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
                              const uint8_t* train, const int64_t* trainOffsets, int nPairs,
                              int descBytes, int normType, float ratio, int* trainIdx, float* dist,
                              uint8_t* ratioPass, int device) {
-    clear_error();
+    MCV_API_ENTER();
     if (nPairs < 0 || !queryOffsets || !trainOffsets) {
         set_error("cvMatchKnn2Batch: bad arguments");
         return -1;
@@ -86,6 +87,20 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
     cudaStream_t sIn = ctx->stream2, sK = ctx->stream, sOut = ctx->stream3;
     MCV_CUDA_TRY(cudaMemsetAsync(dCount, 0, sizeof(int), sK));
 
+    // Caller buffers: CUDA-pinned / registered memory is copied directly.  Pageable memory (what a P/Invoke caller
+    // passes) goes through the pinned ring on the way in (staging.cu) and through a pinned bounce buffer on the way
+    // out, handed to the caller's arrays chunk by chunk while later chunks are still being matched.
+    const bool pageQ = host_is_pageable(query), pageT = host_is_pageable(train);
+    const size_t outBytes = (size_t)totalQ * (8 + 8 + (ratioPass ? 1 : 0));
+    const bool bounceOut = outBytes >= (1u << 20) && host_is_pageable(trainIdx);
+    int* hIdx = trainIdx; float* hDist = dist; uint8_t* hPass = ratioPass;
+    if (bounceOut) {
+        if (ctx->pin[6].reserve(outBytes + 64)) return -1;
+        hIdx = ctx->pin[6].as<int>();
+        hDist = reinterpret_cast<float*>(hIdx + 2 * totalQ);
+        hPass = ratioPass ? reinterpret_cast<uint8_t*>(hDist + 2 * totalQ) : nullptr;
+    }
+
     // chunk the pair list so that copy-in, compute and copy-out overlap on three streams
     const size_t chunkTarget = 32u << 20;
     std::vector<int> bounds(1, 0);
@@ -101,7 +116,7 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
         p0 = p1;
     }
     const int nChunks = (int)bounds.size() - 1;
-    cudaEvent_t* ev = event_pool(ctx, 2 * nChunks);
+    cudaEvent_t* ev = event_pool(ctx, 3 * nChunks);
     if (!ev) { set_error("cvMatchKnn2Batch: cudaEventCreate failed"); return -1; }
     std::vector<int64_t> qo, to;
     for (int c = 0; c < nChunks; ++c) {
@@ -110,14 +125,10 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
         const int64_t t0 = trainOffsets[p0], t1 = trainOffsets[p1];
         // copy-in of chunk c, then its (small) control copy right behind it: the copy engine serves
         // its queue in submission order, so control copies must not sit behind later bulk copies
-        if (q1 > q0)
-            MCV_CUDA_TRY(cudaMemcpyAsync(dQ + q0 * rb, query + q0 * rb, (size_t)(q1 - q0) * rb,
-                                         cudaMemcpyHostToDevice, sIn));
-        if (t1 > t0)
-            MCV_CUDA_TRY(cudaMemcpyAsync(dT + t0 * rb, train + t0 * rb, (size_t)(t1 - t0) * rb,
-                                         cudaMemcpyHostToDevice, sIn));
-        MCV_CUDA_TRY(cudaEventRecord(ev[2 * c], sIn));
-        MCV_CUDA_TRY(cudaStreamWaitEvent(sK, ev[2 * c], 0));
+        if (q1 > q0 && h2d_copy(ctx, dQ + q0 * rb, query + q0 * rb, (size_t)(q1 - q0) * rb, sIn, pageQ)) return -1;
+        if (t1 > t0 && h2d_copy(ctx, dT + t0 * rb, train + t0 * rb, (size_t)(t1 - t0) * rb, sIn, pageT)) return -1;
+        MCV_CUDA_TRY(cudaEventRecord(ev[3 * c], sIn));
+        MCV_CUDA_TRY(cudaStreamWaitEvent(sK, ev[3 * c], 0));
         if (q1 > q0) {
             qo.resize(p1 - p0 + 1);
             to.resize(p1 - p0 + 1);
@@ -129,15 +140,26 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
             a.dTrainIdx = dIdx + 2 * q0; a.dDist = dDist + 2 * q0; a.dRatioPass = dPass + q0;
             a.dPassCount = dCount;
             if (dispatch(ctx, sK, normType, a)) return -1;
-            MCV_CUDA_TRY(cudaEventRecord(ev[2 * c + 1], sK));
-            MCV_CUDA_TRY(cudaStreamWaitEvent(sOut, ev[2 * c + 1], 0));
-            MCV_CUDA_TRY(cudaMemcpyAsync(trainIdx + 2 * q0, dIdx + 2 * q0, (size_t)(q1 - q0) * 8,
+            MCV_CUDA_TRY(cudaEventRecord(ev[3 * c + 1], sK));
+            MCV_CUDA_TRY(cudaStreamWaitEvent(sOut, ev[3 * c + 1], 0));
+            MCV_CUDA_TRY(cudaMemcpyAsync(hIdx + 2 * q0, dIdx + 2 * q0, (size_t)(q1 - q0) * 8,
                                          cudaMemcpyDeviceToHost, sOut));
-            MCV_CUDA_TRY(cudaMemcpyAsync(dist + 2 * q0, dDist + 2 * q0, (size_t)(q1 - q0) * 8,
+            MCV_CUDA_TRY(cudaMemcpyAsync(hDist + 2 * q0, dDist + 2 * q0, (size_t)(q1 - q0) * 8,
                                          cudaMemcpyDeviceToHost, sOut));
             if (ratioPass)
-                MCV_CUDA_TRY(cudaMemcpyAsync(ratioPass + q0, dPass + q0, (size_t)(q1 - q0),
+                MCV_CUDA_TRY(cudaMemcpyAsync(hPass + q0, dPass + q0, (size_t)(q1 - q0),
                                              cudaMemcpyDeviceToHost, sOut));
+        }
+        MCV_CUDA_TRY(cudaEventRecord(ev[3 * c + 2], sOut));
+    }
+    if (bounceOut) {
+        for (int c = 0; c < nChunks; ++c) {
+            const int64_t q0 = queryOffsets[bounds[c]], q1 = queryOffsets[bounds[c + 1]];
+            MCV_CUDA_TRY(cudaEventSynchronize(ev[3 * c + 2]));
+            if (q1 == q0) continue;
+            parallel_memcpy(trainIdx + 2 * q0, hIdx + 2 * q0, (size_t)(q1 - q0) * 8);
+            parallel_memcpy(dist + 2 * q0, hDist + 2 * q0, (size_t)(q1 - q0) * 8);
+            if (ratioPass) memcpy(ratioPass + q0, hPass + q0, (size_t)(q1 - q0));
         }
     }
     int count = 0;
@@ -158,7 +180,7 @@ MCV_API int cvMatchKnn2(const uint8_t* query, int nQuery, const uint8_t* train, 
 
 MCV_API int cvMatchFeatures(const McvDetectorResult* query, const McvDetectorResult* train,
                             float ratio, int* trainIdx, float* dist, uint8_t* ratioPass) {
-    clear_error();
+    MCV_API_ENTER();
     if (!query || !train) { set_error("cvMatchFeatures: null DetectorResult"); return -1; }
     if (query->PointCount <= 0) return 0;
     if (query->DescriptorElementType != train->DescriptorElementType && train->PointCount > 0) {
@@ -182,10 +204,14 @@ MCV_API int cvMatchFeatures(const McvDetectorResult* query, const McvDetectorRes
 MCV_API int cvMatchKnn2ShardKeysDevice(const uint8_t* dQuery, int nQuery, const uint8_t* dTrainShard,
                                        int nTrainShard, int64_t globalIdxBase, int descBytes,
                                        uint64_t* dKeys, int device, void* stream) {
-    clear_error();
+    MCV_API_ENTER();
     if (nQuery < 0 || nTrainShard < 0 || !dKeys) { set_error("cvMatchKnn2ShardKeysDevice: bad arguments"); return -1; }
     if (nQuery == 0) return 0;
-    Context* ctx = get_context(device);
+    if (globalIdxBase < 0 || globalIdxBase + (int64_t)nTrainShard > (1ll << 32)) {
+        set_error("cvMatchKnn2ShardKeysDevice: globalIdxBase + nTrainShard exceeds the 32-bit index field of the packed key");
+        return -1;
+    }
+    Context* ctx = get_context_async(device, static_cast<cudaStream_t>(stream));
     if (!ctx) return -1;
     const int64_t qo[2] = {0, nQuery}, to[2] = {0, nTrainShard};
     KnnArgs a;
@@ -198,12 +224,12 @@ MCV_API int cvMatchKnn2ShardKeysDevice(const uint8_t* dQuery, int nQuery, const 
 MCV_API int cvMergeShardKeysDevice(const uint64_t* dKeys, int nShards, int nQuery, float ratio,
                                    int64_t* dTrainIdx64, float* dDist, uint8_t* dRatioPass,
                                    int device, void* stream) {
-    clear_error();
+    MCV_API_ENTER();
     if (!dKeys || nShards <= 0 || nQuery < 0 || !dTrainIdx64 || !dDist) {
         set_error("cvMergeShardKeysDevice: bad arguments");
         return -1;
     }
-    Context* ctx = get_context(device);
+    Context* ctx = get_context_async(device, static_cast<cudaStream_t>(stream));
     if (!ctx) return -1;
     return launch_merge_keys(ctx, static_cast<cudaStream_t>(stream), dKeys, nShards, nQuery, ratio,
                              dTrainIdx64, dDist, dRatioPass);

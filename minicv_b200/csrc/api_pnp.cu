@@ -3,6 +3,7 @@
 //   solver kind; solveAp3p (reference signature, src/MiniCVNative/ap3p.cpp:282-317); and the batched /
 //   injected-hypotheses forms.  Thin host layer over pnp.cu: stages buffers, never computes on the CPU.
 #include "ransac.cuh"
+#include "staging.cuh"
 
 #include <algorithm>
 #include <string.h>
@@ -33,6 +34,7 @@ PnpParams to_params(const McvPnpParams* p) {
     PnpParams r;
     r.sampleMode = p->sampleMode; r.stopMode = p->stopMode; r.maxIters = p->maxIters; r.refine = p->refine;
     r.threshold = p->threshold; r.confidence = p->confidence; r.seed = p->seed;
+    r.problemIndexBase = p->problemIndexBase;
     return r;
 }
 
@@ -54,10 +56,10 @@ MCV_API int cvSolvePnPRansacBatchDevice(const McvPnpParams* prm, const double* d
                                         const int64_t* offsets, int nProblems, const double* dCams,
                                         double* dRvecs, double* dTvecs, uint8_t* dMasks, int32_t* dInlierCounts,
                                         uint8_t* dOk, int device, void* stream) {
-    clear_error();
+    MCV_API_ENTER();
     if (!prm || check_args(dObj, dImg, offsets, nProblems, dCams)) return -1;
     if (nProblems == 0) return 0;
-    Context* ctx = get_context(device);
+    Context* ctx = get_context_async(device, static_cast<cudaStream_t>(stream));
     if (!ctx) return -1;
     PnpIO io;
     io.dObj = dObj; io.dImg = dImg; io.hOff = offsets; io.nProblems = nProblems; io.dCam = dCams;
@@ -71,7 +73,7 @@ MCV_API int cvSolvePnPRansacBatch(const McvPnpParams* prm, const McvPoint3d* obj
                                   McvVec3d* tvecs, uint8_t* masks, int32_t* inlierCounts, uint8_t* ok,
                                   int32_t* itersRun, int32_t* bestIter, double* minimal, int32_t* dbgCounts,
                                   double* dbgModels, int32_t* dbgSamples, int device) {
-    clear_error();
+    MCV_API_ENTER();
     if (!prm || check_args(obj, img, offsets, nProblems, cams)) return -1;
     if (nProblems == 0) return 0;
     if (!rvecs || !tvecs || !ok) { set_error("cvSolvePnPRansacBatch: null outputs"); return -1; }
@@ -104,8 +106,9 @@ MCV_API int cvSolvePnPRansacBatch(const McvPnpParams* prm, const McvPoint3d* obj
     int* dBestIt = cv.take<int>(np);
     double* dMin = cv.take<double>(np * 6);
     if (total > 0) {
-        MCV_CUDA_TRY(cudaMemcpyAsync(dObj, obj, (size_t)total * 24, cudaMemcpyHostToDevice, st));
-        MCV_CUDA_TRY(cudaMemcpyAsync(dImg, img, (size_t)total * 16, cudaMemcpyHostToDevice, st));
+        if (h2d_copy(ctx, dObj, obj, (size_t)total * 24, st, host_is_pageable(obj)) ||
+            h2d_copy(ctx, dImg, img, (size_t)total * 16, st, host_is_pageable(img)))
+            return -1;
     }
     MCV_CUDA_TRY(cudaMemcpyAsync(dCam, cams, np * 64, cudaMemcpyHostToDevice, st));
     PnpIO io;
@@ -151,7 +154,7 @@ MCV_API bool cvSolvePnPRansac(const McvPoint2d* imgPoints, const McvPoint3d* wor
     if (solverKind != 5)
         return forward_solve_pnp_ransac(imgPoints, worldPoints, N, K, distortionCoeffs, solverKind, iterationsCount,
                                         reprojectionError, confidence, tVec, rVec, inlierCount, outInliers);
-    clear_error();
+    MCV_API_ENTER();
     if (inlierCount) *inlierCount = 0;
     if (N < 4 || !imgPoints || !worldPoints || !tVec || !rVec) {
         if (N >= 0 && N < 4) return false;      // cv::solvePnPRansac asserts npoints >= 4; the shim would throw
@@ -219,7 +222,7 @@ MCV_API bool cvSolvePnPRansac(const McvPoint2d* imgPoints, const McvPoint3d* wor
 
 MCV_API int cvSolveAp3pBatch(const McvPoint2d* img, const McvPoint3d* obj, const double* cam4, int n,
                              McvMatx33d* Rs, McvVec3d* ts, int32_t* counts) {
-    clear_error();
+    MCV_API_ENTER();
     if (n < 0 || (n > 0 && (!img || !obj || !cam4 || !Rs || !ts || !counts))) { set_error("cvSolveAp3pBatch: bad arguments"); return -1; }
     if (n == 0) return 0;
     Context* ctx = get_context(-1);

@@ -41,11 +41,11 @@ MCV_API int cvFindScaledBatchDevice(const double* dCams, const double* dRot, con
                                     const double* dWorld, const double* dObs, const int64_t* offsets,
                                     int nProblems, double* dCosts, double* dBestScales, double* dScaledT,
                                     int32_t* dSigns, int device, void* stream) {
-    clear_error();
+    MCV_API_ENTER();
     if (check_offsets(offsets, nProblems)) return -1;
     if (nProblems == 0) return 0;
     if (offsets[nProblems] > 0 && (!dWorld || !dObs)) { set_error("findScaled: null observation arrays"); return -1; }
-    Context* ctx = get_context(device);
+    Context* ctx = get_context_async(device, static_cast<cudaStream_t>(stream));
     if (!ctx) return -1;
     ScaleIO io;
     io.dCams = dCams; io.dRot = dRot; io.dTrans = dTrans; io.dWorld = dWorld; io.dObs = dObs;
@@ -58,7 +58,7 @@ MCV_API int cvFindScaledBatch(const McvCamera* srcCams, const McvCameraPose* pos
                               const McvPoint2d* obs, const int64_t* offsets, int nProblems, double* costs,
                               McvCameraPose* scaled, double* bestScales, double* candidates, uint8_t* candOk,
                               double* candCosts, int device) {
-    clear_error();
+    MCV_API_ENTER();
     if (check_offsets(offsets, nProblems)) return -1;
     if (nProblems == 0) return 0;
     if (!srcCams || !poses || !costs || !scaled) { set_error("cvFindScaledBatch: null cameras / poses / outputs"); return -1; }
@@ -145,7 +145,7 @@ MCV_API int cvFindScaledBatch(const McvCamera* srcCams, const McvCameraPose* pos
 MCV_API double cvFindScaled(double inlierThreshold, const McvCamera* srcCam, const McvPoint3d* world,
                             const McvPoint2d* obs, int n, const McvCameraPose* pose, McvCameraPose* scaled) {
     (void)inlierThreshold;                                        // unused by the reference as well (countInliers is dead)
-    clear_error();
+    MCV_API_ENTER();
     if (n < 0 || !srcCam || !pose || !scaled) { set_error("cvFindScaled: bad arguments"); return NAN; }
     const int64_t off[2] = {0, n};
     double cost = NAN;
@@ -157,7 +157,7 @@ MCV_API double cvFindScaled(double inlierThreshold, const McvCamera* srcCam, con
 
 MCV_API int cvScaleCosts(const McvCamera* srcCam, const McvCameraPose* pose, const McvPoint3d* world,
                          const McvPoint2d* obs, int n, const double* scales, int nScales, double* costs) {
-    clear_error();
+    MCV_API_ENTER();
     if (n < 0 || nScales < 0 || !srcCam || !pose || (n > 0 && (!world || !obs)) || (nScales > 0 && (!scales || !costs))) {
         set_error("cvScaleCosts: bad arguments");
         return -1;

@@ -1,6 +1,6 @@
 // common.cuh -- host-side plumbing shared by every translation unit of libMiniCVNative.so:
-// per-thread error string, per-(thread, device) context with its own stream and
-// grow-only workspaces, launch accounting.  No OpenCV, no torch types.
+// per-thread error string, pooled per-device contexts (stream set + grow-only workspaces) leased per export
+// call, launch accounting.  No OpenCV, no torch types.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -19,6 +19,7 @@ namespace mcv {
 // ---- error reporting (reference convention: failure value + untouched outputs) ----
 void set_error(const char* fmt, ...);
 void clear_error();
+const char* get_error();          // the calling thread's error string ("" when none)
 
 #define MCV_CUDA_TRY(expr)                                                          \
     do {                                                                            \
@@ -49,6 +50,7 @@ struct DevBuf {
     void*  p = nullptr;
     size_t cap = 0;
     int reserve(size_t bytes);
+    void release();
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -57,21 +59,31 @@ struct PinBuf {
     void*  p = nullptr;
     size_t cap = 0;
     int reserve(size_t bytes);
+    void release();
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// One context per (host thread, device): the exports are re-entrant and may be called
-// from any .NET thread concurrently (threading row), so nothing
-// here is shared between threads except the launch counter.
+// Contexts (stream set + grow-only workspaces + pinned staging) live in a process-wide pool per device.  Every
+// compute export opens an ApiScope; get_context() leases a context to the calling thread until the outermost scope
+// of that thread closes, so the exports are re-entrant from any number of host threads (SURVEY.md section 8b,
+// threading row) while device memory scales with the number of CONCURRENT calls (capped, MINICV_MAX_CONTEXTS per
+// device, default 8; further callers wait), not with the number of threads that ever called.  A thread that
+// retires leaves nothing behind.  mcvTrim() frees the workspaces of every idle context.
+//
+// Asynchronous (*Device) exports leave work queued on the caller's stream when they return: the scope records a
+// "last use" event on that stream, and whoever leases the context next makes its streams wait on it, so scratch
+// buffers are never overwritten under a running kernel whichever stream / thread comes next.
+struct DeviceState;
 struct Context {
     int          device = -1;
     int          sm_count = 148;
+    DeviceState* dev = nullptr;
     cudaStream_t stream = nullptr;       // private stream for host-pointer entry points
     cudaStream_t stream2 = nullptr;      // host->device copy stream (copy/compute overlap)
     cudaStream_t stream3 = nullptr;      // device->host copy stream
     cudaEvent_t  ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DevBuf       ws[72];                 // numbered workspaces, meaning fixed per call site
-    PinBuf       pin[6];
+    DevBuf       ws[80];                 // numbered workspaces, meaning fixed per call site
+    PinBuf       pin[8];
     // tensor-core matcher control arrays, double-buffered so that the host can prepare launch k+1
     // while the copy of launch k is still queued behind launch k-1
     PinBuf       ctlPin[2];
@@ -82,10 +94,11 @@ struct Context {
     cudaEvent_t* evPool = nullptr;
     int          evPoolSize = 0;
     bool         mwc_ready = false;      // ws[28] holds OpenCV's raw RNG stream (ransac.cu)
-    // optional CUDA-event timing of the dominant matcher kernel (mcvKernelTimingStart / Stop)
-    bool         kt_on = false;
-    int          kt_n = 0, kt_cap = 0;
-    cudaEvent_t* kt_ev = nullptr;        // 2 * kt_cap events
+    // pending asynchronous use by the previous lease (see above)
+    cudaEvent_t  lastUse = nullptr;
+    bool         lastUsePending = false;
+    // pinned staging ring for pageable caller buffers (staging.cu)
+    struct StageRing* ring = nullptr;
 };
 // n events from the pool (grown on demand); nullptr on failure
 inline cudaEvent_t* event_pool(Context* c, int n) {
@@ -100,14 +113,27 @@ inline cudaEvent_t* event_pool(Context* c, int n) {
     }
     return c->evPool;
 }
-// Bracket the dominant kernel of a matcher call on its launching stream (no-ops unless enabled).
-inline void kt_begin(Context* c, cudaStream_t s) { if (c->kt_on && c->kt_n < c->kt_cap) cudaEventRecord(c->kt_ev[2 * c->kt_n], s); }
-inline void kt_end(Context* c, cudaStream_t s) { if (c->kt_on && c->kt_n < c->kt_cap) { cudaEventRecord(c->kt_ev[2 * c->kt_n + 1], s); ++c->kt_n; } }
+// Bracket the dominant kernel of a matcher call on its launching stream (no-ops unless mcvKernelTimingStart
+// switched the device's timing on).
+void kt_begin(Context* c, cudaStream_t s);
+void kt_end(Context* c, cudaStream_t s);
 
-// Returns the calling thread's context for `device` (-1: cudaGetDevice()), creating it on
-// first use; nullptr (and an error string) when no CUDA device is usable -- there is no
-// CPU fallback behind this.
+// RAII guard of one export call.  The outermost scope of a thread remembers the caller's current device; when it
+// closes it returns every context the thread leased inside it and restores that device.
+struct ApiScope {
+    ApiScope();
+    ~ApiScope();
+    ApiScope(const ApiScope&) = delete;
+    ApiScope& operator=(const ApiScope&) = delete;
+};
+#define MCV_API_ENTER() ::mcv::ApiScope _mcv_scope; ::mcv::clear_error()
+
+// The calling thread's context for `device` (-1: the caller's current device), leased for the current ApiScope;
+// nullptr (and an error string) when no CUDA device is usable -- there is no CPU fallback behind this.
+// get_context: for exports that synchronise before they return (work goes to the context's own streams).
+// get_context_async: for *Device exports that enqueue on `stream` and return.
 Context* get_context(int device);
+Context* get_context_async(int device, cudaStream_t stream);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

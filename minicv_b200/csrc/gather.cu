@@ -65,12 +65,12 @@ MCV_API int cvGatherMatchesDevice(const double* dKpQuery, const double* dKpTrain
                                   const int64_t* trainOffsets, int nPairs, const int* dTrainIdx,
                                   const uint8_t* dRatioPass, double* dA, double* dB, int64_t* outOffsets,
                                   int device, void* stream) {
-    clear_error();
+    MCV_API_ENTER();
     if (nPairs < 0 || !queryOffsets || !trainOffsets || !outOffsets) { set_error("cvGatherMatchesDevice: bad arguments"); return -1; }
     outOffsets[0] = 0;
     if (nPairs == 0) return 0;
     if (!dKpQuery || !dKpTrain || !dTrainIdx || !dRatioPass || !dA || !dB) { set_error("cvGatherMatchesDevice: null device buffers"); return -1; }
-    Context* ctx = get_context(device);
+    Context* ctx = get_context_async(device, static_cast<cudaStream_t>(stream));
     if (!ctx) return -1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t n1 = (size_t)nPairs + 1;

@@ -40,6 +40,8 @@ int launch_hamming_knn2_tc2(Context* ctx, cudaStream_t stream, const KnnArgs& a)
 // Engine choice: 0 = auto, 1 = integer pipe (XOR + POPC), 2 = tensor cores (int8),
 // 3 = tensor cores with packed accumulators (fp8).
 extern std::atomic<int> g_hamming_engine;
+// L2 engine choice (mcvSetL2Engine): 0 = auto, 1 = fp32 CUDA cores, 2 = tcgen05 bf16 split + exact re-scoring.
+extern std::atomic<int> g_l2_engine;
 // Shared second stage: merges nSplits key pairs per query and emits matches or keys.
 int launch_knn2_finalize(cudaStream_t stream, const uint64_t* dSplitKeys, int nSplits, int64_t totalQ,
                          const KnnArgs& a);

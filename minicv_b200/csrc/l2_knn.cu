@@ -143,13 +143,15 @@ l2_finalize_kernel(const uint64_t* __restrict__ splitKeys, int nSplits, int64_t 
 
 }  // namespace
 
+std::atomic<int> g_l2_engine{0};
+
 int launch_l2_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     if (a.nPairs <= 0) return 0;
     if (a.descBytes <= 0 || a.descBytes % 4 != 0) { set_error("L2 matcher needs float32 rows"); return -1; }
     if (a.emit != KNN_EMIT_MATCHES) { set_error("L2 matcher has no shard-key mode"); return -1; }
     {
-        // engine switch shared with the Hamming matcher: 1 = CUDA cores, >= 2 = tensor cores, 0 = auto
-        const int eng = g_hamming_engine.load(std::memory_order_relaxed);
+        // engine switch (mcvSetL2Engine): 1 = CUDA cores, 2 = tensor cores, 0 = auto
+        const int eng = g_l2_engine.load(std::memory_order_relaxed);
         bool tcEng = false;
         if (eng >= 2) tcEng = l2_tc_supported(a.descBytes);
         else if (eng == 0 && l2_tc_supported(a.descBytes)) {

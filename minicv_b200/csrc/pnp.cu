@@ -677,7 +677,7 @@ int pnp_ransac_batch_device(Context* ctx, cudaStream_t st, const PnpParams& prm,
             MCV_LAUNCH_CHECK();
         } else if (prm.sampleMode == MCV_SAMPLE_COUNTER) {
             dim3 g((maxIters + 127) / 128, np);
-            pnp_sample_counter_kernel<<<g, 128, 0, st>>>(off, maxIters, prm.seed, p0, dSamples, dNIter, dFlags);
+            pnp_sample_counter_kernel<<<g, 128, 0, st>>>(off, maxIters, prm.seed, prm.problemIndexBase + p0, dSamples, dNIter, dFlags);
             MCV_LAUNCH_CHECK();
         } else {
             pnp_sample_mwc_kernel<<<(np + 63) / 64, 64, 0, st>>>(off, np, maxIters, dSamples, dNIter, dFlags);

@@ -1350,7 +1350,7 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             MCV_LAUNCH_CHECK();
         } else if (prm.sampleMode == MCV_SAMPLE_COUNTER) {
             dim3 g((maxIters + 127) / 128, np);
-            sample_counter_kernel<MODEL><<<g, 128, 0, st>>>(pf, off, np, maxIters, prm.seed, p0,
+            sample_counter_kernel<MODEL><<<g, 128, 0, st>>>(pf, off, np, maxIters, prm.seed, prm.pairIndexBase + p0,
                                                             dSamples, dNIter, dFlags);
             MCV_LAUNCH_CHECK();
         } else {

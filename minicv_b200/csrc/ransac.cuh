@@ -16,6 +16,7 @@ struct RansacParams {
     uint64_t seed = 0;
     double   focal = 1.0, ppx = 0.0, ppy = 0.0;   // essential only
     int      refine = 1;                          // homography: OpenCV's refit + LM + re-mask
+    int64_t  pairIndexBase = 0;                   // counter-based sampling: global index of pair 0
 };
 
 inline int model_points(int model) { return model == RM_HOMOGRAPHY ? 4 : model == RM_FUNDAMENTAL ? 7 : 5; }
@@ -96,6 +97,7 @@ struct PnpParams {
     double   confidence = 0.99;
     uint64_t seed = 0;
     int      refine = 1;           // final pose = EPnP over the inliers (what solvePnPRansac returns)
+    int64_t  problemIndexBase = 0; // counter-based sampling: global index of problem 0
 };
 
 struct PnpIO {

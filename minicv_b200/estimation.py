@@ -195,6 +195,42 @@ def recover_pose_batch(cfg: RecoverPoseConfig, a, b, offsets, sample_mode: int =
     return R, t, ms, good, ok
 
 
+def ransac_batch_multi(model: int, a, b, offsets, thr: float, maxIters: int, confidence: float = 0.995,
+                       sample_mode: int = SAMPLE_MWC, stop_mode: int = STOP_ADAPTIVE, seed: int = 0,
+                       focal: float = 1.0, pp=(0.0, 0.0), refine: bool = True,
+                       device_mask: int = 0) -> RansacBatchResult:
+    """``cvRansacBatchMulti``: pairs block-partitioned over the GPUs of ``device_mask`` (0 = all)."""
+    lib = native.load()
+    a, b = _pts(a), _pts(b)
+    off = np.ascontiguousarray(offsets, np.int64)
+    n_pairs = off.size - 1
+    prm = native.RansacParams(model, sample_mode, stop_mode, maxIters, thr, confidence, seed, focal,
+                              pp[0], pp[1], 1 if refine else 0, 0)
+    out = RansacBatchResult(np.zeros((n_pairs, 3, 3)), np.zeros(a.shape[0], np.uint8),
+                            np.zeros(n_pairs, np.int32), np.zeros(n_pairs, np.uint8),
+                            np.zeros(n_pairs, np.int32), np.zeros((n_pairs, 2), np.int32))
+    native.check(lib.cvRansacBatchMulti(C.addressof(prm), _p(a), _p(b), _p(off), n_pairs, _p(out.models),
+                                        _p(out.masks), _p(out.inliers), _p(out.ok), _p(out.iters_run),
+                                        device_mask), "cvRansacBatchMulti")
+    return out
+
+
+def recover_pose_batch_multi(cfg: RecoverPoseConfig, a, b, offsets, sample_mode: int = SAMPLE_MWC,
+                             maxIters: int = 1000, device_mask: int = 0):
+    """``cvRecoverPoseBatchMulti``: returns (R [n,3,3], t [n,3], ms [total], good [n], ok [n])."""
+    lib = native.load()
+    a, b = _pts(a), _pts(b)
+    off = np.ascontiguousarray(offsets, np.int64)
+    n = off.size - 1
+    R = np.zeros((n, 3, 3)); t = np.zeros((n, 3)); ms = np.zeros(a.shape[0], np.uint8)
+    good = np.zeros(n, np.int32); ok = np.zeros(n, np.uint8)
+    c = cfg.native()
+    native.check(lib.cvRecoverPoseBatchMulti(C.addressof(c), _p(a), _p(b), _p(off), n, sample_mode, maxIters,
+                                             _p(R), _p(t), _p(ms), _p(good), _p(ok), device_mask),
+                 "cvRecoverPoseBatchMulti")
+    return R, t, ms, good, ok
+
+
 def recover_pose_from_E(E, a, b, focal=1.0, pp=(0.0, 0.0), mask=None):
     """== ``cv2.recoverPose(E, a, b, focal=, pp=, mask=)`` -> (count, R, t, mask_out, good4)."""
     lib = native.load()

@@ -159,3 +159,97 @@ def set_hamming_engine(engine: int) -> None:
     (XOR + POPC), 2 tcgen05 int8 tensor cores, 3 tcgen05 fp8 with packed accumulators."""
     if native.load().mcvSetHammingEngine(engine) != 0:
         raise ValueError("engine must be 0..3")
+
+
+def set_l2_engine(engine: int) -> None:
+    """Choose the L2 matcher engine: 0 auto, 1 fp32 CUDA cores, 2 tcgen05 bf16 split + exact re-scoring."""
+    if native.load().mcvSetL2Engine(engine) != 0:
+        raise ValueError("engine must be 0..2")
+
+
+def match_knn2_batch_multi(query: np.ndarray, query_offsets, train: np.ndarray, train_offsets,
+                           ratio: float = 0.8, norm: int = NORM_HAMMING, device_mask: int = 0,
+                           out: KnnResult | None = None) -> KnnResult:
+    """``cvMatchKnn2BatchMulti``: one call, pairs block-partitioned over the GPUs of ``device_mask``
+    (bit d = CUDA ordinal d, 0 = all visible devices); same results as ``match_knn2_batch``."""
+    lib = native.load()
+    q, db = _rows(query, norm)
+    t, dbt = _rows(train, norm)
+    qo = np.ascontiguousarray(query_offsets, dtype=np.int64)
+    to = np.ascontiguousarray(train_offsets, dtype=np.int64)
+    if qo.shape != to.shape or qo.ndim != 1 or qo.size < 1:
+        raise ValueError("offset arrays must both have nPairs+1 entries")
+    nq = q.shape[0]
+    if out is None:
+        out = KnnResult(np.full((nq, 2), -1, dtype=np.int32),
+                        np.full((nq, 2), np.finfo(np.float32).max, dtype=np.float32),
+                        np.zeros(nq, dtype=np.uint8), 0)
+    out.n_pass = native.check(
+        lib.cvMatchKnn2BatchMulti(_ptr(q), _ptr(qo), _ptr(t), _ptr(to), qo.size - 1, db or dbt, norm, ratio,
+                                  _ptr(out.train_idx), _ptr(out.distance), _ptr(out.ratio_pass), device_mask),
+        "cvMatchKnn2BatchMulti")
+    return out
+
+
+class LargeDb:
+    """Train set sharded over the GPUs of ``device_mask`` and kept resident (config C5): every
+    ``match`` replicates the queries, all-gathers the per-shard top-2 keys with NCCL inside the
+    library and merges them.  ``train_idx`` are global indices (int64)."""
+
+    def __init__(self, train: np.ndarray, device_mask: int = 0):
+        lib = native.load()
+        t = np.ascontiguousarray(train, dtype=np.uint8)
+        self.desc_bytes = t.shape[1]
+        self._h = lib.cvLargeDbCreate(_ptr(t), t.shape[0], t.shape[1], device_mask)
+        if not self._h:
+            raise native.NativeError("cvLargeDbCreate failed: " + native.last_error())
+        ns, nccl, nt = C.c_int(0), C.c_int(0), C.c_int64(0)
+        lib.cvLargeDbInfo(self._h, C.byref(ns), C.byref(nccl), C.byref(nt))
+        self.n_shards, self.uses_nccl, self.n_train = ns.value, bool(nccl.value), nt.value
+
+    def match(self, query: np.ndarray, ratio: float = 0.8):
+        lib = native.load()
+        q = np.ascontiguousarray(query, dtype=np.uint8)
+        nq = q.shape[0]
+        idx = np.full((nq, 2), -1, dtype=np.int64)
+        dist = np.full((nq, 2), np.finfo(np.float32).max, dtype=np.float32)
+        ok = np.zeros(nq, dtype=np.uint8)
+        n = native.check(lib.cvLargeDbMatch(self._h, _ptr(q), nq, ratio, _ptr(idx), _ptr(dist), _ptr(ok)),
+                         "cvLargeDbMatch")
+        return idx, dist, ok, n
+
+    def close(self):
+        if self._h:
+            native.load().cvLargeDbDestroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PinnedArray:
+    """numpy view over ``mcvAllocPinned`` memory (CUDA-pinned, so the exports DMA it directly)."""
+
+    def __init__(self, shape, dtype):
+        lib = native.load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = lib.mcvAllocPinned(max(self.nbytes, 1))
+        if not self._p:
+            raise native.NativeError("mcvAllocPinned failed: " + native.last_error())
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            native.load().mcvFreePinned(self._p)
+            self._p = None

@@ -68,6 +68,31 @@ SIGNATURES = {
     "mcvKernelLaunchCount": (_i64, []),
     "mcvBuildInfo": (C.c_char_p, []),
     "mcvSetHammingEngine": (_i, [_i]),
+    "mcvSetL2Engine": (_i, [_i]),
+    "mcvTrim": (_i, []),
+    "mcvWorkspaceBytes": (_i64, [_i]),
+    "mcvSetWorkspaceLimit": (_i, [_i64]),
+    "mcvContextCount": (_i, [_i]),
+    "mcvAllocPinned": (_vp, [_i64]),
+    "mcvFreePinned": (None, [_vp]),
+    "mcvHostRegister": (_i, [_vp, _i64]),
+    "mcvHostUnregister": (_i, [_vp]),
+    "mcvSetStagingMode": (_i, [_i]),
+    "mcvCopyThreads": (_i, []),
+    "mcvMeasureCopyBandwidth": (_d, [_i, _i64, _i, _i, _i]),
+    "mcvNcclVersion": (_i, []),
+    "mcvShardCommUniqueId": (_i, [_vp]),
+    "mcvShardCommInit": (_vp, [_vp, _i, _i, _i]),
+    "mcvShardCommDestroy": (None, [_vp]),
+    "cvMatchKnn2ShardedDevice": (_i, [_vp, _vp, _i, _vp, _i64, _i64, _i, _f, _vp, _vp, _vp, _vp]),
+    "cvLargeDbCreate": (_vp, [_vp, _i64, _i, C.c_uint32]),
+    "cvLargeDbMatch": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp]),
+    "cvLargeDbInfo": (_i, [_vp, _vp, _vp, _vp]),
+    "cvLargeDbDestroy": (None, [_vp]),
+    "cvMatchKnn2BatchMulti": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, C.c_uint32]),
+    "cvRansacBatchMulti": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, C.c_uint32]),
+    "cvRecoverPoseBatchMulti": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.c_uint32]),
+    "cvSolvePnPRansacBatchMulti": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32]),
     "mcvKernelTimingStart": (_i, [_i, _i]),
     "mcvKernelTimingStop": (_i, [_i, _vp, _i]),
     "cvMatchKnn2": (_i, [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
@@ -137,14 +162,15 @@ class RansacParams(C.Structure):
     _fields_ = [("model", C.c_int32), ("sampleMode", C.c_int32), ("stopMode", C.c_int32),
                 ("maxIters", C.c_int32), ("threshold", C.c_double), ("confidence", C.c_double),
                 ("seed", C.c_uint64), ("focal", C.c_double), ("ppx", C.c_double), ("ppy", C.c_double),
-                ("refine", C.c_int32), ("reserved", C.c_int32)]
+                ("refine", C.c_int32), ("pairIndexBase", C.c_int32)]
 
 
 
 class PnpParams(C.Structure):
     """``McvPnpParams`` of include/MiniCVNative.h."""
     _fields_ = [("sampleMode", C.c_int32), ("stopMode", C.c_int32), ("maxIters", C.c_int32), ("refine", C.c_int32),
-                ("threshold", C.c_double), ("confidence", C.c_double), ("seed", C.c_uint64)]
+                ("threshold", C.c_double), ("confidence", C.c_double), ("seed", C.c_uint64),
+                ("problemIndexBase", C.c_int64)]
 
 
 _lib = None

@@ -12,10 +12,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True, params=[mcv.ENGINE_POPC, mcv.ENGINE_TENSOR], ids=["fp32-cuda-core", "tcgen05-bf16x2+rescore"])
 def l2_engine(request):
-    # the engine switch is shared with the Hamming matcher: 1 = CUDA cores, 2 = tensor cores
-    mcv.set_hamming_engine(request.param)
+    # mcvSetL2Engine: 1 = CUDA cores, 2 = tensor cores
+    mcv.set_l2_engine(request.param)
     yield
-    mcv.set_hamming_engine(mcv.ENGINE_AUTO)
+    mcv.set_l2_engine(0)
 
 
 def test_l2_golden_cv2():
