@@ -91,7 +91,11 @@ enum {
 };
 enum {
     MCV_STOP_ADAPTIVE = 0,     /* OpenCV's RANSACUpdateNumIters semantics (confidence)   */
-    MCV_STOP_FIXED    = 1      /* score exactly maxIters hypotheses                      */
+    MCV_STOP_FIXED    = 1,     /* score exactly maxIters hypotheses                      */
+    MCV_STOP_LMEDS    = 2      /* not RANSAC: OpenCV's least-median-of-squares registrator (what
+                                  cv::findFundamentalMat runs below 15 points): iteration count fixed up
+                                  front from `confidence`, median-of-errors score, threshold ignored;
+                                  fundamental matrices, at most 32 correspondences per pair              */
 };
 
 /* ---- diagnostics ------------------------------------------------------------ */
@@ -285,7 +289,11 @@ typedef struct {
  * Returns 1 on success, 0 on failure (outputs untouched). */
 MCV_API int cvFindHomography(const McvPoint2d* a, const McvPoint2d* b, int N, double thr,
                              int maxIters, double conf, McvMatx33d* H, uint8_t* mask);
-/* == cv2.findFundamentalMat(a, b, FM_RANSAC, thr, conf, maxIters): best 7-point model. */
+/* == cv2.findFundamentalMat(a, b, FM_RANSAC, thr, conf, maxIters), including OpenCV's dispatch: N < 7 -> 0;
+ * N == 7 -> the 7-point kernel on all points, EVERY real solution written to F (room for 3 matrices required),
+ * mask all ones, returns the number of solutions (1..3); 8 <= N < 15 -> LMedS (MCV_STOP_LMEDS); N >= 15 -> RANSAC,
+ * best 7-point model, no refit.  thr <= 0 is read as 3, a confidence outside (DBL_EPSILON, 1 - DBL_EPSILON) as
+ * 0.99.  Returns 1 (or the solution count) on success, 0 on failure (outputs untouched). */
 MCV_API int cvFindFundamentalMat(const McvPoint2d* a, const McvPoint2d* b, int N, double thr,
                                  double conf, int maxIters, McvMatx33d* F, uint8_t* mask);
 

@@ -8,6 +8,7 @@
 
 #include <vector>
 #include <string.h>
+#include <float.h>
 
 using namespace mcv;
 
@@ -107,8 +108,36 @@ MCV_API int cvFindHomography(const McvPoint2d* a, const McvPoint2d* b, int N, do
 MCV_API int cvFindFundamentalMat(const McvPoint2d* a, const McvPoint2d* b, int N, double thr, double conf,
                                  int maxIters, McvMatx33d* F, uint8_t* mask) {
     MCV_API_ENTER();
+    // cv::findFundamentalMat's dispatch (calib3d/src/fundam.cpp): fewer than 7 points -> nothing; exactly 7 -> the
+    // 7-point kernel on all of them, every real solution returned (up to three, stacked), mask all ones; a
+    // non-positive threshold becomes 3, a confidence outside (eps, 1 - eps) becomes 0.99; below 15 points the
+    // FM_RANSAC method runs LMedS, from 15 points on RANSAC.
+    if (N < 0 || !a || !b || !F) { set_error("cvFindFundamentalMat: bad arguments"); return 0; }
+    if (N < 7) return 0;
+    if (thr <= 0) thr = 3;
+    if (conf < DBL_EPSILON || conf > 1 - DBL_EPSILON) conf = 0.99;
     RansacParams prm;
     prm.model = RM_FUNDAMENTAL; prm.threshold = thr; prm.maxIters = maxIters; prm.confidence = conf;
+    if (N == 7) {
+        McvRansacParams q = {};
+        q.model = RM_FUNDAMENTAL; q.sampleMode = MCV_SAMPLE_OPENCV_MWC; q.stopMode = MCV_STOP_FIXED; q.maxIters = 1;
+        q.threshold = thr; q.confidence = conf;
+        const int64_t off[2] = {0, 7};
+        McvMatx33d best;
+        uint8_t ok = 0;
+        int32_t counts[3] = {-1, -1, -1};
+        double models[27];
+        if (cvRansacBatch(&q, a, b, off, 1, nullptr, nullptr, &best, nullptr, nullptr, &ok, nullptr, nullptr, counts,
+                          models, nullptr, -1) < 0 || !ok)
+            return 0;
+        int k = 0;
+        for (int m = 0; m < 3; ++m)
+            if (counts[m] >= 0) memcpy(F[k++].M, models + 9 * m, 72);
+        if (k == 0) return 0;
+        if (mask) memset(mask, 1, 7);
+        return k;
+    }
+    if (N < 15) prm.stopMode = MCV_STOP_LMEDS;
     const int rc = single_ransac(prm, a, b, N, F, mask, nullptr);
     return rc < 0 ? 0 : rc;
 }

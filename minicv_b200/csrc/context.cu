@@ -77,7 +77,8 @@ struct DeviceState {
 };
 
 static constexpr int kMaxDevices = 64;
-static DeviceState g_dev[kMaxDevices];
+// never destroyed: threads of the host application may still be inside an export while static destructors run
+static DeviceState* const g_dev = new DeviceState[kMaxDevices];
 static std::atomic<int64_t> g_ws_limit{-1};      // bytes per context kept across calls; < 0: unlimited
 
 static int max_contexts() {

@@ -1,19 +1,25 @@
 // l2_knn.cu -- brute-force L2 kNN (k = 2) + ratio test for float32 descriptors (SIFT-style).
 //
 // Contract: cv2.BFMatcher(NORM_L2).knnMatch(q, t, 2) (the reference
-// ships no matcher).  Distance = sqrt(sum_k (a_k - b_k)^2) in float32, accumulated in index order
-// with separate multiply and add (the oracle's definition, oracle/bf_knn.py l2_matrix_seq), so the
-// kernel is bit-exact against the oracle; against OpenCV's SIMD accumulation order it agrees to a
-// few ulp (tests state the tolerance).
+// ships no matcher), bit for bit -- which for floating point means OpenCV's accumulation ORDER, not just its
+// formula.  BFMatcher -> batchDistance -> sqrt(hal::normL2Sqr_) (core/src/norm.cpp), the universal-intrinsic loop at
+// 128-bit width without FMA (restated and pinned in oracle/bf_knn.py l2_matrix_cv against
+// tests/golden/knn_l2_general.npz):
+//     element e of the first 16 * floor(D / 16) goes to partial sum (accumulator a = (e / 4) % 4, lane l = e % 4),
+//     s[l] = ((acc[0][l] + acc[1][l]) + acc[2][l]) + acc[3][l],   d = (s[0] + s[2]) + (s[1] + s[3]),
+//     then the remaining D % 16 elements are added one by one; dist = sqrtf(d).
+// l2_sqr_cv_order() below is that order with ONE partial sum live at a time (the 16 strided partial sums are
+// independent, so they can be finished one after the other), which keeps a 4 x 4 register micro-tile affordable.
 //
-// Mapping: 64 queries x 64 train rows per block step, 16 x 16 threads with a 4 x 4 register
-// micro-tile each; operands staged through shared memory 32 dimensions at a time.  Every thread
-// keeps the top-2 of its 4 queries as packed keys (float bits << 32 | trainIdx) -- non-negative
-// floats order like their bit patterns, so one unsigned min/max pair updates both ranks with the
-// lowest index winning ties; the 16 column threads of a query merge through shared memory.
-// This is the fp32 CUDA-core engine (FP32-pipe bound: 3 flops per dimension, no FMA); the
-// tcgen05 GEMM + rescoring engine of the north-star plan replaces it for large batches later.
+// Mapping: TLT queries x TLT train rows per block step, 16 x 16 threads with a (TLT/16)^2 register
+// micro-tile each; both operand tiles sit in shared memory with ALL dimensions, transposed to [k][row], because
+// the order walks the dimensions with stride 16.  Every thread keeps the top-2 of its queries as packed keys
+// (float bits << 32 | trainIdx) -- non-negative floats order like their bit patterns, so one unsigned min/max
+// pair updates both ranks with the lowest index winning ties; the 16 column threads of a query merge through
+// shared memory.  This is the fp32 CUDA-core engine (FP32-pipe bound: 3 flops per dimension, no FMA); the tcgen05
+// GEMM + exact re-scoring engine (l2_tc.cu) replaces it for large batches.
 #include "knn.cuh"
+#include "l2_order.cuh"
 
 #include <algorithm>
 #include <float.h>
@@ -21,8 +27,6 @@
 namespace mcv {
 namespace {
 
-constexpr int LT = 64;    // tile edge (queries and train rows)
-constexpr int LK = 32;    // dimensions per shared-memory stage
 
 __device__ __forceinline__ void top2_u64(uint64_t& m1, uint64_t& m2, uint64_t key) {
     const uint64_t hi = m1 > key ? m1 : key;
@@ -30,14 +34,18 @@ __device__ __forceinline__ void top2_u64(uint64_t& m1, uint64_t& m2, uint64_t ke
     m2 = m2 < hi ? m2 : hi;
 }
 
+template <int TLT>
 __global__ void __launch_bounds__(256)
 l2_knn2_kernel(const float* __restrict__ query, const float* __restrict__ train,
                const int64_t* __restrict__ qOff, const int64_t* __restrict__ tOff,
                const int* __restrict__ tileStart, int nPairs, int dim, int splitRows, int64_t totalQ,
                uint64_t* __restrict__ splitKeys) {
-    __shared__ float sQ[LK][LT + 1];
-    __shared__ float sT[LK][LT + 1];
-    __shared__ uint64_t sM[LT][16][2];
+    constexpr int MT = TLT / 16;                 // micro-tile edge
+    constexpr int LD = TLT + 1;                  // padded row length of the transposed tiles
+    extern __shared__ __align__(16) float smem[];
+    float* sQ = smem;                            // [dim][LD]
+    float* sT = smem + (size_t)dim * LD;         // [dim][LD]
+    __shared__ uint64_t sM[TLT][16][2];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     int lo = 0, hi = nPairs;
     const int tile = blockIdx.x;
@@ -46,63 +54,48 @@ l2_knn2_kernel(const float* __restrict__ query, const float* __restrict__ train,
         if (tileStart[mid] <= tile) lo = mid; else hi = mid;
     }
     const int p = lo;
-    const int64_t q0 = qOff[p] + (int64_t)(tile - tileStart[p]) * LT, qEnd = qOff[p + 1];
+    const int64_t q0 = qOff[p] + (int64_t)(tile - tileStart[p]) * TLT, qEnd = qOff[p + 1];
     const int64_t tRow0 = tOff[p];
     const int tCount = (int)(tOff[p + 1] - tRow0);
     const int split = blockIdx.y;
     const int t0 = min(tCount, split * splitRows), t1 = min(tCount, t0 + splitRows);
 
-    uint64_t m1[4], m2[4];
+    uint64_t m1[MT], m2[MT];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { m1[i] = ~0ull; m2[i] = ~0ull; }
+    for (int i = 0; i < MT; ++i) { m1[i] = ~0ull; m2[i] = ~0ull; }
 
-    for (int tb = t0; tb < t1; tb += LT) {
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        for (int k0 = 0; k0 < dim; k0 += LK) {
-            // stage 64 x 32 floats of each operand, transposed to [k][row]
-            for (int e = threadIdx.x; e < LT * LK; e += 256) {
-                const int r = e / LK, k = e - r * LK;
-                const int64_t qr = q0 + r;
-                const int tr = tb + r;
-                sQ[k][r] = (qr < qEnd && k0 + k < dim) ? query[qr * dim + k0 + k] : 0.f;
-                sT[k][r] = (tr < t1 && k0 + k < dim) ? train[(tRow0 + tr) * dim + k0 + k] : 0.f;
-            }
-            __syncthreads();
-#pragma unroll 8
-            for (int k = 0; k < LK; ++k) {
-                float a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { a[i] = sQ[k][ty * 4 + i]; b[i] = sT[k][tx * 4 + i]; }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float d = __fsub_rn(a[i], b[j]);
-                        acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(d, d));
-                    }
-            }
-            __syncthreads();
+    // the query tile: all dimensions, once
+    for (int e = threadIdx.x; e < TLT * dim; e += 256) {
+        const int r = e / dim, k = e - r * dim;
+        const int64_t qr = q0 + r;
+        sQ[k * LD + r] = qr < qEnd ? query[qr * dim + k] : 0.f;
+    }
+    for (int tb = t0; tb < t1; tb += TLT) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < TLT * dim; e += 256) {
+            const int r = e / dim, k = e - r * dim;
+            const int tr = tb + r;
+            sT[k * LD + r] = tr < t1 ? train[(tRow0 + tr) * dim + k] : 0.f;
         }
+        __syncthreads();
+        float d[MT][MT];
+        l2_sqr_cv_order<MT>(sQ + ty * MT, sT + tx * MT, LD, dim, d);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MT; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int tr = tb + tx * 4 + j;
+            for (int j = 0; j < MT; ++j) {
+                const int tr = tb + tx * MT + j;
                 if (tr < t1) {
-                    const float dist = __fsqrt_rn(acc[i][j]);
+                    const float dist = __fsqrt_rn(d[i][j]);
                     top2_u64(m1[i], m2[i], ((uint64_t)__float_as_uint(dist) << 32) | (uint32_t)tr);
                 }
             }
     }
     // merge the 16 column threads of each query
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { sM[ty * 4 + i][tx][0] = m1[i]; sM[ty * 4 + i][tx][1] = m2[i]; }
+    for (int i = 0; i < MT; ++i) { sM[ty * MT + i][tx][0] = m1[i]; sM[ty * MT + i][tx][1] = m2[i]; }
     __syncthreads();
-    if (threadIdx.x < LT) {
+    if (threadIdx.x < TLT) {
         const int r = threadIdx.x;
         uint64_t a = ~0ull, b = ~0ull;
         for (int c = 0; c < 16; ++c) { top2_u64(a, b, sM[r][c][0]); top2_u64(a, b, sM[r][c][1]); }
@@ -167,6 +160,11 @@ int launch_l2_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
         return -1;
     }
     const int dim = a.descBytes / 4;
+    // both operand tiles keep every dimension in shared memory (the reference order strides through them): pick the
+    // largest tile edge that fits
+    const size_t smemCap = 200 * 1024;
+    const int TL = 2 * (size_t)dim * 65 * 4 <= smemCap ? 64 : 2 * (size_t)dim * 33 * 4 <= smemCap ? 32 : 16;
+    if (2 * (size_t)dim * 17 * 4 > smemCap) { set_error("L2 matcher supports descriptors of up to 1500 floats"); return -1; }
     const int64_t totalQ = a.hQOff[a.nPairs];
     if (a.hQOff[0] != 0 || a.hTOff[0] != 0) { set_error("offset arrays must start at 0"); return -1; }
     if (totalQ == 0) return 0;
@@ -182,7 +180,7 @@ int launch_l2_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
         const int64_t nq = a.hQOff[p + 1] - a.hQOff[p], nt = a.hTOff[p + 1] - a.hTOff[p];
         if (nq < 0 || nt < 0 || nt > 0x7FFFFFFFll) { set_error("bad offsets at pair %d", p); return -1; }
         hQ[p] = a.hQOff[p]; hT[p] = a.hTOff[p]; hTile[p] = (int)tiles;
-        tiles += (nq + LT - 1) / LT;
+        tiles += (nq + TL - 1) / TL;
         maxT = std::max(maxT, nt);
     }
     hQ[a.nPairs] = a.hQOff[a.nPairs]; hT[a.nPairs] = a.hTOff[a.nPairs]; hTile[a.nPairs] = (int)tiles;
@@ -196,17 +194,28 @@ int launch_l2_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     int64_t wantSplits = 1;
     const int64_t fill = 4ll * ctx->sm_count;
     if (tiles < fill) wantSplits = (fill + tiles - 1) / tiles;
-    wantSplits = std::min<int64_t>(wantSplits, std::max<int64_t>(1, (maxT + LT - 1) / LT));
+    wantSplits = std::min<int64_t>(wantSplits, std::max<int64_t>(1, (maxT + TL - 1) / TL));
     int64_t splitRows = (std::max<int64_t>(maxT, 1) + wantSplits - 1) / wantSplits;
-    splitRows = (splitRows + LT - 1) / LT * LT;
+    splitRows = (splitRows + TL - 1) / TL * TL;
     const int nSplits = (int)std::max<int64_t>(1, (maxT + splitRows - 1) / splitRows);
     if (nSplits > 65535) { set_error("train set too large for one launch"); return -1; }
     if (ctx->ws[3].reserve((size_t)nSplits * totalQ * 16)) return -1;
     uint64_t* dKeys = ctx->ws[3].as<uint64_t>();
     dim3 grid((unsigned)tiles, (unsigned)nSplits);
-    l2_knn2_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(a.dQuery),
-                                             reinterpret_cast<const float*>(a.dTrain), dQOff, dTOff, dTile,
-                                             a.nPairs, dim, (int)splitRows, totalQ, dKeys);
+    {
+        const float* fq = reinterpret_cast<const float*>(a.dQuery);
+        const float* ft = reinterpret_cast<const float*>(a.dTrain);
+        const size_t smem = 2 * (size_t)dim * (TL + 1) * sizeof(float);
+#define MCV_L2(T)                                                                                              \
+        do {                                                                                                   \
+            auto kern = l2_knn2_kernel<T>;                                                                     \
+            if (smem > 48 * 1024)                                                                              \
+                MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            kern<<<grid, 256, smem, stream>>>(fq, ft, dQOff, dTOff, dTile, a.nPairs, dim, (int)splitRows, totalQ, dKeys); \
+        } while (0)
+        if (TL == 64) MCV_L2(64); else if (TL == 32) MCV_L2(32); else MCV_L2(16);
+#undef MCV_L2
+    }
     MCV_LAUNCH_CHECK();
     l2_finalize_kernel<<<(unsigned)((totalQ + 255) / 256), 256, 0, stream>>>(dKeys, nSplits, totalQ, a.ratio,
                                                                             a.dTrainIdx, a.dDist, a.dRatioPass,

@@ -8,11 +8,13 @@
 // The epilogue ranks train rows by  2 a.b - ||b||^2  (||a||^2 is constant per query), keeps the
 // four best per query row and split, and a re-scoring kernel recomputes those candidates with the
 // oracle's arithmetic (sequential fp32, separate multiply and add, sqrt) and takes the best two by
-// (distance, index).  The reported distances are therefore bit-identical to l2_knn.cu; the indices
-// are identical unless more than two other rows lie within the GEMM's rounding noise of the
-// runner-up (tests/test_knn_l2_gpu.py runs both engines against the same oracle).
+// (distance, index).  The reported distances are therefore bit-identical to l2_knn.cu and to cv2.  The
+// indices are certified too: l2_merge_kernel bounds what the approximate ranking could have dropped and sends
+// the (rare) queries it cannot certify to an exact brute-force kernel, so both engines return the same result
+// on any input (tests/test_knn_l2_gpu.py runs both against the oracle and the cv2 goldens).
 #include "knn.cuh"
 #include "tc_ptx.cuh"
+#include "l2_order.cuh"
 
 #include <algorithm>
 #include <float.h>
@@ -38,24 +40,36 @@ __device__ __forceinline__ float bf2f(uint16_t b) { return __uint_as_float((uint
 
 // float rows -> [hi(128 bf16) | lo(128 bf16)] rows of 512 bytes (zero padded past dim), and for
 // train rows also ||b||^2 (fp32, accumulated in double)
+// stats[0] = bit pattern of the largest ||row||^2 seen (non-negative floats order like their bits),
+// stats[1] != 0 when the GEMM's score is not exact for some row: a lo piece is non-zero past bf16's reach, or a
+// squared norm is too large for exact fp32 accumulation (integer-valued SIFT rows leave it 0)
 __global__ void __launch_bounds__(128)
 expand_bf16_kernel(const float* __restrict__ src, int dim, int64_t nRows, uint16_t* __restrict__ dst,
-                   float* __restrict__ norms) {
+                   float* __restrict__ norms, unsigned* __restrict__ stats) {
     const int64_t row = blockIdx.x;
     if (row >= nRows) return;
     const int k = threadIdx.x;            // 128 threads = 128 dimensions
     const float x = k < dim ? src[row * dim + k] : 0.f;
     const uint16_t h = f2bf(x);
-    const uint16_t l = f2bf(x - bf2f(h));
+    const float rest = x - bf2f(h);
+    const uint16_t l = f2bf(rest);
     dst[row * 256 + k] = h;
     dst[row * 256 + 128 + k] = l;
-    if (norms) {
-        double s = (double)x * (double)x;
-        __shared__ double sm[4];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-        if ((k & 31) == 0) sm[k >> 5] = s;
-        __syncthreads();
-        if (k == 0) norms[row] = (float)(sm[0] + sm[1] + sm[2] + sm[3]);
+    const bool inexact = (rest - bf2f(l)) != 0.f || !(x == x) || x != truncf(x);
+    double s = (double)x * (double)x;
+    __shared__ double sm[4];
+    __shared__ int sInexact;
+    if (k == 0) sInexact = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((k & 31) == 0) sm[k >> 5] = s;
+    if (__any_sync(0xFFFFFFFFu, inexact) && (k & 31) == 0) sInexact = 1;
+    __syncthreads();
+    if (k == 0) {
+        const float n2 = (float)(sm[0] + sm[1] + sm[2] + sm[3]);
+        norms[row] = n2;
+        atomicMax(&stats[0], __float_as_uint(n2 >= 0.f ? n2 : __int_as_float(0x7F800000)));
+        if (sInexact || !(n2 < 4194304.f)) stats[1] = 1u;     // sums of integer products stay exact below 2^24
     }
 }
 
@@ -257,14 +271,16 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ C
     }
 }
 
-// exact re-scoring: the oracle's arithmetic (sequential fp32 sum over the dimensions) on every candidate.
-// One thread per (query, slot): its four candidates run as four independent dependency chains over
-// 128-bit loads; adjacent threads share the query row (broadcast loads).  Emits the slot's best two as
-// packed keys (float bits << 32) | index.
+// exact re-scoring: OpenCV's arithmetic AND accumulation order (l2_order.cuh: hal::normL2Sqr_ at 128-bit width, 16
+// strided partial sums, no FMA) on every candidate, so the distances returned are cv2's bit for bit.
+// One thread per (query, slot): its four candidates run as independent dependency chains over 128-bit loads (a
+// float4 is exactly one SIMD lane group of the reference loop); adjacent threads share the query row (broadcast
+// loads).  Emits the slot's best two as packed keys (float bits << 32) | index.
 __global__ void __launch_bounds__(128)
 l2_rescore_kernel(const float* __restrict__ query, const float* __restrict__ train,
                   const int64_t* __restrict__ qOff, const int64_t* __restrict__ tOff, int nPairs, int dim,
-                  const int4* __restrict__ cands, int nSlots, int64_t totalQ, uint64_t* __restrict__ slotKeys) {
+                  const int4* __restrict__ cands, int nSlots, int64_t totalQ, uint64_t* __restrict__ slotKeys,
+                  float* __restrict__ slotMaxSq) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= totalQ * nSlots) return;
     const int64_t q = idx / nSlots;
@@ -281,49 +297,76 @@ l2_rescore_kernel(const float* __restrict__ query, const float* __restrict__ tra
     const float* b[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) b[k] = id[k] < 0 ? a : train + (tRow0 + id[k]) * dim;   // empty slot: any valid row
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float dsq[4];
     const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(query) | reinterpret_cast<uintptr_t>(train)) & 15) == 0;   // rows are 16-byte aligned
     if (vec) {
-        for (int d = 0; d < dim; d += 4) {
-            const float4 av = __ldg(reinterpret_cast<const float4*>(a + d));
-            float4 bv[4];
+        const int nb = dim >> 4;
+        float acc[4][4][4];     // [candidate][accumulator][lane]
 #pragma unroll
-            for (int k = 0; k < 4; ++k) bv[k] = __ldg(reinterpret_cast<const float4*>(b[k] + d));
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float df = __fsub_rn(av.x, bv[k].x); acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
-                df = __fsub_rn(av.y, bv[k].y); acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
-                df = __fsub_rn(av.z, bv[k].z); acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
-                df = __fsub_rn(av.w, bv[k].w); acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
+            for (int ac = 0; ac < 4; ++ac)
+#pragma unroll
+                for (int l = 0; l < 4; ++l) acc[k][ac][l] = 0.f;
+        for (int blk = 0; blk < nb; ++blk) {
+#pragma unroll
+            for (int ac = 0; ac < 4; ++ac) {
+                const int d = 16 * blk + 4 * ac;
+                const float4 av = __ldg(reinterpret_cast<const float4*>(a + d));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(b[k] + d));
+                    float df = __fsub_rn(av.x, bv.x); acc[k][ac][0] = __fadd_rn(__fmul_rn(df, df), acc[k][ac][0]);
+                    df = __fsub_rn(av.y, bv.y); acc[k][ac][1] = __fadd_rn(__fmul_rn(df, df), acc[k][ac][1]);
+                    df = __fsub_rn(av.z, bv.z); acc[k][ac][2] = __fadd_rn(__fmul_rn(df, df), acc[k][ac][2]);
+                    df = __fsub_rn(av.w, bv.w); acc[k][ac][3] = __fadd_rn(__fmul_rn(df, df), acc[k][ac][3]);
+                }
             }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float sl[4];
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+                sl[l] = __fadd_rn(__fadd_rn(__fadd_rn(acc[k][0][l], acc[k][1][l]), acc[k][2][l]), acc[k][3][l]);
+            float d = __fadd_rn(__fadd_rn(sl[0], sl[2]), __fadd_rn(sl[1], sl[3]));
+            for (int e = nb << 4; e < dim; ++e) {
+                const float df = __fsub_rn(a[e], b[k][e]);
+                d = __fadd_rn(d, __fmul_rn(df, df));
+            }
+            dsq[k] = d;
         }
     } else {
-        for (int d = 0; d < dim; ++d) {
-            const float av = a[d];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float df = __fsub_rn(av, b[k][d]);
-                acc[k] = __fadd_rn(acc[k], __fmul_rn(df, df));
-            }
-        }
+        for (int k = 0; k < 4; ++k) dsq[k] = l2_sqr_cv_order_rows(a, b[k], dim);
     }
     uint64_t m1 = ~0ull, m2 = ~0ull;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (id[k] < 0) continue;
-        const uint64_t key = ((uint64_t)__float_as_uint(__fsqrt_rn(acc[k])) << 32) | (uint32_t)id[k];
+        const uint64_t key = ((uint64_t)__float_as_uint(__fsqrt_rn(dsq[k])) << 32) | (uint32_t)id[k];
         const uint64_t hi2 = m1 > key ? m1 : key;
         m1 = m1 < key ? m1 : key;
         m2 = m2 < hi2 ? m2 : hi2;
     }
     reinterpret_cast<ulonglong2*>(slotKeys + idx * 2)[0] = make_ulonglong2(m1, m2);
+    // a slot with an empty entry saw fewer than L2_CAND rows: nothing of it was dropped
+    const bool full = id[0] >= 0 && id[1] >= 0 && id[2] >= 0 && id[3] >= 0;
+    slotMaxSq[idx] = full ? fmaxf(fmaxf(dsq[0], dsq[1]), fmaxf(dsq[2], dsq[3])) : -1.f;
 }
 
-// best two over a query's slots by (distance, index), ratio test in fp32
+// best two over a query's slots by (distance, index), ratio test in fp32 -- with a guarantee.  The GEMM ranks rows by
+// an approximate score (bf16 hi/lo split without the lo.lo term, fp32 accumulation): |score error| <= eps in
+// squared-distance units with eps = 2^-12 (||a||^2 + max ||b||^2), far above the real error, and 0 when every row
+// is integer valued (lo pieces zero, sums exact).  A row the epilogue DROPPED from a slot scored no better than the
+// slot's worst kept candidate, so its exact squared distance is at least  max_kept_exact - 4 eps.  If that bound does
+// not clear the runner-up for some full slot, the query's result cannot be certified and the query is handed to
+// l2_exact_fallback_kernel (brute force in the reference order); certified queries are final here.
 __global__ void __launch_bounds__(256)
-l2_merge_kernel(const uint64_t* __restrict__ slotKeys, int nSlots, int64_t totalQ, float ratio,
+l2_merge_kernel(const uint64_t* __restrict__ slotKeys, const float* __restrict__ slotMaxSq, int nSlots, int64_t totalQ,
+                const float* __restrict__ qNorms, const unsigned* __restrict__ stats, float ratio,
                 int* __restrict__ trainIdx, float* __restrict__ dist, uint8_t* __restrict__ ratioPass,
-                int* __restrict__ passCount) {
+                int* __restrict__ passCount, int* __restrict__ fbCount, int* __restrict__ fbList) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool pass = false;
     if (q < totalQ) {
@@ -342,10 +385,23 @@ l2_merge_kernel(const uint64_t* __restrict__ slotKeys, int nSlots, int64_t total
         float d1 = FLT_MAX, d2 = FLT_MAX;
         if (m1 != ~0ull) { i1 = (int)(uint32_t)m1; d1 = __uint_as_float((uint32_t)(m1 >> 32)); }
         if (m2 != ~0ull) { i2 = (int)(uint32_t)m2; d2 = __uint_as_float((uint32_t)(m2 >> 32)); }
-        reinterpret_cast<int2*>(trainIdx)[q] = make_int2(i1, i2);
-        reinterpret_cast<float2*>(dist)[q] = make_float2(d1, d2);
-        pass = (i2 >= 0) && (d1 < __fmul_rn(ratio, d2));
-        if (ratioPass) ratioPass[q] = pass ? 1 : 0;
+        bool certain = true;
+        if (i2 >= 0) {
+            const float eps = stats[1] ? 0.000244140625f * (qNorms[q] + __uint_as_float(stats[0])) : 0.f;
+            const float d2sq = d2 * d2 * 1.000001f + 4.f * eps;          // upper bound of the runner-up's squared distance + margin
+            for (int s = 0; s < nSlots; ++s) {
+                const float mx = slotMaxSq[q * nSlots + s];
+                if (mx >= 0.f && !(mx > d2sq)) certain = false;          // NaN distances are never certified
+            }
+        }
+        if (certain) {
+            reinterpret_cast<int2*>(trainIdx)[q] = make_int2(i1, i2);
+            reinterpret_cast<float2*>(dist)[q] = make_float2(d1, d2);
+            pass = (i2 >= 0) && (d1 < __fmul_rn(ratio, d2));
+            if (ratioPass) ratioPass[q] = pass ? 1 : 0;
+        } else {
+            fbList[atomicAdd(fbCount, 1)] = (int)q;
+        }
     }
     if (passCount) {
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
@@ -353,11 +409,73 @@ l2_merge_kernel(const uint64_t* __restrict__ slotKeys, int nSlots, int64_t total
     }
 }
 
+// Uncertified queries: exact distances to every train row of the pair, in the reference order; one block per query
+// (grid-stride over the list), 256 threads stride the rows, top-2 by (distance, index) merged through shared memory.
+__global__ void __launch_bounds__(256)
+l2_exact_fallback_kernel(const float* __restrict__ query, const float* __restrict__ train,
+                         const int64_t* __restrict__ qOff, const int64_t* __restrict__ tOff, int nPairs, int dim,
+                         const int* __restrict__ fbCount, const int* __restrict__ fbList, float ratio,
+                         int* __restrict__ trainIdx, float* __restrict__ dist, uint8_t* __restrict__ ratioPass,
+                         int* __restrict__ passCount) {
+    __shared__ uint64_t sK[256][2];
+    const int n = *fbCount;
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const int64_t q = fbList[e];
+        int lo = 0, hi = nPairs;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (qOff[mid] <= q) lo = mid; else hi = mid;
+        }
+        const int64_t tRow0 = tOff[lo];
+        const int tCount = (int)(tOff[lo + 1] - tRow0);
+        const float* a = query + q * dim;
+        uint64_t m1 = ~0ull, m2 = ~0ull;
+        for (int r = threadIdx.x; r < tCount; r += 256) {
+            const float d = __fsqrt_rn(l2_sqr_cv_order_rows(a, train + (tRow0 + r) * dim, dim));
+            const uint64_t key = ((uint64_t)__float_as_uint(d) << 32) | (uint32_t)r;
+            const uint64_t hi2 = m1 > key ? m1 : key;
+            m1 = m1 < key ? m1 : key;
+            m2 = m2 < hi2 ? m2 : hi2;
+        }
+        sK[threadIdx.x][0] = m1; sK[threadIdx.x][1] = m2;
+        __syncthreads();
+        for (int w = 128; w > 0; w >>= 1) {
+            if (threadIdx.x < w) {
+                uint64_t a1 = sK[threadIdx.x][0], a2 = sK[threadIdx.x][1];
+                const uint64_t b1 = sK[threadIdx.x + w][0], b2 = sK[threadIdx.x + w][1];
+                const uint64_t keys[2] = {b1, b2};
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint64_t hi2 = a1 > keys[i] ? a1 : keys[i];
+                    a1 = a1 < keys[i] ? a1 : keys[i];
+                    a2 = a2 < hi2 ? a2 : hi2;
+                }
+                sK[threadIdx.x][0] = a1; sK[threadIdx.x][1] = a2;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            m1 = sK[0][0]; m2 = sK[0][1];
+            int i1 = -1, i2 = -1;
+            float d1 = FLT_MAX, d2 = FLT_MAX;
+            if (m1 != ~0ull) { i1 = (int)(uint32_t)m1; d1 = __uint_as_float((uint32_t)(m1 >> 32)); }
+            if (m2 != ~0ull) { i2 = (int)(uint32_t)m2; d2 = __uint_as_float((uint32_t)(m2 >> 32)); }
+            reinterpret_cast<int2*>(trainIdx)[q] = make_int2(i1, i2);
+            reinterpret_cast<float2*>(dist)[q] = make_float2(d1, d2);
+            const bool pass = (i2 >= 0) && (d1 < __fmul_rn(ratio, d2));
+            if (ratioPass) ratioPass[q] = pass ? 1 : 0;
+            if (passCount && pass) atomicAdd(passCount, 1);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 bool l2_tc_supported(int descBytes) { return descBytes >= 4 && descBytes <= 512 && descBytes % 4 == 0; }
 
-// uses ctx workspaces 0 (control), 3 (candidates), 24 / 25 (bf16 rows), 26 (train norms), 27 (slot keys)
+// uses ctx workspaces 0 (control), 3 (candidates), 72 (stats, query norms, fallback list), 73 (slot maxima),
+// 24 / 25 (bf16 rows), 26 (train norms), 27 (slot keys)
 int launch_l2_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     if (a.nPairs <= 0) return 0;
     const int dim = a.descBytes / 4;
@@ -392,16 +510,23 @@ int launch_l2_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
 
     if (ctx->ws[24].reserve((size_t)totalQ * L2_ROW_BYTES + 1024) ||
         ctx->ws[25].reserve((size_t)std::max<int64_t>(totalT, 1) * L2_ROW_BYTES + 1024) ||
-        ctx->ws[26].reserve((size_t)(totalT + 2 * TILE_N) * 4 + 64))
+        ctx->ws[26].reserve((size_t)(totalT + 2 * TILE_N) * 4 + 64) ||
+        ctx->ws[72].reserve((size_t)totalQ * 8 + 64))
         return -1;
     float* dNorms = ctx->ws[26].as<float>();
+    // ws[22]: [0..1] stats (max norm bits, inexact flag), [2] fallback count, then query norms, then the fallback list
+    unsigned* dStats = ctx->ws[72].as<unsigned>();
+    int* dFbCount = reinterpret_cast<int*>(dStats + 2);
+    float* dQNorms = reinterpret_cast<float*>(dStats + 4);
+    int* dFbList = reinterpret_cast<int*>(dQNorms + totalQ);
+    MCV_CUDA_TRY(cudaMemsetAsync(dStats, 0, 16, stream));
     MCV_CUDA_TRY(cudaMemsetAsync(dNorms + totalT, 0, (size_t)2 * TILE_N * 4, stream));     // read-ahead padding
     expand_bf16_kernel<<<(unsigned)totalQ, 128, 0, stream>>>(reinterpret_cast<const float*>(a.dQuery), dim, totalQ,
-                                                              ctx->ws[24].as<uint16_t>(), nullptr);
+                                                              ctx->ws[24].as<uint16_t>(), dQNorms, dStats);
     MCV_LAUNCH_CHECK();
     if (totalT > 0) {
         expand_bf16_kernel<<<(unsigned)totalT, 128, 0, stream>>>(reinterpret_cast<const float*>(a.dTrain), dim, totalT,
-                                                                  ctx->ws[25].as<uint16_t>(), dNorms);
+                                                                  ctx->ws[25].as<uint16_t>(), dNorms, dStats);
         MCV_LAUNCH_CHECK();
     }
     CUtensorMap mq, mt;
@@ -427,14 +552,21 @@ int launch_l2_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) {
     dim3 grid((unsigned)tiles, (unsigned)nSplits);
     kern<<<grid, L2_THREADS, SMEM, stream>>>(mq, mt, dNorms, dQOff, dTOff, dTile, a.nPairs, (int)splitRows, totalQ, dCands);
     MCV_LAUNCH_CHECK();
-    if (ctx->ws[27].reserve((size_t)nSlots * totalQ * 16)) return -1;
+    if (ctx->ws[27].reserve((size_t)nSlots * totalQ * 16) || ctx->ws[73].reserve((size_t)nSlots * totalQ * 4)) return -1;
     uint64_t* dSlotKeys = ctx->ws[27].as<uint64_t>();
+    float* dSlotMax = ctx->ws[73].as<float>();
     l2_rescore_kernel<<<(unsigned)((totalQ * nSlots + 127) / 128), 128, 0, stream>>>(
         reinterpret_cast<const float*>(a.dQuery), reinterpret_cast<const float*>(a.dTrain), dQOff, dTOff, a.nPairs,
-        dim, dCands, nSlots, totalQ, dSlotKeys);
+        dim, dCands, nSlots, totalQ, dSlotKeys, dSlotMax);
     MCV_LAUNCH_CHECK();
     l2_merge_kernel<<<(unsigned)((totalQ + 255) / 256), 256, 0, stream>>>(
-        dSlotKeys, nSlots, totalQ, a.ratio, a.dTrainIdx, a.dDist, a.dRatioPass, a.dPassCount);
+        dSlotKeys, dSlotMax, nSlots, totalQ, dQNorms, dStats, a.ratio, a.dTrainIdx, a.dDist, a.dRatioPass, a.dPassCount,
+        dFbCount, dFbList);
+    MCV_LAUNCH_CHECK();
+    // queries whose top-2 the approximate ranking could not certify (rare): exact brute force
+    l2_exact_fallback_kernel<<<(unsigned)std::min<int64_t>(totalQ, 8ll * ctx->sm_count), 256, 0, stream>>>(
+        reinterpret_cast<const float*>(a.dQuery), reinterpret_cast<const float*>(a.dTrain), dQOff, dTOff, a.nPairs, dim,
+        dFbCount, dFbList, a.ratio, a.dTrainIdx, a.dDist, a.dRatioPass, a.dPassCount);
     MCV_LAUNCH_CHECK();
     return 0;
 }

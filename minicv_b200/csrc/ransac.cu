@@ -830,6 +830,125 @@ select_kernel(const int64_t* __restrict__ off, int nPairs, int maxIters, int max
 }
 
 // ---------------------------------------------------------------------------------------------
+// LMedS (OpenCV's LMeDSPointSetRegistrator::run, calib3d/src/ptsetreg.cpp): what cv::findFundamentalMat runs
+// instead of RANSAC below 15 points.  The iteration count is fixed up front (outlier ratio 0.45), a model's score
+// is the median of its float32 errors (element n/2 in sorted order), the first strictly smaller median wins, and
+// the mask comes from sigma = 2.5 * 1.4826 * (1 + 5 / (n - mp)) * sqrt(median), floored at 0.001.
+// Small problems only (n <= LMEDS_MAXN): one thread per model holds the errors in registers / local memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int LMEDS_MAXN = 32;
+
+__global__ void __launch_bounds__(128)
+lmeds_select_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off, const double* __restrict__ models,
+                    const int* __restrict__ slotList, const int* __restrict__ nTotal, const int* __restrict__ nIter,
+                    const int* __restrict__ flags, int maxSlots, int* __restrict__ best /*[np][4]*/,
+                    float* __restrict__ bestMedian /*[np]*/) {
+    const int p = blockIdx.x;
+    const int64_t base = off[p];
+    const int n = (int)(off[p + 1] - base);
+    int* o = best + 4 * p;
+    const int fl = flags[p];
+    if (fl & (PAIR_FAIL | PAIR_DIRECT)) {
+        if (threadIdx.x == 0) {
+            o[0] = -1; o[1] = 0; o[2] = 0; o[3] = -1;
+            if ((fl & PAIR_DIRECT) && !(fl & PAIR_FAIL) && nTotal[p] > 0) { o[0] = 0; o[1] = n; o[2] = 1; o[3] = 0; }
+            bestMedian[p] = 0.f;
+        }
+        return;
+    }
+    __shared__ float4 sp[LMEDS_MAXN];
+    __shared__ unsigned long long sKey[4];
+    if (threadIdx.x < n) sp[threadIdx.x] = pf[base + threadIdx.x];
+    __syncthreads();
+    const int total = nTotal[p];
+    unsigned long long key = ~0ull;
+    for (int k = threadIdx.x; k < total; k += blockDim.x) {
+        const int slot = slotList[(int64_t)p * maxSlots + k];
+        const double* src = models + ((int64_t)p * maxSlots + slot) * 9;
+        double m[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) m[j] = src[j];
+        float e[LMEDS_MAXN];
+        for (int i = 0; i < n; ++i) e[i] = f_error(m, (double)sp[i].x, (double)sp[i].y, (double)sp[i].z, (double)sp[i].w);
+        // element n/2 of the sorted errors (rank by value, index breaks ties)
+        float med = __int_as_float(0x7FC00000);
+        bool anyNan = false;
+        for (int i = 0; i < n; ++i) anyNan |= !(e[i] == e[i]);
+        if (!anyNan) {
+            for (int i = 0; i < n; ++i) {
+                int rank = 0;
+                for (int j = 0; j < n; ++j) rank += (e[j] < e[i] || (e[j] == e[i] && j < i)) ? 1 : 0;
+                if (rank == n / 2) med = e[i];
+            }
+        }
+        // `median < minMedian` with minMedian starting at DBL_MAX: only finite medians compete; ties keep the earlier
+        if (med == med && med < __int_as_float(0x7F800000))
+            key = min(key, ((unsigned long long)__float_as_uint(med) << 32) | (unsigned)k);   // errors are >= 0: bit order = value order
+    }
+    for (int d = 16; d > 0; d >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, d));
+    if ((threadIdx.x & 31) == 0) sKey[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)blockDim.x / 32; ++w) key = min(key, sKey[w]);
+        if (key == ~0ull) { o[0] = -1; o[1] = 0; o[2] = nIter[p]; o[3] = -1; bestMedian[p] = 0.f; }
+        else {
+            const int k = (int)(unsigned)key;
+            o[0] = k; o[1] = 0; o[2] = nIter[p]; o[3] = slotList[(int64_t)p * maxSlots + k];
+            bestMedian[p] = __uint_as_float((unsigned)(key >> 32));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64)
+finalize_lmeds_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off, const double* __restrict__ models,
+                      int maxSlots, int maxm, int mp, const int* __restrict__ best, const int* __restrict__ flags,
+                      const float* __restrict__ bestMedian, double* __restrict__ outModels, uint8_t* __restrict__ masks,
+                      int* __restrict__ inlierCounts, uint8_t* __restrict__ ok, int* __restrict__ itersRun,
+                      int* __restrict__ bestOut) {
+    const int p = blockIdx.x;
+    const int64_t base = off[p];
+    const int n = (int)(off[p + 1] - base);
+    const int* b = best + 4 * p;
+    const int slot = b[3];
+    if (threadIdx.x == 0 && itersRun) itersRun[p] = b[2];
+    if (slot < 0) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) masks[base + i] = 0;
+        if (threadIdx.x == 0) {
+            ok[p] = 0;
+            if (inlierCounts) inlierCounts[p] = 0;
+            if (bestOut) { bestOut[2 * p] = -1; bestOut[2 * p + 1] = -1; }
+        }
+        return;
+    }
+    const double* src = models + ((int64_t)p * maxSlots + slot) * 9;
+    double m[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) m[j] = src[j];
+    const bool direct = (flags[p] & PAIR_DIRECT) != 0;
+    double sigma = 2.5 * 1.4826 * (1 + 5. / (n - mp)) * sqrt((double)bestMedian[p]);
+    sigma = fmax(sigma, 0.001);
+    const float t = (float)(sigma * sigma);
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float4 q = pf[base + i];
+        const bool in = direct || f_error(m, (double)q.x, (double)q.y, (double)q.z, (double)q.w) <= t;
+        masks[base + i] = in ? 1 : 0;
+        cnt += in ? 1 : 0;
+    }
+    __shared__ int sc[2];
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+    if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int c = sc[0] + sc[1];
+        if (inlierCounts) inlierCounts[p] = c;
+        ok[p] = c >= mp ? 1 : 0;
+        for (int j = 0; j < 9; ++j) outModels[9 * p + j] = m[j];
+        if (bestOut) { bestOut[2 * p] = slot / maxm; bestOut[2 * p + 1] = slot % maxm; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // finalize
 // ---------------------------------------------------------------------------------------------
 constexpr int FB = 128;   // finalize block size (several blocks per SM overlap the serial thread-0 phases)
@@ -1405,6 +1524,23 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
         // ---- compact
         compact_kernel<<<np, 256, 0, st>>>(dNModels, dNIter, maxIters, MAXM, dIterStart, dSlotList, dNTotal);
         MCV_LAUNCH_CHECK();
+        if (prm.stopMode == MCV_STOP_LMEDS) {
+            // ---- LMedS: median score per model, first minimum wins, sigma-rule mask (fundamental matrices only)
+            if constexpr (MODEL == RM_FUNDAMENTAL) {
+                if (maxN > LMEDS_MAXN) { set_error("LMedS supports at most %d correspondences per pair", LMEDS_MAXN); return -1; }
+                if (ctx->ws[74].reserve((size_t)chunk * 4 + 64)) return -1;
+                float* dMedian = ctx->ws[74].as<float>();
+                lmeds_select_kernel<<<np, 128, 0, st>>>(pf, off, dModels, dSlotList, dNTotal, dNIter, dFlags, (int)slots,
+                                                        dBest, dMedian);
+                MCV_LAUNCH_CHECK();
+                finalize_lmeds_kernel<<<np, 64, 0, st>>>(pf, off, dModels, (int)slots, MAXM, MP, dBest, dFlags, dMedian,
+                                                         io.dModels + (size_t)p0 * 9, io.dMasks,
+                                                         io.dInlierCounts ? io.dInlierCounts + p0 : nullptr, io.dOk + p0,
+                                                         io.dItersRun ? io.dItersRun + p0 : nullptr,
+                                                         io.dBest ? io.dBest + 2 * (size_t)p0 : nullptr);
+                MCV_LAUNCH_CHECK();
+            }
+        } else {
         // ---- score
         {
             const int tiles = (int)((slots + 127) / 128);
@@ -1444,8 +1580,9 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
                                                             dNTotal, thr2, oM, io.dMasks, oCnt, oOk, oIt, oBest);
         }
         MCV_LAUNCH_CHECK();
+        }
         // ---- debug taps
-        if (io.dDbgCounts) {
+        if (io.dDbgCounts && prm.stopMode != MCV_STOP_LMEDS) {
             dim3 g((maxIters + 255) / 256, np);
             dbg_counts_kernel<<<g, 256, 0, st>>>(dIterStart, dCounts, maxIters, MAXM,
                                                  io.dDbgCounts + (size_t)p0 * slots);
@@ -1503,11 +1640,20 @@ int ransac_batch_device(Context* ctx, cudaStream_t stream, const RansacParams& p
     if (io.nPairs <= 0) return 0;
     if (!io.hOff || io.hOff[0] != 0) { set_error("ransac: offsets must start at 0"); return -1; }
     if (!io.dModels || !io.dMasks || !io.dOk) { set_error("ransac: null outputs"); return -1; }
+    if (prm.stopMode < 0 || prm.stopMode > MCV_STOP_LMEDS) { set_error("ransac: unknown stopMode %d", prm.stopMode); return -1; }
     if (!(prm.confidence > 0 && prm.confidence < 1) && prm.stopMode == MCV_STOP_ADAPTIVE) {
         set_error("ransac: confidence must be in (0,1) (OpenCV asserts the same)");
         return -1;
     }
     if (prm.maxIters > (1 << 20)) { set_error("ransac: maxIters too large"); return -1; }
+    if (prm.stopMode == MCV_STOP_LMEDS) {
+        if (prm.model != RM_FUNDAMENTAL) { set_error("ransac: LMedS is implemented for fundamental matrices only"); return -1; }
+        if (!(prm.confidence > 0 && prm.confidence < 1)) { set_error("ransac: confidence must be in (0,1)"); return -1; }
+        RansacParams q = prm;
+        // niters = RANSACUpdateNumIters(confidence, outlierRatio 0.45, modelPoints, maxIters), fixed before the loop
+        q.maxIters = cvm::update_num_iters(prm.confidence, 0.45, 7, std::max(prm.maxIters, 1));
+        return run_model<RM_FUNDAMENTAL>(ctx, stream, q, io);
+    }
     switch (prm.model) {
         case RM_HOMOGRAPHY: return run_model<RM_HOMOGRAPHY>(ctx, stream, prm, io);
         case RM_FUNDAMENTAL: return run_model<RM_FUNDAMENTAL>(ctx, stream, prm, io);

@@ -89,7 +89,9 @@ struct CopyPool {
         for (size_t i = 0; i < queue.size(); ++i) if (queue[i] == &j) { queue.erase(queue.begin() + i); break; }
     }
 };
-CopyPool g_pool;
+// Leaked on purpose: the pool's threads are detached and sleep on its condition variable for the life of the
+// process; destroying a condition variable that still has waiters blocks inside glibc (process exit would hang).
+CopyPool& g_pool = *new CopyPool();
 
 }  // namespace
 

@@ -14,7 +14,7 @@ from . import native
 
 MODEL_H, MODEL_F, MODEL_E = 0, 1, 2
 SAMPLE_MWC, SAMPLE_COUNTER, SAMPLE_INJECTED = 0, 1, 2
-STOP_ADAPTIVE, STOP_FIXED = 0, 1
+STOP_ADAPTIVE, STOP_FIXED, STOP_LMEDS = 0, 1, 2
 MODEL_POINTS = {MODEL_H: 4, MODEL_F: 7, MODEL_E: 5}
 MAX_MODELS = {MODEL_H: 1, MODEL_F: 3, MODEL_E: 10}
 
@@ -125,13 +125,15 @@ def findHomography(a, b, thr: float = 3.0, maxIters: int = 2000, confidence: flo
 
 
 def findFundamentalMat(a, b, thr: float = 3.0, confidence: float = 0.99, maxIters: int = 1000):
-    """== ``cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, thr, confidence, maxIters)``."""
+    """== ``cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, thr, confidence, maxIters)`` with OpenCV's dispatch:
+    7 points -> every solution of the 7-point kernel stacked ([3k, 3], mask all ones), 8..14 -> LMedS,
+    15 and more -> RANSAC; returns (F | None, mask)."""
     lib = native.load()
     a, b = _pts(a), _pts(b)
-    F = np.zeros((3, 3))
+    F = np.zeros((9, 3))
     mask = np.zeros(a.shape[0], np.uint8)
-    ok = lib.cvFindFundamentalMat(_p(a), _p(b), a.shape[0], thr, confidence, maxIters, _p(F), _p(mask))
-    return (F if ok else None), mask
+    k = lib.cvFindFundamentalMat(_p(a), _p(b), a.shape[0], thr, confidence, maxIters, _p(F), _p(mask))
+    return (F[:3 * k].copy() if k > 0 else None), mask
 
 
 @dataclass

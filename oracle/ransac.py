@@ -489,3 +489,78 @@ def find_fundamental(a, b, thr=3.0, conf=0.99, max_iters=1000, samples=None, mod
     if not ok:
         return None, np.zeros(n, np.uint8)
     return F, mask
+
+
+# ------------------------------------------------------------------------------------------
+# LMedS (LMeDSPointSetRegistrator::run) and cv::findFundamentalMat's method dispatch
+# ------------------------------------------------------------------------------------------
+def lmeds_run(cb, m1, m2, conf, max_iters, trace: RansacTrace | None = None):
+    """OpenCV's LMeDSPointSetRegistrator::run (calib3d/src/ptsetreg.cpp).  The iteration count is fixed up front
+    from an assumed outlier ratio of 0.45; every model's score is the MEDIAN (element count/2 of the sorted float32
+    errors); the first strictly smaller median wins; the mask comes from sigma = 2.5 * 1.4826 * (1 + 5 / (N - mp)) *
+    sqrt(median), floored at 0.001.  Returns (ok, model, mask)."""
+    count = m1.shape[0]
+    mp = cb.model_points
+    if count < mp:
+        return False, None, None
+    if count == mp:
+        ms = cb.run_kernel(m1, m2)
+        if len(ms) <= 0:
+            return False, None, None
+        return True, np.vstack(ms), np.ones(count, np.uint8)
+    niters = update_num_iters(conf, 0.45, mp, max_iters)
+    rng = MWC()
+    min_median = np.inf
+    best_model = None
+    for it in range(niters):
+        idx = get_subset(cb, m1, m2, rng)
+        if idx is None:
+            if it == 0:
+                return False, None, None
+            break
+        ms = cb.run_kernel(m1[idx], m2[idx])
+        if trace is not None:
+            trace.samples.append(np.asarray(idx, np.int32))
+            trace.models.append([np.array(m, np.float64) for m in ms])
+        for mi, model in enumerate(ms):
+            err = np.asarray(cb.compute_error(m1, m2, model), np.float32)
+            median = float(np.sort(err)[count // 2])
+            if median < min_median:
+                min_median = median
+                best_model = np.array(model, np.float64)
+                if trace is not None:
+                    trace.best_iter, trace.best_model_idx = it, mi
+    if best_model is None:
+        return False, None, None
+    sigma = 2.5 * 1.4826 * (1 + 5.0 / (count - mp)) * np.sqrt(min_median)
+    sigma = max(sigma, 0.001)
+    good, mask = find_inliers(cb, m1, m2, best_model, sigma)
+    return good >= mp, best_model, mask
+
+
+def cv_find_fundamental(a, b, thr=3.0, conf=0.99, max_iters=1000):
+    """cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, thr, conf, max_iters) with the dispatch of calib3d/src/fundam.cpp:
+    N < 7 -> nothing; N == 7 -> the 7-point kernel directly (up to three stacked models, mask all ones);
+    8 <= N < 15 -> LMedS; N >= 15 -> RANSAC; thr <= 0 -> 3; confidence outside (eps, 1 - eps) -> 0.99.
+    Returns (F [3k x 3] or None, mask or None)."""
+    m1, m2 = FundamentalCB.prepare(a, b)
+    n = m1.shape[0]
+    if n < 7:
+        return None, None
+    if thr <= 0:
+        thr = 3.0
+    eps = np.finfo(np.float64).eps
+    if conf < eps or conf > 1 - eps:
+        conf = 0.99
+    if n == 7:
+        ms = FundamentalCB.run_kernel(m1, m2)
+        if len(ms) <= 0:
+            return None, None
+        return np.vstack(ms), np.ones(n, np.uint8)
+    if n >= 15:
+        ok, F, mask = ransac_run(FundamentalCB, m1, m2, thr, conf, max_iters)
+    else:
+        ok, F, mask = lmeds_run(FundamentalCB, m1, m2, conf, max_iters)
+    if not ok:
+        return None, (np.zeros(n, np.uint8) if mask is None else mask)
+    return F, mask

@@ -50,6 +50,21 @@ def test_l2_oracle_vs_cv2_golden():
     np.testing.assert_array_equal(idx, g["sift_idx"])
     np.testing.assert_array_equal(dist, g["sift_dist"])
     assert tuple(idx[0]) == (3, 9)
-    idx, dist = bf_knn.bf_knn2_l2(g["gen_q"], g["gen_t"])            # general floats: few ulp
+    idx, dist = bf_knn.bf_knn2_l2(g["gen_q"], g["gen_t"])            # general floats: also bit-exact (cv2's order)
     np.testing.assert_array_equal(idx, g["gen_idx"])
-    np.testing.assert_allclose(dist, g["gen_dist"], rtol=2e-6)
+    np.testing.assert_array_equal(dist, g["gen_dist"])
+
+
+@pytest.mark.parametrize("name", ["g128", "g64", "g61", "g7"])
+def test_l2_oracle_follows_cv2_accumulation_order(name):
+    """hal::normL2Sqr_'s 16 strided partial sums + sequential tail, restated in numpy, equals cv2 4.13.0 bit for bit
+    on non-integer descriptors; the plain index-order sum does not."""
+    g = np.load(GOLDEN / "knn_l2_general.npz")
+    q, t = g[f"{name}_q"], g[f"{name}_t"]
+    idx, dist = bf_knn.bf_knn2_l2(q, t)
+    np.testing.assert_array_equal(idx, g[f"{name}_idx"])
+    np.testing.assert_array_equal(dist, g[f"{name}_dist"])
+    if q.shape[1] >= 64:
+        seq = bf_knn.l2_matrix_seq(q, t)
+        got = np.take_along_axis(seq, g[f"{name}_idx"].astype(np.int64), axis=1)
+        assert (got != g[f"{name}_dist"]).any()
