@@ -211,6 +211,28 @@ MCV_API int cvGatherMatchesDevice(const double* dKpQuery, const double* dKpTrain
                                   const int* dTrainIdx, const uint8_t* dRatioPass, double* dA, double* dB,
                                   int64_t* outOffsets, int device, void* stream);
 
+/* The north-star pipeline as ONE host-buffer call: kNN match + ratio test -> homography RANSAC, the hand-off kept on
+ * the device (descriptors and keypoints go up once, H and the counts come back).  Per pair p: query / train descriptor
+ * rows and keypoints kpQuery / kpTrain (the (x, y) of KeyPoint2d as doubles = the V2d arrays a MiniCV caller holds),
+ * rows [offsets[p], offsets[p+1]).  Correspondence k of pair p = its k-th ratio-passing query, in query order:
+ * a = that query's keypoint, b = the keypoint of its nearest train row; then == cv2.findHomography(a, b, RANSAC, thr,
+ * maxIters=, confidence=).  Outputs: H, ok [nPairs]; optional nMatches, nInliers [nPairs]; optional matchQuery,
+ * matchTrain (indices local to the pair) and inlierMask, packed pair after pair with room for one entry per query
+ * row.  Returns the number of pairs with ok = 1, or -1. */
+MCV_API int cvMatchHomographyBatch(const uint8_t* query, const int64_t* queryOffsets,
+                                   const uint8_t* train, const int64_t* trainOffsets,
+                                   const McvPoint2d* kpQuery, const McvPoint2d* kpTrain, int nPairs,
+                                   int descBytes, float ratio, double thr, int maxIters, double conf,
+                                   McvMatx33d* H, uint8_t* ok, int32_t* nMatches, int32_t* nInliers,
+                                   int32_t* matchQuery, int32_t* matchTrain, uint8_t* inlierMask, int device);
+/* Multi-GPU form (see cvMatchKnn2BatchMulti). */
+MCV_API int cvMatchHomographyBatchMulti(const uint8_t* query, const int64_t* queryOffsets,
+                                        const uint8_t* train, const int64_t* trainOffsets,
+                                        const McvPoint2d* kpQuery, const McvPoint2d* kpTrain, int nPairs,
+                                        int descBytes, float ratio, double thr, int maxIters, double conf,
+                                        McvMatx33d* H, uint8_t* ok, int32_t* nMatches, int32_t* nInliers,
+                                        uint32_t deviceMask);
+
 /* Sharded large-database matching: local top-2 of
  * `nQuery` queries against this rank's train shard, emitted as packed keys
  * (dist << 32) | (globalIdxBase + localIdx), 2 per query (UINT64_MAX if absent);

@@ -27,51 +27,17 @@ int dispatch(Context* ctx, cudaStream_t s, int normType, const KnnArgs& a) {
 
 }  // namespace
 
-extern "C" {
+namespace mcv {
 
-MCV_API int cvMatchKnn2BatchDevice(const uint8_t* dQuery, const int64_t* queryOffsets,
-                                   const uint8_t* dTrain, const int64_t* trainOffsets, int nPairs,
-                                   int descBytes, int normType, float ratio, int* dTrainIdx,
-                                   float* dDist, uint8_t* dRatioPass, int device, void* stream) {
-    MCV_API_ENTER();
-    if (nPairs < 0 || !queryOffsets || !trainOffsets || !dTrainIdx || !dDist) {
-        set_error("cvMatchKnn2BatchDevice: bad arguments");
-        return -1;
-    }
-    if (nPairs == 0) return 0;
-    if (check_norm(normType, descBytes)) return -1;
-    Context* ctx = get_context_async(device, static_cast<cudaStream_t>(stream));
-    if (!ctx) return -1;
-    KnnArgs a;
-    a.dQuery = dQuery; a.dTrain = dTrain;
-    a.hQOff = queryOffsets; a.hTOff = trainOffsets;
-    a.nPairs = nPairs; a.descBytes = descBytes; a.ratio = ratio;
-    a.dTrainIdx = dTrainIdx; a.dDist = dDist; a.dRatioPass = dRatioPass;
-    return dispatch(ctx, static_cast<cudaStream_t>(stream), normType, a);
-}
-
-MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
-                             const uint8_t* train, const int64_t* trainOffsets, int nPairs,
-                             int descBytes, int normType, float ratio, int* trainIdx, float* dist,
-                             uint8_t* ratioPass, int device) {
-    MCV_API_ENTER();
-    if (nPairs < 0 || !queryOffsets || !trainOffsets) {
-        set_error("cvMatchKnn2Batch: bad arguments");
-        return -1;
-    }
-    if (nPairs == 0 || queryOffsets[nPairs] == 0) return 0;
-    if (!trainIdx || !dist) { set_error("cvMatchKnn2Batch: null output buffers"); return -1; }
-    if (check_norm(normType, descBytes)) return -1;
-    if (queryOffsets[0] != 0 || trainOffsets[0] != 0) { set_error("offsets must start at 0"); return -1; }
+// The chunked host-buffer matcher behind cvMatchKnn2Batch and cvMatchHomographyBatch: copy-in, matching and copy-out
+// of consecutive chunks of pairs overlap on three streams.  Device results stay in ctx workspaces 6 (trainIdx),
+// 7 (dist), 8 (ratioPass); the matching kernels run on ctx->stream.  Host outputs are optional (all of trainIdx /
+// dist null: nothing is copied back); countOut (optional) receives the number of ratio-passing queries and makes the
+// call wait for the kernels.
+int match_batch_host(Context* ctx, const uint8_t* query, const int64_t* queryOffsets, const uint8_t* train,
+                     const int64_t* trainOffsets, int nPairs, int descBytes, int normType, float ratio, int* trainIdx,
+                     float* dist, uint8_t* ratioPass, int* countOut) {
     const int64_t totalQ = queryOffsets[nPairs], totalT = trainOffsets[nPairs];
-    if (totalQ < 0 || totalT < 0 || (totalQ > 0 && !query) || (totalT > 0 && !train)) {
-        set_error("cvMatchKnn2Batch: bad offsets / null data");
-        return -1;
-    }
-    if (totalQ == 0) return 0;
-    Context* ctx = get_context(device);
-    if (!ctx) return -1;
-
     const size_t rb = (size_t)descBytes;
     if (ctx->ws[4].reserve((size_t)totalQ * rb + 16) || ctx->ws[5].reserve((size_t)totalT * rb + 16) ||
         ctx->ws[6].reserve((size_t)totalQ * 8) || ctx->ws[7].reserve((size_t)totalQ * 8) ||
@@ -91,8 +57,9 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
     // passes) goes through the pinned ring on the way in (staging.cu) and through a pinned bounce buffer on the way
     // out, handed to the caller's arrays chunk by chunk while later chunks are still being matched.
     const bool pageQ = host_is_pageable(query), pageT = host_is_pageable(train);
+    const bool wantOut = trainIdx != nullptr && dist != nullptr;
     const size_t outBytes = (size_t)totalQ * (8 + 8 + (ratioPass ? 1 : 0));
-    const bool bounceOut = outBytes >= (1u << 20) && host_is_pageable(trainIdx);
+    const bool bounceOut = wantOut && outBytes >= (1u << 20) && host_is_pageable(trainIdx);
     int* hIdx = trainIdx; float* hDist = dist; uint8_t* hPass = ratioPass;
     if (bounceOut) {
         if (ctx->pin[6].reserve(outBytes + 64)) return -1;
@@ -140,15 +107,17 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
             a.dTrainIdx = dIdx + 2 * q0; a.dDist = dDist + 2 * q0; a.dRatioPass = dPass + q0;
             a.dPassCount = dCount;
             if (dispatch(ctx, sK, normType, a)) return -1;
-            MCV_CUDA_TRY(cudaEventRecord(ev[3 * c + 1], sK));
-            MCV_CUDA_TRY(cudaStreamWaitEvent(sOut, ev[3 * c + 1], 0));
-            MCV_CUDA_TRY(cudaMemcpyAsync(hIdx + 2 * q0, dIdx + 2 * q0, (size_t)(q1 - q0) * 8,
-                                         cudaMemcpyDeviceToHost, sOut));
-            MCV_CUDA_TRY(cudaMemcpyAsync(hDist + 2 * q0, dDist + 2 * q0, (size_t)(q1 - q0) * 8,
-                                         cudaMemcpyDeviceToHost, sOut));
-            if (ratioPass)
-                MCV_CUDA_TRY(cudaMemcpyAsync(hPass + q0, dPass + q0, (size_t)(q1 - q0),
+            if (wantOut) {
+                MCV_CUDA_TRY(cudaEventRecord(ev[3 * c + 1], sK));
+                MCV_CUDA_TRY(cudaStreamWaitEvent(sOut, ev[3 * c + 1], 0));
+                MCV_CUDA_TRY(cudaMemcpyAsync(hIdx + 2 * q0, dIdx + 2 * q0, (size_t)(q1 - q0) * 8,
                                              cudaMemcpyDeviceToHost, sOut));
+                MCV_CUDA_TRY(cudaMemcpyAsync(hDist + 2 * q0, dDist + 2 * q0, (size_t)(q1 - q0) * 8,
+                                             cudaMemcpyDeviceToHost, sOut));
+                if (ratioPass)
+                    MCV_CUDA_TRY(cudaMemcpyAsync(hPass + q0, dPass + q0, (size_t)(q1 - q0),
+                                                 cudaMemcpyDeviceToHost, sOut));
+            }
         }
         MCV_CUDA_TRY(cudaEventRecord(ev[3 * c + 2], sOut));
     }
@@ -163,9 +132,67 @@ MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
         }
     }
     int count = 0;
-    MCV_CUDA_TRY(cudaMemcpyAsync(&count, dCount, sizeof(int), cudaMemcpyDeviceToHost, sK));
-    MCV_CUDA_TRY(cudaStreamSynchronize(sK));
-    MCV_CUDA_TRY(cudaStreamSynchronize(sOut));
+    if (countOut) {
+        MCV_CUDA_TRY(cudaMemcpyAsync(&count, dCount, sizeof(int), cudaMemcpyDeviceToHost, sK));
+        MCV_CUDA_TRY(cudaStreamSynchronize(sK));
+        *countOut = count;
+    }
+    if (wantOut) MCV_CUDA_TRY(cudaStreamSynchronize(sOut));
+    return 0;
+}
+
+
+}  // namespace mcv
+
+extern "C" {
+
+MCV_API int cvMatchKnn2BatchDevice(const uint8_t* dQuery, const int64_t* queryOffsets,
+                                   const uint8_t* dTrain, const int64_t* trainOffsets, int nPairs,
+                                   int descBytes, int normType, float ratio, int* dTrainIdx,
+                                   float* dDist, uint8_t* dRatioPass, int device, void* stream) {
+    MCV_API_ENTER();
+    if (nPairs < 0 || !queryOffsets || !trainOffsets || !dTrainIdx || !dDist) {
+        set_error("cvMatchKnn2BatchDevice: bad arguments");
+        return -1;
+    }
+    if (nPairs == 0) return 0;
+    if (check_norm(normType, descBytes)) return -1;
+    Context* ctx = get_context_async(device, static_cast<cudaStream_t>(stream));
+    if (!ctx) return -1;
+    KnnArgs a;
+    a.dQuery = dQuery; a.dTrain = dTrain;
+    a.hQOff = queryOffsets; a.hTOff = trainOffsets;
+    a.nPairs = nPairs; a.descBytes = descBytes; a.ratio = ratio;
+    a.dTrainIdx = dTrainIdx; a.dDist = dDist; a.dRatioPass = dRatioPass;
+    return dispatch(ctx, static_cast<cudaStream_t>(stream), normType, a);
+}
+
+MCV_API int cvMatchKnn2Batch(const uint8_t* query, const int64_t* queryOffsets,
+                             const uint8_t* train, const int64_t* trainOffsets, int nPairs,
+                             int descBytes, int normType, float ratio, int* trainIdx, float* dist,
+                             uint8_t* ratioPass, int device) {
+    MCV_API_ENTER();
+    if (nPairs < 0 || !queryOffsets || !trainOffsets) {
+        set_error("cvMatchKnn2Batch: bad arguments");
+        return -1;
+    }
+    if (nPairs == 0 || queryOffsets[nPairs] == 0) return 0;
+    if (!trainIdx || !dist) { set_error("cvMatchKnn2Batch: null output buffers"); return -1; }
+    if (check_norm(normType, descBytes)) return -1;
+    if (queryOffsets[0] != 0 || trainOffsets[0] != 0) { set_error("offsets must start at 0"); return -1; }
+    const int64_t totalQ = queryOffsets[nPairs], totalT = trainOffsets[nPairs];
+    if (totalQ < 0 || totalT < 0 || (totalQ > 0 && !query) || (totalT > 0 && !train)) {
+        set_error("cvMatchKnn2Batch: bad offsets / null data");
+        return -1;
+    }
+    if (totalQ == 0) return 0;
+    Context* ctx = get_context(device);
+    if (!ctx) return -1;
+
+    int count = 0;
+    if (match_batch_host(ctx, query, queryOffsets, train, trainOffsets, nPairs, descBytes, normType, ratio, trainIdx, dist,
+                         ratioPass, &count))
+        return -1;
     return count;
 }
 

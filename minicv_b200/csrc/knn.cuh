@@ -52,6 +52,13 @@ int launch_l2_knn2(Context* ctx, cudaStream_t stream, const KnnArgs& a);
 bool l2_tc_supported(int descBytes);
 int launch_l2_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a);
 
+// Chunked host-buffer matcher (api_match.cu): copy-in, matching and copy-out of consecutive chunks of pairs overlap
+// on the context's three streams.  Device results stay in ctx workspaces 6 (trainIdx), 7 (dist), 8 (ratioPass), the
+// kernels run on ctx->stream.  Host outputs are optional; countOut (optional) makes the call wait for the kernels.
+int match_batch_host(Context* ctx, const uint8_t* query, const int64_t* queryOffsets, const uint8_t* train,
+                     const int64_t* trainOffsets, int nPairs, int descBytes, int normType, float ratio, int* trainIdx,
+                     float* dist, uint8_t* ratioPass, int* countOut);
+
 // Merge nShards x nQuery x 2 packed keys into global top-2 (+ ratio test).
 int launch_merge_keys(Context* ctx, cudaStream_t stream, const uint64_t* dKeys, int nShards,
                       int nQuery, float ratio, int64_t* dTrainIdx64, float* dDist,

@@ -233,6 +233,46 @@ def recover_pose_batch_multi(cfg: RecoverPoseConfig, a, b, offsets, sample_mode:
     return R, t, ms, good, ok
 
 
+@dataclass
+class MatchHomographyResult:
+    H: np.ndarray            # [nPairs, 3, 3]
+    ok: np.ndarray           # [nPairs] uint8
+    n_matches: np.ndarray    # [nPairs]
+    n_inliers: np.ndarray    # [nPairs]
+    match_query: np.ndarray | None = None   # packed per pair (offsets = cumsum of n_matches), local indices
+    match_train: np.ndarray | None = None
+    inlier_mask: np.ndarray | None = None
+
+
+def match_homography_batch(query, query_offsets, train, train_offsets, kp_query, kp_train, ratio: float = 0.8,
+                           thr: float = 3.0, maxIters: int = 2000, confidence: float = 0.995, want_matches: bool = False,
+                           device: int = -1, device_mask: int | None = None) -> MatchHomographyResult:
+    """``cvMatchHomographyBatch`` (one device) / ``cvMatchHomographyBatchMulti`` (``device_mask`` given): Hamming
+    kNN-2 + ratio test -> matched keypoints -> ``findHomography`` semantics, one call, hand-off on the device."""
+    lib = native.load()
+    q = np.ascontiguousarray(query, np.uint8); t = np.ascontiguousarray(train, np.uint8)
+    kq, kt = _pts(kp_query), _pts(kp_train)
+    qo = np.ascontiguousarray(query_offsets, np.int64); to = np.ascontiguousarray(train_offsets, np.int64)
+    n = qo.size - 1
+    r = MatchHomographyResult(np.zeros((n, 3, 3)), np.zeros(n, np.uint8), np.zeros(n, np.int32), np.zeros(n, np.int32))
+    if device_mask is not None:
+        native.check(lib.cvMatchHomographyBatchMulti(_p(q), _p(qo), _p(t), _p(to), _p(kq), _p(kt), n, q.shape[1], ratio,
+                                                     thr, maxIters, confidence, _p(r.H), _p(r.ok), _p(r.n_matches),
+                                                     _p(r.n_inliers), device_mask), "cvMatchHomographyBatchMulti")
+        return r
+    if want_matches:
+        r.match_query = np.zeros(q.shape[0], np.int32); r.match_train = np.zeros(q.shape[0], np.int32)
+        r.inlier_mask = np.zeros(q.shape[0], np.uint8)
+    native.check(lib.cvMatchHomographyBatch(_p(q), _p(qo), _p(t), _p(to), _p(kq), _p(kt), n, q.shape[1], ratio, thr,
+                                            maxIters, confidence, _p(r.H), _p(r.ok), _p(r.n_matches), _p(r.n_inliers),
+                                            _p(r.match_query), _p(r.match_train), _p(r.inlier_mask), device),
+                 "cvMatchHomographyBatch")
+    if want_matches:
+        tot = int(r.n_matches.sum())
+        r.match_query, r.match_train, r.inlier_mask = r.match_query[:tot], r.match_train[:tot], r.inlier_mask[:tot]
+    return r
+
+
 def recover_pose_from_E(E, a, b, focal=1.0, pp=(0.0, 0.0), mask=None):
     """== ``cv2.recoverPose(E, a, b, focal=, pp=, mask=)`` -> (count, R, t, mask_out, good4)."""
     lib = native.load()

@@ -89,6 +89,10 @@ SIGNATURES = {
     "cvLargeDbMatch": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp]),
     "cvLargeDbInfo": (_i, [_vp, _vp, _vp, _vp]),
     "cvLargeDbDestroy": (None, [_vp]),
+    "cvMatchHomographyBatch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _d, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    _vp, _i]),
+    "cvMatchHomographyBatchMulti": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _d, _i, _d, _vp, _vp, _vp, _vp,
+                                         C.c_uint32]),
     "cvMatchKnn2BatchMulti": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, C.c_uint32]),
     "cvRansacBatchMulti": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, C.c_uint32]),
     "cvRecoverPoseBatchMulti": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.c_uint32]),

@@ -50,3 +50,47 @@ def test_device_pipeline_matches_oracle_chain():
         assert dOk[p].item() == 1
         assert np.abs(Hg - Ho).max() / np.abs(Ho).max() < 1e-6
         assert (dMask[off[p]:off[p + 1]].cpu().numpy() == mo).mean() >= 0.999
+
+
+@pytest.mark.parametrize("engine", [mcv.ENGINE_POPC, mcv.ENGINE_TENSOR])
+def test_match_homography_one_call_equals_oracle_chain(engine):
+    """cvMatchHomographyBatch: host buffers in, H + counts (+ match lists, inlier masks) out, the hand-off on the
+    device; every stage equals the oracle chain cv2-style: knnMatch + ratio -> matched keypoints -> findHomography."""
+    P = 5
+    sizes = [(700, 900), (300, 250), (0, 40), (900, 700), (64, 3)]
+    Q, T, KQ, KT = [], [], [], []
+    for p, (nq, nt) in enumerate(sizes):
+        q, t, gt, kq, kt, H = synth.descriptor_pair_geo(170 + p, max(nq, 1), max(nt, 1))
+        Q.append(q[:nq]); T.append(t[:nt]); KQ.append(kq[:nq]); KT.append(kt[:nt])
+    qo = np.concatenate([[0], np.cumsum([s[0] for s in sizes])]); to = np.concatenate([[0], np.cumsum([s[1] for s in sizes])])
+    mcv.set_hamming_engine(engine)
+    try:
+        r = est.match_homography_batch(np.concatenate(Q), qo, np.concatenate(T), to, np.concatenate(KQ), np.concatenate(KT),
+                                       0.8, 3.0, 2000, 0.995, want_matches=True)
+        rm = est.match_homography_batch(np.concatenate(Q), qo, np.concatenate(T), to, np.concatenate(KQ), np.concatenate(KT),
+                                        0.8, 3.0, 2000, 0.995, device_mask=0)
+    finally:
+        mcv.set_hamming_engine(mcv.ENGINE_AUTO)
+    co = np.concatenate([[0], np.cumsum(r.n_matches)])
+    for p, (nq, nt) in enumerate(sizes):
+        idx, dist = bf_knn.bf_knn2_hamming(Q[p], T[p])
+        okq = bf_knn.ratio_test(dist, idx, 0.8).astype(bool)
+        assert r.n_matches[p] == okq.sum()
+        np.testing.assert_array_equal(r.match_query[co[p]:co[p + 1]], np.nonzero(okq)[0])
+        np.testing.assert_array_equal(r.match_train[co[p]:co[p + 1]], idx[okq, 0])
+        a = KQ[p][okq]; b = KT[p][idx[okq, 0]]
+        if okq.sum() < 4:
+            assert r.ok[p] == 0
+            continue
+        Ho, mo = ransac.find_homography(a, b, 3.0, 2000, 0.995)
+        if Ho is None:
+            assert r.ok[p] == 0
+            continue
+        assert r.ok[p] == 1
+        assert np.abs(r.H[p] - Ho).max() / np.abs(Ho).max() < 1e-6
+        assert (r.inlier_mask[co[p]:co[p + 1]] == mo).mean() >= 0.999
+        assert abs(int(r.n_inliers[p]) - int(mo.sum())) <= max(1, int(0.001 * len(mo)))
+    np.testing.assert_array_equal(rm.ok, r.ok)
+    np.testing.assert_array_equal(rm.H, r.H)
+    np.testing.assert_array_equal(rm.n_matches, r.n_matches)
+    np.testing.assert_array_equal(rm.n_inliers, r.n_inliers)
