@@ -188,9 +188,270 @@ def cpu_match_pairs(pairs, threads: int):
 
 
 # ---------------------------------------------------------------------------------------------
-# extra (not the headline `value`): the RANSAC configs C3 / C4 of BASELINE.json, device-resident,
-# next to the same OpenCV calls on the host cores (one pair per task, cv2.setNumThreads(1),
-# a pool of `cores` workers -- OpenCV's RANSAC loops do not multi-thread)
+# host-buffer path (what a caller on the reference's side of the C ABI gets): every config of
+# BASELINE.json through the host-pointer exports, copies inside the timed region, on every rank
+# (weak scaling), with CUDA-pinned and with ordinary pageable caller buffers.
+# ---------------------------------------------------------------------------------------------
+def _pinned_like(arrs):
+    """Copies of numpy arrays in CUDA-pinned host memory (torch as the allocator; plumbing only)."""
+    import torch
+    out = []
+    for a in arrs:
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype).pin_memory()
+        t.numpy()[...] = a
+        out.append(t)
+    return out
+
+
+def _timed_host(fn, barrier, reduce_max, reps=3):
+    """Seconds per synchronous host-API call: one warm-up, then `reps` calls timed together on the host clock
+    (the exports return when their results are in the caller's buffers); max over ranks."""
+    fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return reduce_max((time.perf_counter() - t0) / reps)
+
+
+def host_path_configs(lib, local, rank, world, barrier, reduce_max, with_cpu):
+    """Returns (e2e others, cpu others, device-resident figures [rank 0], stage rows [rank 0])."""
+    import torch
+    import minicv_b200 as mcv
+    from minicv_b200 import estimation as est, synth
+    cores = os.cpu_count() or 1
+    out, cpu, devres, kernels = {}, {}, {}, []
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+
+    def timed_dev(fn, reps=3):
+        fn(); fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(max(reps, 3)):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts)) / 1e3
+
+    def both(name, arrays, call, pairs, extra):
+        """call(arrays) with pageable numpy arrays, then with pinned copies."""
+        t_page = _timed_host(lambda: call(arrays), barrier, reduce_max)
+        pins = _pinned_like(arrays)
+        parr = [t.numpy() for t in pins]
+        t_pin = _timed_host(lambda: call(parr), barrier, reduce_max)
+        del pins, parr
+        h2d = int(sum(a.nbytes for a in arrays))
+        out[name] = dict({"value": world * pairs / t_pin, "unit": UNIT, "pageable": world * pairs / t_page,
+                          "ms_per_batch": t_pin * 1e3, "pairs_per_gpu": pairs, "h2d_bytes_per_step": h2d}, **extra)
+
+    # ---- C3: homography 4-pt and fundamental 7-pt, 2000 correspondences, 4096 hypotheses, 1024 pairs
+    P, N, HYP = 1024, 2000, 4096
+    off = np.arange(P + 1, dtype=np.int64) * N
+    for kind, model, gen, thr, conf in (("H", est.MODEL_H, synth.homography_pair, 3.0, 0.995),
+                                        ("F", est.MODEL_F, synth.two_view_pair, 3.0, 0.99)):
+        A = np.empty((P * N, 2)); B = np.empty((P * N, 2))
+        for p in range(P):
+            r = gen(rank * P + p, N)
+            A[p * N:(p + 1) * N] = r[0]; B[p * N:(p + 1) * N] = r[1]
+        res = {}
+
+        def call(arr, model=model, thr=thr, conf=conf):
+            res["r"] = est.ransac_batch(model, arr[0], arr[1], off, thr, HYP, conf, sample_mode=est.SAMPLE_COUNTER,
+                                        stop_mode=est.STOP_FIXED, seed=1, device=local)
+        both(f"C3_{kind}", [A, B], call, P,
+             {"api": "cvRansacBatch (host buffers): points up, models + masks + counts back",
+              "correspondences": N, "hypotheses_per_pair": HYP, "mode": "counter-based sampling, fixed hypothesis count"})
+        out[f"C3_{kind}"]["ok_pairs"] = int(res["r"].ok.sum())
+        out[f"C3_{kind}"]["d2h_bytes_per_step"] = int(res["r"].models.nbytes + res["r"].masks.nbytes + res["r"].inliers.nbytes + P * 13)
+        if rank == 0:
+            dA = torch.from_numpy(A).to(dev); dB = torch.from_numpy(B).to(dev)
+            dM = torch.empty((P, 9), dtype=torch.float64, device=dev); dMask = torch.empty(P * N, dtype=torch.uint8, device=dev)
+            dCnt = torch.empty(P, dtype=torch.int32, device=dev); dOk = torch.empty(P, dtype=torch.uint8, device=dev)
+
+            def run(model=model, thr=thr, conf=conf):
+                est.ransac_batch_device(model, dA, dB, off, thr, HYP, dM, dMask, dCnt, dOk, confidence=conf,
+                                        sample_mode=est.SAMPLE_COUNTER, stop_mode=est.STOP_FIXED, seed=1,
+                                        device=local, stream=stream.cuda_stream)
+            t = timed_dev(run)
+            devres[f"C3_{kind}"] = {"pairs_per_s": P / t, "ms_per_batch": t * 1e3, "pairs": P,
+                                    "ghyp_x_corr_per_s": P * N * HYP / t / 1e9, "ok_pairs": int(dOk.sum().item())}
+            rows, _ = stage_breakdown(lib, local, f"C3_{kind}", run,
+                                      {14: {"gevals_per_s": P * N * HYP * (1 if kind == "H" else 2.7) / 1e9},
+                                       12: {"ghyp_per_s": P * HYP / 1e9}})
+            kernels += rows
+            del dA, dB, dM, dMask
+        if with_cpu and rank == 0:
+            k = max(cores, 8) if kind == "H" else cores
+            cpu[f"C3_{kind}"] = cpu_ransac_pairs_per_s(kind, [(A[p * N:(p + 1) * N], B[p * N:(p + 1) * N]) for p in range(k)], cores)
+        barrier()
+        del A, B
+    # ---- C4: essential 5-pt RANSAC + recoverPose, 5000 correspondences, 512 pairs (cvRecoverPose semantics)
+    P, N = 512, 5000
+    off4 = np.arange(P + 1, dtype=np.int64) * N
+    A = np.empty((P * N, 2)); B = np.empty((P * N, 2))
+    for p in range(P):
+        r = synth.two_view_pair(rank * P + p, N)
+        A[p * N:(p + 1) * N] = r[0]; B[p * N:(p + 1) * N] = r[1]
+    cfg = est.RecoverPoseConfig(800.0, (320.0, 240.0), 0.999, 1.0)
+    res = {}
+
+    def call4(arr):
+        res["r"] = est.recover_pose_batch(cfg, arr[0], arr[1], off4, device=local)
+    both("C4_E_pose", [A, B], call4, P,
+         {"api": "cvRecoverPoseBatch (host buffers): points up, R, t, RANSAC masks, cheirality counts back",
+          "correspondences": N, "max_iters": 1000, "mode": "OpenCV MWC sampling + adaptive stop (cvRecoverPose semantics)"})
+    out["C4_E_pose"]["ok_pairs"] = int(res["r"][4].sum())
+    out["C4_E_pose"]["mean_cheirality_inliers"] = float(res["r"][3].mean())
+    if rank == 0:
+        dA = torch.from_numpy(A).to(dev); dB = torch.from_numpy(B).to(dev)
+        dE = torch.empty((P, 9), dtype=torch.float64, device=dev); dR = torch.empty((P, 9), dtype=torch.float64, device=dev)
+        dT = torch.empty((P, 3), dtype=torch.float64, device=dev); dMs = torch.empty(P * N, dtype=torch.uint8, device=dev)
+        dGood = torch.empty(P, dtype=torch.int32, device=dev); dOk = torch.empty(P, dtype=torch.uint8, device=dev)
+
+        def run_e():
+            est.recover_pose_batch_device(cfg, dA, dB, off4, dE, dR, dT, dMs, dGood, dOk, sample_mode=est.SAMPLE_MWC,
+                                          maxIters=1000, device=local, stream=stream.cuda_stream)
+        t = timed_dev(run_e)
+        devres["C4_E_pose"] = {"pairs_per_s": P / t, "ms_per_batch": t * 1e3, "pairs": P, "ok_pairs": int(dOk.sum().item())}
+        rows, _ = stage_breakdown(lib, local, "C4", run_e, {12: {"ghyp_per_s": P * 1000 / 1e9}})
+        kernels += rows
+        del dA, dB, dMs
+    if with_cpu and rank == 0:
+        cpu["C4_E_pose"] = cpu_ransac_pairs_per_s("E", [(A[p * N:(p + 1) * N], B[p * N:(p + 1) * N]) for p in range(cores)], cores)
+    barrier()
+    del A, B
+    # ---- match + homography RANSAC (the north-star pipeline), one call, 256 pairs of 8192 x 8192
+    Pp = 256
+    Q = np.empty((Pp * NQ, DESC_BYTES), np.uint8); T = np.empty((Pp * NT, DESC_BYTES), np.uint8)
+    KQ = np.empty((Pp * NQ, 2)); KT = np.empty((Pp * NT, 2))
+    for p in range(Pp):
+        q, t, gt, kq, kt, H = synth.descriptor_pair_geo(rank * Pp + p)
+        Q[p * NQ:(p + 1) * NQ] = q; T[p * NT:(p + 1) * NT] = t; KQ[p * NQ:(p + 1) * NQ] = kq; KT[p * NT:(p + 1) * NT] = kt
+    qo = np.arange(Pp + 1, dtype=np.int64) * NQ; to = np.arange(Pp + 1, dtype=np.int64) * NT
+    res = {}
+
+    def callp(arr):
+        res["r"] = est.match_homography_batch(arr[0], qo, arr[1], to, arr[2], arr[3], RATIO, 3.0, 2000, 0.995, device=local)
+    both("match_plus_H", [Q, T, KQ, KT], callp, Pp,
+         {"api": "cvMatchHomographyBatch (host buffers): descriptors + keypoints up, H + counts back; kNN-2 + ratio -> "
+                 "device hand-off -> findHomography semantics (OpenCV MWC sampling, maxIters 2000, conf .995, refit + LM)",
+          "n_query": NQ, "n_train": NT})
+    out["match_plus_H"]["ok_pairs"] = int(res["r"].ok.sum())
+    out["match_plus_H"]["mean_matches"] = float(res["r"].n_matches.mean())
+    out["match_plus_H"]["mean_inliers"] = float(res["r"].n_inliers.mean())
+    if rank == 0:
+        dq = torch.from_numpy(Q).to(dev); dt = torch.from_numpy(T).to(dev)
+        dkq = torch.from_numpy(KQ).to(dev); dkt = torch.from_numpy(KT).to(dev)
+        didx = torch.empty((Pp * NQ, 2), dtype=torch.int32, device=dev); ddist = torch.empty((Pp * NQ, 2), dtype=torch.float32, device=dev)
+        dok = torch.empty(Pp * NQ, dtype=torch.uint8, device=dev)
+        da = torch.empty((Pp * NQ, 2), dtype=torch.float64, device=dev); db = torch.empty((Pp * NQ, 2), dtype=torch.float64, device=dev)
+        dM = torch.empty((Pp, 9), dtype=torch.float64, device=dev); dMask = torch.empty(Pp * NQ, dtype=torch.uint8, device=dev)
+        dCnt = torch.empty(Pp, dtype=torch.int32, device=dev); dOkp = torch.empty(Pp, dtype=torch.uint8, device=dev)
+
+        def run_pipe():
+            mcv.match_knn2_batch_device(dq, qo, dt, to, DESC_BYTES, RATIO, didx, ddist, dok, device=local, stream=stream.cuda_stream)
+            off2 = mcv.gather_matches_device(dkq, dkt, qo, to, didx, dok, da, db, device=local, stream=stream.cuda_stream)
+            est.ransac_batch_device(est.MODEL_H, da, db, off2, 3.0, 2000, dM, dMask, dCnt, dOkp, confidence=0.995,
+                                    sample_mode=est.SAMPLE_MWC, stop_mode=est.STOP_ADAPTIVE, device=local, stream=stream.cuda_stream)
+        t = timed_dev(run_pipe)
+        devres["match_plus_H"] = {"pairs_per_s": Pp / t, "ms_per_batch": t * 1e3, "pairs": Pp, "ok_pairs": int(dOkp.sum().item())}
+        rows, _ = stage_breakdown(lib, local, "match_plus_H", run_pipe)
+        kernels += rows
+        del dq, dt, dkq, dkt, didx, ddist, dok, da, db, dMask
+    if with_cpu and rank == 0:
+        try:
+            import cv2
+            cv2.setNumThreads(cores)
+            bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+            k = 12
+            t0 = time.perf_counter()
+            for p in range(k):
+                m = bf.knnMatch(Q[p * NQ:(p + 1) * NQ], T[p * NT:(p + 1) * NT], 2)
+                good = [(a.queryIdx, a.trainIdx) for a, b_ in m if a.distance < RATIO * b_.distance]
+                gi = np.array(good)
+                cv2.findHomography(KQ[p * NQ:(p + 1) * NQ][gi[:, 0]], KT[p * NT:(p + 1) * NT][gi[:, 1]], cv2.RANSAC, 3.0,
+                                   maxIters=2000, confidence=0.995)
+            dtc = time.perf_counter() - t0
+            cpu["match_plus_H"] = {"pairs_per_s": k / dtc, "cores": cores, "sample_pairs": k,
+                                   "note": "cv2 knnMatch (all cores) + ratio + findHomography per pair"}
+        except ImportError:
+            pass
+    barrier()
+    for name, c in cpu.items():
+        if c:
+            out[name]["speedup_vs_cpu"] = out[name]["value"] / world / c["pairs_per_s"] if world == 1 else None
+            out[name]["speedup_vs_cpu_per_gpu"] = out[name]["value"] / world / c["pairs_per_s"]
+    torch.cuda.empty_cache()
+    return out, cpu, devres, kernels
+
+
+def h2d_ceiling(lib, local, world, barrier, all_gather_floats):
+    """The box's host->device ceiling: every rank copies 256 MiB pinned blocks at the same time (one
+    cudaMemcpyAsync per copy, CUDA events around 8 of them), alone and with a concurrent device->host stream."""
+    barrier()
+    up = lib.mcvMeasureCopyBandwidth(local, 256 << 20, 8, 0, 0)
+    barrier()
+    both = lib.mcvMeasureCopyBandwidth(local, 256 << 20, 8, 2, 0)
+    barrier()
+    page = lib.mcvMeasureCopyBandwidth(local, 256 << 20, 4, 0, 1)
+    barrier()
+    plain = lib.mcvMeasureCopyBandwidth(local, 256 << 20, 2, 0, 2)
+    ups = all_gather_floats(up); boths = all_gather_floats(both); pages = all_gather_floats(page); plains = all_gather_floats(plain)
+    return {"h2d_pinned_gbs_per_rank": ups, "h2d_pinned_gbs_aggregate": float(sum(ups)),
+            "h2d_plus_d2h_pinned_gbs_aggregate": float(sum(boths)),
+            "h2d_pageable_ring_gbs_aggregate": float(sum(pages)), "h2d_pageable_plain_gbs_aggregate": float(sum(plains)),
+            "copy_threads": int(lib.mcvCopyThreads()),
+            "how": "all ranks at once: 8 x 256 MiB cudaMemcpyAsync from cudaMallocHost memory per rank, CUDA events on the "
+                   "copy stream (mcvMeasureCopyBandwidth); 'plus_d2h' runs a device->host stream beside it and sums both"}
+
+
+STAGE_NAMES = {0: "matcher", 1: "expand_bits_kernel", 2: "knn2_finalize_kernel", 3: "l2", 10: "prep_points_kernel",
+               11: "sample", 12: "solve", 13: "compact_kernel", 14: "score_kernel", 15: "select_kernel", 16: "finalize",
+               17: "pose (decompose + cheirality + select)", 18: "gather_kernel", 19: "scale_search"}
+KERNEL_OF = {
+    ("C2", 0): "hamming_tc_kernel<2,2,6>",
+    ("C3_H", 11): "sample_counter_kernel<0>", ("C3_H", 12): "solve_kernel<0>", ("C3_H", 14): "score_kernel<0>",
+    ("C3_H", 16): "finalize_homography_kernel",
+    ("C3_F", 11): "sample_counter_kernel<1>", ("C3_F", 12): "solve_kernel<1>", ("C3_F", 14): "score_kernel<1>",
+    ("C3_F", 16): "finalize_plain_kernel<1>",
+    ("C4", 11): "sample_mwc_par_kernel<2>", ("C4", 12): "solve_e_stage1 + solve_e_roots + solve_e_models",
+    ("C4", 14): "score_kernel<2>", ("C4", 16): "finalize_plain_kernel<2>", ("C4", 17): "decompose + cheirality + pose_select",
+}
+
+
+def stage_breakdown(lib, local, config, run, units=None):
+    """CUDA-event time of every instrumented stage of one device-resident step of `config` (events recorded by
+    the library on the launching stream around each kernel / kernel group)."""
+    import torch
+    run(); torch.cuda.synchronize()
+    lib.mcvKernelTimingStart(local, 4096)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream())
+    run()
+    e1.record(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    ms = np.zeros(4096, np.float32); tags = np.zeros(4096, np.int32)
+    n = lib.mcvKernelTimingStopTagged(local, ms.ctypes.data, tags.ctypes.data, 4096)
+    step = e0.elapsed_time(e1)
+    rows = []
+    for tag in sorted(set(tags[:n].tolist())):
+        sel = tags[:n] == tag
+        t = float(ms[:n][sel].sum())
+        row = {"config": config, "stage": STAGE_NAMES.get(tag, str(tag)), "kernel": KERNEL_OF.get((config, tag), STAGE_NAMES.get(tag, str(tag))),
+               "launch_groups": int(sel.sum()), "ms_per_step": t, "share_of_step": t / step if step > 0 else None}
+        if units and tag in units:
+            row.update({k: (v / (t / 1e3) if t > 0 else None) for k, v in units[tag].items()})
+        rows.append(row)
+    return rows, step
+
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arms of the RANSAC configs: the same OpenCV calls on the host cores (one pair per task,
+# cv2.setNumThreads(1), a pool of `cores` workers -- OpenCV's RANSAC loops do not multi-thread); and the
+# side measurements that stay in `extra` (488-bit Hamming, L2, PnP, scale search: device-resident)
 # ---------------------------------------------------------------------------------------------
 def _cpu_ransac_init():
     import cv2
@@ -256,85 +517,7 @@ def extra_ransac(local, with_cpu=True):
             ts.append(e0.elapsed_time(e1))
         return float(np.median(ts)) / 1e3
 
-    # ---- C3: homography 4-pt and fundamental 7-pt, 2000 correspondences, 4096 hypotheses, 1024 pairs
-    P, N, HYP = 1024, 2000, 4096
-    off = np.arange(P + 1, dtype=np.int64) * N
-    for kind, model, gen, thr, conf in (("H", est.MODEL_H, synth.homography_pair, 3.0, 0.995),
-                                        ("F", est.MODEL_F, synth.two_view_pair, 3.0, 0.99)):
-        A = np.empty((P * N, 2)); B = np.empty((P * N, 2))
-        gts = []
-        for p in range(P):
-            r = gen(p, N)
-            A[p * N:(p + 1) * N] = r[0]; B[p * N:(p + 1) * N] = r[1]; gts.append(r[2])
-        dA = torch.from_numpy(A).to(dev); dB = torch.from_numpy(B).to(dev)
-        dM = torch.empty((P, 9), dtype=torch.float64, device=dev)
-        dMask = torch.empty(P * N, dtype=torch.uint8, device=dev)
-        dCnt = torch.empty(P, dtype=torch.int32, device=dev)
-        dOk = torch.empty(P, dtype=torch.uint8, device=dev)
-
-        def run():
-            est.ransac_batch_device(model, dA, dB, off, thr, HYP, dM, dMask, dCnt, dOk, confidence=conf,
-                                    sample_mode=est.SAMPLE_COUNTER, stop_mode=est.STOP_FIXED, seed=1,
-                                    device=local, stream=stream.cuda_stream)
-        t = timed(run)
-        mask = dMask.cpu().numpy().reshape(P, N).astype(bool)
-        gt = np.array(gts)
-        recall = float((mask & gt).sum() / gt.sum())
-        out[f"C3_{kind}"] = {"pairs_per_s": P / t, "ms_per_batch": t * 1e3, "pairs": P, "correspondences": N,
-                             "hypotheses_per_pair": HYP, "ghyp_x_corr_per_s": P * N * HYP / t / 1e9,
-                             "ok_pairs": int(dOk.sum().item()), "gt_inlier_recall": recall,
-                             "mode": "counter-based sampling, fixed hypothesis count"}
-        if with_cpu:
-            k = max(cores, 8) if kind == "H" else cores
-            out[f"C3_{kind}"]["cpu"] = cpu_ransac_pairs_per_s(kind, [(A[p * N:(p + 1) * N], B[p * N:(p + 1) * N]) for p in range(k)], cores)
-        del dA, dB
-    # ---- match -> gather -> homography, device resident (the "match + H-RANSAC" pipeline of north_star)
-    Pp = 256
-    qs, ts, kqs, kts = [], [], [], []
-    for p in range(Pp):
-        q, t, gt, kq, kt, H = synth.descriptor_pair_geo(p)
-        qs.append(q); ts.append(t); kqs.append(kq); kts.append(kt)
-    qo = np.arange(Pp + 1, dtype=np.int64) * NQ; to = np.arange(Pp + 1, dtype=np.int64) * NT
-    dq = torch.from_numpy(np.concatenate(qs)).to(dev); dt = torch.from_numpy(np.concatenate(ts)).to(dev)
-    dkq = torch.from_numpy(np.concatenate(kqs)).to(dev); dkt = torch.from_numpy(np.concatenate(kts)).to(dev)
-    didx = torch.empty((Pp * NQ, 2), dtype=torch.int32, device=dev)
-    ddist = torch.empty((Pp * NQ, 2), dtype=torch.float32, device=dev)
-    dok = torch.empty(Pp * NQ, dtype=torch.uint8, device=dev)
-    da = torch.empty((Pp * NQ, 2), dtype=torch.float64, device=dev); db = torch.empty((Pp * NQ, 2), dtype=torch.float64, device=dev)
-    dM = torch.empty((Pp, 9), dtype=torch.float64, device=dev); dMask = torch.empty(Pp * NQ, dtype=torch.uint8, device=dev)
-    dCnt = torch.empty(Pp, dtype=torch.int32, device=dev); dOkp = torch.empty(Pp, dtype=torch.uint8, device=dev)
     import minicv_b200 as mcv
-
-    def run_pipe():
-        mcv.match_knn2_batch_device(dq, qo, dt, to, DESC_BYTES, RATIO, didx, ddist, dok, device=local,
-                                    stream=stream.cuda_stream)
-        off2 = mcv.gather_matches_device(dkq, dkt, qo, to, didx, dok, da, db, device=local, stream=stream.cuda_stream)
-        est.ransac_batch_device(est.MODEL_H, da, db, off2, 3.0, 2000, dM, dMask, dCnt, dOkp, confidence=0.995,
-                                sample_mode=est.SAMPLE_MWC, stop_mode=est.STOP_ADAPTIVE, device=local,
-                                stream=stream.cuda_stream)
-    t = timed(run_pipe)
-    out["C2_match_plus_H"] = {"pairs_per_s": Pp / t, "ms_per_batch": t * 1e3, "pairs": Pp,
-                              "ok_pairs": int(dOkp.sum().item()), "mean_inliers": float(dCnt.float().mean().item()),
-                              "mode": "device-resident: kNN-2 + ratio -> gather -> findHomography semantics "
-                                      "(OpenCV MWC sampling, maxIters 2000, conf .995, refit + LM)"}
-    if with_cpu:
-        try:
-            import cv2
-            cv2.setNumThreads(cores)
-            bf = cv2.BFMatcher(cv2.NORM_HAMMING)
-            k = 12
-            t0 = time.perf_counter()
-            for p in range(k):
-                m = bf.knnMatch(qs[p], ts[p], 2)
-                good = [(a.queryIdx, a.trainIdx) for a, b_ in m if a.distance < RATIO * b_.distance]
-                gi = np.array(good)
-                cv2.findHomography(kqs[p][gi[:, 0]], kts[p][gi[:, 1]], cv2.RANSAC, 3.0, maxIters=2000, confidence=0.995)
-            dtc = time.perf_counter() - t0
-            out["C2_match_plus_H"]["cpu"] = {"pairs_per_s": k / dtc, "cores": cores, "sample_pairs": k,
-                                             "note": "cv2 knnMatch (all cores) + findHomography per pair"}
-        except ImportError:
-            pass
-    del dq, dt, dkq, dkt, didx, ddist, dok, da, db, dMask
     # ---- M1 at 488 bit (AKAZE-MLDB, 61-byte rows): both Hamming engines, 128 pairs of 8192 x 8192
     Pa = 128
     qa = np.empty((Pa * NQ, 61), np.uint8); ta = np.empty((Pa * NT, 61), np.uint8)
@@ -412,30 +595,6 @@ def extra_ransac(local, with_cpu=True):
             fn()
         lat[name] = (time.perf_counter() - t0) / 5 * 1e3
     out["single_call_ms"] = lat
-    # ---- C4: essential 5-pt RANSAC + recoverPose, 5000 correspondences, 512 pairs (cvRecoverPose semantics)
-    P, N = 512, 5000
-    off = np.arange(P + 1, dtype=np.int64) * N
-    A = np.empty((P * N, 2)); B = np.empty((P * N, 2))
-    for p in range(P):
-        r = synth.two_view_pair(p, N)
-        A[p * N:(p + 1) * N] = r[0]; B[p * N:(p + 1) * N] = r[1]
-    dA = torch.from_numpy(A).to(dev); dB = torch.from_numpy(B).to(dev)
-    dE = torch.empty((P, 9), dtype=torch.float64, device=dev); dR = torch.empty((P, 9), dtype=torch.float64, device=dev)
-    dT = torch.empty((P, 3), dtype=torch.float64, device=dev); dMs = torch.empty(P * N, dtype=torch.uint8, device=dev)
-    dGood = torch.empty(P, dtype=torch.int32, device=dev); dOk = torch.empty(P, dtype=torch.uint8, device=dev)
-    cfg = est.RecoverPoseConfig(800.0, (320.0, 240.0), 0.999, 1.0)
-
-    def run_e():
-        est.recover_pose_batch_device(cfg, dA, dB, off, dE, dR, dT, dMs, dGood, dOk, sample_mode=est.SAMPLE_MWC,
-                                      maxIters=1000, device=local, stream=stream.cuda_stream)
-    t = timed(run_e, reps=2)
-    out["C4_E_pose"] = {"pairs_per_s": P / t, "ms_per_batch": t * 1e3, "pairs": P, "correspondences": N,
-                        "max_iters": 1000, "ok_pairs": int(dOk.sum().item()),
-                        "mean_cheirality_inliers": float(dGood.float().mean().item()),
-                        "mode": "OpenCV MWC sampling + adaptive stop (cvRecoverPose semantics)"}
-    if with_cpu:
-        out["C4_E_pose"]["cpu"] = cpu_ransac_pairs_per_s("E", [(A[p * N:(p + 1) * N], B[p * N:(p + 1) * N]) for p in range(cores)], cores)
-    del dA, dB
     # ---- PnP RANSAC: cvSolvePnPRansac(AP3P) semantics, 2000 correspondences, 30 % inliers
     P, N = 1024, 2000
     off = np.arange(P + 1, dtype=np.int64) * N
@@ -499,12 +658,14 @@ def extra_ransac(local, with_cpu=True):
     return out
 
 
-def extra_large_db(local, rank, world, n_train=4 * 1024 * 1024, n_query=10000):
-    """C5: train set sharded by contiguous range over the ranks, queries replicated, local top-2
-    keys all_gathered over NCCL and merged on the device.  Time = max over ranks."""
+def extra_large_db(lib, local, rank, world, n_train=4 * 1024 * 1024, n_query=10000):
+    """C5: train set sharded by contiguous range over the ranks, queries replicated, local top-2 keys gathered with
+    ncclAllGather INSIDE the library (cvMatchKnn2ShardedDevice; the communicator is built from an id rank 0 obtains
+    from the library and torch.distributed only carries those 128 bytes), merged on the device.  Time = max over ranks."""
+    import ctypes as C
     import torch
     import torch.distributed as dist
-    from minicv_b200 import sharding
+    from minicv_b200 import native, sharding
     dev = torch.device("cuda", local)
     lo, hi = sharding.block_range(n_train, world, rank)
     g = torch.Generator(device=dev)
@@ -515,18 +676,38 @@ def extra_large_db(local, rank, world, n_train=4 * 1024 * 1024, n_query=10000):
     q = torch.randint(0, 256, (n_query, DESC_BYTES), dtype=torch.uint8, device=dev, generator=gq)
     if lo == 0:
         q[: n_query // 2] = shard[: n_query // 2] ^ 1       # half the queries have a near-duplicate in shard 0
+    idt = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (C.c_uint8 * 128)()
+        native.check(lib.mcvShardCommUniqueId(buf), "mcvShardCommUniqueId")
+        idt = torch.tensor(list(buf), dtype=torch.uint8)
     if world > 1:
         dist.broadcast(q, 0)
+        idd = idt.to(dev)
+        dist.broadcast(idd, 0)
+        idt = idd.cpu()
+    idb = (C.c_uint8 * 128)(*idt.tolist())
+    comm = lib.mcvShardCommInit(idb, world, rank, local)
+    if not comm:
+        raise RuntimeError("mcvShardCommInit failed: " + native.last_error())
     stream = torch.cuda.current_stream()
-    sharding.match_large_db(q, shard, lo, DESC_BYTES, RATIO, device=local)
+    idx = torch.empty((n_query, 2), dtype=torch.int64, device=dev)
+    dd = torch.empty((n_query, 2), dtype=torch.float32, device=dev)
+    ok = torch.empty(n_query, dtype=torch.uint8, device=dev)
+
+    def run():
+        native.check(lib.cvMatchKnn2ShardedDevice(comm, q.data_ptr(), n_query, shard.data_ptr(), hi - lo, lo, DESC_BYTES, RATIO,
+                                                  idx.data_ptr(), dd.data_ptr(), ok.data_ptr(), stream.cuda_stream),
+                     "cvMatchKnn2ShardedDevice")
+    run()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    reps = 3
+    reps = 5
     e0.record(stream)
     for _ in range(reps):
-        idx, dd, ok = sharding.match_large_db(q, shard, lo, DESC_BYTES, RATIO, device=local)
+        run()
     e1.record(stream)
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
@@ -534,10 +715,65 @@ def extra_large_db(local, rank, world, n_train=4 * 1024 * 1024, n_query=10000):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     found = int((idx[: n_query // 2, 0] == torch.arange(n_query // 2, device=dev)).sum().item())
+    lib.mcvShardCommDestroy(comm)
     return {"ms_per_image": ms, "images_per_s": 1e3 / ms, "n_train_total": n_train, "n_query": n_query,
             "shards": world, "gdist_per_s": n_query * n_train / ms / 1e6,
-            "planted_matches_found": found, "planted": n_query // 2,
-            "collective": "all_gather of Q x 2 x 8 B per rank" if world > 1 else "none (1 rank)"}
+            "planted_matches_found": found, "planted": n_query // 2, "nccl_version": int(lib.mcvNcclVersion()),
+            "api": "cvMatchKnn2ShardedDevice (local keys -> ncclAllGather inside libMiniCVNative -> merge)",
+            "collective": "ncclAllGather of Q x 2 x 8 B per rank, issued by the library" if world > 1 else "none (1 rank)"}
+
+
+def single_call_multi_gpu(lib, n_dev, pairs_per_dev=256):
+    """ONE cvMatchKnn2BatchMulti call from this process over every visible device (pinned host buffers): what a
+    P/Invoke caller on the reference's side of the boundary gets from an 8-GPU box, no torch / torchrun in the data
+    path.  Also the in-process large-database form (cvLargeDb*, ncclCommInitAll + grouped all-gather)."""
+    import minicv_b200 as mcv
+    from minicv_b200 import synth
+    P = pairs_per_dev * n_dev
+    pq = mcv.PinnedArray((P * NQ, DESC_BYTES), np.uint8); pt = mcv.PinnedArray((P * NT, DESC_BYTES), np.uint8)
+    base_q, _, base_t, _ = synth.descriptor_batch(5000, 16, NQ, NT, DESC_BYTES)
+    for k in range(P // 16):
+        pq.array[k * 16 * NQ:(k + 1) * 16 * NQ] = np.roll(base_q, k, axis=1)
+        pt.array[k * 16 * NT:(k + 1) * 16 * NT] = np.roll(base_t, k, axis=1)
+    pi = mcv.PinnedArray((P * NQ, 2), np.int32); pd = mcv.PinnedArray((P * NQ, 2), np.float32); po = mcv.PinnedArray((P * NQ,), np.uint8)
+    qo = np.arange(P + 1, dtype=np.int64) * NQ; to = np.arange(P + 1, dtype=np.int64) * NT
+    out = mcv.KnnResult(pi.array, pd.array, po.array, 0)
+    res = {}
+    for nd in sorted({1, n_dev}):
+        mask = (1 << nd) - 1
+        Pn = pairs_per_dev * nd
+        o2 = mcv.KnnResult(pi.array[:Pn * NQ], pd.array[:Pn * NQ], po.array[:Pn * NQ], 0)
+        mcv.match_knn2_batch_multi(pq.array[:Pn * NQ], qo[:Pn + 1], pt.array[:Pn * NT], to[:Pn + 1], RATIO, device_mask=mask, out=o2)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            mcv.match_knn2_batch_multi(pq.array[:Pn * NQ], qo[:Pn + 1], pt.array[:Pn * NT], to[:Pn + 1], RATIO, device_mask=mask, out=o2)
+        dt = (time.perf_counter() - t0) / reps
+        res[f"{nd}_gpu"] = {"pairs_per_s": Pn / dt, "pairs": Pn, "ms_per_call": dt * 1e3, "n_pass": int(o2.n_pass)}
+    res["api"] = "cvMatchKnn2BatchMulti(deviceMask): one C call, one host thread + stream set per device, pinned host buffers"
+    if n_dev > 1:
+        res["scaling_1_to_n"] = res[f"{n_dev}_gpu"]["pairs_per_s"] / res["1_gpu"]["pairs_per_s"]
+    for x in (pq, pt, pi, pd, po):
+        x.free()
+    # in-process large database over every visible device
+    rng = np.random.default_rng(7)
+    n_train, n_query = 4 * 1024 * 1024, 10000
+    train = rng.integers(0, 256, (n_train, DESC_BYTES), dtype=np.uint8)
+    query = rng.integers(0, 256, (n_query, DESC_BYTES), dtype=np.uint8)
+    query[: n_query // 2] = train[: n_query // 2] ^ 1
+    db_res = {}
+    for nd in sorted({1, n_dev}):
+        with mcv.LargeDb(train, (1 << nd) - 1) as db:
+            db.match(query, RATIO)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                idx, dist_, ok, npass = db.match(query, RATIO)
+            dt = (time.perf_counter() - t0) / 5
+            db_res[f"{nd}_gpu"] = {"ms_per_image": dt * 1e3, "shards": db.n_shards, "uses_nccl": db.uses_nccl,
+                                   "planted_matches_found": int((idx[: n_query // 2, 0] == np.arange(n_query // 2)).sum())}
+    db_res["api"] = "cvLargeDbCreate / cvLargeDbMatch: shards resident, queries from host memory, ncclCommInitAll + grouped ncclAllGather inside the library, result back in host memory"
+    res["large_db"] = db_res
+    return res
 
 
 def run_reference(args):
@@ -661,7 +897,7 @@ def run_ours(args):
     barrier()
     launches0 = lib.mcvKernelLaunchCount()
     # CUDA events around the dominant kernel alone, recorded by the library on the launching stream
-    lib.mcvKernelTimingStart(local, (args.steps + 1) * 256)
+    lib.mcvKernelTimingStart(local, (args.steps + 1) * 256)        # capacity in event pairs; ~57 per step at C2
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -675,10 +911,19 @@ def run_ours(args):
     launches = lib.mcvKernelLaunchCount() - launches0
     ms_total = e0.elapsed_time(e1)
     kbuf = np.zeros((args.steps + 1) * 256, dtype=np.float32)
-    nk = lib.mcvKernelTimingStop(local, kbuf.ctypes.data, len(kbuf))
+    ktag = np.zeros((args.steps + 1) * 256, dtype=np.int32)
+    nk_all = lib.mcvKernelTimingStopTagged(local, kbuf.ctypes.data, ktag.ctypes.data, len(kbuf))
     # the matcher launches hamming_tc_kernel once per L2-sized chunk of pairs: sum per step
-    kern_ms = float(kbuf[:nk].sum()) / args.steps if nk > 0 else None
+    sel0 = ktag[:nk_all] == 0
+    nk = int(sel0.sum())
+    kern_ms = float(kbuf[:nk_all][sel0].sum()) / args.steps if nk > 0 else None
     kern_launches_per_step = nk / args.steps if nk > 0 else None
+    c2_rows = []
+    for tag in sorted(set(ktag[:nk_all].tolist())):
+        tms = float(kbuf[:nk_all][ktag[:nk_all] == tag].sum()) / args.steps
+        c2_rows.append({"config": "C2", "stage": STAGE_NAMES.get(tag, str(tag)),
+                        "kernel": KERNEL_OF.get(("C2", tag), STAGE_NAMES.get(tag, str(tag))),
+                        "launch_groups": int((ktag[:nk_all] == tag).sum() / args.steps), "ms_per_step": tms})
     clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -687,28 +932,60 @@ def run_ours(args):
     value = world * P / (ms_step / 1e3)
     n_pass_dev = int(dok.sum().item())
 
-    # --- e2e: the host-buffer C-ABI call, pinned host inputs and outputs, copies inside the timing
+    # --- e2e: the host-buffer C-ABI call, host inputs and outputs, copies inside the timing.  Twice: with CUDA-pinned
+    #     buffers (direct DMA) and with ordinary pageable arrays (what a P/Invoke caller passes; staged by the library)
+    def reduce_max(x):
+        te = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item())
+
+    def all_gather_floats(x):
+        te = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            outl = [torch.zeros_like(te) for _ in range(world)]
+            dist.all_gather(outl, te)
+            return [float(o.item()) for o in outl]
+        return [float(x)]
+
     out = mcv.KnnResult(torch.empty((P * NQ, 2), dtype=torch.int32).pin_memory().numpy(),
                         torch.empty((P * NQ, 2), dtype=torch.float32).pin_memory().numpy(),
                         torch.empty(P * NQ, dtype=torch.uint8).pin_memory().numpy(), 0)
     e2e_steps = max(2, min(args.steps, 5))
-    mcv.match_knn2_batch(q_np, qo, t_np, to, RATIO, device=local, out=out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        mcv.match_knn2_batch(q_np, qo, t_np, to, RATIO, device=local, out=out)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * P / float(te.item())
+    e2e_s = _timed_host(lambda: mcv.match_knn2_batch(q_np, qo, t_np, to, RATIO, device=local, out=out), barrier, reduce_max,
+                        reps=e2e_steps)
+    e2e_value = world * P / e2e_s
     assert out.n_pass == n_pass_dev, "host-path and device-path results differ"
+    q_pg, t_pg = np.array(q_np, copy=True), np.array(t_np, copy=True)           # ordinary (pageable) memory
+    out_pg = mcv.KnnResult(np.empty((P * NQ, 2), np.int32), np.empty((P * NQ, 2), np.float32), np.empty(P * NQ, np.uint8), 0)
+    e2e_pg_s = _timed_host(lambda: mcv.match_knn2_batch(q_pg, qo, t_pg, to, RATIO, device=local, out=out_pg), barrier, reduce_max,
+                           reps=e2e_steps)
+    assert out_pg.n_pass == n_pass_dev and np.array_equal(out_pg.train_idx, out.train_idx)
+    lib.mcvSetStagingMode(1)
+    e2e_plain_s = _timed_host(lambda: mcv.match_knn2_batch(q_pg, qo, t_pg, to, RATIO, device=local, out=out_pg), barrier, reduce_max,
+                              reps=2)
+    lib.mcvSetStagingMode(0)
+    del q_pg, t_pg, out_pg
+    h2d_bytes = int(q_np.nbytes + t_np.nbytes)
+    d2h_bytes = int(out.train_idx.nbytes + out.distance.nbytes + out.ratio_pass.nbytes)
+    ceiling = h2d_ceiling(lib, local, world, barrier, all_gather_floats)
+    e2e_h2d_gbs = world * h2d_bytes / e2e_s / 1e9
 
-    # --- C5 (all ranks): 4 Mi train descriptors sharded over the ranks, 10 000 queries, keys all_gathered
+    # --- C5 (all ranks): 4 Mi train descriptors sharded over the ranks, 10 000 queries, keys all-gathered in the library
     c5 = None
+    others = cpu_others = devres = krows = None
     if not args.no_extra:
-        c5 = extra_large_db(local, rank, world)
+        c5 = extra_large_db(lib, local, rank, world)
+        del dq, dt, didx, ddist, dok
+        torch.cuda.empty_cache()
+        os.sched_setaffinity(0, all_cpus)      # CPU arms may use every core
+        others, cpu_others, devres, krows = host_path_configs(lib, local, rank, world, barrier, reduce_max,
+                                                              with_cpu=not args.no_cpu_baseline)
+    # --- one C call driving every visible device (rank 0, the other ranks wait)
+    multi = None
+    if not args.no_extra and rank == 0 and world == 1 and lib.mcvDeviceCount() > 1:
+        multi = single_call_multi_gpu(lib, lib.mcvDeviceCount())
+    barrier()
 
     if rank != 0:
         if world > 1:
@@ -789,10 +1066,45 @@ def run_ours(args):
 
     extra = None
     if not args.no_extra:
-        del dq, dt, didx, ddist, dok
-        torch.cuda.empty_cache()
         extra = extra_ransac(local, with_cpu=not args.no_cpu_baseline)
         extra["C5_large_db"] = c5
+        extra["device_resident"] = devres
+        if multi is not None:
+            extra["single_call_multi_gpu"] = multi
+
+    # ncu-derived pipe utilisations of the kernels (profiles/r02_kernels.json, captured with the recipe's
+    # `ncu --set full` on this same workload) attached to the live per-stage times
+    ncu = {}
+    nj = ROOT / "profiles" / "r02_kernels.json"
+    if nj.exists():
+        try:
+            ncu = json.loads(nj.read_text())
+        except Exception:
+            ncu = {}
+    kernels = c2_rows + (krows or [])
+    for row in kernels:
+        if row["config"] == "C2" and ms_step > 0:
+            row["share_of_step"] = row["ms_per_step"] / ms_step
+        extra_info = ncu.get(row["kernel"])
+        if extra_info:
+            row["ncu"] = extra_info
+    roofline["kernels"] = kernels
+
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+           "steps": e2e_steps, "api": "cvMatchKnn2Batch (host buffers, CUDA-pinned)",
+           "pageable": {"value": world * P / e2e_pg_s, "unit": UNIT,
+                        "api": "cvMatchKnn2Batch, ordinary pageable numpy arrays in and out (what a P/Invoke caller passes): "
+                               "staged through the library's pinned ring by its copy threads",
+                        "plain_cudaMemcpyAsync": world * P / e2e_plain_s, "copy_threads": ceiling["copy_threads"]},
+           "h2d": dict(ceiling, e2e_h2d_gbs=e2e_h2d_gbs,
+                       frac_of_h2d_ceiling=e2e_h2d_gbs / ceiling["h2d_pinned_gbs_aggregate"] if ceiling["h2d_pinned_gbs_aggregate"] > 0 else None,
+                       note="e2e_h2d_gbs = bytes the e2e step moves host->device per second over all ranks; the ceiling is the "
+                            "aggregate rate of bare pinned copies issued by all ranks at once on this box"),
+           "others": others}
+    if cpu is not None and cpu_others:
+        cpu["others"] = cpu_others
+    if cpu is not None:
+        e2e["speedup_vs_cpu_per_gpu"] = e2e_value / world / cpu["value"]
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -800,10 +1112,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": dict(workload_config(args), engine=("tcgen05 int8 GEMM" if use_tc else "integer pipe XOR+POPC")),
         "gdist_per_s": gdist,
-        "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": int(q_np.nbytes + t_np.nbytes),
-                "d2h_bytes_per_step": int(out.train_idx.nbytes + out.distance.nbytes + out.ratio_pass.nbytes),
-                "steps": e2e_steps, "api": "cvMatchKnn2Batch (host buffers, pinned)"},
+        "e2e": e2e,
         "numa_binding": numa, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "ratio_pass_per_pair": n_pass_dev / P, "extra": extra,
     }

@@ -113,6 +113,10 @@ MCV_API int64_t mcvKernelLaunchCount(void);
  * order) and returns how many.  Used by bench.py for the roofline figure. */
 MCV_API int mcvKernelTimingStart(int device, int capacity);
 MCV_API int mcvKernelTimingStop(int device, float* ms, int capacity);
+/* Same, for every instrumented stage: tags[i] names the stage of ms[i] (0 matcher kernel, 1 train-bit expansion,
+ * 2 kNN finalize, 3 L2 matcher, 10 point preparation, 11 sampling, 12 minimal solvers, 13 compaction, 14 scoring,
+ * 15 selection, 16 finalize / refit, 17 pose recovery, 18 match gather, 19 scale search), in launch order. */
+MCV_API int mcvKernelTimingStopTagged(int device, float* ms, int* tags, int capacity);
 /* Hamming matcher engine: 0 = auto (default), 1 = integer pipe (XOR + POPC), 2 = tcgen05
  * tensor cores.  Both engines are bit-identical in their results; returns 0, or -1 if bad. */
 MCV_API int mcvSetHammingEngine(int engine);

@@ -115,7 +115,13 @@ inline cudaEvent_t* event_pool(Context* c, int n) {
 }
 // Bracket the dominant kernel of a matcher call on its launching stream (no-ops unless mcvKernelTimingStart
 // switched the device's timing on).
-void kt_begin(Context* c, cudaStream_t s);
+// Stage tags (mcvKernelTimingStopTagged): 0 = the dominant matcher kernel (tcgen05 GEMM + top-2, or XOR/POPC).
+enum KtTag {
+    KT_MATCH = 0, KT_EXPAND = 1, KT_KNN_FINALIZE = 2, KT_L2 = 3,
+    KT_PREP = 10, KT_SAMPLE = 11, KT_SOLVE = 12, KT_COMPACT = 13, KT_SCORE = 14, KT_SELECT = 15, KT_FINALIZE = 16,
+    KT_POSE = 17, KT_GATHER = 18, KT_SCALE = 19
+};
+void kt_begin(Context* c, cudaStream_t s, int tag = KT_MATCH);
 void kt_end(Context* c, cudaStream_t s);
 
 // RAII guard of one export call.  The outermost scope of a thread remembers the caller's current device; when it

@@ -74,6 +74,7 @@ struct DeviceState {
     std::atomic<bool>       ktOn{false};
     int                     ktN = 0, ktCap = 0;
     cudaEvent_t*            ktEv = nullptr;   // 2 * ktCap events
+    int*                    ktTag = nullptr;  // ktCap stage tags (common.cuh KT_*)
 };
 
 static constexpr int kMaxDevices = 64;
@@ -90,11 +91,11 @@ static int max_contexts() {
     return n;
 }
 
-void kt_begin(Context* c, cudaStream_t s) {
+void kt_begin(Context* c, cudaStream_t s, int tag) {
     DeviceState* d = c->dev;
     if (!d->ktOn.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(d->ktMu);
-    if (d->ktOn && d->ktN < d->ktCap) cudaEventRecord(d->ktEv[2 * d->ktN], s);
+    if (d->ktOn && d->ktN < d->ktCap) { cudaEventRecord(d->ktEv[2 * d->ktN], s); d->ktTag[d->ktN] = tag; }
 }
 void kt_end(Context* c, cudaStream_t s) {
     DeviceState* d = c->dev;
@@ -298,7 +299,9 @@ MCV_API int mcvKernelTimingStart(int device, int capacity) {
         for (int i = 0; i < 2 * capacity; ++i) cudaEventCreate(&ev[i]);
         for (int i = 0; i < 2 * d->ktCap; ++i) cudaEventDestroy(d->ktEv[i]);
         delete[] d->ktEv;
+        delete[] d->ktTag;
         d->ktEv = ev;
+        d->ktTag = new int[(size_t)capacity];
         d->ktCap = capacity;
     }
     d->ktN = 0;
@@ -306,23 +309,30 @@ MCV_API int mcvKernelTimingStart(int device, int capacity) {
     return 0;
 }
 
-MCV_API int mcvKernelTimingStop(int device, float* ms, int capacity) {
+MCV_API int mcvKernelTimingStopTagged(int device, float* ms, int* tags, int capacity) {
     MCV_API_ENTER();
     mcv::Context* c = mcv::get_context(device);
-    if (!c) return -1;
+    if (!c || !ms) return -1;
     mcv::DeviceState* d = c->dev;
     std::lock_guard<std::mutex> lk(d->ktMu);
     d->ktOn = false;
     int n = 0;
-    for (; n < d->ktN && n < capacity; ++n) {
-        if (cudaEventSynchronize(d->ktEv[2 * n + 1]) != cudaSuccess ||
-            cudaEventElapsedTime(&ms[n], d->ktEv[2 * n], d->ktEv[2 * n + 1]) != cudaSuccess) {
+    for (int i = 0; i < d->ktN && n < capacity; ++i) {
+        if (!tags && d->ktTag[i] != 0) continue;        // untagged form: the dominant matcher kernel only
+        if (cudaEventSynchronize(d->ktEv[2 * i + 1]) != cudaSuccess ||
+            cudaEventElapsedTime(&ms[n], d->ktEv[2 * i], d->ktEv[2 * i + 1]) != cudaSuccess) {
             cudaGetLastError();
             break;
         }
+        if (tags) tags[n] = d->ktTag[i];
+        ++n;
     }
     d->ktN = 0;
     return n;
+}
+
+MCV_API int mcvKernelTimingStop(int device, float* ms, int capacity) {
+    return mcvKernelTimingStopTagged(device, ms, nullptr, capacity);
 }
 
 MCV_API int mcvSetHammingEngine(int engine) {

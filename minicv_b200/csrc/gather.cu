@@ -96,9 +96,11 @@ MCV_API int cvGatherMatchesDevice(const double* dKpQuery, const double* dKpTrain
     hO[nPairs] = acc;
     memcpy(outOffsets, hO, n1 * 8);
     MCV_CUDA_TRY(cudaMemcpyAsync(dO, hO, n1 * 8, cudaMemcpyHostToDevice, st));
+    kt_begin(ctx, st, KT_GATHER);
     gather_kernel<<<nPairs, 256, 0, st>>>(reinterpret_cast<const double2*>(dKpQuery), reinterpret_cast<const double2*>(dKpTrain),
                                           dQ, dT, dO, dTrainIdx, dRatioPass, reinterpret_cast<double2*>(dA),
                                           reinterpret_cast<double2*>(dB));
+    kt_end(ctx, st);
     MCV_LAUNCH_CHECK();
     MCV_CUDA_TRY(cudaEventRecord(ctx->ev[7], st));
     return (int)std::min<int64_t>(acc, 0x7FFFFFFF);

@@ -636,8 +636,10 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
         if (chunkTiles > 0) {
             const int64_t n16 = (tB - tA) * (rowBytes / 16);
             if (n16 > 0) {
+                kt_begin(ctx, stream, KT_EXPAND);
                 expand_bits_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, stream>>>(
                     a.dTrain + tA * a.descBytes, a.descBytes, tB - tA, rowBytes, trainScale, ctx->ws[25].as<uint4>());
+                kt_end(ctx, stream);
                 MCV_LAUNCH_CHECK();
             }
             CUtensorMap mt;
@@ -656,7 +658,10 @@ int launch_hamming_knn2_tc(Context* ctx, cudaStream_t stream, const KnnArgs& a) 
         tile0 += chunkTiles;
         p0 = p1;
     }
-    return launch_knn2_finalize(stream, dSplitKeys, nSlots, totalQ, a);
+    kt_begin(ctx, stream, KT_KNN_FINALIZE);
+    const int rcf = launch_knn2_finalize(stream, dSplitKeys, nSlots, totalQ, a);
+    kt_end(ctx, stream);
+    return rcf;
 }
 
 }  // namespace mcv

@@ -152,10 +152,11 @@ int recover_pose_batch_device(Context* ctx, cudaStream_t st, const PoseIO& io) {
     double* R1 = io.dR1 ? io.dR1 : wR1;
     double* R2 = io.dR2 ? io.dR2 : wR2;
     double* T = io.dT ? io.dT : wT;
+    kt_begin(ctx, st, KT_POSE);
     decompose_kernel<<<(nPairs + 63) / 64, 64, 0, st>>>(io.dE, io.dOk, nPairs, R1, R2, T);
     MCV_LAUNCH_CHECK();
     const bool wantPose = io.dR || io.dTsel || io.dGood || io.dGood4 || io.dMaskOut;
-    if (!wantPose) return 0;
+    if (!wantPose) { kt_end(ctx, st); return 0; }
     if (ctx->ws[21].reserve((size_t)std::max<int64_t>(total, 1) * 32) ||
         ctx->ws[23].reserve((size_t)std::max<int64_t>(total, 1)))
         return -1;
@@ -183,6 +184,7 @@ int recover_pose_batch_device(Context* ctx, cudaStream_t st, const PoseIO& io) {
         pose_mask_kernel<<<g, 256, 0, st>>>(dOff, wChoice, cand, io.dMaskOut);
         MCV_LAUNCH_CHECK();
     }
+    kt_end(ctx, st);
     return 0;
 }
 

@@ -1413,9 +1413,11 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
     }
     if (total > 0) {
         const double invf = 1.0 / prm.focal;
+        kt_begin(ctx, st, KT_PREP);
         prep_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
             reinterpret_cast<const double2*>(io.dA), reinterpret_cast<const double2*>(io.dB), total,
             MODEL == RM_ESSENTIAL ? 1 : 0, invf, -prm.ppx * invf, -prm.ppy * invf, pf, pd);
+        kt_end(ctx, st);
         MCV_LAUNCH_CHECK();
     }
 
@@ -1458,6 +1460,7 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
         for (int p = p0; p < p0 + np; ++p) maxN = std::max(maxN, io.hOff[p + 1] - io.hOff[p]);
 
         // ---- sample
+        kt_begin(ctx, st, KT_SAMPLE);
         if (io.dInjModels) {
             injected_setup_kernel<<<(np + 255) / 256, 256, 0, st>>>(off, np, maxIters, MP, dNIter, dFlags);
             MCV_LAUNCH_CHECK();
@@ -1501,7 +1504,9 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             kern<<<np, 32, smemBytes, st>>>(pf, off, np, maxIters, smemPts, dSamples, dNIter, dFlags, dNeedSeq);
             MCV_LAUNCH_CHECK();
         }
+        kt_end(ctx, st);
         // ---- solve
+        kt_begin(ctx, st, KT_SOLVE);
         if (io.dInjModels) {
             const int64_t nh = (int64_t)np * maxIters;
             inject_models_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(
@@ -1521,8 +1526,11 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             solve_kernel<MODEL><<<g, 64, 0, st>>>(pf, pd, off, maxIters, dSamples, dNIter, dModels, dNModels);
             MCV_LAUNCH_CHECK();
         }
+        kt_end(ctx, st);
         // ---- compact
+        kt_begin(ctx, st, KT_COMPACT);
         compact_kernel<<<np, 256, 0, st>>>(dNModels, dNIter, maxIters, MAXM, dIterStart, dSlotList, dNTotal);
+        kt_end(ctx, st);
         MCV_LAUNCH_CHECK();
         if (prm.stopMode == MCV_STOP_LMEDS) {
             // ---- LMedS: median score per model, first minimum wins, sigma-rule mask (fundamental matrices only)
@@ -1553,15 +1561,19 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             zs = (int)((std::max<int64_t>(maxN, 1) + chunkPts - 1) / chunkPts);
             if (zs > 1) MCV_CUDA_TRY(cudaMemsetAsync(dCounts, 0, (size_t)np * slots * 4, st));
             dim3 g(tiles, np, zs);
+            kt_begin(ctx, st, KT_SCORE);
             score_kernel<MODEL><<<g, 128, 0, st>>>(pf, pd, off, dModels, dSlotList, dNTotal, (int)slots,
                                                    thr2, chunkPts, dCounts);
+            kt_end(ctx, st);
             MCV_LAUNCH_CHECK();
         }
         // ---- select
+        kt_begin(ctx, st, KT_SELECT);
         select_kernel<<<(np + 3) / 4, 128, 0, st>>>(off, np, maxIters, MAXM, MP,
                                                     prm.stopMode == MCV_STOP_ADAPTIVE ? 1 : 0,
                                                     prm.confidence, dNIter, dFlags, dIterStart, dSlotList,
                                                     dCounts, dBest);
+        kt_end(ctx, st);
         MCV_LAUNCH_CHECK();
         // ---- finalize
         double* oM = io.dModels + (size_t)p0 * 9;
@@ -1569,6 +1581,7 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
         int* oCnt = io.dInlierCounts ? io.dInlierCounts + p0 : nullptr;
         int* oIt = io.dItersRun ? io.dItersRun + p0 : nullptr;
         int* oBest = io.dBest ? io.dBest + 2 * (size_t)p0 : nullptr;
+        kt_begin(ctx, st, KT_FINALIZE);
         if (MODEL == RM_HOMOGRAPHY && prm.refine) {
             // small blocks once there are enough pairs to fill the machine with them: 7 x 64 threads per SM keep every
             // pair of a 1024-pair batch resident, so the serial warp-0 phases of all refits overlap (one wave instead of three)
@@ -1579,6 +1592,7 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             finalize_plain_kernel<MODEL><<<np, FB, 0, st>>>(pf, pd, off, dModels, (int)slots, dBest, dFlags,
                                                             dNTotal, thr2, oM, io.dMasks, oCnt, oOk, oIt, oBest);
         }
+        kt_end(ctx, st);
         MCV_LAUNCH_CHECK();
         }
         // ---- debug taps

@@ -195,7 +195,7 @@ int scale_costs_device(Context* ctx, cudaStream_t st, const double* dCams, const
     int threads = 128;
     while (threads > 32 && ((maxScales + threads - 1) / threads) * (int64_t)nProblems < 2ll * ctx->sm_count) threads >>= 1;
     dim3 g((unsigned)((maxScales + threads - 1) / threads), nProblems);
-    kt_begin(ctx, st);
+    kt_begin(ctx, st, KT_SCALE);
     scale_cost_kernel<<<g, threads, 0, st>>>(dCams, dRot, dTrans, dWorld, dObs, dOff, dScales, dScaleOk, dScaleOff, dCosts);
     kt_end(ctx, st);
     MCV_LAUNCH_CHECK();

@@ -99,6 +99,7 @@ SIGNATURES = {
     "cvSolvePnPRansacBatchMulti": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32]),
     "mcvKernelTimingStart": (_i, [_i, _i]),
     "mcvKernelTimingStop": (_i, [_i, _vp, _i]),
+    "mcvKernelTimingStopTagged": (_i, [_i, _vp, _vp, _i]),
     "cvMatchKnn2": (_i, [_vp, _i, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "cvMatchKnn2Batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i]),
     "cvMatchKnn2BatchDevice": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp]),
