@@ -86,6 +86,14 @@ int match_batch_host(Context* ctx, const uint8_t* query, const int64_t* queryOff
     cudaEvent_t* ev = event_pool(ctx, 3 * nChunks);
     if (!ev) { set_error("cvMatchKnn2Batch: cudaEventCreate failed"); return -1; }
     std::vector<int64_t> qo, to;
+    int drained = 0;
+    auto drain = [&](int c) {      // chunk c's results: pinned bounce buffer -> the caller's arrays
+        const int64_t q0 = queryOffsets[bounds[c]], q1 = queryOffsets[bounds[c + 1]];
+        if (q1 == q0) return;
+        parallel_memcpy(trainIdx + 2 * q0, hIdx + 2 * q0, (size_t)(q1 - q0) * 8);
+        parallel_memcpy(dist + 2 * q0, hDist + 2 * q0, (size_t)(q1 - q0) * 8);
+        if (ratioPass) memcpy(ratioPass + q0, hPass + q0, (size_t)(q1 - q0));
+    };
     for (int c = 0; c < nChunks; ++c) {
         const int p0 = bounds[c], p1 = bounds[c + 1];
         const int64_t q0 = queryOffsets[p0], q1 = queryOffsets[p1];
@@ -120,15 +128,16 @@ int match_batch_host(Context* ctx, const uint8_t* query, const int64_t* queryOff
             }
         }
         MCV_CUDA_TRY(cudaEventRecord(ev[3 * c + 2], sOut));
+        // hand finished chunks to the caller's pageable arrays while the copy engines and the matcher work on later ones
+        if (bounceOut) {
+            while (drained < c && cudaEventQuery(ev[3 * drained + 2]) == cudaSuccess) drain(drained++);
+            cudaGetLastError();      // cudaErrorNotReady is an answer, not a failure
+        }
     }
     if (bounceOut) {
-        for (int c = 0; c < nChunks; ++c) {
-            const int64_t q0 = queryOffsets[bounds[c]], q1 = queryOffsets[bounds[c + 1]];
-            MCV_CUDA_TRY(cudaEventSynchronize(ev[3 * c + 2]));
-            if (q1 == q0) continue;
-            parallel_memcpy(trainIdx + 2 * q0, hIdx + 2 * q0, (size_t)(q1 - q0) * 8);
-            parallel_memcpy(dist + 2 * q0, hDist + 2 * q0, (size_t)(q1 - q0) * 8);
-            if (ratioPass) memcpy(ratioPass + q0, hPass + q0, (size_t)(q1 - q0));
+        for (; drained < nChunks; ++drained) {
+            MCV_CUDA_TRY(cudaEventSynchronize(ev[3 * drained + 2]));
+            drain(drained);
         }
     }
     int count = 0;
