@@ -42,6 +42,7 @@ int stage_points(Staged& s, const McvPoint2d* a, const McvPoint2d* b, int64_t to
     s.dModels = c->ws[32].as<double>(); s.dMasks = c->ws[33].as<uint8_t>();
     s.dCnt = c->ws[34].as<int>(); s.dOk = c->ws[35].as<uint8_t>();
     s.dIters = c->ws[36].as<int>(); s.dBest = c->ws[37].as<int>();
+    MCV_CUDA_TRY(cudaMemsetAsync(s.dModels, 0, (size_t)nPairs * 72, s.st));     // pairs without a model report a zero matrix
     if (total > 0) {
         // pageable caller arrays (P/Invoke) go through the pinned ring, pinned ones are copied directly
         if (h2d_copy(c, s.dA, a, (size_t)total * 16, s.st, host_is_pageable(a)) ||

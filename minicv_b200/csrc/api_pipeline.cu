@@ -63,6 +63,7 @@ MCV_API int cvMatchHomographyBatch(const uint8_t* query, const int64_t* queryOff
     int* dCnt = reinterpret_cast<int*>(dModels + 9 * np1);
     uint8_t* dOk = reinterpret_cast<uint8_t*>(dCnt + np1);
     uint8_t* dMasks = dOk + ((np1 + 15) & ~(size_t)15);
+    MCV_CUDA_TRY(cudaMemsetAsync(dModels, 0, np1 * 72, sK));       // pairs without a model report a zero matrix
     if (h2d_copy(ctx, dKq, kpQuery, (size_t)totalQ * 16, sIn, host_is_pageable(kpQuery))) return -1;
     if (totalT > 0 && h2d_copy(ctx, dKt, kpTrain, (size_t)totalT * 16, sIn, host_is_pageable(kpTrain))) return -1;
     MCV_CUDA_TRY(cudaEventRecord(ctx->ev[4], sIn));
