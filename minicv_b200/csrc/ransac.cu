@@ -361,35 +361,223 @@ solve_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
 // compacted in root order inside a 16-lane group, so the models land exactly where the single kernel put them.
 constexpr int E5_SCR = 96;          // doubles per hypothesis: EE 36 | b 39 | coef 11 | roots 10
 
+// Stage 1a -- null space (one thread per hypothesis): the 5 x 9 epipolar system's rows are orthonormalised and OpenCV's
+// basis completion run on them (cvmath.cuh nullspace_rows: the vt rows 5..8 of cv::SVD, without the Jacobi sweeps); the
+// 9 x 9 working matrix sits in shared memory, interleaved by thread (element e of thread t at [e * 64 + t]), the current
+// row in registers.  Writes EE (4 x 9) to the hypothesis' scratch record.
+// Hypothesis source: RANSAC samples (pd / off / samples / nIter, grid.y = pair) or explicit 5-point sets (dirA / dirB).
 __global__ void __launch_bounds__(64)
-solve_e_stage1_kernel(const double* __restrict__ pd, const int64_t* __restrict__ off, int maxIters,
-                      const int* __restrict__ samples, const int* __restrict__ nIter, double* __restrict__ scr,
-                      int* __restrict__ nRoots) {
+solve_e_null_kernel(const double* __restrict__ pd, const int64_t* __restrict__ off, int maxIters,
+                    const int* __restrict__ samples, const int* __restrict__ nIter, const double* __restrict__ dirA,
+                    const double* __restrict__ dirB, int64_t nDirect, double* __restrict__ scr, int* __restrict__ nRoots) {
     constexpr int MP = 5;
+    __shared__ double sAt[45 * 64];
     const int it = blockIdx.x * blockDim.x + threadIdx.x;
-    const int p = blockIdx.y;
-    if (it >= maxIters) return;
-    const int64_t h = (int64_t)p * maxIters + it;
-    nRoots[h] = -1;                                          // -1: no system (skipped iteration / bad sample / singular)
-    if (it >= nIter[p]) return;
-    const int64_t base = off[p];
-    const int n = (int)(off[p + 1] - base);
-    const int* idx = samples + h * MP;
-    bool bad = false;
-    for (int i = 0; i < MP; ++i) bad |= (idx[i] < 0 || idx[i] >= n);
-    if (bad) return;
+    int64_t h;
     double a[2 * MP], b[2 * MP];
-    for (int i = 0; i < MP; ++i) {
-        const double* q = pd + 4 * (base + idx[i]);
-        a[2 * i] = q[0]; a[2 * i + 1] = q[1]; b[2 * i] = q[2]; b[2 * i + 1] = q[3];
+    if (dirA) {
+        h = it;
+        if (h >= nDirect) return;
+        nRoots[h] = -1;
+        for (int k = 0; k < 10; ++k) { a[k] = dirA[10 * h + k]; b[k] = dirB[10 * h + k]; }
+    } else {
+        const int p = blockIdx.y;
+        if (it >= maxIters) return;
+        h = (int64_t)p * maxIters + it;
+        nRoots[h] = -1;                                      // -1: no system (skipped iteration / bad sample / singular)
+        if (it >= nIter[p]) return;
+        const int64_t base = off[p];
+        const int n = (int)(off[p + 1] - base);
+        const int* idx = samples + h * MP;
+        bool bad = false;
+        for (int i = 0; i < MP; ++i) bad |= (idx[i] < 0 || idx[i] >= n);
+        if (bad) return;
+        for (int i = 0; i < MP; ++i) {
+            const double* q = pd + 4 * (base + idx[i]);
+            a[2 * i] = q[0]; a[2 * i + 1] = q[1]; b[2 * i] = q[2]; b[2 * i + 1] = q[3];
+        }
     }
-    double EE[36], bb[39], coef[11];
-    if (!e5_stage1(a, b, EE, bb, coef)) return;
+    double* At = sAt + threadIdx.x;
+    for (int i = 0; i < 5; ++i) {
+        const double x1 = a[2 * i], y1 = a[2 * i + 1], x2 = b[2 * i], y2 = b[2 * i + 1];
+        double* q = At + 9 * i * 64;
+        q[0] = x1 * x2; q[1 * 64] = y1 * x2; q[2 * 64] = x2; q[3 * 64] = x1 * y2; q[4 * 64] = y1 * y2; q[5 * 64] = y2;
+        q[6 * 64] = x1; q[7 * 64] = y1; q[8 * 64] = 1.0;
+    }
+    double EE[36];
+    nullspace_rows<9, 5, 9, 64>(At, EE);
     double* o = scr + h * E5_SCR;
     for (int k = 0; k < 36; ++k) o[k] = EE[k];
-    for (int k = 0; k < 39; ++k) o[36 + k] = bb[k];
-    for (int k = 0; k < 11; ++k) o[75 + k] = coef[k];
     nRoots[h] = 0;
+}
+
+// Stage 1b -- constraints, elimination, det B(z): ten lanes per hypothesis, three hypotheses per warp.
+//   * lane r of a group builds row r of the 10 x 20 constraint matrix in registers (row 0 = det E, rows 1..9 =
+//     2 E E^T E - tr(E E^T) E), from the group's EE and the six E E^T polynomials in shared memory;
+//   * Gauss-Jordan with partial pivoting runs ACROSS the lanes: the pivot is an arg-max over the group (four rotation
+//     shuffles of a key that carries the lane), the pivot row is broadcast by shuffles and every other lane eliminates
+//     its own row in registers -- no local memory, no shared-memory matrix;
+//   * the lanes that ended up holding rows 4..9 hand them to lanes 0..2, which form the three rows of B(z); lanes 0..5
+//     expand one permutation term of det B(z) each and lane 0 adds them in the fixed order of the serial code.
+// (As one thread per hypothesis this stage held a 3.3 KB local frame, wrote 10x its useful bytes back to DRAM and
+// issued on 9 % of the cycles, see profiles/r01_filtered_scoring_ncu.md.)
+constexpr int E5_HPB = 12;        // hypotheses per 128-thread block: 4 warps x 3 groups of 10 lanes
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+
+__global__ void __launch_bounds__(128)
+solve_e_elim_kernel(int64_t nHyp, double* __restrict__ scr, int* __restrict__ nRoots) {
+    __shared__ double sEE[E5_HPB][36];
+    __shared__ double sEet[E5_HPB][6][10];
+    __shared__ double sB[E5_HPB][39];
+    __shared__ double sTerm[E5_HPB][6][11];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / 10, pos = lane - 10 * g;            // lanes 30, 31: g == 3, idle
+    const int slot = warp * 3 + (g < 3 ? g : 0);
+    const int64_t h = ((int64_t)blockIdx.x * 4 + warp) * 3 + g;
+    const bool live = g < 3 && h < nHyp && nRoots[h] == 0;
+    const int gbase = 10 * (g < 3 ? g : 0);
+    double (&EE)[36] = sEE[slot];
+    if (live) for (int k = pos; k < 36; k += 10) EE[k] = scr[h * E5_SCR + k];
+    __syncwarp();
+    // E[i][j] as a degree-1 polynomial in (x, y, z, 1): coefficient of basis b at EE[b * 9 + (i * 3 + j)]
+    auto e1 = [&](int k, double* o) { o[0] = EE[k]; o[1] = EE[9 + k]; o[2] = EE[18 + k]; o[3] = EE[27 + k]; };
+    if (live && pos < 6) {
+        const int i = pos < 3 ? 0 : (pos < 5 ? 1 : 2), j = pos < 3 ? pos : (pos < 5 ? pos - 2 : 2);
+        double acc[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[k] = 0;
+        for (int m = 0; m < 3; ++m) {
+            double u[4], v[4], t[10];
+            e1(i * 3 + m, u); e1(j * 3 + m, v);
+            p5::mul11(u, v, t);
+            // same association as the serial code: (t0 + t1) + t2
+#pragma unroll
+            for (int k = 0; k < 10; ++k) acc[k] = m == 0 ? t[k] : acc[k] + t[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) sEet[slot][pos][k] = acc[k];
+    }
+    __syncwarp();
+    double row[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) row[k] = 0;
+    if (live) {
+        if (pos == 0) {
+            double m[10], u[4], v[4], w[4];
+            e1(4, u); e1(8, v); p5::mul11(u, v, m); e1(0, w); p5::mul21_acc(m, w, 1., row);
+            e1(5, u); e1(7, v); p5::mul11(u, v, m); p5::mul21_acc(m, w, -1., row);
+            e1(3, u); e1(8, v); p5::mul11(u, v, m); e1(1, w); p5::mul21_acc(m, w, -1., row);
+            e1(5, u); e1(6, v); p5::mul11(u, v, m); p5::mul21_acc(m, w, 1., row);
+            e1(3, u); e1(7, v); p5::mul11(u, v, m); e1(2, w); p5::mul21_acc(m, w, 1., row);
+            e1(4, u); e1(6, v); p5::mul11(u, v, m); p5::mul21_acc(m, w, -1., row);
+        } else {
+            const int i = (pos - 1) / 3, j = (pos - 1) - 3 * i;
+            auto pairIdx = [](int a, int b) { const int lo = a < b ? a : b, hi = a < b ? b : a; return lo == 0 ? hi : (lo == 1 ? 2 + hi : 5); };
+            for (int k = 0; k < 3; ++k) {
+                double pe[10], u[4];
+                const double* src = sEet[slot][pairIdx(i, k)];
+#pragma unroll
+                for (int q = 0; q < 10; ++q) pe[q] = src[q];
+                e1(k * 3 + j, u);
+                p5::mul21_acc(pe, u, 2., row);
+            }
+            double tr[10], u[4];
+#pragma unroll
+            for (int q = 0; q < 10; ++q) tr[q] = sEet[slot][0][q] + sEet[slot][3][q] + sEet[slot][5][q];
+            e1(i * 3 + j, u);
+            p5::mul21_acc(tr, u, -1., row);
+        }
+    }
+    // ---- Gauss-Jordan on the ten leading columns, rows spread over the group's lanes
+    bool used = false, singular = false;
+    int myCol = -1;
+#pragma unroll
+    for (int c = 0; c < 10; ++c) {
+        // arg-max of |row[c]| over the lanes that are not pivots yet; ties and near-ties (below 2^-48) go to the lower lane
+        unsigned long long key = 0;
+        if (live && !used) key = ((unsigned long long)__double_as_longlong(fabs(row[c])) & ~15ull) | (unsigned long long)(15 - pos);
+#pragma unroll
+        for (int d = 1; d <= 4; d <<= 1) {
+            const int src = gbase + (pos + d >= 10 ? pos + d - 10 : pos + d);
+            const unsigned long long o = __shfl_sync(0xFFFFFFFFu, key, src);
+            key = o > key ? o : key;
+        }
+        {   // windows of 8 consecutive lanes so far: one more rotation by 2 covers all ten
+            const int src = gbase + (pos + 2 >= 10 ? pos - 8 : pos + 2);
+            const unsigned long long o = __shfl_sync(0xFFFFFFFFu, key, src);
+            key = o > key ? o : key;
+        }
+        const int pl = gbase + (15 - (int)(key & 15ull));
+        if ((key >> 4) == 0) singular = true;                // no usable pivot (the serial code returns false)
+        const bool isPivot = live && lane == pl && !used;
+        const double pv = shfl_d(row[c], pl);
+        const double inv = 1 / pv;
+        const double f = row[c];
+#pragma unroll
+        for (int k = c + 1; k < 20; ++k) {
+            const double t = shfl_d(row[k], pl) * inv;       // the normalised pivot row
+            row[k] = isPivot ? t : row[k] - f * t;
+        }
+        row[c] = isPivot ? 1.0 : 0.0;
+        if (isPivot) { used = true; myCol = c; }
+    }
+    // ---- rows 4..9 (by pivot column) -> B(z): lane i in 0..2 takes rows 2 i + 4 and 2 i + 5
+    int src1 = gbase, src2 = gbase;
+#pragma unroll
+    for (int c = 4; c < 10; ++c) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, myCol == c);
+        const unsigned mg = (m >> gbase) & 0x3FFu;
+        const int who = gbase + (mg ? __ffs(mg) - 1 : 0);
+        if (c == 2 * pos + 4) src1 = who;
+        if (c == 2 * pos + 5) src2 = who;
+    }
+    double r1[10], r2[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) { r1[k] = shfl_d(row[10 + k], src1); r2[k] = shfl_d(row[10 + k], src2); }
+    if (live && pos < 3) {
+        double row1[13], row2[13];
+#pragma unroll
+        for (int k = 0; k < 13; ++k) { row1[k] = 0; row2[k] = 0; }
+        row1[1] = r1[0]; row1[2] = r1[1]; row1[3] = r1[2];
+        row1[5] = r1[3]; row1[6] = r1[4]; row1[7] = r1[5];
+        row1[9] = r1[6]; row1[10] = r1[7]; row1[11] = r1[8]; row1[12] = r1[9];
+        row2[0] = r2[0]; row2[1] = r2[1]; row2[2] = r2[2];
+        row2[4] = r2[3]; row2[5] = r2[4]; row2[6] = r2[5];
+        row2[8] = r2[6]; row2[9] = r2[7]; row2[10] = r2[8]; row2[11] = r2[9];
+#pragma unroll
+        for (int k = 0; k < 13; ++k) sB[slot][13 * pos + k] = row1[k] - row2[k];
+    }
+    __syncwarp();
+    if (live && pos < 6) {
+        // permutation terms of det B(z): columns 0 -> x-part (deg 3), 1 -> y-part (deg 3), 2 -> 1-part (deg 4)
+        const int p0 = pos == 0 ? 0 : pos == 1 ? 1 : pos == 2 ? 2 : pos == 3 ? 0 : pos == 4 ? 1 : 2;
+        const int p1 = pos == 0 ? 1 : pos == 1 ? 2 : pos == 2 ? 0 : pos == 3 ? 2 : pos == 4 ? 0 : 1;
+        const int p2 = pos == 0 ? 2 : pos == 1 ? 0 : pos == 2 ? 1 : pos == 3 ? 1 : pos == 4 ? 2 : 0;
+        double xy[7], full[11];
+        upoly_mul(sB[slot] + 13 * p0 + 0, 4, sB[slot] + 13 * p1 + 4, 4, xy);
+        upoly_mul(xy, 7, sB[slot] + 13 * p2 + 8, 5, full);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) sTerm[slot][pos][k] = full[k];
+    }
+    __syncwarp();
+    // a group is singular when any of its lanes saw an empty pivot column
+    const unsigned sm = __ballot_sync(0xFFFFFFFFu, singular);
+    const bool groupSing = ((sm >> gbase) & 0x3FFu) != 0;
+    if (live) {
+        double* o = scr + h * E5_SCR;
+        if (groupSing) { if (pos == 0) nRoots[h] = -1; }
+        else {
+            for (int k = pos; k < 39; k += 10) o[36 + k] = sB[slot][k];
+            if (pos == 0) {
+                for (int k = 0; k < 11; ++k) {
+                    double cf = 0;
+                    for (int t = 0; t < 6; ++t) cf += (t < 3 ? 1. : -1.) * sTerm[slot][t][k];
+                    o[75 + k] = cf;
+                }
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(128)
@@ -432,23 +620,6 @@ solve_e_models_kernel(int64_t nHyp, const double* __restrict__ scr, const int* _
     if (live && r == 0) nModels[h] = (uint8_t)__popc(grp);
 }
 
-// cvFivePoint / cvFivePointBatch: the same three stages over explicit 5-point sets (a, b: [nSets][5][2]).
-__global__ void __launch_bounds__(64)
-five_point_stage1_kernel(const double* __restrict__ a, const double* __restrict__ b, int nSets,
-                         double* __restrict__ scr, int* __restrict__ nRoots) {
-    const int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= nSets) return;
-    nRoots[h] = -1;
-    double pa[10], pb[10];
-    for (int k = 0; k < 10; ++k) { pa[k] = a[10 * (int64_t)h + k]; pb[k] = b[10 * (int64_t)h + k]; }
-    double EE[36], bb[39], coef[11];
-    if (!e5_stage1(pa, pb, EE, bb, coef)) return;
-    double* o = scr + (int64_t)h * E5_SCR;
-    for (int k = 0; k < 36; ++k) o[k] = EE[k];
-    for (int k = 0; k < 39; ++k) o[36 + k] = bb[k];
-    for (int k = 0; k < 11; ++k) o[75 + k] = coef[k];
-    nRoots[h] = 0;
-}
 __global__ void __launch_bounds__(256)
 widen_counts_kernel(const uint8_t* __restrict__ in, int n, int* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1515,7 +1686,9 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
         } else if constexpr (MODEL == RM_ESSENTIAL) {
             const int64_t nh = (int64_t)np * maxIters;
             dim3 g((maxIters + 63) / 64, np);
-            solve_e_stage1_kernel<<<g, 64, 0, st>>>(pd, off, maxIters, dSamples, dNIter, dE5Scr, dE5Roots);
+            solve_e_null_kernel<<<g, 64, 0, st>>>(pd, off, maxIters, dSamples, dNIter, nullptr, nullptr, 0, dE5Scr, dE5Roots);
+            MCV_LAUNCH_CHECK();
+            solve_e_elim_kernel<<<(unsigned)((nh + E5_HPB - 1) / E5_HPB), 128, 0, st>>>(nh, dE5Scr, dE5Roots);
             MCV_LAUNCH_CHECK();
             solve_e_roots_kernel<<<(unsigned)((nh + 127) / 128), 128, 0, st>>>(nh, dE5Scr, dE5Roots);
             MCV_LAUNCH_CHECK();
@@ -1639,7 +1812,9 @@ int five_point_device(Context* ctx, cudaStream_t st, const double* dA, const dou
     double* scr = ctx->ws[68].as<double>();
     int* nRoots = ctx->ws[69].as<int>();
     uint8_t* nModels = reinterpret_cast<uint8_t*>(nRoots + n);
-    five_point_stage1_kernel<<<(nSets + 63) / 64, 64, 0, st>>>(dA, dB, nSets, scr, nRoots);
+    solve_e_null_kernel<<<(nSets + 63) / 64, 64, 0, st>>>(nullptr, nullptr, 0, nullptr, nullptr, dA, dB, nSets, scr, nRoots);
+    MCV_LAUNCH_CHECK();
+    solve_e_elim_kernel<<<(unsigned)((n + E5_HPB - 1) / E5_HPB), 128, 0, st>>>((int64_t)n, scr, nRoots);
     MCV_LAUNCH_CHECK();
     solve_e_roots_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((int64_t)n, scr, nRoots);
     MCV_LAUNCH_CHECK();
