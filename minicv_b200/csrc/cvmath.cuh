@@ -28,6 +28,7 @@
 #else
 #define MCV_HD inline
 #define MCV_HDN
+#define MCV_UNROLL
 #endif
 
 namespace mcv {
