@@ -1155,10 +1155,25 @@ MCV_HDN inline bool e5_root_to_E(const double* EE /*[36]*/, const double* b /*[3
         bz[j * 3 + 1] = br[4] * z3 + br[5] * z2 + br[6] * z1 + br[7];
         bz[j * 3 + 2] = br[8] * z4 + br[9] * z3 + br[10] * z2 + br[11] * z1 + br[12];
     }
-    // SVD::solveZ(Bz): right singular vector of the smallest singular value
-    double w3[3], u3[9], vt3[9];
-    svd_square<3>(bz, w3, u3, vt3);
-    const double vx = vt3[6], vy = vt3[7], vw = vt3[8];
+    // SVD::solveZ(Bz) in the reference: the right singular vector of the smallest singular value, used only through
+    // the ratios x = v0 / v2, y = v1 / v2 (its sign cancels).  At a root of det B(z) the matrix has rank two and that
+    // vector is the cross product of any two independent rows; the best conditioned of the three cross products is
+    // taken and scaled to unit length, so the |v2| < 1e-10 rejection keeps the reference's meaning.  (A 3 x 3 Jacobi
+    // SVD per root was most of this stage's arithmetic.)
+    double c0[3], c1[3], c2[3];
+    c0[0] = bz[1] * bz[5] - bz[2] * bz[4]; c0[1] = bz[2] * bz[3] - bz[0] * bz[5]; c0[2] = bz[0] * bz[4] - bz[1] * bz[3];   // r0 x r1
+    c1[0] = bz[1] * bz[8] - bz[2] * bz[7]; c1[1] = bz[2] * bz[6] - bz[0] * bz[8]; c1[2] = bz[0] * bz[7] - bz[1] * bz[6];   // r0 x r2
+    c2[0] = bz[4] * bz[8] - bz[5] * bz[7]; c2[1] = bz[5] * bz[6] - bz[3] * bz[8]; c2[2] = bz[3] * bz[7] - bz[4] * bz[6];   // r1 x r2
+    const double n0 = c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2];
+    const double n1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2];
+    const double n2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
+    const double* cb = c0;
+    double nb = n0;
+    if (n1 > nb) { cb = c1; nb = n1; }
+    if (n2 > nb) { cb = c2; nb = n2; }
+    if (!(nb > 0)) return false;
+    const double inb = 1 / sqrt(nb);
+    const double vx = cb[0] * inb, vy = cb[1] * inb, vw = cb[2] * inb;
     if (fabs(vw) < 1e-10) return false;
     const double xs = vx / vw, ys = vy / vw;
     double nrm = 0;

@@ -580,17 +580,159 @@ solve_e_elim_kernel(int64_t nHyp, double* __restrict__ scr, int* __restrict__ nR
     }
 }
 
+// Stage 2 -- real roots of det B(z) (degree 10), one thread per hypothesis.  Same arithmetic as cvmath.cuh real_roots10
+// (Laguerre iterations with deflation by real linear / quadratic factors, every root polished by Newton steps on the
+// original polynomial, |Im| <= 1e-10 keeps a root), but run as a FLAT state machine: one trip of the warp-uniform loop
+// is one polynomial evaluation followed by one Laguerre or one Newton update of whatever root the lane is working on.
+// A lane that finishes a root starts its next one in the following trip instead of idling until the slowest lane of the
+// warp has finished the same root -- the nested-loop form ran with 15 of 32 lanes active.  Coefficients, working
+// polynomial and roots live in registers (all loops are unrolled with predicates on the current degree).
 __global__ void __launch_bounds__(128)
 solve_e_roots_kernel(int64_t nHyp, double* __restrict__ scr, int* __restrict__ nRoots) {
     const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= nHyp || nRoots[h] < 0) return;
-    double coef[11], roots[10];
-    const double* c = scr + h * E5_SCR + 75;
-    for (int k = 0; k < 11; ++k) coef[k] = c[k];
-    const int nr = real_roots10(coef, roots);
+    bool active = h < nHyp && nRoots[h] >= 0;
+    double a0[11], w[11], out[10];
+    int deg = 10, n = 0;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) a0[k] = 0;
+    if (active) {
+        const double* c = scr + h * E5_SCR + 75;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) a0[k] = c[k];
+        // strip leading zero coefficients (degenerate systems)
+        for (int guard = 0; guard < 10 && deg > 0 && a0[0] == 0; ++guard) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) a0[k] = a0[k + 1];
+            a0[10] = 0;
+            --deg;
+        }
+        if (deg == 0) active = false;
+    }
+#pragma unroll
+    for (int k = 0; k < 11; ++k) w[k] = a0[k];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) out[k] = 0;
+    const int deg0 = deg;
+    // per-root state
+    bool lag = true;                 // true: Laguerre on the working polynomial, false: Newton polish on the original
+    double xr = 0, xi = 0;           // Laguerre estimate (also what the working polynomial is deflated by)
+    double pr = 0, pi = 0;           // polished estimate
+    int it = 0;
+    if (active && deg == 1) { xr = -w[1] / w[0]; xi = 0; pr = xr; pi = 0; lag = false; it = 0; }
+    while (__any_sync(0xFFFFFFFFu, active)) {
+        if (!active) continue;
+        const double er = lag ? xr : pr, ei = lag ? xi : pi;
+        const int dsel = lag ? deg : deg0;
+        double br = lag ? w[0] : a0[0], bi = 0, dr = 0, di = 0, fr = 0, fi = 0;
+        double err = fabs(br);
+        const double ax = sqrt(er * er + ei * ei);
+#pragma unroll
+        for (int j = 1; j <= 10; ++j) {
+            if (j <= dsel) {
+                const double cj = lag ? w[j] : a0[j];
+                const double nfr = er * fr - ei * fi + dr, nfi = er * fi + ei * fr + di;
+                const double ndr = er * dr - ei * di + br, ndi = er * di + ei * dr + bi;
+                const double nbr = er * br - ei * bi + cj, nbi = er * bi + ei * br;
+                fr = nfr; fi = nfi; dr = ndr; di = ndi; br = nbr; bi = nbi;
+                err = sqrt(br * br + bi * bi) + ax * err;
+            }
+        }
+        bool rootDone = false;
+        if (lag) {
+            bool conv = false;
+            const double babs = sqrt(br * br + bi * bi);
+            if (babs <= err * 2e-16) conv = true;                 // at the rounding floor of p(x)
+            else {
+                const double b2 = br * br + bi * bi;
+                const double gr = (dr * br + di * bi) / b2, gi = (di * br - dr * bi) / b2;
+                const double g2r = gr * gr - gi * gi, g2i = 2 * gr * gi;
+                const double qr = (fr * br + fi * bi) / b2, qi = (fi * br - fr * bi) / b2;
+                const double hr = g2r - 2 * qr, hi = g2i - 2 * qi;
+                const double tr = (deg - 1) * (deg * hr - g2r), ti = (deg - 1) * (deg * hi - g2i);
+                const double tm = sqrt(tr * tr + ti * ti);
+                double sr = sqrt(fmax(0.0, 0.5 * (tm + tr))), si = sqrt(fmax(0.0, 0.5 * (tm - tr)));
+                if (ti < 0) si = -si;
+                double p1r = gr + sr, p1i = gi + si;
+                const double p2r = gr - sr, p2i = gi - si;
+                const double m1 = p1r * p1r + p1i * p1i, m2 = p2r * p2r + p2i * p2i;
+                if (m2 > m1) { p1r = p2r; p1i = p2i; }
+                const double pm = fmax(m1, m2);
+                double dxr, dxi;
+                if (pm > 0) { dxr = deg * p1r / pm; dxi = -deg * p1i / pm; }
+                else { dxr = (1 + ax) * cos((double)it); dxi = (1 + ax) * sin((double)it); }
+                const double nxr = xr - dxr, nxi = xi - dxi;
+                if (nxr == xr && nxi == xi) conv = true;
+                else {
+                    xr = nxr; xi = nxi;
+                    if (fabs(dxr) + fabs(dxi) <= 1e-16 * (fabs(xr) + fabs(xi))) conv = true;
+                }
+            }
+            ++it;
+            if (conv || it >= 80) { lag = false; pr = xr; pi = xi; it = 0; }
+        } else {
+            // one Newton step on the original polynomial (at most four), kept only while it is a small correction
+            bool stop = false;
+            const double d2 = dr * dr + di * di;
+            if (d2 == 0) stop = true;
+            else {
+                const double sr = (br * dr + bi * di) / d2, si = (bi * dr - br * di) / d2;
+                if (fabs(sr) + fabs(si) > 1e-3 * (fabs(pr) + fabs(pi)) + 1e-300) stop = true;
+                else {
+                    pr -= sr; pi -= si;
+                    if (fabs(sr) + fabs(si) <= 1e-16 * (fabs(pr) + fabs(pi))) stop = true;
+                }
+            }
+            ++it;
+            if (stop || it >= 4) rootDone = true;
+        }
+        if (rootDone) {
+            if (fabs(pi) <= 1e-10) {
+#pragma unroll
+                for (int k = 0; k < 10; ++k) if (k == n) out[k] = pr;
+                ++n;
+            }
+            // deflate the working polynomial by a real factor
+            if (fabs(xi) <= 1e-12 * (1 + fabs(xr)) || deg == 1) {
+                double rem = w[0];
+#pragma unroll
+                for (int j = 1; j < 10; ++j)
+                    if (j < deg) { const double t = w[j] + rem * xr; w[j] = t; rem = t; }
+                deg -= 1;
+            } else {
+                const double pcoef = 2 * xr, qcoef = -(xr * xr + xi * xi);
+                double b0 = w[0], b1 = w[1] + pcoef * b0;
+                w[1] = b1;
+#pragma unroll
+                for (int j = 2; j <= 8; ++j)
+                    if (j <= deg - 2) { const double t = w[j] + pcoef * b1 + qcoef * b0; b0 = b1; b1 = t; w[j] = t; }
+                deg -= 2;
+            }
+            if (deg < 1) active = false;
+            else if (deg == 1) { xr = -w[1] / w[0]; xi = 0; pr = xr; pi = 0; lag = false; it = 0; }
+            else { xr = 0; xi = 0; lag = true; it = 0; }
+        }
+    }
+    if (!(h < nHyp) || nRoots[h] < 0) return;
+    // ascending order (deterministic model order), then drop estimates that polished onto the same root
+    const double inf = __longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) if (k >= n) out[k] = inf;
+#pragma unroll
+    for (int i = 1; i < 10; ++i) {
+#pragma unroll
+        for (int j = i; j > 0; --j) {
+            const double lo = fmin(out[j - 1], out[j]), hi2 = fmax(out[j - 1], out[j]);
+            out[j - 1] = lo; out[j] = hi2;
+        }
+    }
     double* o = scr + h * E5_SCR + 86;
-    for (int k = 0; k < nr; ++k) o[k] = roots[k];
-    nRoots[h] = nr;
+    int m = 0;
+    double last = 0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        if (i < n && (m == 0 || fabs(out[i] - last) > 1e-13 * (fabs(out[i]) + fabs(last)))) { o[m] = out[i]; last = out[i]; ++m; }
+    }
+    nRoots[h] = m;
 }
 
 __global__ void __launch_bounds__(128)
