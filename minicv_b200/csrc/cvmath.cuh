@@ -952,15 +952,16 @@ MCV_HDN inline void laguerre_step_poly(const double* a, int deg, double& xr, dou
             const double ndr = xr * dr - xi * di + br, ndi = xr * di + xi * dr + bi;
             const double nbr = xr * br - xi * bi + a[j], nbi = xr * bi + xi * br;
             fr = nfr; fi = nfi; dr = ndr; di = ndi; br = nbr; bi = nbi;
-            err = sqrt(br * br + bi * bi) + ax * err;
+            err = (fabs(br) + fabs(bi)) + ax * err;           // |b| <= |Re| + |Im|: a bound, no square root per term
         }
-        const double babs = sqrt(br * br + bi * bi);
-        if (babs <= err * 2e-16) return;                      // at the rounding floor of p(x)
-        // G = d/b, G2 = G^2, H = G2 - 2 f / b
         const double b2 = br * br + bi * bi;
-        const double gr = (dr * br + di * bi) / b2, gi = (di * br - dr * bi) / b2;
+        const double floor_ = err * 2e-16;
+        if (b2 <= floor_ * floor_) return;                    // at the rounding floor of p(x)
+        // G = d/b, G2 = G^2, H = G2 - 2 f / b
+        const double ib2 = 1 / b2;
+        const double gr = (dr * br + di * bi) * ib2, gi = (di * br - dr * bi) * ib2;
         const double g2r = gr * gr - gi * gi, g2i = 2 * gr * gi;
-        const double qr = (fr * br + fi * bi) / b2, qi = (fi * br - fr * bi) / b2;
+        const double qr = (fr * br + fi * bi) * ib2, qi = (fi * br - fr * bi) * ib2;
         const double hr = g2r - 2 * qr, hi = g2i - 2 * qi;
         // sq = sqrt((deg-1) * (deg*H - G2))
         const double tr = (deg - 1) * (deg * hr - g2r), ti = (deg - 1) * (deg * hi - g2i);
@@ -972,7 +973,7 @@ MCV_HDN inline void laguerre_step_poly(const double* a, int deg, double& xr, dou
         if (m2 > m1) { p1r = p2r; p1i = p2i; }
         const double pm = fmax(m1, m2);
         double dxr, dxi;
-        if (pm > 0) { dxr = deg * p1r / pm; dxi = -deg * p1i / pm; }
+        if (pm > 0) { const double ipm = deg / pm; dxr = p1r * ipm; dxi = -p1i * ipm; }
         else { dxr = (1 + ax) * cos((double)iter); dxi = (1 + ax) * sin((double)iter); }
         const double nxr = xr - dxr, nxi = xi - dxi;
         if (nxr == xr && nxi == xi) return;
@@ -1005,7 +1006,8 @@ MCV_HDN inline int real_roots10(const double* c, double* out) {
             }
             const double d2 = dr * dr + di * di;
             if (d2 == 0) break;
-            const double sr = (br * dr + bi * di) / d2, si = (bi * dr - br * di) / d2;
+            const double id2 = 1 / d2;
+            const double sr = (br * dr + bi * di) * id2, si = (bi * dr - br * di) * id2;
             // accept the step only while it stays a small correction of the estimate
             if (fabs(sr) + fabs(si) > 1e-3 * (fabs(pr) + fabs(pi)) + 1e-300) break;
             pr -= sr; pi -= si;

@@ -43,18 +43,50 @@ normalize_kernel(const double2* __restrict__ a, const double2* __restrict__ b, i
     o[3] = dadd(dmul(pb.y, invf), ny);
 }
 
-// one correspondence per thread, four pose candidates each
+// The points recoverPose triangulates are those of the input mask (the RANSAC inliers, typically a quarter of the
+// correspondences).  pose_compact_kernel lists them per pair (ordered), so that the triangulation kernel below runs on
+// full blocks of masked points instead of blocks in which three warps of four have nothing to do.
+__global__ void __launch_bounds__(256)
+pose_compact_kernel(const int64_t* __restrict__ off, const uint8_t* __restrict__ ok, const uint8_t* __restrict__ maskIn,
+                    int* __restrict__ list /*[total]*/, int* __restrict__ counts /*[nPairs]*/, uint8_t* __restrict__ cand) {
+    const int p = blockIdx.x;
+    const int64_t base = off[p];
+    const int n = (int)(off[p + 1] - base);
+    if (ok && !ok[p]) { if (threadIdx.x == 0) counts[p] = 0; return; }
+    __shared__ int sWarp[8];
+    __shared__ int sBase;
+    if (threadIdx.x == 0) sBase = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c0 = 0; c0 < n; c0 += 256) {
+        const int i = c0 + threadIdx.x;
+        const bool want = i < n && (!maskIn || maskIn[base + i]);
+        if (i < n) cand[base + i] = 0;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, want);
+        if (lane == 0) sWarp[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 8; ++w) { if (w < warp) before += sWarp[w]; total += sWarp[w]; }
+        if (want) list[base + sBase + before + __popc(bal & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) sBase += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[p] = sBase;
+}
+
+// one masked correspondence per thread, four pose candidates each
 __global__ void __launch_bounds__(128)
 cheirality_kernel(const double* __restrict__ pd, const int64_t* __restrict__ off,
                   const uint8_t* __restrict__ ok, const double* __restrict__ R1,
                   const double* __restrict__ R2, const double* __restrict__ T,
-                  const uint8_t* __restrict__ maskIn, uint8_t* __restrict__ cand /*[total] bit k*/,
+                  const int* __restrict__ list, const int* __restrict__ counts, uint8_t* __restrict__ cand /*[total] bit k*/,
                   int* __restrict__ good4) {
     const int p = blockIdx.y;
     if (ok && !ok[p]) return;
+    const int cnt = min(128, counts[p] - (int)blockIdx.x * 128);
+    if (cnt <= 0) return;
     const int64_t base = off[p];
-    const int n = (int)(off[p + 1] - base);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ double sR[18], sT[3];
     if (threadIdx.x < 9) { sR[threadIdx.x] = R1[9 * p + threadIdx.x]; sR[9 + threadIdx.x] = R2[9 * p + threadIdx.x]; }
     if (threadIdx.x < 3) sT[threadIdx.x] = T[3 * p + threadIdx.x];
@@ -62,24 +94,11 @@ cheirality_kernel(const double* __restrict__ pd, const int64_t* __restrict__ off
     // scratch of the 4 x 4 Jacobi SVDs in thread-interleaved shared memory (as local arrays the resident threads'
     // frames exceed L2 and are written back to DRAM)
     __shared__ double sScr[32 * 128];
-    __shared__ int sIdx[128];
-    __shared__ int sWarpCnt[4];
     double* scr = sScr + threadIdx.x;
-    // Only the points of the input mask (the RANSAC inliers, typically a quarter) are triangulated.  They are
-    // compacted inside the block first, so the SVDs run on full warps instead of on 8 of 32 lanes.
-    const bool want = i < n && (!maskIn || maskIn[base + i]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned wb = __ballot_sync(0xFFFFFFFFu, want);
-    if (lane == 0) sWarpCnt[warp] = __popc(wb);
-    if (i < n && !want) cand[base + i] = 0;
-    __syncthreads();
-    int before = 0, cnt = 0;
-    for (int w = 0; w < 4; ++w) { if (w < warp) before += sWarpCnt[w]; cnt += sWarpCnt[w]; }
-    if (want) sIdx[before + __popc(wb & ((1u << lane) - 1u))] = i;
-    __syncthreads();
     unsigned bits = 0;
     if ((int)threadIdx.x < cnt) {
-        const int j = sIdx[threadIdx.x];
+        const int j = list[base + blockIdx.x * 128 + threadIdx.x];
         const double* q = pd + 4 * (base + j);
         const double tp[3] = {sT[0], sT[1], sT[2]}, tn[3] = {-sT[0], -sT[1], -sT[2]};
         if (cheirality_ok_at<128>(sR, tp, q[0], q[1], q[2], q[3], 50.0, scr)) bits |= 1;
@@ -158,10 +177,13 @@ int recover_pose_batch_device(Context* ctx, cudaStream_t st, const PoseIO& io) {
     const bool wantPose = io.dR || io.dTsel || io.dGood || io.dGood4 || io.dMaskOut;
     if (!wantPose) { kt_end(ctx, st); return 0; }
     if (ctx->ws[21].reserve((size_t)std::max<int64_t>(total, 1) * 32) ||
-        ctx->ws[23].reserve((size_t)std::max<int64_t>(total, 1)))
+        ctx->ws[23].reserve((size_t)std::max<int64_t>(total, 1)) ||
+        ctx->ws[47].reserve((size_t)std::max<int64_t>(total, 1) * 4 + (size_t)nPairs * 4 + 64))
         return -1;
     double* pd = ctx->ws[21].as<double>();
     uint8_t* cand = ctx->ws[23].as<uint8_t>();
+    int* dCounts = ctx->ws[47].as<int>();
+    int* dList = dCounts + nPairs;
     int64_t maxN = 0;
     for (int p = 0; p < nPairs; ++p) maxN = std::max(maxN, io.hOff[p + 1] - io.hOff[p]);
     int* good4 = io.dGood4 ? io.dGood4 : wGood4;
@@ -172,8 +194,10 @@ int recover_pose_batch_device(Context* ctx, cudaStream_t st, const PoseIO& io) {
             reinterpret_cast<const double2*>(io.dA), reinterpret_cast<const double2*>(io.dB), total,
             invf, -io.ppx * invf, -io.ppy * invf, pd);
         MCV_LAUNCH_CHECK();
+        pose_compact_kernel<<<nPairs, 256, 0, st>>>(dOff, io.dOk, io.dMaskIn, dList, dCounts, cand);
+        MCV_LAUNCH_CHECK();
         dim3 g((unsigned)((maxN + 127) / 128), nPairs);
-        cheirality_kernel<<<g, 128, 0, st>>>(pd, dOff, io.dOk, R1, R2, T, io.dMaskIn, cand, good4);
+        cheirality_kernel<<<g, 128, 0, st>>>(pd, dOff, io.dOk, R1, R2, T, dList, dCounts, cand, good4);
         MCV_LAUNCH_CHECK();
     }
     pose_select_kernel<<<(nPairs + 63) / 64, 64, 0, st>>>(nPairs, io.dOk, R1, R2, T, good4, io.dR,

@@ -634,19 +634,20 @@ solve_e_roots_kernel(int64_t nHyp, double* __restrict__ scr, int* __restrict__ n
                 const double ndr = er * dr - ei * di + br, ndi = er * di + ei * dr + bi;
                 const double nbr = er * br - ei * bi + cj, nbi = er * bi + ei * br;
                 fr = nfr; fi = nfi; dr = ndr; di = ndi; br = nbr; bi = nbi;
-                err = sqrt(br * br + bi * bi) + ax * err;
+                err = (fabs(br) + fabs(bi)) + ax * err;           // |b| <= |Re| + |Im|: a bound, no square root per term
             }
         }
         bool rootDone = false;
         if (lag) {
             bool conv = false;
-            const double babs = sqrt(br * br + bi * bi);
-            if (babs <= err * 2e-16) conv = true;                 // at the rounding floor of p(x)
+            const double b2 = br * br + bi * bi;
+            const double floor_ = err * 2e-16;
+            if (b2 <= floor_ * floor_) conv = true;               // at the rounding floor of p(x)
             else {
-                const double b2 = br * br + bi * bi;
-                const double gr = (dr * br + di * bi) / b2, gi = (di * br - dr * bi) / b2;
+                const double ib2 = 1 / b2;
+                const double gr = (dr * br + di * bi) * ib2, gi = (di * br - dr * bi) * ib2;
                 const double g2r = gr * gr - gi * gi, g2i = 2 * gr * gi;
-                const double qr = (fr * br + fi * bi) / b2, qi = (fi * br - fr * bi) / b2;
+                const double qr = (fr * br + fi * bi) * ib2, qi = (fi * br - fr * bi) * ib2;
                 const double hr = g2r - 2 * qr, hi = g2i - 2 * qi;
                 const double tr = (deg - 1) * (deg * hr - g2r), ti = (deg - 1) * (deg * hi - g2i);
                 const double tm = sqrt(tr * tr + ti * ti);
@@ -658,7 +659,7 @@ solve_e_roots_kernel(int64_t nHyp, double* __restrict__ scr, int* __restrict__ n
                 if (m2 > m1) { p1r = p2r; p1i = p2i; }
                 const double pm = fmax(m1, m2);
                 double dxr, dxi;
-                if (pm > 0) { dxr = deg * p1r / pm; dxi = -deg * p1i / pm; }
+                if (pm > 0) { const double ipm = deg / pm; dxr = p1r * ipm; dxi = -p1i * ipm; }
                 else { dxr = (1 + ax) * cos((double)it); dxi = (1 + ax) * sin((double)it); }
                 const double nxr = xr - dxr, nxi = xi - dxi;
                 if (nxr == xr && nxi == xi) conv = true;
@@ -675,7 +676,8 @@ solve_e_roots_kernel(int64_t nHyp, double* __restrict__ scr, int* __restrict__ n
             const double d2 = dr * dr + di * di;
             if (d2 == 0) stop = true;
             else {
-                const double sr = (br * dr + bi * di) / d2, si = (bi * dr - br * di) / d2;
+                const double id2 = 1 / d2;
+                const double sr = (br * dr + bi * di) * id2, si = (bi * dr - br * di) * id2;
                 if (fabs(sr) + fabs(si) > 1e-3 * (fabs(pr) + fabs(pi)) + 1e-300) stop = true;
                 else {
                     pr -= sr; pi -= si;
@@ -1075,18 +1077,23 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
 // ---------------------------------------------------------------------------------------------
 // select: OpenCV's sequential accept rule + adaptive iteration count, replayed over the counts
 // ---------------------------------------------------------------------------------------------
-// One warp per pair.  A window of 32 compacted models is examined at once: a warp prefix-max marks
-// the strict records (the only candidates OpenCV's loop would accept), which are then replayed in
-// order so RANSACUpdateNumIters shrinks the horizon exactly as in the sequential loop.
+// One block per pair.  Only the strict records of the count sequence (counts above everything before them and above
+// modelPoints - 1) can be accepted by OpenCV's loop, and there are few of them (O(log n) for unordered counts), so the
+// scan is split from the replay: every warp takes a contiguous quarter of the compacted model list -- pass 1 finds the
+// quarter maxima, pass 2 re-reads the quarter knowing the maximum of everything before it and appends its records, in
+// order, to a shared list (four independent loads in flight per lane: as one warp per pair walking 32 models at a time
+// this kernel was a chain of dependent DRAM round trips) -- and thread 0 then replays the records in order, shrinking
+// the iteration horizon with RANSACUpdateNumIters exactly as the sequential loop does.
+constexpr int SEL_CAP = 384;      // records kept per warp (a quarter); beyond that thread 0 falls back to the plain scan
+
 __global__ void __launch_bounds__(128)
 select_kernel(const int64_t* __restrict__ off, int nPairs, int maxIters, int maxm, int mp,
               int adaptive, double confidence, const int* __restrict__ nIter,
               const int* __restrict__ flags, const int* __restrict__ iterStart,
               const int* __restrict__ slotList, const int* __restrict__ counts,
               int* __restrict__ best /*[nPairs][4]*/) {
-    const int lane = threadIdx.x & 31;
-    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (p >= nPairs) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = blockIdx.x;
     const int n = (int)(off[p + 1] - off[p]);
     int* o = best + 4 * p;   // compacted index, count, iterations run, iteration*maxm+model
     const int fl = flags[p];
@@ -1094,52 +1101,82 @@ select_kernel(const int64_t* __restrict__ off, int nPairs, int maxIters, int max
     const int* c = counts + (int64_t)p * maxIters * maxm;
     const int* sl = slotList + (int64_t)p * maxIters * maxm;
     if (fl & (PAIR_FAIL | PAIR_DIRECT)) {
-        if (lane == 0) {
+        if (threadIdx.x == 0) {
             o[0] = -1; o[1] = 0; o[2] = 0; o[3] = -1;
             if ((fl & PAIR_DIRECT) && !(fl & PAIR_FAIL) && is[1] - is[0] > 0) { o[0] = 0; o[1] = n; o[2] = 1; o[3] = 0; }
         }
         return;
     }
+    __shared__ int sQMax[4], sCnt[4];
+    __shared__ int sRecK[4][SEL_CAP], sRecX[4][SEL_CAP];
+    const int total = is[min(nIter[p], maxIters)];
+    const int Q = ((total + 3) / 4 + 31) & ~31;
+    const int k0 = warp * Q, k1 = min(total, k0 + Q);
+    // pass 1: maximum of the quarter
+    int m = -1;
+    for (int k = k0 + lane; k < k1; k += 32) m = max(m, c[k]);
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if (lane == 0) sQMax[warp] = m;
+    __syncthreads();
+    int carry = mp - 1;
+    for (int w = 0; w < warp; ++w) carry = max(carry, sQMax[w]);
+    // pass 2: records of the quarter, in order
+    int cnt = 0;
+    if (sQMax[warp] > carry) {               // otherwise nothing in this quarter can be a record
+        for (int w0 = k0; w0 < k1; w0 += 128) {
+            int x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int k = w0 + 32 * u + lane; x[u] = k < k1 ? c[k] : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int pm = x[u];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xFFFFFFFFu, pm, d);
+                    if (lane >= d) pm = max(pm, t);
+                }
+                int excl = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
+                if (lane == 0) excl = -1;
+                const bool rec = x[u] > max(excl, carry);
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, rec);
+                if (rec) {
+                    const int at = cnt + __popc(bal & ((1u << lane) - 1u));
+                    if (at < SEL_CAP) { sRecK[warp][at] = w0 + 32 * u + lane; sRecX[warp][at] = x[u]; }
+                }
+                cnt += __popc(bal);
+                carry = max(carry, __shfl_sync(0xFFFFFFFFu, pm, 31));
+            }
+        }
+    }
+    if (lane == 0) sCnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     // OpenCV checks `iter < niters` once per iteration: every model of an iteration that was
     // started is evaluated even if an earlier model of the same iteration shrank niters.
     int niters = max(maxIters, 1);
-    const int total = is[min(nIter[p], maxIters)];
     int maxGood = 0, bestK = -1, bestSlot = -1, curIt = -1;
-    bool done = false;
-    for (int w = 0; w < total && !done; w += 32) {
-        const int k = w + lane;
-        const int slot = k < total ? sl[k] : 0x7FFFFFFF;
-        const int itk = slot == 0x7FFFFFFF ? 0x7FFFFFFF : slot / maxm;
-        const bool valid = k < total && (itk < niters || itk == curIt);
-        const int x = valid ? c[k] : -1;
-        int pm = x;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xFFFFFFFFu, pm, d);
-            if (lane >= d) pm = max(pm, t);
+    const bool overflow = sCnt[0] > SEL_CAP || sCnt[1] > SEL_CAP || sCnt[2] > SEL_CAP || sCnt[3] > SEL_CAP;
+    auto accept = [&](int k, int x) -> bool {        // false: the horizon shrank past this record's iteration
+        const int slot = sl[k];
+        const int itb = slot / maxm;
+        if (itb != curIt && itb >= niters) return false;
+        curIt = itb; maxGood = x; bestK = k; bestSlot = slot;
+        if (adaptive) niters = min(niters, update_num_iters(confidence, (double)(n - x) / n, mp, niters));
+        return true;
+    };
+    if (!overflow) {
+        bool go = true;
+        for (int w = 0; w < 4 && go; ++w)
+            for (int r = 0; r < sCnt[w] && go; ++r) go = accept(sRecK[w][r], sRecX[w][r]);
+    } else {
+        int run = mp - 1;
+        for (int k = 0; k < total; ++k) {
+            const int x = c[k];
+            if (x > run) { run = x; if (!accept(k, x)) break; }
         }
-        int excl = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
-        if (lane == 0) excl = -1;
-        const bool rec = valid && x > max(max(excl, maxGood), mp - 1);
-        unsigned recs = __ballot_sync(0xFFFFFFFFu, rec);
-        const unsigned inval = __ballot_sync(0xFFFFFFFFu, !valid);
-        while (recs) {
-            const int b = __ffs(recs) - 1;
-            recs &= recs - 1;
-            const int xb = __shfl_sync(0xFFFFFFFFu, x, b);
-            const int itb = __shfl_sync(0xFFFFFFFFu, itk, b);
-            const int sb = __shfl_sync(0xFFFFFFFFu, slot, b);
-            if (itb != curIt && itb >= niters) { done = true; break; }   // horizon shrank past this iteration
-            curIt = itb;
-            maxGood = xb; bestK = w + b; bestSlot = sb;
-            if (adaptive) niters = min(niters, update_num_iters(confidence, (double)(n - xb) / n, mp, niters));
-        }
-        if (inval) done = true;                              // reached the end of the horizon
     }
-    if (lane == 0) {
-        // iterations OpenCV's loop would have executed
-        o[0] = bestK; o[1] = maxGood; o[2] = min(niters, nIter[p]); o[3] = bestSlot;
-    }
+    // iterations OpenCV's loop would have executed
+    o[0] = bestK; o[1] = maxGood; o[2] = min(niters, nIter[p]); o[3] = bestSlot;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1884,7 +1921,7 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
         }
         // ---- select
         kt_begin(ctx, st, KT_SELECT);
-        select_kernel<<<(np + 3) / 4, 128, 0, st>>>(off, np, maxIters, MAXM, MP,
+        select_kernel<<<np, 128, 0, st>>>(off, np, maxIters, MAXM, MP,
                                                     prm.stopMode == MCV_STOP_ADAPTIVE ? 1 : 0,
                                                     prm.confidence, dNIter, dFlags, dIterStart, dSlotList,
                                                     dCounts, dBest);
@@ -1940,7 +1977,7 @@ int ransac_compact(cudaStream_t st, int np, const uint8_t* dNModels, const int* 
 int ransac_select(cudaStream_t st, const int64_t* dOff, int np, int maxIters, int maxm, int mp, bool adaptive,
                   double confidence, const int* dNIter, const int* dFlags, const int* dIterStart,
                   const int* dSlotList, const int* dCounts, int* dBest) {
-    select_kernel<<<(np + 3) / 4, 128, 0, st>>>(dOff, np, maxIters, maxm, mp, adaptive ? 1 : 0, confidence, dNIter,
+    select_kernel<<<np, 128, 0, st>>>(dOff, np, maxIters, maxm, mp, adaptive ? 1 : 0, confidence, dNIter,
                                                 dFlags, dIterStart, dSlotList, dCounts, dBest);
     MCV_LAUNCH_CHECK();
     return 0;
