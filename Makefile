@@ -20,7 +20,20 @@ $(LIB): $(OBJS)
 	@mkdir -p $(dir $(LIB))
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(OBJS) -ldl -lpthread
 
+# Debug variants for the sanitizer runs recorded in profiles/ (never loaded by the package): the homography refit with
+# its thread-0 helpers force-inlined and the 5-point solver composed into one device function -- the two forms round 1
+# saw mis-execute and worked around.
+DBGDIR    := build/dbg
+DBGLIB    := $(DBGDIR)/libMiniCVNative.so
+DBGOBJS   := $(patsubst $(CSRC)/%.cu,$(DBGDIR)/obj/%.o,$(SRCS))
+$(DBGDIR)/obj/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(DBGDIR)/obj
+	$(NVCC) $(NVFLAGS) -DMCV_DEBUG_INLINE_REFIT -DMCV_DEBUG_COMPOSED_E5 -c $< -o $@
+$(DBGLIB): $(DBGOBJS)
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(DBGOBJS) -ldl -lpthread
+debug-variants: $(DBGLIB)
+
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all clean
+.PHONY: all clean debug-variants

@@ -636,7 +636,8 @@ int pnp_ransac_batch_device(Context* ctx, cudaStream_t st, const PnpParams& prm,
 
     const size_t slots = (size_t)maxIters;
     const size_t perProblem = slots * (MODEL_D * 8 + MP * 4 + 16);
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nProblems, ((size_t)1 << 30) / std::max<size_t>(perProblem, 1)));
+    const int chunk = std::min(65535,     // the problem index is gridDim.y of several stage kernels
+                               (int)std::max<size_t>(1, std::min<size_t>((size_t)nProblems, ((size_t)1 << 30) / std::max<size_t>(perProblem, 1))));
     if (ctx->ws[52].reserve((size_t)chunk * slots * MP * 4) ||          // samples
         ctx->ws[53].reserve((size_t)chunk * 8 + 64) ||                  // nIter, flags
         ctx->ws[54].reserve((size_t)chunk * slots * MODEL_D * 8) ||     // models

@@ -82,9 +82,9 @@ cheirality_kernel(const double* __restrict__ pd, const int64_t* __restrict__ off
                   const double* __restrict__ R2, const double* __restrict__ T,
                   const int* __restrict__ list, const int* __restrict__ counts, uint8_t* __restrict__ cand /*[total] bit k*/,
                   int* __restrict__ good4) {
-    const int p = blockIdx.y;
+    const int p = blockIdx.x;            // pairs on grid.x (no 65535 limit), tiles of 128 masked points on grid.y
     if (ok && !ok[p]) return;
-    const int cnt = min(128, counts[p] - (int)blockIdx.x * 128);
+    const int cnt = min(128, counts[p] - (int)blockIdx.y * 128);
     if (cnt <= 0) return;
     const int64_t base = off[p];
     __shared__ double sR[18], sT[3];
@@ -98,7 +98,7 @@ cheirality_kernel(const double* __restrict__ pd, const int64_t* __restrict__ off
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned bits = 0;
     if ((int)threadIdx.x < cnt) {
-        const int j = list[base + blockIdx.x * 128 + threadIdx.x];
+        const int j = list[base + blockIdx.y * 128 + threadIdx.x];
         const double* q = pd + 4 * (base + j);
         const double tp[3] = {sT[0], sT[1], sT[2]}, tn[3] = {-sT[0], -sT[1], -sT[2]};
         if (cheirality_ok_at<128>(sR, tp, q[0], q[1], q[2], q[3], 50.0, scr)) bits |= 1;
@@ -140,10 +140,10 @@ pose_select_kernel(int nPairs, const uint8_t* __restrict__ ok, const double* __r
 __global__ void __launch_bounds__(256)
 pose_mask_kernel(const int64_t* __restrict__ off, const int* __restrict__ choice,
                  const uint8_t* __restrict__ cand, uint8_t* __restrict__ maskOut) {
-    const int p = blockIdx.y;
+    const int p = blockIdx.x;
     const int64_t base = off[p];
     const int n = (int)(off[p + 1] - base);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int k = choice[p];
     maskOut[base + i] = (k >= 0 && ((cand[base + i] >> k) & 1)) ? 1 : 0;
@@ -196,7 +196,8 @@ int recover_pose_batch_device(Context* ctx, cudaStream_t st, const PoseIO& io) {
         MCV_LAUNCH_CHECK();
         pose_compact_kernel<<<nPairs, 256, 0, st>>>(dOff, io.dOk, io.dMaskIn, dList, dCounts, cand);
         MCV_LAUNCH_CHECK();
-        dim3 g((unsigned)((maxN + 127) / 128), nPairs);
+        if ((maxN + 127) / 128 > 65535) { set_error("recoverPose: more than 8.3 M correspondences in one pair"); return -1; }
+        dim3 g(nPairs, (unsigned)((maxN + 127) / 128));
         cheirality_kernel<<<g, 128, 0, st>>>(pd, dOff, io.dOk, R1, R2, T, dList, dCounts, cand, good4);
         MCV_LAUNCH_CHECK();
     }
@@ -204,7 +205,7 @@ int recover_pose_batch_device(Context* ctx, cudaStream_t st, const PoseIO& io) {
                                                           io.dTsel, io.dGood, wChoice);
     MCV_LAUNCH_CHECK();
     if (io.dMaskOut && total > 0) {
-        dim3 g((unsigned)((maxN + 255) / 256), nPairs);
+        dim3 g(nPairs, (unsigned)((maxN + 255) / 256));
         pose_mask_kernel<<<g, 256, 0, st>>>(dOff, wChoice, cand, io.dMaskOut);
         MCV_LAUNCH_CHECK();
     }

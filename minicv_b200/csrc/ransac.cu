@@ -764,6 +764,22 @@ solve_e_models_kernel(int64_t nHyp, const double* __restrict__ scr, const int* _
     if (live && r == 0) nModels[h] = (uint8_t)__popc(grp);
 }
 
+#ifdef MCV_DEBUG_COMPOSED_E5
+// Debug build only: the whole 5-point solver as ONE device function per thread (cvmath.cuh e_solve5), the form round 1
+// saw disagree with the host build of the same source; kept buildable for the sanitizer runs recorded in profiles/.
+__global__ void __launch_bounds__(64)
+five_point_composed_kernel(const double* __restrict__ a, const double* __restrict__ b, int nSets,
+                           double* __restrict__ Es, int* __restrict__ counts) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nSets) return;
+    double pa[10], pb[10], E[90];
+    for (int k = 0; k < 10; ++k) { pa[k] = a[10 * (int64_t)h + k]; pb[k] = b[10 * (int64_t)h + k]; }
+    const int n = e_solve5(pa, pb, E);
+    for (int k = 0; k < 9 * n; ++k) Es[90 * (int64_t)h + k] = E[k];
+    counts[h] = n;
+}
+#endif
+
 __global__ void __launch_bounds__(256)
 widen_counts_kernel(const uint8_t* __restrict__ in, int n, int* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1396,13 +1412,19 @@ finalize_plain_kernel(const float4* __restrict__ pf, const double* __restrict__ 
 }
 
 // Thread-0 helpers of the homography refit, kept out of line so the kernel's register and
-// stack footprint stay small.
+// stack footprint stay small.  -DMCV_DEBUG_INLINE_REFIT builds the fully inlined form that round 1 saw mis-execute
+// (eigenvectors returned as the identity) -- kept buildable for the sanitizer runs recorded in profiles/.
+#ifdef MCV_DEBUG_INLINE_REFIT
+#define MCV_REFIT_NOINLINE __forceinline__
+#else
+#define MCV_REFIT_NOINLINE __noinline__
+#endif
 // H from the 45 upper-triangle sums of L'L (runKernel of the refit), executed by one warp: the symmetric 9 x 9
 // eigen-decomposition (cvmath.cuh, jacobi_eigen_sym: same operations) is the longest serial stretch of the refit,
 // and inside a Jacobi rotation every element update is independent, so lanes 0-8 take the column / row updates of L
 // and lanes 16-24 the eigenvector rows.  No sum changes its order (the rotation angle and the convergence sums are
 // computed redundantly by every lane, in the serial order), so H is bit-identical to the single-thread form's.
-__device__ __noinline__ void h_from_ltl_warp(const double* ltl45, double cmx, double cmy, double cMx, double cMy,
+__device__ MCV_REFIT_NOINLINE void h_from_ltl_warp(const double* ltl45, double cmx, double cmy, double cMx, double cMy,
                                              double smx, double smy, double sMx, double sMy, double* H,
                                              double* L /*smem [81]*/, double* V /*smem [81]*/) {
     const int lane = threadIdx.x & 31;
@@ -1467,7 +1489,7 @@ __device__ __noinline__ void h_from_ltl_warp(const double* ltl45, double cmx, do
 }
 
 // one LM trial step: d = solve(A + lambda*diag(D), v), xd = x - d
-__device__ __noinline__ void lm_trial(const double* A, const double* v, const double* D, double lam,
+__device__ MCV_REFIT_NOINLINE void lm_trial(const double* A, const double* v, const double* D, double lam,
                                       const double* x, double* d, double* xd) {
     double Ap[64], vv[8], dd[8];
     for (int k = 0; k < 64; ++k) Ap[k] = A[k];
@@ -1476,7 +1498,7 @@ __device__ __noinline__ void lm_trial(const double* A, const double* v, const do
     for (int r = 0; r < 8; ++r) { d[r] = dd[r]; xd[r] = x[r] - dd[r]; }
 }
 
-__device__ __noinline__ double lm_reseed(const double* A) {
+__device__ MCV_REFIT_NOINLINE double lm_reseed(const double* A) {
     double M[64];
     for (int k = 0; k < 64; ++k) M[k] = A[k];
     return max_diag_pinv_sym<8>(M);
@@ -1774,6 +1796,7 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
     // pair chunks bound the per-hypothesis workspaces (~1 GB of models at most)
     const size_t perPair = (size_t)maxIters * MAXM * 72;
     int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nPairs, ((size_t)1 << 30) / std::max<size_t>(perPair, 1)));
+    chunk = std::min(chunk, 65535);      // the pair index is gridDim.y of several stage kernels
     const size_t slots = (size_t)maxIters * MAXM;
     if (ctx->ws[12].reserve((size_t)chunk * maxIters * MP * 4) ||       // samples
         ctx->ws[13].reserve((size_t)chunk * 8 + 64) ||                  // nIter, flags
@@ -1986,6 +2009,11 @@ int ransac_select(cudaStream_t st, const int64_t* dOff, int np, int maxIters, in
 int five_point_device(Context* ctx, cudaStream_t st, const double* dA, const double* dB, int nSets, double* dEs,
                       int* dCounts) {
     if (nSets <= 0) return 0;
+#ifdef MCV_DEBUG_COMPOSED_E5
+    five_point_composed_kernel<<<(nSets + 63) / 64, 64, 0, st>>>(dA, dB, nSets, dEs, dCounts);
+    MCV_LAUNCH_CHECK();
+    return 0;
+#endif
     const size_t n = (size_t)nSets;
     if (ctx->ws[68].reserve(n * E5_SCR * 8) || ctx->ws[69].reserve(n * 4 + n + 64)) return -1;
     double* scr = ctx->ws[68].as<double>();

@@ -190,6 +190,7 @@ int scale_costs_device(Context* ctx, cudaStream_t st, const double* dCams, const
                        const double* dScales, const uint8_t* dScaleOk, const int64_t* dScaleOff, int64_t maxScales,
                        double* dCosts) {
     if (nProblems <= 0 || maxScales <= 0) return 0;
+    if (nProblems > 65535) { set_error("scale search: at most 65535 problems per call (split the batch)"); return -1; }
     // the sum over the observations cannot be split (its order is the result), so parallelism is candidates x
     // problems only: narrow blocks when that does not fill the machine
     int threads = 128;
