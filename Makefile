@@ -28,7 +28,7 @@ DBGLIB    := $(DBGDIR)/libMiniCVNative.so
 DBGOBJS   := $(patsubst $(CSRC)/%.cu,$(DBGDIR)/obj/%.o,$(SRCS))
 $(DBGDIR)/obj/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(DBGDIR)/obj
-	$(NVCC) $(NVFLAGS) -DMCV_DEBUG_INLINE_REFIT -DMCV_DEBUG_COMPOSED_E5 -c $< -o $@
+	$(NVCC) $(NVFLAGS) -DMCV_DEBUG_INLINE_REFIT -DMCV_DEBUG_COMPOSED_E5 $(DBGEXTRA) -c $< -o $@
 $(DBGLIB): $(DBGOBJS)
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(DBGOBJS) -ldl -lpthread
 debug-variants: $(DBGLIB)

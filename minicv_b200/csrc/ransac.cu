@@ -777,6 +777,20 @@ five_point_composed_kernel(const double* __restrict__ a, const double* __restric
     const int n = e_solve5(pa, pb, E);
     for (int k = 0; k < 9 * n; ++k) Es[90 * (int64_t)h + k] = E[k];
     counts[h] = n;
+#ifdef MCV_DEBUG_E5_TRACE
+    if (h == 0) {
+        double EE[36], bb[39], coef[11], roots[10];
+        e5_stage1(pa, pb, EE, bb, coef);
+        const int nr = real_roots10(coef, roots);
+        printf("composed n=%d staged-in-thread nr=%d\n", n, nr);
+        for (int r = 0; r < nr; ++r) {
+            double Er[9];
+            const bool okr = e5_root_to_E(EE, bb, roots[r], Er);
+            printf("  root %d z=%.17g ok=%d E0=%.15g E8=%.15g | composed E0=%.15g E8=%.15g\n", r, roots[r], (int)okr, Er[0], Er[8],
+                   r < n ? E[9 * r] : 0., r < n ? E[9 * r + 8] : 0.);
+        }
+    }
+#endif
 }
 #endif
 
