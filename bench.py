@@ -388,23 +388,35 @@ def host_path_configs(lib, local, rank, world, barrier, reduce_max, with_cpu):
 
 
 def h2d_ceiling(lib, local, world, barrier, all_gather_floats):
-    """The box's host->device ceiling: every rank copies 256 MiB pinned blocks at the same time (one
-    cudaMemcpyAsync per copy, CUDA events around 8 of them), alone and with a concurrent device->host stream."""
-    barrier()
-    up = lib.mcvMeasureCopyBandwidth(local, 256 << 20, 8, 0, 0)
-    barrier()
-    both = lib.mcvMeasureCopyBandwidth(local, 256 << 20, 8, 2, 0)
+    """The box's host<->device ceiling, measured with every rank copying AT THE SAME TIME: each rank allocates 64 MiB
+    pinned + device blocks (mcvCopyProbeCreate), all ranks meet at a barrier, then every rank keeps its copy engines busy
+    for 0.6 s of wall time (one cudaMemcpyAsync per copy, CUDA events around the whole window) -- host->device alone,
+    and in the 4 : 1 up : down byte mix of the C2 host-buffer path."""
+    import ctypes as C
+    from minicv_b200 import native
+    probe = lib.mcvCopyProbeCreate(local, 64 << 20)
+    if not probe:
+        raise RuntimeError("mcvCopyProbeCreate failed: " + native.last_error())
+    out = (C.c_double * 2)()
+    res = {}
+    for name, direction in (("h2d_only", 0), ("c2_mix", 3), ("both_1to1", 2)):
+        barrier()
+        native.check(lib.mcvCopyProbeRun(probe, 0.6, direction, out), "mcvCopyProbeRun")
+        res[name] = (all_gather_floats(out[0]), all_gather_floats(out[1]))
+    lib.mcvCopyProbeDestroy(probe)
     barrier()
     page = lib.mcvMeasureCopyBandwidth(local, 256 << 20, 4, 0, 1)
     barrier()
     plain = lib.mcvMeasureCopyBandwidth(local, 256 << 20, 2, 0, 2)
-    ups = all_gather_floats(up); boths = all_gather_floats(both); pages = all_gather_floats(page); plains = all_gather_floats(plain)
-    return {"h2d_pinned_gbs_per_rank": ups, "h2d_pinned_gbs_aggregate": float(sum(ups)),
-            "h2d_plus_d2h_pinned_gbs_aggregate": float(sum(boths)),
+    pages = all_gather_floats(page); plains = all_gather_floats(plain)
+    return {"h2d_pinned_gbs_per_rank": res["h2d_only"][0], "h2d_pinned_gbs_aggregate": float(sum(res["h2d_only"][0])),
+            "c2_mix_h2d_gbs_aggregate": float(sum(res["c2_mix"][0])), "c2_mix_d2h_gbs_aggregate": float(sum(res["c2_mix"][1])),
+            "both_1to1_h2d_gbs_aggregate": float(sum(res["both_1to1"][0])), "both_1to1_d2h_gbs_aggregate": float(sum(res["both_1to1"][1])),
             "h2d_pageable_ring_gbs_aggregate": float(sum(pages)), "h2d_pageable_plain_gbs_aggregate": float(sum(plains)),
             "copy_threads": int(lib.mcvCopyThreads()),
-            "how": "all ranks at once: 8 x 256 MiB cudaMemcpyAsync from cudaMallocHost memory per rank, CUDA events on the "
-                   "copy stream (mcvMeasureCopyBandwidth); 'plus_d2h' runs a device->host stream beside it and sums both"}
+            "how": "all ranks at once after a barrier: 0.6 s of back-to-back 64 MiB cudaMemcpyAsync from cudaMallocHost memory "
+                   "per rank, CUDA events around the window (mcvCopyProbeRun); c2_mix = one block device->host for every four "
+                   "host->device (the byte mix of the timed C2 call), both_1to1 = equal bytes each way"}
 
 
 STAGE_NAMES = {0: "matcher", 1: "expand_bits_kernel", 2: "knn2_finalize_kernel", 3: "l2", 10: "prep_points_kernel",
@@ -1096,10 +1108,13 @@ def run_ours(args):
                         "api": "cvMatchKnn2Batch, ordinary pageable numpy arrays in and out (what a P/Invoke caller passes): "
                                "staged through the library's pinned ring by its copy threads",
                         "plain_cudaMemcpyAsync": world * P / e2e_plain_s, "copy_threads": ceiling["copy_threads"]},
-           "h2d": dict(ceiling, e2e_h2d_gbs=e2e_h2d_gbs,
-                       frac_of_h2d_ceiling=e2e_h2d_gbs / ceiling["h2d_pinned_gbs_aggregate"] if ceiling["h2d_pinned_gbs_aggregate"] > 0 else None,
-                       note="e2e_h2d_gbs = bytes the e2e step moves host->device per second over all ranks; the ceiling is the "
-                            "aggregate rate of bare pinned copies issued by all ranks at once on this box"),
+           "h2d": dict(ceiling, e2e_h2d_gbs=e2e_h2d_gbs, e2e_d2h_gbs=world * d2h_bytes / e2e_s / 1e9,
+                       frac_of_h2d_ceiling=e2e_h2d_gbs / ceiling["c2_mix_h2d_gbs_aggregate"] if ceiling["c2_mix_h2d_gbs_aggregate"] > 0 else None,
+                       frac_of_h2d_only_ceiling=e2e_h2d_gbs / ceiling["h2d_pinned_gbs_aggregate"] if ceiling["h2d_pinned_gbs_aggregate"] > 0 else None,
+                       note="e2e_h2d_gbs = bytes the e2e step moves host->device per second over all ranks; frac_of_h2d_ceiling "
+                            "divides it by the host->device rate bare pinned copies reach on this box when all ranks copy at "
+                            "once WITH the same share of device->host traffic beside them (c2_mix); frac_of_h2d_only_ceiling by "
+                            "the rate with no return traffic"),
            "others": others}
     if cpu is not None and cpu_others:
         cpu["others"] = cpu_others

@@ -150,6 +150,13 @@ MCV_API int mcvCopyThreads(void);
  * 1 = pageable through the staging ring, 2 = pageable through plain cudaMemcpyAsync.  < 0 on error.  bench.py runs
  * it on every rank at once to measure the box's aggregate ceiling. */
 MCV_API double mcvMeasureCopyBandwidth(int device, int64_t bytes, int reps, int direction, int hostKind);
+/* Two-phase form for measuring several devices AT ONCE (one thread or process per device): Create allocates pinned
+ * host and device blocks of `bytes`; after the callers have synchronised among themselves, Run keeps the copy
+ * engines busy for about `seconds` of wall time (direction 0 host->device, 1 device->host, 2 both, 3 both in the
+ * 4 : 1 byte mix of the C2 host-buffer path) and writes outGbs[0] = host->device, outGbs[1] = device->host GB/s. */
+MCV_API void* mcvCopyProbeCreate(int device, int64_t bytes);
+MCV_API int mcvCopyProbeRun(void* probe, double seconds, int direction, double* outGbs);
+MCV_API void mcvCopyProbeDestroy(void* probe);
 /* Library build tag: "minicv_b200 sm_100a <date>". */
 MCV_API const char* mcvBuildInfo(void);
 

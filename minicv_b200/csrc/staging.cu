@@ -44,7 +44,7 @@ struct CopyPool {
         int n = e ? atoi(e) : 0;
         if (n <= 0) {
             const unsigned hc = std::thread::hardware_concurrency();
-            n = hc >= 16 ? 4 : hc >= 8 ? 3 : hc >= 4 ? 2 : 1;
+            n = hc >= 32 ? 8 : hc >= 16 ? 4 : hc >= 8 ? 3 : hc >= 4 ? 2 : 1;
         }
         n = std::min(n, 32);
         nThreads = n;
@@ -317,6 +317,112 @@ MCV_API double mcvMeasureCopyBandwidth(int device, int64_t bytes, int reps, int 
     else { free(h0); free(h1); }
     cudaGetLastError();
     return result;
+}
+
+// Two-phase form of the same probe, for measuring SEVERAL devices at once (one caller thread or process per device):
+// Create allocates the pinned host and the device blocks, the callers synchronise among themselves (bench.py: a
+// barrier), Run then keeps both copy directions busy for about `seconds` of wall time and returns what it moved per
+// second (direction: 0 host->device, 1 device->host, 2 both concurrently, 3 both in the 4 : 1 byte mix of the C2
+// host-buffer path; out[0] = host->device GB/s, out[1] = device->host GB/s).  Long, simultaneous windows are what makes the per-device figures add up to the box's ceiling.
+struct CopyProbe {
+    uint32_t magic = 0x4D435650u;
+    int device = 0;
+    size_t bytes = 0;
+    void *h0 = nullptr, *h1 = nullptr, *d0 = nullptr, *d1 = nullptr;
+    cudaStream_t sUp = nullptr, sDown = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, f0 = nullptr, f1 = nullptr;
+};
+
+MCV_API void mcvCopyProbeDestroy(void* handle) {
+    CopyProbe* p = static_cast<CopyProbe*>(handle);
+    if (!p || p->magic != 0x4D435650u) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(p->device);
+    if (p->sUp) { cudaStreamSynchronize(p->sUp); cudaStreamDestroy(p->sUp); }
+    if (p->sDown) { cudaStreamSynchronize(p->sDown); cudaStreamDestroy(p->sDown); }
+    for (cudaEvent_t e : {p->e0, p->e1, p->f0, p->f1}) if (e) cudaEventDestroy(e);
+    if (p->d0) cudaFree(p->d0);
+    if (p->d1) cudaFree(p->d1);
+    if (p->h0) cudaFreeHost(p->h0);
+    if (p->h1) cudaFreeHost(p->h1);
+    p->magic = 0;
+    delete p;
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+}
+
+MCV_API void* mcvCopyProbeCreate(int device, int64_t bytes) {
+    MCV_API_ENTER();
+    using namespace mcv;
+    if (bytes <= 0) { set_error("mcvCopyProbeCreate: bad size"); return nullptr; }
+    Context* c = get_context(device);      // validates the device and makes it current
+    if (!c) return nullptr;
+    CopyProbe* p = new CopyProbe();
+    p->device = c->device;
+    p->bytes = (size_t)bytes;
+    bool ok = cudaMallocHost(&p->h0, p->bytes) == cudaSuccess && cudaMallocHost(&p->h1, p->bytes) == cudaSuccess &&
+              cudaMalloc(&p->d0, p->bytes) == cudaSuccess && cudaMalloc(&p->d1, p->bytes) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->sUp, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->sDown, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&p->e0) == cudaSuccess && cudaEventCreate(&p->e1) == cudaSuccess &&
+              cudaEventCreate(&p->f0) == cudaSuccess && cudaEventCreate(&p->f1) == cudaSuccess;
+    if (ok) {
+        memset(p->h0, 1, p->bytes);
+        memset(p->h1, 2, p->bytes);
+        ok = cudaMemcpyAsync(p->d0, p->h0, p->bytes, cudaMemcpyHostToDevice, p->sUp) == cudaSuccess &&
+             cudaMemcpyAsync(p->h1, p->d1, p->bytes, cudaMemcpyDeviceToHost, p->sDown) == cudaSuccess &&
+             cudaStreamSynchronize(p->sUp) == cudaSuccess && cudaStreamSynchronize(p->sDown) == cudaSuccess;
+    }
+    if (!ok) {
+        set_error("mcvCopyProbeCreate: allocation / warm-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+        mcvCopyProbeDestroy(p);
+        return nullptr;
+    }
+    return p;
+}
+
+MCV_API int mcvCopyProbeRun(void* handle, double seconds, int direction, double* outGbs) {
+    MCV_API_ENTER();
+    using namespace mcv;
+    CopyProbe* p = static_cast<CopyProbe*>(handle);
+    if (!p || p->magic != 0x4D435650u || direction < 0 || direction > 3 || !outGbs || !(seconds > 0)) {
+        set_error("mcvCopyProbeRun: bad arguments");
+        return -1;
+    }
+    if (!get_context(p->device)) return -1;
+    const bool up = direction != 1, down = direction != 0;
+    // calibrate: copies per batch so that a batch lasts ~10 ms, then batches until the wall time is spent
+    const int per = 4 * (int)std::max<double>(1.0, 0.010 * 40e9 / (double)p->bytes / 4);
+    int64_t nUp = 0, nDown = 0;
+    if (up) cudaEventRecord(p->e0, p->sUp);
+    if (down) cudaEventRecord(p->f0, p->sDown);
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (;;) {
+        for (int i = 0; i < per; ++i) {
+            if (up) { MCV_CUDA_TRY(cudaMemcpyAsync(p->d0, p->h0, p->bytes, cudaMemcpyHostToDevice, p->sUp)); ++nUp; }
+            // direction 3: the byte mix of the C2 host-buffer path, one block back for every four blocks up
+            if (down && (direction != 3 || (i & 3) == 3)) {
+                MCV_CUDA_TRY(cudaMemcpyAsync(p->h1, p->d1, p->bytes, cudaMemcpyDeviceToHost, p->sDown));
+                ++nDown;
+            }
+        }
+        // one batch in flight at a time: the loop tracks the wall clock and both directions stay concurrent
+        if (up) MCV_CUDA_TRY(cudaStreamSynchronize(p->sUp));
+        if (down) MCV_CUDA_TRY(cudaStreamSynchronize(p->sDown));
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) >= seconds) break;
+    }
+    if (up) cudaEventRecord(p->e1, p->sUp);
+    if (down) cudaEventRecord(p->f1, p->sDown);
+    MCV_CUDA_TRY(cudaStreamSynchronize(p->sUp));
+    MCV_CUDA_TRY(cudaStreamSynchronize(p->sDown));
+    outGbs[0] = outGbs[1] = 0;
+    float ms = 0;
+    if (up && cudaEventElapsedTime(&ms, p->e0, p->e1) == cudaSuccess && ms > 0) outGbs[0] = (double)p->bytes * nUp / (ms * 1e6);
+    if (down && cudaEventElapsedTime(&ms, p->f0, p->f1) == cudaSuccess && ms > 0) outGbs[1] = (double)p->bytes * nDown / (ms * 1e6);
+    return 0;
 }
 
 }  // extern "C"

@@ -80,6 +80,9 @@ SIGNATURES = {
     "mcvSetStagingMode": (_i, [_i]),
     "mcvCopyThreads": (_i, []),
     "mcvMeasureCopyBandwidth": (_d, [_i, _i64, _i, _i, _i]),
+    "mcvCopyProbeCreate": (_vp, [_i, _i64]),
+    "mcvCopyProbeRun": (_i, [_vp, _d, _i, _vp]),
+    "mcvCopyProbeDestroy": (None, [_vp]),
     "mcvNcclVersion": (_i, []),
     "mcvShardCommUniqueId": (_i, [_vp]),
     "mcvShardCommInit": (_vp, [_vp, _i, _i, _i]),
