@@ -997,7 +997,9 @@ MCV_HDN inline int real_roots10(const double* c, double* out) {
         // polish on the original polynomial: complex Newton steps (local, so the polished value
         // stays with the root the deflated estimate belongs to)
         double pr = xr, pi = xi;
-        for (int it = 0; it < 4; ++it) {
+        // a clearly complex estimate cannot polish into a real root (|Im| <= 1e-10): it is only deflated away
+        const int polishSteps = fabs(xi) > 1e-4 * (1 + fabs(xr)) ? 0 : 4;
+        for (int it = 0; it < polishSteps; ++it) {
             double br = a0[0], bi = 0, dr = 0, di = 0;
             for (int j = 1; j <= deg0; ++j) {
                 const double ndr = pr * dr - pi * di + br, ndi = pr * di + pi * dr + bi;

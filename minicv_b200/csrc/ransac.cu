@@ -669,7 +669,13 @@ solve_e_roots_kernel(int64_t nHyp, double* __restrict__ scr, int* __restrict__ n
                 }
             }
             ++it;
-            if (conv || it >= 80) { lag = false; pr = xr; pi = xi; it = 0; }
+            if (conv || it >= 80) {
+                pr = xr; pi = xi; it = 0;
+                // a clearly complex estimate cannot polish into a real root (|Im| <= 1e-10): skip its Newton steps on
+                // the full-degree polynomial -- it is only deflated away (same rule in cvmath.cuh real_roots10)
+                if (fabs(xi) > 1e-4 * (1 + fabs(xr))) rootDone = true;
+                else lag = false;
+            }
         } else {
             // one Newton step on the original polynomial (at most four), kept only while it is a small correction
             bool stop = false;
