@@ -100,8 +100,11 @@ int match_batch_host(Context* ctx, const uint8_t* query, const int64_t* queryOff
         const int64_t t0 = trainOffsets[p0], t1 = trainOffsets[p1];
         // copy-in of chunk c, then its (small) control copy right behind it: the copy engine serves
         // its queue in submission order, so control copies must not sit behind later bulk copies
-        if (q1 > q0 && h2d_copy(ctx, dQ + q0 * rb, query + q0 * rb, (size_t)(q1 - q0) * rb, sIn, pageQ)) return -1;
-        if (t1 > t0 && h2d_copy(ctx, dT + t0 * rb, train + t0 * rb, (size_t)(t1 - t0) * rb, sIn, pageT)) return -1;
+        {
+            const H2dSeg segs[2] = {{dQ + q0 * rb, query + q0 * rb, (size_t)(q1 - q0) * rb, pageQ},
+                                    {dT + t0 * rb, train + t0 * rb, (size_t)(t1 - t0) * rb, pageT}};
+            if (h2d_copy_segs(ctx, segs, 2, sIn)) return -1;
+        }
         MCV_CUDA_TRY(cudaEventRecord(ev[3 * c], sIn));
         MCV_CUDA_TRY(cudaStreamWaitEvent(sK, ev[3 * c], 0));
         if (q1 > q0) {

@@ -16,6 +16,7 @@
 #include <condition_variable>
 #include <functional>
 #include <thread>
+#include <vector>
 #include <stdlib.h>
 
 namespace mcv {
@@ -118,8 +119,9 @@ void parallel_memcpy(void* dst, const void* src, size_t bytes) {
 
 // ---- pinned ring --------------------------------------------------------------------------------------------
 struct StageRing {
-    static constexpr int SLOTS = 8;
-    static constexpr size_t SLOT_BYTES = 4u << 20;
+    static constexpr int SLOTS = 16;
+    static constexpr size_t SLOT_BYTES = 2u << 20;
+    uint64_t cursor = 0;                     // pieces staged so far (next slot = cursor % SLOTS)
     void*       slot[SLOTS] = {};
     cudaEvent_t ev[SLOTS] = {};
     std::atomic<uint64_t> turn[SLOTS];       // number of pieces that went through the slot
@@ -165,17 +167,29 @@ bool host_is_pageable(const void* p) {
 
 static std::atomic<int> g_stage_mode{0};     // 0 = auto (ring for pageable), 1 = never stage (plain cudaMemcpyAsync)
 
-int h2d_copy(Context* c, void* dDst, const void* hSrc, size_t bytes, cudaStream_t s, bool pageable) {
-    if (bytes == 0) return 0;
-    if (!pageable || bytes < (256u << 10) || g_stage_mode.load(std::memory_order_relaxed) == 1) {
-        MCV_CUDA_TRY(cudaMemcpyAsync(dDst, hSrc, bytes, cudaMemcpyHostToDevice, s));
-        return 0;
+int h2d_copy_segs(Context* c, const H2dSeg* segs, int nSegs, cudaStream_t s) {
+    // direct DMA for pinned / small segments; everything else is cut into slot-sized pieces
+    struct Piece { char* dst; const char* src; size_t len; };
+    std::vector<Piece> pieces;
+    const size_t SB = StageRing::SLOT_BYTES;
+    const bool noStage = g_stage_mode.load(std::memory_order_relaxed) == 1;
+    for (int i = 0; i < nSegs; ++i) {
+        const H2dSeg& g = segs[i];
+        if (g.bytes == 0) continue;
+        if (!g.pageable || g.bytes < (256u << 10) || noStage) {
+            MCV_CUDA_TRY(cudaMemcpyAsync(g.dst, g.src, g.bytes, cudaMemcpyHostToDevice, s));
+            continue;
+        }
+        for (size_t o = 0; o < g.bytes; o += SB)
+            pieces.push_back(Piece{(char*)g.dst + o, (const char*)g.src + o, std::min(SB, g.bytes - o)});
     }
+    const size_t n = pieces.size();
+    if (n == 0) return 0;
     StageRing* r = ring_of(c);
     if (!r) return -1;
-    const size_t SB = StageRing::SLOT_BYTES;
-    const size_t n = (bytes + SB - 1) / SB;
-    // piece i uses slot (base + i) % SLOTS as that slot's next turn; turns hand the slot from piece to piece in order
+    // piece i takes slot (cursor + i) % SLOTS as that slot's next turn: the ring is walked round-robin across calls,
+    // and turns hand a slot from piece to piece in order
+    const uint64_t cursor = r->cursor;
     uint64_t base[StageRing::SLOTS];
     for (int k = 0; k < StageRing::SLOTS; ++k) base[k] = r->turn[k].load();
     std::atomic<size_t> next{0};
@@ -186,23 +200,29 @@ int h2d_copy(Context* c, void* dDst, const void* hSrc, size_t bytes, cudaStream_
         for (;;) {
             const size_t i = next.fetch_add(1);
             if (i >= n) break;
-            const int k = (int)(i % StageRing::SLOTS);
+            const int k = (int)((cursor + i) % StageRing::SLOTS);
+            // pieces of this call that used slot k before piece i: those with index i - SLOTS, i - 2 SLOTS, ...
             const uint64_t myTurn = base[k] + i / StageRing::SLOTS;
             while (r->turn[k].load(std::memory_order_acquire) != myTurn) std::this_thread::yield();
             if (myTurn > 0 && cudaEventSynchronize(r->ev[k]) != cudaSuccess) err.store(1);
-            const size_t o = i * SB, len = std::min(SB, bytes - o);
-            memcpy(r->slot[k], (const char*)hSrc + o, len);
-            if (cudaMemcpyAsync((char*)dDst + o, r->slot[k], len, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+            memcpy(r->slot[k], pieces[i].src, pieces[i].len);
+            if (cudaMemcpyAsync(pieces[i].dst, r->slot[k], pieces[i].len, cudaMemcpyHostToDevice, s) != cudaSuccess ||
                 cudaEventRecord(r->ev[k], s) != cudaSuccess)
                 err.store(1);
             r->turn[k].store(myTurn + 1, std::memory_order_release);
         }
     });
+    r->cursor = cursor + n;
     if (err.load()) {
         set_error("staged host->device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         return -1;
     }
     return 0;
+}
+
+int h2d_copy(Context* c, void* dDst, const void* hSrc, size_t bytes, cudaStream_t s, bool pageable) {
+    const H2dSeg g{dDst, hSrc, bytes, pageable};
+    return h2d_copy_segs(c, &g, 1, s);
 }
 
 }  // namespace mcv
