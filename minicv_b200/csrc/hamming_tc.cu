@@ -22,11 +22,13 @@
 //     (value, 0xFFFF - chunk number, column) and merged into the row's running top-2 with six
 //     more min/max -- again no branch, so a warp never serialises on the rows that improve.
 //
-// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..17 = epilogue.  TMEM lane quarter = warp % 4; each group of four warps owns one of the
-// four accumulator buffers, i.e. one (query tile, stage parity), and reads all 128 columns of it.
-// One CTA sweeps the train rows of its split for 256 queries (two M = 128 tiles share every train
-// stage, halving L2 -> SM traffic).  Results leave the kernel as packed keys
+// Warp roles (64 + (12 + 4) * 32 = 576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..13 = epilogue (three groups of four warps, one group per 128-column accumulator buffer; TMEM lane quarter =
+// warp % 4), warps 14..17 = stagers that expand the NEXT work item's packed query rows into TMEM (columns 0..127)
+// while the current item is swept.  TMEM: query tiles in the first 128 columns, NBUF = 3 accumulator buffers in the
+// remaining 384.  One CTA is persistent (one per SM) and walks (query tile, train split) work items; per item it
+// sweeps the train rows of its split for 256 queries (two M = 128 tiles share every train stage, halving L2 -> SM
+// traffic).  Results leave the kernel as packed keys
 // (dist << 32) | trainIdx and go through the same finalize kernel as the integer-pipe engine
 // (hamming_knn.cu), so tie-breaking is identical.
 #include "knn.cuh"

@@ -21,6 +21,9 @@
 
 #include <algorithm>
 
+// Built only with -DMCV_WITH_TC2 (make EXTRA=-DMCV_WITH_TC2): the engine was evaluated and rejected (41.5 ms per C2
+// step); the default library answers "not supported" for engine 3 and falls back to the int8 engine.
+#ifdef MCV_WITH_TC2
 namespace mcv {
 namespace {
 
@@ -425,3 +428,11 @@ int launch_hamming_knn2_tc2(Context* ctx, cudaStream_t stream, const KnnArgs& a)
 }
 
 }  // namespace mcv
+
+#else
+#include "knn.cuh"
+namespace mcv {
+bool hamming_tc2_supported(int) { return false; }
+int launch_hamming_knn2_tc2(Context*, cudaStream_t, const KnnArgs&) { set_error("the packed-accumulator engine is not built (make EXTRA=-DMCV_WITH_TC2)"); return -1; }
+}  // namespace mcv
+#endif

@@ -11,7 +11,9 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[mcv.ENGINE_TENSOR, mcv.ENGINE_TENSOR_PACKED], ids=["int8", "fp8-packed"])
+# engine 3 (fp8 packed accumulators) is a build option since round 2 (make EXTRA=-DMCV_WITH_TC2); in the default library the
+# switch value falls back to the int8 engine, which the second parameter checks
+@pytest.fixture(autouse=True, params=[mcv.ENGINE_TENSOR, mcv.ENGINE_TENSOR_PACKED], ids=["int8", "engine3-switch"])
 def tensor_engine(request):
     mcv.set_hamming_engine(request.param)
     yield
