@@ -426,10 +426,10 @@ KERNEL_OF = {
     ("C2", 0): "hamming_tc_kernel<2,2,6>",
     ("C3_H", 11): "sample_counter_kernel<0>", ("C3_H", 12): "solve_kernel<0>", ("C3_H", 14): "score_kernel<0>",
     ("C3_H", 16): "finalize_homography_kernel",
-    ("C3_F", 11): "sample_counter_kernel<1>", ("C3_F", 12): "solve_kernel<1>", ("C3_F", 14): "score_kernel<1>",
+    ("C3_F", 11): "sample_counter_kernel<1>", ("C3_F", 12): "solve_kernel<1>", ("C3_F", 14): "score_tc_kernel<1>",
     ("C3_F", 16): "finalize_plain_kernel<1>",
     ("C4", 11): "sample_mwc_par_kernel<2>", ("C4", 12): "solve_e_stage1 + solve_e_roots + solve_e_models",
-    ("C4", 14): "score_kernel<2>", ("C4", 16): "finalize_plain_kernel<2>", ("C4", 17): "decompose + cheirality + pose_select",
+    ("C4", 14): "score_tc_kernel<2>", ("C4", 16): "finalize_plain_kernel<2>", ("C4", 17): "decompose + cheirality + pose_select",
 }
 
 

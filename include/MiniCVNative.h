@@ -122,6 +122,14 @@ MCV_API int mcvKernelTimingStopTagged(int device, float* ms, int* tags, int capa
 MCV_API int mcvSetHammingEngine(int engine);
 /* L2 matcher engine: 0 = auto (default), 1 = fp32 CUDA cores, 2 = tcgen05 bf16-split GEMM + exact re-scoring. */
 MCV_API int mcvSetL2Engine(int engine);
+/* Scoring engine of the F / E RANSAC stage: 0 = auto (default), 1 = fp32-filter kernel (one model per thread),
+ * 2 = tcgen05: the epipolar residuals of a tile as a TF32 GEMM, one comparison per evaluation in the epilogue, survivors
+ * to the fp32 filter and the exact test.  The inlier counts are the exact test's with either engine. */
+MCV_API int mcvSetScoreEngine(int engine);
+/* Audit mode of the tcgen05 scoring engine (tests): while on, every level-0 value is also recomputed in fp64 and the
+ * largest |error| / budget seen since it was switched on is kept; mcvScoreAuditMax returns it (must stay below 1). */
+MCV_API int mcvSetScoreAudit(int on);
+MCV_API float mcvScoreAuditMax(void);
 /* Contexts (stream set + grow-only workspaces) live in a per-device pool and are leased per call, so device
  * memory scales with the number of concurrent calls (at most $MINICV_MAX_CONTEXTS per device, default 8), not
  * with the number of host threads.  mcvTrim frees the workspaces and staging buffers of every idle context and

@@ -82,7 +82,7 @@ struct Context {
     cudaStream_t stream2 = nullptr;      // host->device copy stream (copy/compute overlap)
     cudaStream_t stream3 = nullptr;      // device->host copy stream
     cudaEvent_t  ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DevBuf       ws[80];                 // numbered workspaces, meaning fixed per call site
+    DevBuf       ws[96];                 // numbered workspaces, meaning fixed per call site
     PinBuf       pin[8];
     // tensor-core matcher control arrays, double-buffered so that the host can prepare launch k+1
     // while the copy of launch k is still queued behind launch k-1

@@ -1945,7 +1945,13 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             }
         } else {
         // ---- score
-        {
+        if (MODEL != RM_HOMOGRAPHY && score_tc_eligible(MODEL, maxN, (int)slots, np, ctx->sm_count)) {
+            kt_begin(ctx, st, KT_SCORE);
+            const int rc = score_tc_run(ctx, st, MODEL, pf, pd, off, io.hOff + p0, p0, np, dModels, dSlotList, dNTotal,
+                                        (int)slots, thr2, dCounts);
+            kt_end(ctx, st);
+            if (rc) return rc;
+        } else {
             const int tiles = (int)((slots + 127) / 128);
             int zs = 1;
             const int64_t blocksXY = (int64_t)tiles * np;

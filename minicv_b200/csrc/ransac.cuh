@@ -57,6 +57,14 @@ int ransac_select(cudaStream_t st, const int64_t* dOff, int np, int maxIters, in
                   double confidence, const int* dNIter, const int* dFlags, const int* dIterStart,
                   const int* dSlotList, const int* dCounts, int* dBest);
 
+// Scoring with the tensor-core first-level filter (score_tc.cu; F / E only): counts [np][slots] over the compacted model
+// lists, identical to score_kernel's.  dOff / hOff point at the chunk's first pair (absolute offsets), pairBase = its
+// index.  Uses ctx workspaces 80..84.
+bool score_tc_eligible(int model, int64_t maxN, int slots, int np, int smCount);
+int score_tc_run(Context* ctx, cudaStream_t st, int model, const float4* pf, const double* pd, const int64_t* dOff,
+                 const int64_t* hOff, int64_t pairBase, int np, const double* dModels, const int* dSlotList,
+                 const int* dNTotal, int slots, float thr2, int* dCounts);
+
 // Asynchronous on `stream`.  Uses ctx workspaces 10..21 and pinned buffer 1.
 int ransac_batch_device(Context* ctx, cudaStream_t stream, const RansacParams& prm, const RansacIO& io);
 

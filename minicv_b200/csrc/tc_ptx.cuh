@@ -38,6 +38,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// the same for a warp whose wait is long (producer / issuer behind a slower consumer): sleep between polls instead of
+// spinning in the issue slots the consumer warps need
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns = 500) {
+    const uint32_t a = smem_u32(bar);
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}\n" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -131,6 +147,22 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+// kind::tf32: A, B = TF32 (fp32 containers, 10 mantissa bits used), K = 8 per instruction, fp32 accumulation
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// K-major, SWIZZLE_64B operand descriptor: 64-byte rows, 8-row groups 512 B apart (SBO), version 1, layout 4.
+// Within a group the 16-byte chunk c of row r sits at chunk position c ^ ((r >> 1) & 3).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma / TMA reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // 1-D bulk copy global -> shared, completion on an mbarrier (bytes multiple of 16, 16-byte aligned)
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -17,6 +17,23 @@ SAMPLE_MWC, SAMPLE_COUNTER, SAMPLE_INJECTED = 0, 1, 2
 STOP_ADAPTIVE, STOP_FIXED, STOP_LMEDS = 0, 1, 2
 MODEL_POINTS = {MODEL_H: 4, MODEL_F: 7, MODEL_E: 5}
 MAX_MODELS = {MODEL_H: 1, MODEL_F: 3, MODEL_E: 10}
+SCORE_AUTO, SCORE_FP32_FILTER, SCORE_TENSOR = 0, 1, 2
+
+
+def set_score_engine(engine: int) -> None:
+    """Scoring engine of the F / E RANSAC stage (the counts are the exact test's with either): 0 auto, 1 the fp32-filter
+    kernel (one model per thread), 2 tcgen05 (residuals as a TF32 GEMM, one comparison per evaluation)."""
+    if native.load().mcvSetScoreEngine(engine) != 0:
+        raise ValueError("engine must be 0..2")
+
+
+def score_audit(on: bool) -> float:
+    """Switch the audit mode of the tcgen05 scoring engine; returns the largest |level-0 error| / budget recorded
+    since it was last switched on."""
+    lib = native.load()
+    worst = float(lib.mcvScoreAuditMax())
+    lib.mcvSetScoreAudit(1 if on else 0)
+    return worst
 
 
 @dataclass

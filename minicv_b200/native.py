@@ -69,6 +69,9 @@ SIGNATURES = {
     "mcvBuildInfo": (C.c_char_p, []),
     "mcvSetHammingEngine": (_i, [_i]),
     "mcvSetL2Engine": (_i, [_i]),
+    "mcvSetScoreEngine": (_i, [_i]),
+    "mcvSetScoreAudit": (_i, [_i]),
+    "mcvScoreAuditMax": (_f, []),
     "mcvTrim": (_i, []),
     "mcvWorkspaceBytes": (_i64, [_i]),
     "mcvSetWorkspaceLimit": (_i, [_i64]),

@@ -266,3 +266,98 @@ void hm_h_filter(const double* H, int nModels, const float* a, const float* b, i
     }
 }
 }
+
+// ---- level-0 (tensor-core) filter of the F / E scoring stage (filter0.cuh) ------------------------------------------
+#include "../../minicv_b200/csrc/filter0.cuh"
+#include <vector>
+#include <algorithm>
+#include <numeric>
+extern "C" {
+// Emulates score_tc.cu on the host: per-pair normalisation from the finite coordinate ranges, correspondences sorted by
+// image-1 cell (sorted != 0) or left in input order (boxes as large as the image: must still be conservative), split-TF32
+// rows for models and correspondences, stage boxes and thresholds, r~ accumulated over the 27 split terms in fp32 in index
+// order (mode 0), in reverse order (mode 1) or in fp64 (mode 2) -- the tensor core's own accumulation order is unspecified;
+// its error is budgeted, these three bracket it.  Outputs in INPUT order:
+// filt[k*n+i] = level 0 says "certainly outlier", exact[k*n+i] = the reference's exact test,
+// cls[k*n+i] = the two-sided fp32 classifier (0 outlier, 1 inlier, 2 undecided).
+void hm_filter0(int isE, const double* M, int nModels, const double* a, const double* b, int n, float thr, int mode, int sorted,
+                unsigned char* filt, unsigned char* exact, unsigned char* cls) {
+    const int NT = 64;
+    double lo[4] = {DBL_MAX, DBL_MAX, DBL_MAX, DBL_MAX}, hi[4] = {-DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
+    float mx[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        const double c[4] = {a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]};
+        for (int j = 0; j < 4; ++j) {
+            if (fabs(c[j]) <= DBL_MAX) { if (c[j] < lo[j]) lo[j] = c[j]; if (c[j] > hi[j]) hi[j] = c[j]; }
+            const float v = fabsf((float)c[j]);
+            if (v != v || (mx[j] == mx[j] && v > mx[j])) mx[j] = v;    // a NaN sticks (the kernel takes the max of bit patterns)
+        }
+    }
+    PairNorm pn;
+    pair_norm_init(lo, hi, pn);
+    pn.X1 = mx[0]; pn.Y1 = mx[1]; pn.X2 = mx[2]; pn.Y2 = mx[3];
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::vector<Hat> hat(n);
+    for (int i = 0; i < n; ++i) hat[i] = hat_coords(pn, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]);
+    if (sorted) std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return hat_cell(hat[x]) < hat_cell(hat[y]); });
+    std::vector<float> rows((size_t)n * F0_K);
+    double pmax = 0, vmax = 0;
+    for (int s = 0; s < n; ++s) {
+        double v2;
+        const double n2 = filter0_features(hat[order[s]], rows.data() + (size_t)s * F0_K, &v2);
+        if (n2 > pmax) pmax = n2;
+        if (v2 > vmax) vmax = v2;
+    }
+    pn.psiMax = (float)(sqrt(pmax) * (1.0 + 1e-6)) * 1.0000002f;
+    pn.v2Max = (float)(vmax * (1.0 + 1e-6)) * 1.0000002f;
+    const int nst = (n + NT - 1) / NT;
+    std::vector<StageBox> box(nst);
+    for (int st = 0; st < nst; ++st) {
+        double ulo = DBL_MAX, uhi = -DBL_MAX, vlo = DBL_MAX, vhi = -DBL_MAX;
+        for (int s = st * NT; s < n && s < (st + 1) * NT; ++s) {
+            const Hat& h = hat[order[s]];
+            ulo = fmin(ulo, h.u1); uhi = fmax(uhi, h.u1); vlo = fmin(vlo, h.v1); vhi = fmax(vhi, h.v1);
+        }
+        StageBox bx;
+        bx.cu = (float)(0.5 * ulo + 0.5 * uhi); bx.cv = (float)(0.5 * vlo + 0.5 * vhi);
+        double pu = 0, pv = 0;
+        for (int s = st * NT; s < n && s < (st + 1) * NT; ++s) {
+            const Hat& h = hat[order[s]];
+            pu = fmax(pu, fabs(h.u1 - (double)bx.cu)); pv = fmax(pv, fabs(h.v1 - (double)bx.cv));
+        }
+        bx.pu = (float)(pu * (1.0 + 1e-6)) * 1.0000002f; bx.pv = (float)(pv * (1.0 + 1e-6)) * 1.0000002f;
+        box[st] = bx;
+    }
+    for (int k = 0; k < nModels; ++k) {
+        float fr[F0_K];
+        Model0 m0;
+        filter0_model(isE, pn, M + 9 * k, thr, fr, m0);
+        const double thrk = (double)thr * pn.k * pn.k;
+        const float thrkM = (float)(thrk * (double)CLASS_MARGIN), thrkL = (float)(thrk * (double)CLASS_LOW);
+        for (int s = 0; s < n; ++s) {
+            const int i = order[s];
+            const float T = filter0_threshold(m0, box[s / NT]);
+            const float* p = rows.data() + (size_t)s * F0_K;
+            float r;
+            if (mode == 2) { double acc = 0; for (int j = 0; j < 27; ++j) acc += (double)fr[j] * (double)p[j]; r = (float)acc; }
+            else if (mode == 1) { volatile float acc = 0; for (int j = 26; j >= 0; --j) { volatile float t = fr[j] * p[j]; acc = acc + t; } r = acc; }
+            else { volatile float acc = 0; for (int j = 0; j < 27; ++j) { volatile float t = fr[j] * p[j]; acc = acc + t; } r = acc; }
+            filt[(size_t)k * n + i] = (fabsf(r) > T) ? 1 : 0;
+            const Hat& h = hat[i];
+            cls[(size_t)k * n + i] = (unsigned char)hat_classify(isE, m0, thrkM, thrkL, (float)h.u1, (float)h.v1, (float)h.u2, (float)h.v2);
+            if (isE) {
+                exact[(size_t)k * n + i] = e_inlier(M + 9 * k, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], thr) ? 1 : 0;
+            } else {
+                const float x1 = (float)a[2 * i], y1 = (float)a[2 * i + 1], x2 = (float)b[2 * i], y2 = (float)b[2 * i + 1];
+                exact[(size_t)k * n + i] = f_inlier(M + 9 * k, (double)x1, (double)y1, (double)x2, (double)y2, thr) ? 1 : 0;
+            }
+        }
+    }
+}
+}
+extern "C" {
+void hm_tf32_split(const float* x, int n, float* hi, float* lo) {
+    for (int i = 0; i < n; ++i) tf32_split(x[i], hi[i], lo[i]);
+}
+}

@@ -388,3 +388,129 @@ def test_h_filter_is_conservative(hm):
         filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8)
         hm.hm_h_filter(p(M), len(M), p(A_), p(bf), n, C.c_float(9.0), p(filt), p(exact))
         assert not (filt & exact).any()
+
+
+# ---- level 0 of the tensor-core scoring engine (filter0.cuh): host emulation of score_tc.cu -------------------------------
+def _filter0(hm, is_e, M, a, b, thr, mode=0, sorted_=1):
+    M = np.ascontiguousarray(M, np.float64)
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    n = len(a)
+    filt = np.zeros((len(M), n), np.uint8); exact = np.zeros((len(M), n), np.uint8); cls = np.zeros((len(M), n), np.uint8)
+    hm.hm_filter0(int(is_e), p(M), len(M), p(a), p(b), n, C.c_float(thr), mode, sorted_, p(filt), p(exact), p(cls))
+    return filt, exact, cls
+
+
+def _check_filter0(filt, exact, cls, msg=""):
+    assert not (filt & exact).any(), f"level 0 rejected an inlier {msg}"
+    assert not ((cls == 0) & (exact == 1)).any(), f"classifier called an inlier an outlier {msg}"
+    assert not ((cls == 1) & (exact == 0)).any(), f"classifier called an outlier an inlier {msg}"
+
+
+def _adversarial_models(base, rng):
+    out = [base.copy()]
+    for s in (1e-12, 1e-9, 1e-7, 1e-5, 1e-3, 1e-1):
+        for _ in range(4):
+            out.append(base * (1 + rng.normal(0, s, 9)))
+    for sc in (1e-40, 1e-33, 1e-20, 1e-6, 1e6, 1e15, 1e20, 1e29, 1e35, 1e300):
+        out.append(base * sc)
+    z = base.copy(); z[:6] = 0; out.append(z)
+    z = base.copy(); z[:6] *= 1e-25; out.append(z)
+    z = base.copy(); z[6:] = 0; out.append(z)
+    z = base.copy(); z[[0, 1, 3, 4]] = 0; out.append(z)
+    z = base.copy(); z[4] = np.nan; out.append(z)
+    z = base.copy(); z[8] = np.inf; out.append(z)
+    out.append(np.zeros(9))
+    out.append(rng.normal(0, 1, 9))
+    return out
+
+
+def test_f_level0_and_classifier_are_conservative(hm):
+    """Level 0 (split-TF32 residual against a per-stage threshold) may only fire where f_inlier is false, and the two-sided
+    fp32 classifier may only decide what f_inlier decides the same way -- random 7-point models, near-perfect ones
+    (decisions at the threshold), rescaled / degenerate / non-finite ones, far-off-centre and badly scaled coordinates,
+    NaN coordinates, three accumulation orders, sorted and unsorted stages -- and level 0 must remove most of the work."""
+    rng = np.random.default_rng(17)
+    a, b, gt, R, t = synth.two_view_pair(2, 3000)
+    af, bf = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    models = []
+    F7 = np.zeros(27)
+    inl = np.flatnonzero(gt)
+    for it in range(260):
+        idx = rng.permutation(len(af))[:7] if it < 200 else rng.choice(inl, 7, replace=False)
+        k = hm.hm_f_solve7(p(np.ascontiguousarray(af[idx])), p(np.ascontiguousarray(bf[idx])), p(F7))
+        for j in range(k):
+            models.append(F7[9 * j:9 * j + 9].copy())
+    n_random = len(models)
+    g = np.load(GOLDEN / "ransac_hf.npz")
+    models += _adversarial_models(g["f2_F"].ravel().copy(), rng)
+    M = np.stack(models)
+    for thr in (9.0, 1.0, 1e-4, 400.0):
+        for mode in (0, 1, 2):
+            filt, exact, cls = _filter0(hm, 0, M, af, bf, thr, mode)
+            _check_filter0(filt, exact, cls, f"thr {thr} mode {mode}")
+        if thr == 9.0:
+            wrong = exact[:n_random].sum(axis=1) < 0.05 * len(af)
+            assert filt[:n_random][wrong].mean() > 0.94                       # ~3 % survive
+            assert (cls[:n_random] == 2).mean() < 2e-3                        # the exact test is rare
+            assert ((cls[:n_random] == 1) == (exact[:n_random] == 1)).mean() > 0.998
+    filt, exact, cls = _filter0(hm, 0, M, af, bf, 9.0, 0, sorted_=0)          # boxes as large as the image
+    _check_filter0(filt, exact, cls, "unsorted")
+    # far-off-centre pairs (the exact test's own fp64 noise grows), badly scaled rows, a NaN coordinate
+    for shift in (1e4, 1e7, 1e10, 1e14):
+        filt, exact, cls = _filter0(hm, 0, M, af.astype(np.float64) + shift, bf.astype(np.float64) - 0.5 * shift, 9.0)
+        _check_filter0(filt, exact, cls, f"shift {shift}")
+    sc = rng.choice([1e-20, 1e-3, 1.0, 1e3, 1e15], size=(len(af), 1))
+    filt, exact, cls = _filter0(hm, 0, M, af * sc, bf * sc[::-1], 9.0)
+    _check_filter0(filt, exact, cls, "scaled rows")
+    a3 = af.astype(np.float64).copy(); a3[5, 0] = np.nan
+    filt, exact, cls = _filter0(hm, 0, M, a3, bf, 9.0)
+    _check_filter0(filt, exact, cls, "nan")
+    assert not filt.any()                                                      # level 0 is off for the pair
+    filt, exact, cls = _filter0(hm, 0, M, af[:9], bf[:9], 9.0)
+    _check_filter0(filt, exact, cls, "tiny")
+
+
+def test_e_level0_and_classifier_are_conservative(hm):
+    """The same for e_inlier (Sampson error, fp64 normalised coordinates)."""
+    rng = np.random.default_rng(19)
+    a, b, gt, R, t = synth.two_view_pair(3, 5000)
+    x1 = np.ascontiguousarray(essential.normalize_points(a, 800.0, (320.0, 240.0)))
+    x2 = np.ascontiguousarray(essential.normalize_points(b, 800.0, (320.0, 240.0)))
+    models = []
+    Es = np.zeros(90)
+    inl = np.flatnonzero(gt)
+    for it in range(160):
+        idx = rng.permutation(len(x1))[:5] if it < 120 else rng.choice(inl, 5, replace=False)
+        k = hm.hm_e_solve5(p(np.ascontiguousarray(x1[idx])), p(np.ascontiguousarray(x2[idx])), p(Es))
+        for j in range(k):
+            models.append(Es[9 * j:9 * j + 9].copy())
+    n_random = len(models)
+    models += _adversarial_models(models[0], rng)
+    M = np.stack(models)
+    for thr in ((1.0 / 800) ** 2, 0.005 ** 2, 1e-12):
+        for mode in (0, 1, 2):
+            filt, exact, cls = _filter0(hm, 1, M, x1, x2, thr, mode)
+            _check_filter0(filt, exact, cls, f"thr {thr} mode {mode}")
+        if thr == (1.0 / 800) ** 2:
+            wrong = exact[:n_random].sum(axis=1) < 0.05 * len(x1)
+            assert filt[:n_random][wrong].mean() > 0.95
+            assert (cls[:n_random] == 2).mean() < 2e-3
+    filt, exact, cls = _filter0(hm, 1, M, x1, x2, (1.0 / 800) ** 2, 0, sorted_=0)
+    _check_filter0(filt, exact, cls, "unsorted")
+    for shift in (1e3, 1e6, 1e9):
+        filt, exact, cls = _filter0(hm, 1, M, x1 + shift, x2 - 0.5 * shift, (1.0 / 800) ** 2)
+        _check_filter0(filt, exact, cls, f"shift {shift}")
+    sc = rng.choice([1e-20, 1e-3, 1.0, 1e3, 1e15], size=(len(x1), 1))
+    filt, exact, cls = _filter0(hm, 1, M, x1 * sc, x2 * sc[::-1], (1.0 / 800) ** 2)
+    _check_filter0(filt, exact, cls, "scaled rows")
+
+
+def test_tf32_split_is_what_the_kernel_assumes(hm):
+    """hi + lo reproduces a float to 2^-22 relative and both pieces are TF32 values (13 low mantissa bits clear)."""
+    rng = np.random.default_rng(23)
+    x = np.concatenate([rng.normal(0, 1, 4000) * 10.0 ** rng.integers(-30, 30, 4000), [0.0, 1.0, -1.0, 3e38, 1e-38]]).astype(np.float32)
+    hi = np.zeros_like(x); lo = np.zeros_like(x)
+    hm.hm_tf32_split(p(x), len(x), p(hi), p(lo))
+    assert not (hi.view(np.uint32) & 0x1FFF).any() and not (lo.view(np.uint32) & 0x1FFF).any()
+    err = np.abs(x.astype(np.float64) - hi.astype(np.float64) - lo.astype(np.float64))
+    assert (err <= 2.0 ** -22 * np.abs(x.astype(np.float64)) + 2e-41).all()      # + the subnormal grid
