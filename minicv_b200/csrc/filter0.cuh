@@ -221,14 +221,24 @@ MCV_HD void filter0_model(int isE, const PairNorm& pn, const double* F, float th
     m0.g2 = (float)(g2 * (1.0 + 1.2e-7));
 }
 
-// threshold of one (model, stage): fp32, every rounding inside the 2^-17 / slack margins of stk and base
-MCV_HD float filter0_threshold(const Model0& m0, const StageBox& b) {
+// threshold of one (model, stage): fp32, every rounding inside the 2^-17 / slack margins of stk and base (the device
+// build takes sqrt.approx, 2^-22 relative)
+MCV_HD float f0_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+MCV_HD float filter0_threshold(int isE, const Model0& m0, const StageBox& b) {
     const float a0 = fmaf(m0.g[0], b.cu, fmaf(m0.g[1], b.cv, m0.g[2]));
     const float a1 = fmaf(m0.g[3], b.cu, fmaf(m0.g[4], b.cv, m0.g[5]));
     const float e0 = fmaf(fabsf(m0.g[0]), b.pu, fabsf(m0.g[1]) * b.pv);
     const float e1 = fmaf(fabsf(m0.g[3]), b.pu, fabsf(m0.g[4]) * b.pv);
-    const float bound = sqrtf(fmaf(a0, a0, a1 * a1)) + sqrtf(fmaf(e0, e0, e1 * e1));
-    const float tot = sqrtf(fmaf(bound, bound, m0.g2));
+    const float bound = f0_sqrt(fmaf(a0, a0, a1 * a1)) + f0_sqrt(fmaf(e0, e0, e1 * e1));
+    const float tot = isE ? f0_sqrt(fmaf(bound, bound, m0.g2)) : bound;
     return fmaf(m0.stk, tot, m0.base);
 }
 

@@ -366,7 +366,7 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
         if (elect_one()) {
             for (int j = 0; j < nStages; ++j) {
                 const int s = j % ST_STAGES;
-                mbar_wait_backoff(b_empty + s, ((j / ST_STAGES) & 1) ^ 1, 2000);
+                mbar_wait_backoff(b_empty + s, ((j / ST_STAGES) & 1) ^ 1);
                 mbar_expect_tx(b_full + s, B_BYTES);
                 bulk_load_1d(sB + s * B_BYTES, img + (int64_t)j * B_BYTES, B_BYTES, b_full + s);
             }
@@ -379,8 +379,8 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
             const uint32_t aBase = smem_u32(sA);
             for (int j = 0; j < nStages; ++j) {
                 const int s = j % ST_STAGES, buf = j & 1;
-                mbar_wait_backoff(b_full + s, (j / ST_STAGES) & 1, 500);
-                mbar_wait_backoff(acc_empty + buf, ((j >> 1) & 1) ^ 1, 500);
+                mbar_wait_backoff(b_full + s, (j / ST_STAGES) & 1);
+                mbar_wait_backoff(acc_empty + buf, ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t bBase = smem_u32(sB + s * B_BYTES);
 #pragma unroll
@@ -474,7 +474,7 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(bx + j));
             StageBox sb;
             sb.cu = b4.x; sb.cv = b4.y; sb.pu = b4.z; sb.pv = b4.w;
-            const float T = filter0_threshold(mc, sb);
+            const float T = filter0_threshold(isE, mc, sb);
             // the stage's coordinate block of the global image (8 lines) into L1: the queue drains gather from it
             if (lane < 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(img + (int64_t)j * ST_STAGE_BYTES + ST_NT * 128 + lane * 128));
             mbar_wait(acc_full + buf, (j >> 1) & 1);
@@ -537,11 +537,16 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
             //      a lane without a survivor classifies column 0 and drops the result): own model in registers, coordinates
             //      from shared memory
             {
-                unsigned long long m64 = ((unsigned long long)mhi << 32) | mlo;
                 int bsel[ST_INPLACE], cls[ST_INPLACE];
 #pragma unroll
-                for (int t = 0; t < ST_INPLACE; ++t) { bsel[t] = __ffsll((long long)m64) - 1; m64 &= m64 - 1; }
-                mlo = (uint32_t)m64; mhi = (uint32_t)(m64 >> 32);
+                for (int t = 0; t < ST_INPLACE; ++t) {           // lowest set bit of (mhi:mlo), -1 if none, cleared
+                    const bool lo = mlo != 0;
+                    const uint32_t cur = lo ? mlo : mhi;
+                    bsel[t] = cur ? __ffs(cur) - 1 + (lo ? 0 : 32) : -1;
+                    const uint32_t rest = cur & (cur - 1);
+                    mhi = lo ? mhi : rest;
+                    mlo = lo ? rest : 0u;
+                }
                 bool anyUnd = false;
 #pragma unroll
                 for (int t = 0; t < ST_INPLACE; ++t) {
@@ -567,8 +572,14 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
                 }
                 int pos = qn + incl - mine;
                 const uint32_t tag = ((uint32_t)c0 << 5) | (uint32_t)lane;
-                while (mlo) { const int b = __ffs(mlo) - 1; mlo &= mlo - 1; q[pos++] = tag + ((uint32_t)b << 5); }
-                while (mhi) { const int b = __ffs(mhi) - 1; mhi &= mhi - 1; q[pos++] = tag + ((uint32_t)(b + 32) << 5); }
+                while (mlo | mhi) {                              // one trip per leftover of the fullest lane
+                    const bool lo = mlo != 0;
+                    const uint32_t cur = lo ? mlo : mhi;
+                    q[pos++] = tag + ((uint32_t)(__ffs(cur) - 1 + (lo ? 0 : 32)) << 5);
+                    const uint32_t rest = cur & (cur - 1);
+                    mhi = lo ? mhi : rest;
+                    mlo = lo ? rest : 0u;
+                }
                 qn += __shfl_sync(FULL, incl, 31);
             }
             __syncwarp();

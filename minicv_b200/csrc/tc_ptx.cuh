@@ -38,20 +38,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// the same for a warp whose wait is long (producer / issuer behind a slower consumer): sleep between polls instead of
-// spinning in the issue slots the consumer warps need
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns = 500) {
+// the same for a warp whose wait is long (producer / issuer behind a slower consumer): try_wait with a suspend-time hint
+// parks the thread in hardware until the phase completes or the hint expires, instead of polling in the issue slots the
+// consumer warps need
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns = 20000) {
     const uint32_t a = smem_u32(bar);
     for (;;) {
         uint32_t done;
         asm volatile(
             "{\n\t"
             ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, P1;\n\t"
-            "}\n" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+            "}\n" : "=r"(done) : "r"(a), "r"(parity), "r"(ns) : "memory");
         if (done) break;
-        __nanosleep(ns);
     }
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {

@@ -337,7 +337,7 @@ void hm_filter0(int isE, const double* M, int nModels, const double* a, const do
         const float thrkM = (float)(thrk * (double)CLASS_MARGIN), thrkL = (float)(thrk * (double)CLASS_LOW);
         for (int s = 0; s < n; ++s) {
             const int i = order[s];
-            const float T = filter0_threshold(m0, box[s / NT]);
+            const float T = filter0_threshold(isE, m0, box[s / NT]);
             const float* p = rows.data() + (size_t)s * F0_K;
             float r;
             if (mode == 2) { double acc = 0; for (int j = 0; j < 27; ++j) acc += (double)fr[j] * (double)p[j]; r = (float)acc; }
