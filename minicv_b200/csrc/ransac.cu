@@ -21,6 +21,7 @@
 #include "filter_pass.cuh"
 #include "cvmath.cuh"
 
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 
@@ -1817,6 +1818,10 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
     const size_t perPair = (size_t)maxIters * MAXM * 72;
     int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nPairs, ((size_t)1 << 30) / std::max<size_t>(perPair, 1)));
     chunk = std::min(chunk, 65535);      // the pair index is gridDim.y of several stage kernels
+    if (const char* e = getenv("MINICV_RANSAC_CHUNK_PAIRS")) {           // tests: force chunk seams on small batches
+        const int c = atoi(e);
+        if (c > 0) chunk = std::min(chunk, c);
+    }
     const size_t slots = (size_t)maxIters * MAXM;
     if (ctx->ws[12].reserve((size_t)chunk * maxIters * MP * 4) ||       // samples
         ctx->ws[13].reserve((size_t)chunk * 8 + 64) ||                  // nIter, flags

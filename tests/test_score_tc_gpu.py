@@ -108,3 +108,42 @@ def test_engines_agree_count_by_count(model, n, iters, kw):
     # the audit recomputed the level-0 values in fp64: the arithmetic error stayed inside its budget with room to spare
     assert 0 < worst < 0.5, worst
     print(f"level-0 audit, model {model}, n {n}: worst |error| / budget = {worst:.3f}")
+
+
+@pytest.mark.parametrize("model,kw", [
+    (est.MODEL_F, dict(thr=2.0)),
+    (est.MODEL_E, dict(thr=1.5, focal=800.0, pp=(320.0, 240.0))),
+])
+def test_ragged_batch_and_chunk_seams(model, kw, monkeypatch):
+    """Pairs of very different sizes in one batch (empty, below the sample size, below / at / just above one stage of 64,
+    several stages), processed in one chunk and in chunks of two pairs (every buffer of the tensor-core engine is addressed
+    relative to the chunk's first pair): both engines return the same counts, models and masks, chunked or not."""
+    sizes = [2000, 0, 5, 64, 65, 777, 63, 1, 130, 1024, 8]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    A = np.empty((offs[-1], 2)); B = np.empty((offs[-1], 2))
+    for p, n in enumerate(sizes):
+        if n:
+            r = synth.two_view_pair(200 + p, n)
+            A[offs[p]:offs[p + 1]] = r[0]; B[offs[p]:offs[p + 1]] = r[1]
+
+    def run(engine, chunk):
+        if chunk:
+            monkeypatch.setenv("MINICV_RANSAC_CHUNK_PAIRS", str(chunk))
+        else:
+            monkeypatch.delenv("MINICV_RANSAC_CHUNK_PAIRS", raising=False)
+        est.set_score_engine(engine)
+        try:
+            return est.ransac_batch(model, A, B, offs, kw["thr"], 200, 0.99, sample_mode=est.SAMPLE_COUNTER,
+                                    stop_mode=est.STOP_FIXED, seed=9, debug=True,
+                                    **{k: v for k, v in kw.items() if k != "thr"})
+        finally:
+            est.set_score_engine(est.SCORE_AUTO)
+
+    ref = run(est.SCORE_FP32_FILTER, 0)
+    for engine, chunk in ((est.SCORE_TENSOR, 0), (est.SCORE_TENSOR, 2), (est.SCORE_FP32_FILTER, 3), (est.SCORE_TENSOR, 1)):
+        got = run(engine, chunk)
+        np.testing.assert_array_equal(got.dbg_counts, ref.dbg_counts, err_msg=f"engine {engine} chunk {chunk}")
+        np.testing.assert_array_equal(got.masks, ref.masks)
+        np.testing.assert_array_equal(got.ok, ref.ok)
+        np.testing.assert_array_equal(got.models, ref.models)
+    assert ref.ok[0] and not ref.ok[1] and not ref.ok[2]
