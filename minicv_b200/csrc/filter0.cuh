@@ -242,6 +242,94 @@ MCV_HD float filter0_threshold(int isE, const Model0& m0, const StageBox& b) {
     return fmaf(m0.stk, tot, m0.base);
 }
 
+// ---- homography ------------------------------------------------------------------------------------------------------
+// The reprojection residual g = (X - u w, Y - v w), (X, Y, w) = H (x, y, 1), is bilinear in (H, correspondence) as well, and
+// the reference's error is |g|^2 / w^2 (h_error, float32).  One accumulator per evaluation carries the component of g along
+// the diagonal, s = k (gx + gy) = f^ . psi with psi = (u^, v^, 1, -t u^, -t v^, -t), t = p^ + q^ (recentred source (u^, v^) and
+// target (p^, q^)), f^ = (h^0 + h^3, h^1 + h^4, h^2 + h^5, h^6, h^7, h^8), h^ = T2 H T1^-1 (so g^ = k g, w^ = w).  |s| <=
+// sqrt(2) k |g|, hence  |s| > sqrt(2) k R  proves |g| > R.  An outlier whose residual happens to be perpendicular to the
+// diagonal is not caught (a few per cent); like every survivor it gets the exact test.  R comes from the float32 path's own
+// roundings (cvmath.cuh, h_certain_outlier: with Xb = |h0| Xm + |h1| Ym + |h2|, Wb = |h6| Xm + |h7| Ym + 1 over the pair's
+// coordinate maxima, the float32 X, Y, w are within 3u Xb, 3u Yb, 3u Wb of the real values and
+// |d_f| >= |g_e / w_f| (1 - 4.1u) - 3.1u (Um, Vm) componentwise), which give, with a = 4u (Xb + Um Wb, Yb + Vm Wb), aw = 4u Wb,
+//     err_f > thr   if   |g| > [sqrt(thr) (1 + 2u) + 3.1u |(Um, Vm)|] (|w| + aw) (1 + 5u) + |a|
+// (a zero, infinite or NaN float32 w makes h_error inf / NaN, an outlier as well).  |w| <= |w^ . c| + |h^6| pu + |h^7| pv over
+// the stage's source box.  H here is the float32 matrix the exact test uses (entries 0..7 rounded, h33 = 1).
+MCV_HD double filter0_features_h(const Hat& h, float* row) {
+    const double t = h.u2 + h.v2;
+    const double psi[6] = {h.u1, h.v1, 1.0, -t * h.u1, -t * h.v1, -t};
+    double n2 = 0;
+    for (int i = 0; i < 6; ++i) {
+        float hi, lo;
+        tf32_split((float)psi[i], hi, lo);
+        row[i] = hi; row[6 + i] = lo; row[12 + i] = hi;
+        n2 += psi[i] * psi[i];
+    }
+    for (int i = 18; i < F0_K; ++i) row[i] = 0.f;
+    return n2;
+}
+// m0.g[0..5] = f^ (audit), g[6..8] = h^6, h^7, h^8 (stage threshold), stk, base; K2, K1, KD, g2 unused
+MCV_HD void filter0_model_h(const PairNorm& pn, const float* Hf, float thr, float* row, Model0& m0, double* fhOut = nullptr,
+                            double* emOut = nullptr) {
+    const double k = pn.k, ik = 1.0 / k;
+    const double c1x = pn.c1x, c1y = pn.c1y, c2x = pn.c2x, c2y = pn.c2y;
+    bool on = pn.on != 0 && thr >= 0.f && thr <= 1e30f;
+    double h[9];
+    for (int i = 0; i < 8; ++i) {
+        h[i] = (double)Hf[i];
+        const double v = fabs(h[i]);
+        if (!(v <= 1e30) || (v != 0.0 && v < 1e-30)) on = false;
+    }
+    h[8] = 1.0;
+    const double r0 = h[0] * c1x + h[1] * c1y + h[2], r1 = h[3] * c1x + h[4] * c1y + h[5], rw = h[6] * c1x + h[7] * c1y + 1.0;
+    const double s0 = fabs(h[0] * c1x) + fabs(h[1] * c1y) + fabs(h[2]), s1 = fabs(h[3] * c1x) + fabs(h[4] * c1y) + fabs(h[5]);
+    const double sw = fabs(h[6] * c1x) + fabs(h[7] * c1y) + 1.0;
+    double hh[9];
+    hh[0] = h[0] - c2x * h[6]; hh[1] = h[1] - c2x * h[7]; hh[2] = k * (r0 - c2x * rw);
+    hh[3] = h[3] - c2y * h[6]; hh[4] = h[4] - c2y * h[7]; hh[5] = k * (r1 - c2y * rw);
+    hh[6] = h[6] * ik;         hh[7] = h[7] * ik;         hh[8] = rw;
+    // sum of the absolute terms every entry is built from (fp64 rounding of the transform)
+    const double S = fabs(h[0]) + fabs(h[1]) + fabs(h[3]) + fabs(h[4]) + (fabs(c2x) + fabs(c2y)) * (fabs(h[6]) + fabs(h[7])) +
+                     k * (s0 + s1 + (fabs(c2x) + fabs(c2y)) * sw) + (fabs(h[6]) + fabs(h[7])) * ik + sw;
+    const double fh[6] = {hh[0] + hh[3], hh[1] + hh[4], hh[2] + hh[5], hh[6], hh[7], hh[8]};
+    double nf = 0;
+    for (int i = 0; i < 6; ++i) {
+        nf += fh[i] * fh[i];
+        float hi, lo;
+        tf32_split((float)fh[i], hi, lo);
+        row[i] = hi; row[6 + i] = hi; row[12 + i] = lo;
+    }
+    for (int i = 18; i < F0_K; ++i) row[i] = 0.f;
+    nf = sqrt(nf);
+    const double up = 1.0 + 1e-6, u32 = 5.9604644775390625e-08;
+    const double Xm = pn.X1 * up, Ym = pn.Y1 * up, Um = pn.X2 * up, Vm = pn.Y2 * up;
+    const double Xb = fabs(h[0]) * Xm + fabs(h[1]) * Ym + fabs(h[2]), Yb = fabs(h[3]) * Xm + fabs(h[4]) * Ym + fabs(h[5]);
+    const double Wb = fabs(h[6]) * Xm + fabs(h[7]) * Ym + 1.0;
+    const double ax = 4.0 * u32 * (Xb + Um * Wb), ay = 4.0 * u32 * (Yb + Vm * Wb), aw = 4.0 * u32 * Wb;
+    const double st = sqrt((double)thr) * (1.0 + 2.0 * u32) + 3.1 * u32 * sqrt(Um * Um + Vm * Vm);
+    const double psiMax = pn.psiMax;
+    const double em = 1.52587890625e-05 * nf * psiMax + 3.5527136788005009e-15 * S * psiMax;    // 2^-16, 2^-48
+    const double r2k = 1.4142135623730951 * k;
+    const double stk = r2k * st * (1.0 + 5.0 * u32) * (1.0 + 7.62939453125e-06);                // (1 + 2^-17)
+    const double slack = 9.5367431640625e-07 * (fabs(hh[6]) + fabs(hh[7]) + fabs(hh[8])) + 3.5527136788005009e-15 * S;
+    const double base = (stk * (aw + slack) + r2k * sqrt(ax * ax + ay * ay) + em) * (1.0 + 9.5367431640625e-07) + 1e-30;
+    if (fhOut) { for (int i = 0; i < 6; ++i) fhOut[i] = fh[i]; fhOut[6] = fhOut[7] = fhOut[8] = 0; }
+    if (emOut) *emOut = em;
+    if (!(Xb < 1e100) || !(Yb < 1e100) || !(Wb < 1e100) || !(S < 1e100) || !(base < 1e30) || !(stk < 1e30) || !(nf < 1e30) ||
+        !(Um < 1e100) || !(Vm < 1e100))
+        on = false;                                                                              // NaN too
+    for (int i = 0; i < 6; ++i) m0.g[i] = (float)fh[i];
+    m0.g[6] = (float)hh[6]; m0.g[7] = (float)hh[7]; m0.g[8] = (float)hh[8];
+    m0.stk = (float)(stk * (1.0 + 1.2e-7));
+    m0.base = on ? (float)(base * (1.0 + 1.2e-7)) : INFINITY;
+    m0.g2 = 0.f; m0.K2 = m0.K1 = m0.KD = INFINITY;
+}
+MCV_HD float filter0_threshold_h(const Model0& m0, const StageBox& b) {
+    const float w0 = fabsf(fmaf(m0.g[6], b.cu, fmaf(m0.g[7], b.cv, m0.g[8])));
+    const float e0 = fmaf(fabsf(m0.g[6]), b.pu, fabsf(m0.g[7]) * b.pv);
+    return fmaf(m0.stk, w0 + e0, m0.base);
+}
+
 // ---- two-sided fp32 classifier in front of f_inlier / e_inlier (survivors of level 0) ----------------------------------
 // The quantities of f_certain_outlier / e_certain_outlier (cvmath.cuh) -- residual d, line norms n2 = a^2 + b^2 (line F x1
 // in image 2) and n1 (line F' x2 in image 1) -- evaluated in fp32 for BOTH epipolar lines, in the pair's coordinates, and

@@ -1950,7 +1950,7 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             }
         } else {
         // ---- score
-        if (MODEL != RM_HOMOGRAPHY && score_tc_eligible(MODEL, maxN, (int)slots, np, ctx->sm_count)) {
+        if (score_tc_eligible(MODEL, maxN, (int)slots, np, ctx->sm_count)) {
             kt_begin(ctx, st, KT_SCORE);
             const int rc = score_tc_run(ctx, st, MODEL, pf, pd, off, io.hOff + p0, p0, np, dModels, dSlotList, dNTotal,
                                         (int)slots, thr2, dCounts);

@@ -80,6 +80,7 @@ score_tc_features_kernel(const float4* __restrict__ pf, const double* __restrict
                          int64_t pairBase, PairNorm* __restrict__ norms, float* __restrict__ feat,
                          void* __restrict__ sortedRaw, StageBox* __restrict__ boxes) {
     constexpr int isE = MODEL == RM_ESSENTIAL ? 1 : 0;
+    constexpr bool isH = MODEL == RM_HOMOGRAPHY;
     const int p = blockIdx.x;
     const int64_t base = off[p];
     const int n = (int)(off[p + 1] - base);
@@ -180,8 +181,8 @@ score_tc_features_kernel(const float4* __restrict__ pf, const double* __restrict
         const Hat h = hat_coords(pn, x1, y1, x2, y2);
         const int pos = atomicAdd(&sHist[hat_cell(h)], 1);
         float row[F0_K];
-        double v2;
-        const double n2 = filter0_features(h, row, &v2);
+        double v2 = 0;
+        const double n2 = isH ? filter0_features_h(h, row) : filter0_features(h, row, &v2);
         if (n2 > pmax) pmax = n2;                        // NaN: not taken (the pair is switched off through X1..Y2)
         if (v2 > vmax) vmax = v2;
         uint8_t* st = img + (int64_t)(pos / ST_NT) * ST_STAGE_BYTES;
@@ -189,7 +190,10 @@ score_tc_features_kernel(const float4* __restrict__ pf, const double* __restrict
         float4* out = reinterpret_cast<float4*>(st + (rs >> 3) * 1024 + r * 128);
 #pragma unroll
         for (int c = 0; c < 8; ++c) out[c ^ r] = make_float4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
-        reinterpret_cast<float4*>(st + ST_NT * 128)[rs] = make_float4((float)h.u1, (float)h.v1, (float)h.u2, (float)h.v2);
+        // coordinate block of the stage: recentred (F / E: the classifier works in the pair's coordinates) or original
+        // (H: the survivors get the float32 exact test directly)
+        reinterpret_cast<float4*>(st + ST_NT * 128)[rs] = isH ? make_float4((float)x1, (float)y1, (float)x2, (float)y2)
+                                                              : make_float4((float)h.u1, (float)h.v1, (float)h.u2, (float)h.v2);
         if (isE) reinterpret_cast<double4*>(sortedRaw)[row0 + pos] = make_double4(x1, y1, x2, y2);
         else reinterpret_cast<float4*>(sortedRaw)[row0 + pos] = make_float4((float)x1, (float)y1, (float)x2, (float)y2);
     }
@@ -279,6 +283,7 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
                 const double* __restrict__ models, const int* __restrict__ slotList, const int* __restrict__ nTotal,
                 int maxSlots, float thr2, int* __restrict__ counts, unsigned long long* __restrict__ audit) {
     constexpr int isE = MODEL == RM_ESSENTIAL ? 1 : 0;
+    constexpr bool isH = MODEL == RM_HOMOGRAPHY;
     constexpr int A_BYTES = ST_ROWS * ST_ROW_BYTES;           // 32 KB
     constexpr int B_BYTES = ST_STAGE_BYTES;                   // 9 KB per stage: 64 operand rows + 64 coordinate quadruples
     const int p = blockIdx.y;
@@ -328,6 +333,7 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
     const int row = tileM * 128 + quarter * 32 + lane;          // row of the CTA's 256 (valid for warps >= 2)
     Model0 mc;
     mc.base = INFINITY;
+    float Hf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // homography: the float32 matrix of the exact test
     bool active = false;
     double fhA[AUDIT ? 9 : 1];
     double emA = 0;
@@ -345,13 +351,19 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
             for (int j = 0; j < 9; ++j) m[j] = 0;
         }
         float frow[F0_K];
-        filter0_model(isE, pn, m, thr2, frow, mc, AUDIT ? fhA : nullptr, AUDIT ? &emA : nullptr);
+        if (isH) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) Hf[j] = (float)m[j];
+            filter0_model_h(pn, Hf, thr2, frow, mc, AUDIT ? fhA : nullptr, AUDIT ? &emA : nullptr);
+        } else {
+            filter0_model(isE, pn, m, thr2, frow, mc, AUDIT ? fhA : nullptr, AUDIT ? &emA : nullptr);
+        }
         const int r = row & 7;
         float4* arow = reinterpret_cast<float4*>(sA + (row >> 3) * 1024 + r * 128);
 #pragma unroll
         for (int c = 0; c < 8; ++c) arow[c ^ r] = make_float4(frow[4 * c], frow[4 * c + 1], frow[4 * c + 2], frow[4 * c + 3]);
 #pragma unroll
-        for (int j = 0; j < 9; ++j) sM0[j * ST_ROWS + row] = mc.g[j];
+        for (int j = 0; j < 9; ++j) sM0[j * ST_ROWS + row] = isH ? (j < 8 ? Hf[j] : 0.f) : mc.g[j];
         sSlot[row] = slot;
         sM0[9 * ST_ROWS + row] = mc.K2; sM0[10 * ST_ROWS + row] = mc.K1; sM0[11 * ST_ROWS + row] = mc.KD;
         sCnt[row] = 0;
@@ -452,6 +464,12 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
                 }
             }
         };
+        // one (model, correspondence): 0 outlier, 1 inlier, 2 undecided.  F / E: the two-sided classifier in the pair's
+        // coordinates; H: the float32 exact test itself on the original coordinates (35 instructions, nothing to decide later)
+        auto classify = [&](const Model0& mm, const float4& h) {
+            if (isH) return h_error(mm.g, h.x, h.y, h.z, h.w) <= thr2 ? 1 : 0;
+            return hat_classify(isE, mm, thrkM, thrkL, h.x, h.y, h.z, h.w);
+        };
         // 32 queued leftovers, one per lane (all lanes call): model constants from shared memory, coordinates from the
         // stage image in global memory (its shared-memory copy may be gone)
         auto resolve_item = [&](uint32_t item, bool valid) {
@@ -461,10 +479,10 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
                 const int j = (int)(item >> 5);
                 const Model0 mm = load_m0(r);
                 const float4 h = __ldg(reinterpret_cast<const float4*>(img + (int64_t)(j / ST_NT) * ST_STAGE_BYTES + ST_NT * 128) + (j % ST_NT));
-                cls = hat_classify(isE, mm, thrkM, thrkL, h.x, h.y, h.z, h.w);
+                cls = classify(mm, h);
                 if (cls == 1) atomicAdd(&sCnt[r], 1);
             }
-            push_undecided(cls == 2, item);
+            if (!isH) push_undecided(cls == 2, item);
         };
 
         for (int j = 0; j < nStages; ++j) {
@@ -474,7 +492,7 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(bx + j));
             StageBox sb;
             sb.cu = b4.x; sb.cv = b4.y; sb.pu = b4.z; sb.pv = b4.w;
-            const float T = filter0_threshold(isE, mc, sb);
+            const float T = isH ? filter0_threshold_h(mc, sb) : filter0_threshold(isE, mc, sb);
             // the stage's coordinate block of the global image (8 lines) into L1: the queue drains gather from it
             if (lane < 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(img + (int64_t)j * ST_STAGE_BYTES + ST_NT * 128 + lane * 128));
             mbar_wait(acc_full + buf, (j >> 1) & 1);
@@ -493,8 +511,10 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
                         if (isE) { const double4 c = reinterpret_cast<const double4*>(sortedRaw)[row0 + c0 + i]; x1 = c.x; y1 = c.y; x2 = c.z; y2 = c.w; }
                         else { const float4 c = reinterpret_cast<const float4*>(sortedRaw)[row0 + c0 + i]; x1 = c.x; y1 = c.y; x2 = c.z; y2 = c.w; }
                         const Hat h = hat_coords(pn, x1, y1, x2, y2);
-                        const double ref = fhA[0] * h.u2 * h.u1 + fhA[1] * h.u2 * h.v1 + fhA[2] * h.u2 + fhA[3] * h.v2 * h.u1 +
-                                           fhA[4] * h.v2 * h.v1 + fhA[5] * h.v2 + fhA[6] * h.u1 + fhA[7] * h.v1 + fhA[8];
+                        const double tt = h.u2 + h.v2;
+                        const double ref = isH ? fhA[0] * h.u1 + fhA[1] * h.v1 + fhA[2] - tt * (fhA[3] * h.u1 + fhA[4] * h.v1 + fhA[5])
+                                               : fhA[0] * h.u2 * h.u1 + fhA[1] * h.u2 * h.v1 + fhA[2] * h.u2 + fhA[3] * h.v2 * h.u1 +
+                                                     fhA[4] * h.v2 * h.v1 + fhA[5] * h.v2 + fhA[6] * h.u1 + fhA[7] * h.v1 + fhA[8];
                         const float ratio = (float)(fabs((double)__int_as_float(v[i]) - ref) / emA);
                         if (active && mc.base < INFINITY && ratio > auditMax) auditMax = ratio;
                     }
@@ -522,12 +542,12 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
                 const uint32_t dlo = __shfl_sync(FULL, mlo, dm), dhi = __shfl_sync(FULL, mhi, dm);
                 const Model0 mm = load_m0(rowBase + dm);
                 const float4 h0 = sHat[lane], h1 = sHat[32 + lane];
-                int c0cls = hat_classify(isE, mm, thrkM, thrkL, h0.x, h0.y, h0.z, h0.w);
-                int c1cls = hat_classify(isE, mm, thrkM, thrkL, h1.x, h1.y, h1.z, h1.w);
+                int c0cls = classify(mm, h0);
+                int c1cls = classify(mm, h1);
                 if (!((dlo >> lane) & 1u)) c0cls = 0;
                 if (!((dhi >> lane) & 1u)) c1cls = 0;
                 const int c = __popc(__ballot_sync(FULL, c0cls == 1)) + __popc(__ballot_sync(FULL, c1cls == 1));
-                if (__any_sync(FULL, c0cls == 2 || c1cls == 2)) {
+                if (!isH && __any_sync(FULL, c0cls == 2 || c1cls == 2)) {
                     push_undecided(c0cls == 2, ((uint32_t)(c0 + lane) << 5) | (uint32_t)dm);
                     push_undecided(c1cls == 2, ((uint32_t)(c0 + 32 + lane) << 5) | (uint32_t)dm);
                 }
@@ -551,12 +571,12 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
 #pragma unroll
                 for (int t = 0; t < ST_INPLACE; ++t) {
                     const float4 h = sHat[bsel[t] & 63];
-                    cls[t] = hat_classify(isE, mc, thrkM, thrkL, h.x, h.y, h.z, h.w);
+                    cls[t] = isH ? (h_error(Hf, h.x, h.y, h.z, h.w) <= thr2 ? 1 : 0) : hat_classify(isE, mc, thrkM, thrkL, h.x, h.y, h.z, h.w);
                     if (bsel[t] < 0) cls[t] = 0;
                     cnt += cls[t] == 1 ? 1 : 0;
                     anyUnd |= cls[t] == 2;
                 }
-                if (__any_sync(FULL, anyUnd)) {
+                if (!isH && __any_sync(FULL, anyUnd)) {
 #pragma unroll
                     for (int t = 0; t < ST_INPLACE; ++t) push_undecided(cls[t] == 2, ((uint32_t)(c0 + bsel[t]) << 5) | (uint32_t)lane);
                 }
@@ -591,7 +611,7 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
             __syncwarp();
         }
         resolve_item(q[lane], lane < qn);
-        if (lane < q2n) exact_item(q2[lane]);
+        if (!isH && lane < q2n) exact_item(q2[lane]);
         __syncwarp();
         if (active) counts[(int64_t)p * maxSlots + m0 + row] = cnt + sCnt[row];
         if (AUDIT) {
@@ -662,7 +682,7 @@ std::atomic<uint32_t> g_score_audit_max{0};
 // can also split the correspondences of a pair over blocks)
 bool score_tc_eligible(int model, int64_t maxN, int slots, int np, int smCount) {
     const int eng = g_score_engine.load(std::memory_order_relaxed);
-    if (eng == 1 || model == RM_HOMOGRAPHY) return false;
+    if (eng == 1) return false;
     if (maxN >= (1 << 26) || maxN < 1) return false;
     if (eng == 2) return true;
     return maxN >= 256 && slots >= 256 && (int64_t)np * ((slots + ST_ROWS - 1) / ST_ROWS) >= 2ll * smCount;
@@ -674,7 +694,9 @@ int score_tc_run(Context* ctx, cudaStream_t st, int model, const float4* pf, con
     float am = 0.f;
     float* ap = g_score_audit.load(std::memory_order_relaxed) ? &am : nullptr;
     int rc;
-    if (model == RM_FUNDAMENTAL)
+    if (model == RM_HOMOGRAPHY)
+        rc = run<RM_HOMOGRAPHY>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap);
+    else if (model == RM_FUNDAMENTAL)
         rc = run<RM_FUNDAMENTAL>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap);
     else
         rc = run<RM_ESSENTIAL>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap);

@@ -273,6 +273,7 @@ void hm_h_filter(const double* H, int nModels, const float* a, const float* b, i
 #include <algorithm>
 #include <numeric>
 extern "C" {
+// isE: 0 fundamental, 1 essential, 2 homography (M rows = H with h33 = 1; no classifier, cls = exact).
 // Emulates score_tc.cu on the host: per-pair normalisation from the finite coordinate ranges, correspondences sorted by
 // image-1 cell (sorted != 0) or left in input order (boxes as large as the image: must still be conservative), split-TF32
 // rows for models and correspondences, stage boxes and thresholds, r~ accumulated over the 27 split terms in fp32 in index
@@ -280,9 +281,14 @@ extern "C" {
 // its error is budgeted, these three bracket it.  Outputs in INPUT order:
 // filt[k*n+i] = level 0 says "certainly outlier", exact[k*n+i] = the reference's exact test,
 // cls[k*n+i] = the two-sided fp32 classifier (0 outlier, 1 inlier, 2 undecided).
-void hm_filter0(int isE, const double* M, int nModels, const double* a, const double* b, int n, float thr, int mode, int sorted,
+void hm_filter0(int isE, const double* M, int nModels, const double* a_in, const double* b_in, int n, float thr, int mode, int sorted,
                 unsigned char* filt, unsigned char* exact, unsigned char* cls) {
     const int NT = 64;
+    // H and F work on the float32 view of the coordinates (prep_points_kernel), E on the fp64 normalised coordinates
+    std::vector<double> av(a_in, a_in + 2 * (size_t)n), bv(b_in, b_in + 2 * (size_t)n);
+    if (isE != 1) for (size_t i = 0; i < av.size(); ++i) { av[i] = (double)(float)av[i]; bv[i] = (double)(float)bv[i]; }
+    const double* a = av.data();
+    const double* b = bv.data();
     double lo[4] = {DBL_MAX, DBL_MAX, DBL_MAX, DBL_MAX}, hi[4] = {-DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
     float mx[4] = {0, 0, 0, 0};
     for (int i = 0; i < n; ++i) {
@@ -305,7 +311,8 @@ void hm_filter0(int isE, const double* M, int nModels, const double* a, const do
     double pmax = 0, vmax = 0;
     for (int s = 0; s < n; ++s) {
         double v2;
-        const double n2 = filter0_features(hat[order[s]], rows.data() + (size_t)s * F0_K, &v2);
+        const double n2 = isE == 2 ? filter0_features_h(hat[order[s]], rows.data() + (size_t)s * F0_K)
+                                   : filter0_features(hat[order[s]], rows.data() + (size_t)s * F0_K, &v2);
         if (n2 > pmax) pmax = n2;
         if (v2 > vmax) vmax = v2;
     }
@@ -332,12 +339,15 @@ void hm_filter0(int isE, const double* M, int nModels, const double* a, const do
     for (int k = 0; k < nModels; ++k) {
         float fr[F0_K];
         Model0 m0;
-        filter0_model(isE, pn, M + 9 * k, thr, fr, m0);
+        float Hf[8];
+        for (int j = 0; j < 8; ++j) Hf[j] = (float)M[9 * k + j];
+        if (isE == 2) filter0_model_h(pn, Hf, thr, fr, m0);
+        else filter0_model(isE, pn, M + 9 * k, thr, fr, m0);
         const double thrk = (double)thr * pn.k * pn.k;
         const float thrkM = (float)(thrk * (double)CLASS_MARGIN), thrkL = (float)(thrk * (double)CLASS_LOW);
         for (int s = 0; s < n; ++s) {
             const int i = order[s];
-            const float T = filter0_threshold(isE, m0, box[s / NT]);
+            const float T = isE == 2 ? filter0_threshold_h(m0, box[s / NT]) : filter0_threshold(isE, m0, box[s / NT]);
             const float* p = rows.data() + (size_t)s * F0_K;
             float r;
             if (mode == 2) { double acc = 0; for (int j = 0; j < 27; ++j) acc += (double)fr[j] * (double)p[j]; r = (float)acc; }
@@ -345,6 +355,12 @@ void hm_filter0(int isE, const double* M, int nModels, const double* a, const do
             else { volatile float acc = 0; for (int j = 0; j < 27; ++j) { volatile float t = fr[j] * p[j]; acc = acc + t; } r = acc; }
             filt[(size_t)k * n + i] = (fabsf(r) > T) ? 1 : 0;
             const Hat& h = hat[i];
+            if (isE == 2) {
+                const bool in = h_error(Hf, (float)a[2 * i], (float)a[2 * i + 1], (float)b[2 * i], (float)b[2 * i + 1]) <= thr;
+                exact[(size_t)k * n + i] = in ? 1 : 0;
+                cls[(size_t)k * n + i] = in ? 1 : 0;
+                continue;
+            }
             cls[(size_t)k * n + i] = (unsigned char)hat_classify(isE, m0, thrkM, thrkL, (float)h.u1, (float)h.v1, (float)h.u2, (float)h.v2);
             if (isE) {
                 exact[(size_t)k * n + i] = e_inlier(M + 9 * k, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], thr) ? 1 : 0;

@@ -514,3 +514,43 @@ def test_tf32_split_is_what_the_kernel_assumes(hm):
     assert not (hi.view(np.uint32) & 0x1FFF).any() and not (lo.view(np.uint32) & 0x1FFF).any()
     err = np.abs(x.astype(np.float64) - hi.astype(np.float64) - lo.astype(np.float64))
     assert (err <= 2.0 ** -22 * np.abs(x.astype(np.float64)) + 2e-41).all()      # + the subnormal grid
+
+
+def test_h_level0_is_conservative(hm):
+    """Homography: one accumulator carries the diagonal component of the reprojection residual; level 0 may only fire where
+    the float32 exact test says outlier (random 4-point models, near-perfect ones, rescaled / degenerate / non-finite ones,
+    off-centre and badly scaled coordinates) and must remove most of the work."""
+    rng = np.random.default_rng(29)
+    a, b, gt, H = synth.homography_pair(4, 3000)
+    af, bf = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    models = []
+    Hh = np.zeros(9)
+    inl = np.flatnonzero(gt)
+    for it in range(400):
+        idx = rng.permutation(len(af))[:4] if it < 300 else rng.choice(inl, 4, replace=False)
+        if hm.hm_h_solve4(p(np.ascontiguousarray(af[idx])), p(np.ascontiguousarray(bf[idx])), p(Hh)):
+            models.append(Hh.copy())
+    n_random = len(models)
+    base = (H / H[2, 2]).ravel()
+    for m in _adversarial_models(base, rng):
+        m = m.copy(); m[8] = 1.0
+        models.append(m)
+    M = np.stack(models)
+    for thr in (9.0, 1.0, 1e-4, 400.0):
+        for mode in (0, 1, 2):
+            filt, exact, cls = _filter0(hm, 2, M, af, bf, thr, mode)
+            assert not (filt & exact).any(), f"level 0 rejected an inlier, thr {thr} mode {mode}"
+        if thr == 9.0:
+            wrong = exact[:n_random].sum(axis=1) < 0.05 * len(af)
+            assert wrong.sum() > 100 and filt[:n_random][wrong].mean() > 0.95
+    filt, exact, cls = _filter0(hm, 2, M, af, bf, 9.0, 0, sorted_=0)
+    assert not (filt & exact).any()
+    for shift in (1e4, 1e6, 1e9):
+        filt, exact, cls = _filter0(hm, 2, M, af.astype(np.float64) + shift, bf.astype(np.float64) - 0.5 * shift, 9.0)
+        assert not (filt & exact).any(), f"shift {shift}"
+    sc = rng.choice([1e-20, 1e-3, 1.0, 1e3, 1e15], size=(len(af), 1))
+    filt, exact, cls = _filter0(hm, 2, M, af * sc, bf * sc[::-1], 9.0)
+    assert not (filt & exact).any()
+    a3 = af.astype(np.float64).copy(); a3[7, 1] = np.nan
+    filt, exact, cls = _filter0(hm, 2, M, a3, bf, 9.0)
+    assert not filt.any()

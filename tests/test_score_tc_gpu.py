@@ -50,6 +50,31 @@ def test_fundamental_level0_never_changes_a_count(tensor_engine):
             np.testing.assert_array_equal(counts_device(est.MODEL_F, a, b, M, thr), want, err_msg=f"thr {thr}")
 
 
+def test_homography_level0_never_changes_a_count(tensor_engine):
+    rng = np.random.default_rng(1)
+    a, b, gt, H = synth.homography_pair(21, 3000)
+    M = adversarial(H / H[2, 2], rng, n_random=300, fix33=True)
+    with np.errstate(all="ignore"):
+        for name, aa, bb in point_variants(a, b, rng):
+            m1, m2 = ransac.HomographyCB.prepare(aa, bb)
+            want = np.array([ransac.find_inliers(ransac.HomographyCB, m1, m2, m.reshape(3, 3), 3.0)[0] for m in M])
+            np.testing.assert_array_equal(counts_device(est.MODEL_H, aa, bb, M, 3.0), want, err_msg=name)
+        for shift in (1e4, 1e6):
+            aa, bb = a + shift, b - 0.5 * shift
+            m1, m2 = ransac.HomographyCB.prepare(aa, bb)
+            want = np.array([ransac.find_inliers(ransac.HomographyCB, m1, m2, m.reshape(3, 3), 3.0)[0] for m in M])
+            np.testing.assert_array_equal(counts_device(est.MODEL_H, aa, bb, M, 3.0), want, err_msg=f"shift {shift}")
+        inl = gt.astype(bool)
+        m1, m2 = ransac.HomographyCB.prepare(a[inl], b[inl])
+        want = np.array([ransac.find_inliers(ransac.HomographyCB, m1, m2, m.reshape(3, 3), 3.0)[0] for m in M])
+        np.testing.assert_array_equal(counts_device(est.MODEL_H, a[inl], b[inl], M, 3.0), want)
+        assert want[0] == inl.sum()
+        for thr in (0.05, 30.0):
+            m1, m2 = ransac.HomographyCB.prepare(a, b)
+            want = np.array([ransac.find_inliers(ransac.HomographyCB, m1, m2, m.reshape(3, 3), thr)[0] for m in M])
+            np.testing.assert_array_equal(counts_device(est.MODEL_H, a, b, M, thr), want, err_msg=f"thr {thr}")
+
+
 def test_essential_level0_never_changes_a_count(tensor_engine):
     rng = np.random.default_rng(3)
     a, b, gt, R, t = synth.two_view_pair(23, 3000)
@@ -75,7 +100,7 @@ def test_essential_level0_never_changes_a_count(tensor_engine):
 def _batch(model, n_pairs, n, iters, **kw):
     A = np.empty((n_pairs * n, 2)); B = np.empty((n_pairs * n, 2))
     for p in range(n_pairs):
-        r = synth.two_view_pair(100 + p, n)
+        r = synth.homography_pair(100 + p, n) if model == est.MODEL_H else synth.two_view_pair(100 + p, n)
         A[p * n:(p + 1) * n] = r[0]; B[p * n:(p + 1) * n] = r[1]
     off = np.arange(n_pairs + 1, dtype=np.int64) * n
     return est.ransac_batch(model, A, B, off, kw.pop("thr"), iters, 0.99, sample_mode=est.SAMPLE_COUNTER,
@@ -83,6 +108,8 @@ def _batch(model, n_pairs, n, iters, **kw):
 
 
 @pytest.mark.parametrize("model,n,iters,kw", [
+    (est.MODEL_H, 2000, 2048, dict(thr=3.0, refine=False)),
+    (est.MODEL_H, 501, 300, dict(thr=1.0)),
     (est.MODEL_F, 2000, 1024, dict(thr=3.0)),
     (est.MODEL_F, 777, 300, dict(thr=1.0)),                       # ragged: last stage partly filled, last tile partly filled
     (est.MODEL_E, 5000, 256, dict(thr=1.0, focal=800.0, pp=(320.0, 240.0))),
@@ -111,6 +138,7 @@ def test_engines_agree_count_by_count(model, n, iters, kw):
 
 
 @pytest.mark.parametrize("model,kw", [
+    (est.MODEL_H, dict(thr=2.0)),
     (est.MODEL_F, dict(thr=2.0)),
     (est.MODEL_E, dict(thr=1.5, focal=800.0, pp=(320.0, 240.0))),
 ])
@@ -123,7 +151,7 @@ def test_ragged_batch_and_chunk_seams(model, kw, monkeypatch):
     A = np.empty((offs[-1], 2)); B = np.empty((offs[-1], 2))
     for p, n in enumerate(sizes):
         if n:
-            r = synth.two_view_pair(200 + p, n)
+            r = synth.homography_pair(200 + p, n) if model == est.MODEL_H else synth.two_view_pair(200 + p, n)
             A[offs[p]:offs[p + 1]] = r[0]; B[offs[p]:offs[p + 1]] = r[1]
 
     def run(engine, chunk):
@@ -146,4 +174,4 @@ def test_ragged_batch_and_chunk_seams(model, kw, monkeypatch):
         np.testing.assert_array_equal(got.masks, ref.masks)
         np.testing.assert_array_equal(got.ok, ref.ok)
         np.testing.assert_array_equal(got.models, ref.models)
-    assert ref.ok[0] and not ref.ok[1] and not ref.ok[2]
+    assert ref.ok[0] and not ref.ok[1] and not ref.ok[7]                  # 2000, 0 and 1 correspondences

@@ -1,5 +1,5 @@
 """C3-F and C4 device-resident with both scoring engines: step time (CUDA events, median of 5) and the per-stage
-CUDA-event breakdown of the library.   python tools/score_probe.py [pairsF pairsE] [engines, e.g. 12]"""
+CUDA-event breakdown of the library.   python tools/score_probe.py [pairsHF pairsE] [engines, e.g. 12] [configs, e.g. HFE]"""
 import sys
 from pathlib import Path
 
@@ -35,7 +35,27 @@ if __name__ == "__main__":
         print(tag, "median ms", round(float(np.median(ts)), 3), "stages", st, flush=True)
 
     N, HYP = 2000, 4096
-    if PF > 0:
+    if PF > 0 and "H" in (sys.argv[4] if len(sys.argv) > 4 else "HFE"):
+        A = np.empty((PF * N, 2)); B = np.empty((PF * N, 2))
+        for p in range(PF):
+            r = synth.homography_pair(p, N)
+            A[p * N:(p + 1) * N] = r[0]; B[p * N:(p + 1) * N] = r[1]
+        off = np.arange(PF + 1, dtype=np.int64) * N
+        dA = torch.from_numpy(A).to(dev); dB = torch.from_numpy(B).to(dev)
+        dM = torch.empty((PF, 9), dtype=torch.float64, device=dev); dMask = torch.empty(PF * N, dtype=torch.uint8, device=dev)
+        dCnt = torch.empty(PF, dtype=torch.int32, device=dev); dOk = torch.empty(PF, dtype=torch.uint8, device=dev)
+        res = {}
+        for eng in engines:
+            est.set_score_engine(eng)
+            timed(lambda: est.ransac_batch_device(est.MODEL_H, dA, dB, off, 3.0, HYP, dM, dMask, dCnt, dOk, confidence=0.995,
+                                                  sample_mode=est.SAMPLE_COUNTER, stop_mode=est.STOP_FIXED, seed=1,
+                                                  stream=s.cuda_stream), f"C3-H {PF} pairs engine {eng}")
+            res[eng] = (dM.cpu().numpy().copy(), dCnt.cpu().numpy().copy(), dMask.cpu().numpy().copy())
+        if len(engines) > 1:
+            a, b = res[engines[0]], res[engines[1]]
+            print("H identical:", all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, b)), "mean inliers", a[1].mean())
+        del dA, dB, dM, dMask
+    if PF > 0 and "F" in (sys.argv[4] if len(sys.argv) > 4 else "HFE"):
         A = np.empty((PF * N, 2)); B = np.empty((PF * N, 2))
         for p in range(PF):
             r = synth.two_view_pair(p, N)
@@ -55,7 +75,7 @@ if __name__ == "__main__":
             a, b = res[engines[0]], res[engines[1]]
             print("F identical:", all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, b)), "mean inliers", a[1].mean())
         del dA, dB, dM, dMask
-    if PE > 0:
+    if PE > 0 and "E" in (sys.argv[4] if len(sys.argv) > 4 else "HFE"):
         N = 5000
         A = np.empty((PE * N, 2)); B = np.empty((PE * N, 2))
         for p in range(PE):
