@@ -424,7 +424,7 @@ STAGE_NAMES = {0: "matcher", 1: "expand_bits_kernel", 2: "knn2_finalize_kernel",
                17: "pose (decompose + cheirality + select)", 18: "gather_kernel", 19: "scale_search"}
 KERNEL_OF = {
     ("C2", 0): "hamming_tc_kernel<2,2,6>",
-    ("C3_H", 11): "sample_counter_kernel<0>", ("C3_H", 12): "solve_kernel<0>", ("C3_H", 14): "score_kernel<0>",
+    ("C3_H", 11): "sample_counter_kernel<0>", ("C3_H", 12): "solve_kernel<0>", ("C3_H", 14): "score_tc_kernel<0>",
     ("C3_H", 16): "finalize_homography_kernel",
     ("C3_F", 11): "sample_counter_kernel<1>", ("C3_F", 12): "solve_kernel<1>", ("C3_F", 14): "score_tc_kernel<1>",
     ("C3_F", 16): "finalize_plain_kernel<1>",

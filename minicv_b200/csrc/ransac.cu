@@ -907,8 +907,9 @@ __global__ void __launch_bounds__(128)
 score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
              const int64_t* __restrict__ off, const double* __restrict__ models,
              const int* __restrict__ slotList, const int* __restrict__ nTotal, int maxSlots,
-             float thr2, int chunkPts, int* __restrict__ counts) {
+             float thr2, int chunkPts, int* __restrict__ counts, const int* __restrict__ gate) {
     constexpr int TP = (MODEL == RM_ESSENTIAL) ? 512 : 1024;   // 16 KB per stage
+    if (gate && !score_gate_dense(gate)) return;               // the tensor-core kernel scores this chunk
     __shared__ __align__(16) unsigned char sraw[16384];
     __shared__ int smax[4];
     __shared__ __align__(16) float spair_e[(MODEL == RM_ESSENTIAL) ? 4 * 512 : 4];    // essential: fp32 rounding of the tile
@@ -1950,28 +1951,36 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             }
         } else {
         // ---- score
-        if (score_tc_eligible(MODEL, maxN, (int)slots, np, ctx->sm_count)) {
+        {
+            const int tcMode = score_tc_mode(MODEL, maxN, (int)slots, np, ctx->sm_count);
+            const int* gate = nullptr;
             kt_begin(ctx, st, KT_SCORE);
-            const int rc = score_tc_run(ctx, st, MODEL, pf, pd, off, io.hOff + p0, p0, np, dModels, dSlotList, dNTotal,
-                                        (int)slots, thr2, dCounts);
+            if (tcMode == 2) {
+                gate = score_tc_pilot(ctx, st, MODEL, pf, pd, off, np, dModels, dSlotList, dNTotal, (int)slots, thr2);
+                if (!gate) return -1;
+            }
+            if (tcMode) {
+                const int rc = score_tc_run(ctx, st, MODEL, pf, pd, off, io.hOff + p0, p0, np, dModels, dSlotList, dNTotal,
+                                            (int)slots, thr2, dCounts, gate);
+                if (rc) return rc;
+            }
+            if (tcMode != 1) {
+                const int tiles = (int)((slots + 127) / 128);
+                int zs = 1;
+                const int64_t blocksXY = (int64_t)tiles * np;
+                const int64_t fill = 4ll * ctx->sm_count;
+                const int TPmin = (MODEL == RM_ESSENTIAL) ? 512 : 1024;
+                if (blocksXY < fill) zs = (int)std::min<int64_t>((fill + blocksXY - 1) / blocksXY, std::max<int64_t>(1, (maxN + TPmin - 1) / TPmin));
+                int chunkPts = (int)((std::max<int64_t>(maxN, 1) + zs - 1) / zs);
+                zs = (int)((std::max<int64_t>(maxN, 1) + chunkPts - 1) / chunkPts);
+                if (gate) { zs = 1; chunkPts = (int)std::max<int64_t>(maxN, 1); }     // a gated chunk always fills the machine
+                if (zs > 1) MCV_CUDA_TRY(cudaMemsetAsync(dCounts, 0, (size_t)np * slots * 4, st));
+                dim3 g(tiles, np, zs);
+                score_kernel<MODEL><<<g, 128, 0, st>>>(pf, pd, off, dModels, dSlotList, dNTotal, (int)slots,
+                                                       thr2, chunkPts, dCounts, gate);
+                MCV_LAUNCH_CHECK();
+            }
             kt_end(ctx, st);
-            if (rc) return rc;
-        } else {
-            const int tiles = (int)((slots + 127) / 128);
-            int zs = 1;
-            const int64_t blocksXY = (int64_t)tiles * np;
-            const int64_t fill = 4ll * ctx->sm_count;
-            const int TPmin = (MODEL == RM_ESSENTIAL) ? 512 : 1024;
-            if (blocksXY < fill) zs = (int)std::min<int64_t>((fill + blocksXY - 1) / blocksXY, std::max<int64_t>(1, (maxN + TPmin - 1) / TPmin));
-            int chunkPts = (int)((std::max<int64_t>(maxN, 1) + zs - 1) / zs);
-            zs = (int)((std::max<int64_t>(maxN, 1) + chunkPts - 1) / chunkPts);
-            if (zs > 1) MCV_CUDA_TRY(cudaMemsetAsync(dCounts, 0, (size_t)np * slots * 4, st));
-            dim3 g(tiles, np, zs);
-            kt_begin(ctx, st, KT_SCORE);
-            score_kernel<MODEL><<<g, 128, 0, st>>>(pf, pd, off, dModels, dSlotList, dNTotal, (int)slots,
-                                                   thr2, chunkPts, dCounts);
-            kt_end(ctx, st);
-            MCV_LAUNCH_CHECK();
         }
         // ---- select
         kt_begin(ctx, st, KT_SELECT);

@@ -78,9 +78,10 @@ template <int MODEL>
 __global__ void __launch_bounds__(256)
 score_tc_features_kernel(const float4* __restrict__ pf, const double* __restrict__ pd, const int64_t* __restrict__ off,
                          int64_t pairBase, PairNorm* __restrict__ norms, float* __restrict__ feat,
-                         void* __restrict__ sortedRaw, StageBox* __restrict__ boxes) {
+                         void* __restrict__ sortedRaw, StageBox* __restrict__ boxes, const int* __restrict__ gate) {
     constexpr int isE = MODEL == RM_ESSENTIAL ? 1 : 0;
     constexpr bool isH = MODEL == RM_HOMOGRAPHY;
+    if (gate && score_gate_dense(gate)) return;               // the fp32-filter kernel scores this chunk
     const int p = blockIdx.x;
     const int64_t base = off[p];
     const int n = (int)(off[p + 1] - base);
@@ -281,10 +282,12 @@ __global__ void __launch_bounds__(ST_THREADS, 2)
 score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNorm* __restrict__ norms,
                 const float* __restrict__ feat, const void* __restrict__ sortedRaw, const StageBox* __restrict__ boxes,
                 const double* __restrict__ models, const int* __restrict__ slotList, const int* __restrict__ nTotal,
-                int maxSlots, float thr2, int* __restrict__ counts, unsigned long long* __restrict__ audit) {
+                int maxSlots, float thr2, int* __restrict__ counts, unsigned long long* __restrict__ audit,
+                const int* __restrict__ gate) {
     constexpr int isE = MODEL == RM_ESSENTIAL ? 1 : 0;
     constexpr bool isH = MODEL == RM_HOMOGRAPHY;
     constexpr int A_BYTES = ST_ROWS * ST_ROW_BYTES;           // 32 KB
+    if (gate && score_gate_dense(gate)) return;
     constexpr int B_BYTES = ST_STAGE_BYTES;                   // 9 KB per stage: 64 operand rows + 64 coordinate quadruples
     const int p = blockIdx.y;
     const int total = nTotal[p];
@@ -632,7 +635,7 @@ constexpr size_t ST_SMEM = 1024 + ST_ROWS * ST_ROW_BYTES + ST_STAGES * ST_STAGE_
 template <int MODEL>
 int run(Context* ctx, cudaStream_t st, const float4* pf, const double* pd, const int64_t* dOff, const int64_t* hOff,
         int64_t pairBase, int np, const double* dModels, const int* dSlotList, const int* dNTotal, int slots, float thr2,
-        int* dCounts, float* auditOut) {
+        int* dCounts, float* auditOut, const int* gate) {
     // buffers of the pairs [0, np) of this chunk (dOff / hOff already point at the chunk's first pair), addressed relative
     // to the chunk's first pair
     const int64_t s0 = stage_base(hOff[0], pairBase), s1 = stage_base(hOff[np], pairBase + np) + 2;
@@ -646,14 +649,14 @@ int run(Context* ctx, cudaStream_t st, const float4* pf, const double* pd, const
     StageBox* boxes = ctx->ws[83].as<StageBox>() - s0;
     PairNorm* norms = ctx->ws[81].as<PairNorm>();
     unsigned long long* audit = ctx->ws[84].as<unsigned long long>();
-    score_tc_features_kernel<MODEL><<<np, 256, 0, st>>>(pf, pd, dOff, pairBase, norms, feat, raw, boxes);
+    score_tc_features_kernel<MODEL><<<np, 256, 0, st>>>(pf, pd, dOff, pairBase, norms, feat, raw, boxes, gate);
     MCV_LAUNCH_CHECK();
     dim3 g((slots + ST_ROWS - 1) / ST_ROWS, np);
     if (auditOut) {
         MCV_CUDA_TRY(cudaMemsetAsync(audit, 0, 8, st));
         auto kern = score_tc_kernel<MODEL, true>;
         MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
-        kern<<<g, ST_THREADS, ST_SMEM, st>>>(dOff, pairBase, norms, feat, raw, boxes, dModels, dSlotList, dNTotal, slots, thr2, dCounts, audit);
+        kern<<<g, ST_THREADS, ST_SMEM, st>>>(dOff, pairBase, norms, feat, raw, boxes, dModels, dSlotList, dNTotal, slots, thr2, dCounts, audit, gate);
         MCV_LAUNCH_CHECK();
         unsigned long long h = 0;
         MCV_CUDA_TRY(cudaMemcpyAsync(&h, audit, 8, cudaMemcpyDeviceToHost, st));
@@ -665,7 +668,7 @@ int run(Context* ctx, cudaStream_t st, const float4* pf, const double* pd, const
     } else {
         auto kern = score_tc_kernel<MODEL, false>;
         MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
-        kern<<<g, ST_THREADS, ST_SMEM, st>>>(dOff, pairBase, norms, feat, raw, boxes, dModels, dSlotList, dNTotal, slots, thr2, dCounts, audit);
+        kern<<<g, ST_THREADS, ST_SMEM, st>>>(dOff, pairBase, norms, feat, raw, boxes, dModels, dSlotList, dNTotal, slots, thr2, dCounts, audit, gate);
         MCV_LAUNCH_CHECK();
     }
     return 0;
@@ -676,30 +679,88 @@ int run(Context* ctx, cudaStream_t st, const float4* pf, const double* pd, const
 std::atomic<int> g_score_audit{0};
 std::atomic<uint32_t> g_score_audit_max{0};
 
-// true when the tensor-core scoring path takes this chunk (engine 1 = fp32-filter kernel only, 2 = tensor cores whenever
-// the shapes allow, 0 = tensor cores when the chunk has enough (pair, 256-model) work items to fill the machine twice and
-// enough correspondences per pair to amortise the per-CTA model conversion; small calls keep the fp32-filter kernel, which
-// can also split the correspondences of a pair over blocks)
-bool score_tc_eligible(int model, int64_t maxN, int slots, int np, int smCount) {
+namespace {
+
+// 32 models x 128 correspondences per pair through the exact test: how many of the sampled models fit (keep >= 1/8)?
+template <int MODEL>
+__global__ void __launch_bounds__(32)
+score_pilot_kernel(const float4* __restrict__ pf, const double* __restrict__ pd, const int64_t* __restrict__ off,
+                   const double* __restrict__ models, const int* __restrict__ slotList, const int* __restrict__ nTotal,
+                   int maxSlots, float thr2, int* __restrict__ gate) {
+    const int p = blockIdx.x, lane = threadIdx.x;
+    const int total = nTotal[p];
+    const int64_t base = off[p];
+    const int n = (int)min((int64_t)128, off[p + 1] - base);
+    const bool active = lane < total && n >= 16;
+    double m[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) m[j] = 0;
+    if (active) {
+        const double* src = models + ((int64_t)p * maxSlots + slotList[(int64_t)p * maxSlots + lane]) * 9;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) m[j] = src[j];
+    }
+    float Hf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Hf[j] = (float)m[j];
+    int cnt = 0;
+    if (active) {
+        for (int j = 0; j < n; ++j) {
+            if (MODEL == RM_ESSENTIAL) {
+                const double4 c = reinterpret_cast<const double4*>(pd)[base + j];
+                cnt += e_inlier(m, c.x, c.y, c.z, c.w, thr2) ? 1 : 0;
+            } else {
+                const float4 c = pf[base + j];
+                if (MODEL == RM_HOMOGRAPHY) cnt += h_error(Hf, c.x, c.y, c.z, c.w) <= thr2 ? 1 : 0;
+                else cnt += f_inlier(m, (double)c.x, (double)c.y, (double)c.z, (double)c.w, thr2) ? 1 : 0;
+            }
+        }
+    }
+    const unsigned looked = __ballot_sync(0xFFFFFFFFu, active), fit = __ballot_sync(0xFFFFFFFFu, active && cnt * 8 >= n);
+    if (lane == 0 && looked) { atomicAdd(gate, __popc(fit)); atomicAdd(gate + 1, __popc(looked)); }
+}
+
+}  // namespace
+
+int score_tc_mode(int model, int64_t maxN, int slots, int np, int smCount) {
     const int eng = g_score_engine.load(std::memory_order_relaxed);
-    if (eng == 1) return false;
-    if (maxN >= (1 << 26) || maxN < 1) return false;
-    if (eng == 2) return true;
-    return maxN >= 256 && slots >= 256 && (int64_t)np * ((slots + ST_ROWS - 1) / ST_ROWS) >= 2ll * smCount;
+    if (eng == 1) return 0;
+    if (maxN >= (1 << 26) || maxN < 1) return 0;
+    if (eng == 2) return 1;
+    // auto: enough (pair, 256-model) work items to fill the machine twice, enough correspondences per pair to amortise the
+    // per-CTA model conversion; then the device decides from what the models look like
+    const bool big = maxN >= 256 && slots >= 256 && (int64_t)np * ((slots + ST_ROWS - 1) / ST_ROWS) >= 2ll * smCount;
+    return big ? 2 : 0;
+}
+
+int* score_tc_pilot(Context* ctx, cudaStream_t st, int model, const float4* pf, const double* pd, const int64_t* dOff, int np,
+                    const double* dModels, const int* dSlotList, const int* dNTotal, int slots, float thr2) {
+    if (ctx->ws[85].reserve(64)) return nullptr;
+    int* gate = ctx->ws[85].as<int>();
+    if (cudaMemsetAsync(gate, 0, 8, st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return nullptr; }
+    if (model == RM_HOMOGRAPHY)
+        score_pilot_kernel<RM_HOMOGRAPHY><<<np, 32, 0, st>>>(pf, pd, dOff, dModels, dSlotList, dNTotal, slots, thr2, gate);
+    else if (model == RM_FUNDAMENTAL)
+        score_pilot_kernel<RM_FUNDAMENTAL><<<np, 32, 0, st>>>(pf, pd, dOff, dModels, dSlotList, dNTotal, slots, thr2, gate);
+    else
+        score_pilot_kernel<RM_ESSENTIAL><<<np, 32, 0, st>>>(pf, pd, dOff, dModels, dSlotList, dNTotal, slots, thr2, gate);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) { set_error("score_pilot_kernel launch failed"); return nullptr; }
+    return gate;
 }
 
 int score_tc_run(Context* ctx, cudaStream_t st, int model, const float4* pf, const double* pd, const int64_t* dOff,
                  const int64_t* hOff, int64_t pairBase, int np, const double* dModels, const int* dSlotList,
-                 const int* dNTotal, int slots, float thr2, int* dCounts) {
+                 const int* dNTotal, int slots, float thr2, int* dCounts, const int* gate) {
     float am = 0.f;
     float* ap = g_score_audit.load(std::memory_order_relaxed) ? &am : nullptr;
     int rc;
     if (model == RM_HOMOGRAPHY)
-        rc = run<RM_HOMOGRAPHY>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap);
+        rc = run<RM_HOMOGRAPHY>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap, gate);
     else if (model == RM_FUNDAMENTAL)
-        rc = run<RM_FUNDAMENTAL>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap);
+        rc = run<RM_FUNDAMENTAL>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap, gate);
     else
-        rc = run<RM_ESSENTIAL>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap);
+        rc = run<RM_ESSENTIAL>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap, gate);
     if (ap) {
         uint32_t bits;
         memcpy(&bits, &am, 4);

@@ -175,3 +175,30 @@ def test_ragged_batch_and_chunk_seams(model, kw, monkeypatch):
         np.testing.assert_array_equal(got.ok, ref.ok)
         np.testing.assert_array_equal(got.models, ref.models)
     assert ref.ok[0] and not ref.ok[1] and not ref.ok[7]                  # 2000, 0 and 1 correspondences
+
+
+@pytest.mark.parametrize("inlier_frac", [0.3, 0.9])
+def test_auto_mode_selects_on_the_device(inlier_frac):
+    """Auto mode on a batch large enough for the tensor-core engine: a pilot kernel looks at the first models of every pair
+    and the gate lets exactly one of the two scoring kernels run (level 0 when almost every model is wrong, the fp32-filter
+    kernel when many models fit, as on ratio-tested matches).  Whichever runs, the results are those of either engine."""
+    n_pairs, n, iters = 40, 600, 2048
+    A = np.empty((n_pairs * n, 2)); B = np.empty((n_pairs * n, 2))
+    for p in range(n_pairs):
+        r = synth.homography_pair(300 + p, n, inlier_frac=inlier_frac)
+        A[p * n:(p + 1) * n] = r[0]; B[p * n:(p + 1) * n] = r[1]
+    off = np.arange(n_pairs + 1, dtype=np.int64) * n
+    out = {}
+    for engine in (est.SCORE_FP32_FILTER, est.SCORE_TENSOR, est.SCORE_AUTO):
+        est.set_score_engine(engine)
+        try:
+            out[engine] = est.ransac_batch(est.MODEL_H, A, B, off, 3.0, iters, 0.995, sample_mode=est.SAMPLE_COUNTER,
+                                           stop_mode=est.STOP_FIXED, seed=3, debug=True)
+        finally:
+            est.set_score_engine(est.SCORE_AUTO)
+    ref = out[est.SCORE_FP32_FILTER]
+    for engine in (est.SCORE_TENSOR, est.SCORE_AUTO):
+        np.testing.assert_array_equal(out[engine].dbg_counts, ref.dbg_counts)
+        np.testing.assert_array_equal(out[engine].masks, ref.masks)
+        np.testing.assert_array_equal(out[engine].models, ref.models)
+    assert ref.ok.all() and abs(ref.inliers.mean() / n - inlier_frac) < 0.1
