@@ -708,13 +708,16 @@ MCV_HDN inline bool h_check_subset(const float* src, const float* dst) {
 }
 
 // ---- homography from 4 correspondences ------------------------------------------------------
-// Same normalisation as HomographyEstimatorCallback::runKernel; the exact interpolating H
-// is obtained from the 8x9 DLT system by elimination with complete pivoting (OpenCV takes the
-// smallest eigenvector of the 9x9 normal matrix -- same H up to rounding for a minimal set).
 // src/dst: 4 (x,y) float pairs.  H: 9 doubles, scaled so H[8] = 1.  Returns false if degenerate.
-// Ab: 72 doubles of scratch with element stride S (the 8 x 9 system; 1 = plain array, blockDim = thread-interleaved smem)
-template <int S>
-MCV_HDN inline bool h_solve4_at(const float* src, const float* dst, double* H, double* Ab) {
+// OpenCV's kernel (HomographyEstimatorCallback::runKernel) normalises the points per axis and takes the eigenvector of the
+// smallest eigenvalue of the 9 x 9 L'L; with four points that vector is the unique null vector of the 8 x 9 system, so any
+// exact method returns the same matrix up to rounding.  Here, in registers: the projective-basis form.  With P_i = (X_i, Y_i,
+// 1) (normalised source), M = [P1 P2 P3], lambda = adj(M) P4, the map A = M diag(lambda) takes the canonical basis e1, e2,
+// e3, e1 + e2 + e3 to P1..P4; likewise B = N diag(mu) for the targets.  H_n = B A^-1 ~ N diag(c) adj(M) with c_i = mu_i
+// lambda_j lambda_k, and the rows of adj(M) are the cross products P2 x P3, P3 x P1, P1 x P2.  ~130 flops instead of a
+// full-pivot 8 x 9 elimination in shared memory (round 1/2: 2.0 ms of a C3-H step).  A vanishing lambda_i / mu_i means
+// three of the four points are collinear: no model (the sampler's degeneracy test rejects those subsets beforehand).
+MCV_HDN inline bool h_solve4(const float* src, const float* dst, double* H) {
     double cMx = 0, cMy = 0, cmx = 0, cmy = 0;
     for (int i = 0; i < 4; ++i) { cmx += dst[2 * i]; cmy += dst[2 * i + 1]; cMx += src[2 * i]; cMy += src[2 * i + 1]; }
     cmx /= 4; cmy /= 4; cMx /= 4; cMy /= 4;
@@ -726,44 +729,32 @@ MCV_HDN inline bool h_solve4_at(const float* src, const float* dst, double* H, d
     if (fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON)
         return false;
     smx = 4 / smx; smy = 4 / smy; sMx = 4 / sMx; sMy = 4 / sMy;
+    double X[4], Y[4], x[4], y[4];
     for (int i = 0; i < 4; ++i) {
-        const double x = (dst[2 * i] - cmx) * smx, y = (dst[2 * i + 1] - cmy) * smy;
-        const double X = (src[2 * i] - cMx) * sMx, Y = (src[2 * i + 1] - cMy) * sMy;
-        double* r0 = Ab + (2 * i) * 9 * S;
-        double* r1 = Ab + (2 * i + 1) * 9 * S;
-        r0[0 * S] = X; r0[1 * S] = Y; r0[2 * S] = 1; r0[3 * S] = 0; r0[4 * S] = 0; r0[5 * S] = 0; r0[6 * S] = -x * X; r0[7 * S] = -x * Y; r0[8 * S] = -x;
-        r1[0 * S] = 0; r1[1 * S] = 0; r1[2 * S] = 0; r1[3 * S] = X; r1[4 * S] = Y; r1[5 * S] = 1; r1[6 * S] = -y * X; r1[7 * S] = -y * Y; r1[8 * S] = -y;
+        x[i] = (dst[2 * i] - cmx) * smx; y[i] = (dst[2 * i + 1] - cmy) * smy;
+        X[i] = (src[2 * i] - cMx) * sMx; Y[i] = (src[2 * i + 1] - cMy) * sMy;
     }
-    int perm[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
-    for (int c = 0; c < 8; ++c) {
-        int pr = c, pc = c;
-        double best = -1;
-        for (int r = c; r < 8; ++r)
-            for (int k = c; k < 9; ++k) {
-                const double v = fabs(Ab[((r) * 9 + (k)) * S]);
-                if (v > best) { best = v; pr = r; pc = k; }
-            }
-        if (!(best > 1e-14)) return false;
-        if (pr != c) for (int k = 0; k < 9; ++k) { double t = Ab[((c) * 9 + (k)) * S]; Ab[((c) * 9 + (k)) * S] = Ab[((pr) * 9 + (k)) * S]; Ab[((pr) * 9 + (k)) * S] = t; }
-        if (pc != c) {
-            for (int r = 0; r < 8; ++r) { double t = Ab[((r) * 9 + (c)) * S]; Ab[((r) * 9 + (c)) * S] = Ab[((r) * 9 + (pc)) * S]; Ab[((r) * 9 + (pc)) * S] = t; }
-            int t = perm[c]; perm[c] = perm[pc]; perm[pc] = t;
-        }
-        const double inv = 1 / Ab[((c) * 9 + (c)) * S];
-        for (int r = c + 1; r < 8; ++r) {
-            const double f = Ab[((r) * 9 + (c)) * S] * inv;
-            if (f != 0) for (int k = c; k < 9; ++k) Ab[((r) * 9 + (k)) * S] -= f * Ab[((c) * 9 + (k)) * S];
-        }
+    // rows of adj([P1 P2 P3]) for the sources, lambda = adj . P4
+    const double r[3][3] = {{Y[1] - Y[2], X[2] - X[1], X[1] * Y[2] - X[2] * Y[1]},
+                            {Y[2] - Y[0], X[0] - X[2], X[2] * Y[0] - X[0] * Y[2]},
+                            {Y[0] - Y[1], X[1] - X[0], X[0] * Y[1] - X[1] * Y[0]}};
+    double lam[3], mu[3];
+    for (int i = 0; i < 3; ++i) lam[i] = r[i][0] * X[3] + r[i][1] * Y[3] + r[i][2];
+    // the same for the targets: mu = adj([p1 p2 p3]) p4
+    mu[0] = (y[1] - y[2]) * x[3] + (x[2] - x[1]) * y[3] + (x[1] * y[2] - x[2] * y[1]);
+    mu[1] = (y[2] - y[0]) * x[3] + (x[0] - x[2]) * y[3] + (x[2] * y[0] - x[0] * y[2]);
+    mu[2] = (y[0] - y[1]) * x[3] + (x[1] - x[0]) * y[3] + (x[0] * y[1] - x[1] * y[0]);
+    for (int i = 0; i < 3; ++i)
+        if (!(fabs(lam[i]) > 1e-13) || !(fabs(mu[i]) > 1e-13)) return false;
+    const double c[3] = {mu[0] * lam[1] * lam[2], mu[1] * lam[0] * lam[2], mu[2] * lam[0] * lam[1]};
+    double h[9];
+    for (int j = 0; j < 3; ++j) {
+        const double t0 = c[0] * r[0][j], t1 = c[1] * r[1][j], t2 = c[2] * r[2][j];
+        h[j] = x[0] * t0 + x[1] * t1 + x[2] * t2;
+        h[3 + j] = y[0] * t0 + y[1] * t1 + y[2] * t2;
+        h[6 + j] = t0 + t1 + t2;
     }
-    double h[9], sol[9];
-    sol[8] = 1;
-    for (int c = 7; c >= 0; --c) {
-        double s = 0;
-        for (int k = c + 1; k < 9; ++k) s += Ab[((c) * 9 + (k)) * S] * sol[k];
-        sol[c] = -s / Ab[((c) * 9 + (c)) * S];
-    }
-    for (int k = 0; k < 9; ++k) h[perm[k]] = sol[k];
-    // H = invHnorm * h0 * Hnorm2
+    // H = invHnorm * h * Hnorm2
     const double iH[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
     const double N2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
     double T[9];
@@ -776,11 +767,6 @@ MCV_HDN inline bool h_solve4_at(const float* src, const float* dst, double* H, d
     for (int k = 0; k < 9; ++k) H[k] *= sc;
     for (int k = 0; k < 9; ++k) if (!(fabs(H[k]) < 1e300)) return false;
     return true;
-}
-
-MCV_HDN inline bool h_solve4(const float* src, const float* dst, double* H) {
-    double A[8 * 9];
-    return h_solve4_at<1>(src, dst, H, A);
 }
 
 // ---- cv::solveCubic (closed form); coeffs c[0] x^3 + c[1] x^2 + c[2] x + c[3] -----------------

@@ -336,11 +336,8 @@ solve_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
             s[2 * i] = q.x; s[2 * i + 1] = q.y; d[2 * i] = q.z; d[2 * i + 1] = q.w;
         }
         if (MODEL == RM_HOMOGRAPHY) {
-            // 8 x 9 elimination matrix in thread-interleaved shared memory (as a local array it was the kernel's
-            // whole cost: 11.5 GB of local-memory write-back per launch)
-            __shared__ double sAb[(MODEL == RM_HOMOGRAPHY) ? 72 * 64 : 1];
             double H[9];
-            cnt = h_solve4_at<64>(s, d, H, sAb + threadIdx.x) ? 1 : 0;
+            cnt = h_solve4(s, d, H) ? 1 : 0;             // closed form, registers only (cvmath.cuh)
             if (cnt) for (int k = 0; k < 9; ++k) out[k] = H[k];
         } else {
             // the 7 x 9 design matrix of the Jacobi SVD lives in shared memory, interleaved by thread (element e of
@@ -1889,8 +1886,10 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
                 auto kern = sample_mwc_par_kernel<MODEL>;
                 const size_t smemBytes = (size_t)smemPts * 16 + (MWC_BLOCK + MWC_MAXDRAW) * 4 + (size_t)MWC_BLOCK * MP * 2 +
                                          (MWC_BLOCK / MP + 8) * 2 + MWC_BLOCK + 64;
-                if (smemBytes > 48 * 1024)
-                    MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+                // the attribute is shared by every host thread that launches this kernel: always the largest size
+                const size_t smemMax = (size_t)8192 * 16 + (MWC_BLOCK + MWC_MAXDRAW) * 4 + (size_t)MWC_BLOCK * MP * 2 +
+                                       (MWC_BLOCK / MP + 8) * 2 + MWC_BLOCK + 64;
+                MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax));
                 kern<<<np, 256, smemBytes, st>>>(pf, off, np, maxIters, smemPts, dRaw, dSamples, dNIter, dFlags, dNeedSeq);
                 MCV_LAUNCH_CHECK();
             }
@@ -1898,8 +1897,8 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             const int smemPts = (int)std::min<int64_t>(maxN, 12288);       // up to 192 KB of float4 points
             auto kern = sample_mwc_kernel<MODEL>;
             const size_t smemBytes = MODEL == RM_ESSENTIAL ? 0 : (size_t)smemPts * 16;
-            if (smemBytes > 48 * 1024)
-                MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+            if (MODEL != RM_ESSENTIAL)
+                MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 16));
             kern<<<np, 32, smemBytes, st>>>(pf, off, np, maxIters, smemPts, dSamples, dNIter, dFlags, dNeedSeq);
             MCV_LAUNCH_CHECK();
         }
