@@ -339,11 +339,12 @@ MCV_HDN inline void solve_sym_eig(const double* A, const double* b, double* x) {
     }
 }
 
-// Same solve, fast path: Cholesky when A is comfortably positive definite (the usual LM case:
-// J^T J + lambda diag), where it equals the eigen-solve to rounding; the thresholded eigen-solve
-// stays for ill-conditioned systems, where its pseudo-inverse semantics matter.
+// Same solve, fast path: Cholesky when A is comfortably positive definite (J^T J + lambda diag with a healthy
+// lambda), where it equals the eigen-solve to rounding; returns false (x untouched) when a pivot falls below
+// 1e-12 of the largest diagonal entry -- the thresholded eigen-solve, whose pseudo-inverse semantics matter for
+// ill-conditioned systems, takes over.
 template <int N>
-MCV_HDN inline void solve_sym_chol_or_eig(const double* A, const double* b, double* x) {
+MCV_HDN inline bool solve_sym_chol(const double* A, const double* b, double* x) {
     double L[N * N];
     double dmax = 0;
     for (int i = 0; i < N; ++i) dmax = fmax(dmax, fabs(A[i * N + i]));
@@ -360,7 +361,7 @@ MCV_HDN inline void solve_sym_chol_or_eig(const double* A, const double* b, doub
             L[i * N + j] = s / ljj;
         }
     }
-    if (!ok) { solve_sym_eig<N>(A, b, x); return; }
+    if (!ok) return false;
     double y[N];
     for (int i = 0; i < N; ++i) {
         double s = b[i];
@@ -372,9 +373,13 @@ MCV_HDN inline void solve_sym_chol_or_eig(const double* A, const double* b, doub
         for (int k = i + 1; k < N; ++k) s -= L[k * N + i] * x[k];
         x[i] = s / L[i * N + i];
     }
+    return true;
+}
+template <int N>
+MCV_HDN inline void solve_sym_chol_or_eig(const double* A, const double* b, double* x) {
+    if (!solve_sym_chol<N>(A, b, x)) solve_sym_eig<N>(A, b, x);
 }
 
-// max |diag| of pinv(A) for symmetric A (LMSolver's lambda re-seed: invert(A, Ap, DECOMP_EIG))
 template <int N>
 MCV_HDN inline double max_diag_pinv_sym(const double* A) {
     double M[N * N], w[N], V[N * N];

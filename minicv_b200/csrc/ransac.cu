@@ -1507,20 +1507,114 @@ __device__ MCV_REFIT_NOINLINE void h_from_ltl_warp(const double* ltl45, double c
     }
 }
 
-// one LM trial step: d = solve(A + lambda*diag(D), v), xd = x - d
-__device__ MCV_REFIT_NOINLINE void lm_trial(const double* A, const double* v, const double* D, double lam,
-                                      const double* x, double* d, double* xd) {
-    double Ap[64], vv[8], dd[8];
-    for (int k = 0; k < 64; ++k) Ap[k] = A[k];
-    for (int r = 0; r < 8; ++r) { Ap[r * 8 + r] += lam * D[r]; vv[r] = v[r]; }
-    solve_sym_chol_or_eig<8>(Ap, vv, dd);
-    for (int r = 0; r < 8; ++r) { d[r] = dd[r]; xd[r] = x[r] - dd[r]; }
+// Symmetric N x N eigen-decomposition by one warp, in shared memory: the operations of cvmath.cuh jacobi_eigen_sym in the same
+// order (rotation angle and convergence sums computed redundantly by every lane, element updates of a rotation spread over
+// the lanes), so w and V are bit-identical to the single-thread form's.  A is destroyed (diagonal = eigenvalues), V rows =
+// eigenvectors.  All 32 lanes of the warp must call.
+template <int N>
+__device__ __forceinline__ void jacobi_eigen_sym_warp(double* A, double* V) {
+    const int lane = threadIdx.x & 31;
+    for (int idx = lane; idx < N * N; idx += 32) V[idx] = (idx / N == idx % N) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0, diag = 0;
+        for (int i = 0; i < N; ++i) {
+            diag += A[i * N + i] * A[i * N + i];
+            for (int j = i + 1; j < N; ++j) off += A[i * N + j] * A[i * N + j];
+        }
+        if (off <= 1e-32 * diag || off == 0) break;
+        for (int p = 0; p < N - 1; ++p)
+            for (int q = p + 1; q < N; ++q) {
+                const double apq = A[p * N + q];
+                if (apq == 0) continue;
+                const double app = A[p * N + p], aqq = A[q * N + q];
+                const double theta = (aqq - app) / (2 * apq);
+                const double t = (theta >= 0 ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1));
+                const double c = 1 / sqrt(t * t + 1), sn = t * c;
+                __syncwarp();                                   // everyone has read app, aqq, apq
+                if (lane < N) {
+                    const int k = lane;
+                    const double akp = A[k * N + p], akq = A[k * N + q];
+                    A[k * N + p] = c * akp - sn * akq;
+                    A[k * N + q] = sn * akp + c * akq;
+                } else if (lane >= 16 && lane < 16 + N) {
+                    const int k = lane - 16;
+                    const double vp = V[p * N + k], vq = V[q * N + k];
+                    V[p * N + k] = c * vp - sn * vq;
+                    V[q * N + k] = sn * vp + c * vq;
+                }
+                __syncwarp();
+                if (lane < N) {
+                    const int k = lane;
+                    const double apk = A[p * N + k], aqk = A[q * N + k];
+                    A[p * N + k] = c * apk - sn * aqk;
+                    A[q * N + k] = sn * apk + c * aqk;
+                }
+                __syncwarp();
+            }
+    }
+    __syncwarp();
 }
 
-__device__ MCV_REFIT_NOINLINE double lm_reseed(const double* A) {
-    double M[64];
-    for (int k = 0; k < 64; ++k) M[k] = A[k];
-    return max_diag_pinv_sym<8>(M);
+// One LM trial step by warp 0: d = solve(A + lambda diag(D), v), xd = x - d.  Lane 0 tries the Cholesky fast path of
+// cvmath.cuh solve_sym_chol_or_eig; homography normal equations are badly scaled (the two projective parameters), so the
+// thresholded eigen-solve (cv::solve DECOMP_EIG) is the usual path, and its Jacobi sweeps run on the whole warp.
+// sM, sVe: shared scratch, 64 doubles each.
+__device__ MCV_REFIT_NOINLINE void lm_trial_warp(const double* A, const double* v, const double* D, double lam,
+                                                 const double* x, double* d, double* xd, double* sM, double* sVe) {
+    const int lane = threadIdx.x & 31;
+    int ok = 0;
+    if (lane == 0) {
+        double Ap[64], vv[8], dd[8];
+        for (int k = 0; k < 64; ++k) Ap[k] = A[k];
+        for (int r = 0; r < 8; ++r) { Ap[r * 8 + r] += lam * D[r]; vv[r] = v[r]; }
+        ok = cvm::solve_sym_chol<8>(Ap, vv, dd) ? 1 : 0;
+        if (ok) for (int r = 0; r < 8; ++r) { d[r] = dd[r]; xd[r] = x[r] - dd[r]; }
+        else for (int k = 0; k < 64; ++k) sM[k] = Ap[k];
+    }
+    ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+    if (ok) return;
+    __syncwarp();
+    jacobi_eigen_sym_warp<8>(sM, sVe);
+    if (lane == 0) {                                     // cvmath.cuh solve_sym_eig, after the decomposition
+        double w[8], dd[8];
+        double sum = 0;
+        for (int i = 0; i < 8; ++i) { w[i] = sM[i * 8 + i]; sum += fabs(w[i]); }
+        const double thr = DBL_EPSILON * 2 * sum;
+        for (int i = 0; i < 8; ++i) dd[i] = 0;
+        for (int i = 0; i < 8; ++i) {
+            if (fabs(w[i]) <= thr) continue;
+            double sdot = 0;
+            for (int k = 0; k < 8; ++k) sdot += sVe[i * 8 + k] * v[k];
+            sdot /= w[i];
+            for (int k = 0; k < 8; ++k) dd[k] += sdot * sVe[i * 8 + k];
+        }
+        for (int r = 0; r < 8; ++r) { d[r] = dd[r]; xd[r] = x[r] - dd[r]; }
+    }
+    __syncwarp();
+}
+
+// cvmath.cuh max_diag_pinv_sym<8> by warp 0 (valid in lane 0)
+__device__ MCV_REFIT_NOINLINE double lm_reseed_warp(const double* A, double* sM, double* sVe) {
+    const int lane = threadIdx.x & 31;
+    for (int k = lane; k < 64; k += 32) sM[k] = A[k];
+    __syncwarp();
+    jacobi_eigen_sym_warp<8>(sM, sVe);
+    double maxval = DBL_EPSILON;
+    if (lane == 0) {
+        double w[8];
+        double sum = 0;
+        for (int i = 0; i < 8; ++i) { w[i] = sM[i * 8 + i]; sum += fabs(w[i]); }
+        const double thr = DBL_EPSILON * 2 * sum;
+        for (int k = 0; k < 8; ++k) {
+            double dsum = 0;
+            for (int i = 0; i < 8; ++i)
+                if (fabs(w[i]) > thr) dsum += sVe[i * 8 + k] * sVe[i * 8 + k] / w[i];
+            maxval = fmax(maxval, fabs(dsum));
+        }
+    }
+    __syncwarp();
+    return maxval;
 }
 
 // Homography with OpenCV's post-processing: runKernel on the inliers, LMSolver(10), mask
@@ -1692,38 +1786,50 @@ finalize_homography_kernel(const float4* __restrict__ pf, const int64_t* __restr
     }
     __syncthreads();
     __shared__ double sDvec[8];
+    __shared__ double sEigM[64], sEigV[64];
     for (int iter = 0; iter < 10; ++iter) {
-        if (tid == 0) lm_trial(sA, sV, sD, sLam, sH, sDvec, sXd);
+        if (tid < 32) lm_trial_warp(sA, sV, sD, sLam, sH, sDvec, sXd, sEigM, sEigV);
         __syncthreads();
         const double Sd = residual_sq(sXd);
-        if (tid == 0) {
+        if (tid < 32) {
             const double S = sS;
-            double dS = 0, tdv = 0;
-            for (int r = 0; r < 8; ++r) {
-                double Ad = 0;
-                for (int c = 0; c < 8; ++c) Ad += sA[r * 8 + c] * sDvec[c];
-                dS += sDvec[r] * (-Ad + 2 * sV[r]);
-                tdv += sDvec[r] * sV[r];
+            int reseed = 0;
+            double nu = 0;
+            if (tid == 0) {
+                double dS = 0, tdv = 0;
+                for (int r = 0; r < 8; ++r) {
+                    double Ad = 0;
+                    for (int c = 0; c < 8; ++c) Ad += sA[r * 8 + c] * sDvec[c];
+                    dS += sDvec[r] * (-Ad + 2 * sV[r]);
+                    tdv += sDvec[r] * sV[r];
+                }
+                const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
+                if (R > 0.75) {
+                    sLam *= 0.5;
+                    if (sLam < sLc) sLam = 0;
+                } else if (R < 0.25) {
+                    nu = (Sd - S) / (fabs(tdv) > DBL_EPSILON ? tdv : 1) + 2;
+                    nu = fmin(fmax(nu, 2.), 10.);
+                    if (sLam == 0) reseed = 1;
+                    else sLam *= nu;
+                }
+#ifdef MCV_DEBUG_REFIT
+                printf(" lm iter=%d S=%g Sd=%g dS=%g R=%g lam=%g d0=%g\n", iter, S, Sd, dS, R, sLam, sDvec[0]);
+#endif
             }
-            const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
-            if (R > 0.75) {
-                sLam *= 0.5;
-                if (sLam < sLc) sLam = 0;
-            } else if (R < 0.25) {
-                double nu = (Sd - S) / (fabs(tdv) > DBL_EPSILON ? tdv : 1) + 2;
-                nu = fmin(fmax(nu, 2.), 10.);
-                if (sLam == 0) {
-                    const double maxval = lm_reseed(sA);
+            reseed = __shfl_sync(0xFFFFFFFFu, reseed, 0);
+            if (reseed) {                                 // lambda was switched off: restart it from the pseudo-inverse's diagonal
+                const double maxval = lm_reseed_warp(sA, sEigM, sEigV);
+                if (tid == 0) {
                     sLam = sLc = 1. / maxval;
                     nu *= 0.5;
+                    sLam *= nu;
                 }
-                sLam *= nu;
             }
-#ifdef MCV_DEBUG_REFIT
-            printf(" lm iter=%d S=%g Sd=%g dS=%g R=%g lam=%g d0=%g\n", iter, S, Sd, dS, R, sLam, sDvec[0]);
-#endif
-            sCtl[0] = (Sd < S) ? 1 : 0;
-            if (Sd < S) for (int r = 0; r < 8; ++r) sH[r] = sXd[r];
+            if (tid == 0) {
+                sCtl[0] = (Sd < S) ? 1 : 0;
+                if (Sd < S) for (int r = 0; r < 8; ++r) sH[r] = sXd[r];
+            }
         }
         __syncthreads();
         if (sCtl[0] != 0) accumulate(sH);
