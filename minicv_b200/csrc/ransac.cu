@@ -904,7 +904,8 @@ __global__ void __launch_bounds__(128)
 score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
              const int64_t* __restrict__ off, const double* __restrict__ models,
              const int* __restrict__ slotList, const int* __restrict__ nTotal, int maxSlots,
-             float thr2, int chunkPts, int* __restrict__ counts, const int* __restrict__ gate) {
+             float thr2, int chunkPts, int* __restrict__ counts, const int* __restrict__ gate,
+             const int* __restrict__ nBegin) {
     constexpr int TP = (MODEL == RM_ESSENTIAL) ? 512 : 1024;   // 16 KB per stage
     if (gate && !score_gate_dense(gate)) return;               // the tensor-core kernel scores this chunk
     __shared__ __align__(16) unsigned char sraw[16384];
@@ -914,8 +915,9 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
     const int p = blockIdx.y;
     const int total = nTotal[p];
     const int k = blockIdx.x * 128 + threadIdx.x;
-    if (blockIdx.x * 128 >= total) return;
-    const bool active = k < total;
+    const int begin = nBegin ? nBegin[p] : 0;                  // models [begin, total) of the compacted list
+    if (blockIdx.x * 128 >= total || blockIdx.x * 128 + 128 <= begin) return;
+    const bool active = k < total && k >= begin;
     const int64_t base = off[p];
     const int n = (int)(off[p + 1] - base);
     const int i0 = blockIdx.z * chunkPts;
@@ -1879,6 +1881,52 @@ dbg_counts_kernel(const int* __restrict__ iterStart, const int* __restrict__ cou
         out[((int64_t)p * maxIters + it) * maxm + m] = (m < k1 - k0) ? counts[(int64_t)p * maxIters * maxm + k0 + m] : -1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Adaptive stop in two phases.  OpenCV's loop shrinks its iteration horizon every time a better model turns up and
+// never grows it again, so once the first K iterations are scored, nothing at or beyond the horizon those K
+// iterations leave can ever be evaluated.  Phase 1 scores iterations [0, K), horizon_kernel replays the accept /
+// RANSACUpdateNumIters rule over them (the rule select_kernel applies to the whole list afterwards) and cuts the
+// pair's iteration count to that horizon, phase 2 scores what is left below it.  On ratio-tested matches the horizon
+// after 128 iterations is a few dozen: 2000 hypotheses per pair are solved, ~128 are scored.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+phase_limit_kernel(int np, int maxIters, int K, const int* __restrict__ nIter, const int* __restrict__ iterStart,
+                   const int* __restrict__ nTotal, const int* __restrict__ gate, int* __restrict__ phaseEnd) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    // the pilot saw (almost) no fitting model: the horizon will not shrink, phase 1 is the whole list (no phase 2)
+    if (gate && !score_gate_dense(gate)) { phaseEnd[p] = nTotal[p]; return; }
+    phaseEnd[p] = iterStart[(int64_t)p * (maxIters + 1) + min(min(K, nIter[p]), maxIters)];
+}
+__global__ void __launch_bounds__(128)
+horizon_kernel(const int64_t* __restrict__ off, int np, int maxIters, int maxm, int mp, int K, double confidence,
+               int* __restrict__ nIter, const int* __restrict__ flags, const int* __restrict__ iterStart,
+               const int* __restrict__ slotList, const int* __restrict__ counts, const int* __restrict__ gate,
+               int* __restrict__ phaseBegin, int* __restrict__ phaseEnd) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    const int* is = iterStart + (int64_t)p * (maxIters + 1);
+    const int scored = phaseEnd[p];                      // models of the first K iterations (or all of them)
+    phaseBegin[p] = scored;
+    if ((gate && !score_gate_dense(gate)) || (flags[p] & (PAIR_FAIL | PAIR_DIRECT))) { phaseEnd[p] = scored; return; }
+    const int n = (int)(off[p + 1] - off[p]);
+    const int* c = counts + (int64_t)p * maxIters * maxm;
+    const int* sl = slotList + (int64_t)p * maxIters * maxm;
+    int niters = max(maxIters, 1), run = mp - 1, curIt = -1;
+    for (int k = 0; k < scored; ++k) {
+        const int x = c[k];
+        if (x > run) {
+            const int itb = sl[k] / maxm;
+            if (itb != curIt && itb >= niters) break;    // the loop had already stopped
+            curIt = itb; run = x;
+            niters = min(niters, update_num_iters(confidence, (double)(n - x) / n, mp, niters));
+        }
+    }
+    const int lim = min(nIter[p], max(niters, min(K, nIter[p])));
+    nIter[p] = lim;
+    phaseEnd[p] = is[min(lim, maxIters)];
+}
+
 template <int MODEL>
 int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const RansacIO& io) {
     constexpr int MP = MT<MODEL>::MP, MAXM = MT<MODEL>::MAXM;
@@ -2055,18 +2103,15 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
                 MCV_LAUNCH_CHECK();
             }
         } else {
-        // ---- score
-        {
-            const int tcMode = score_tc_mode(MODEL, maxN, (int)slots, np, ctx->sm_count);
-            const int* gate = nullptr;
-            kt_begin(ctx, st, KT_SCORE);
-            if (tcMode == 2) {
-                gate = score_tc_pilot(ctx, st, MODEL, pf, pd, off, np, dModels, dSlotList, dNTotal, (int)slots, thr2);
-                if (!gate) return -1;
-            }
-            if (tcMode) {
-                const int rc = score_tc_run(ctx, st, MODEL, pf, pd, off, io.hOff + p0, p0, np, dModels, dSlotList, dNTotal,
-                                            (int)slots, thr2, dCounts, gate);
+        // ---- score: models [dBegin[p], dEnd[p]) of every pair's compacted list; slotsEff bounds dEnd (grid size)
+        // engine: tensor cores / fp32-filter kernel / both launched behind the device-side gate (score_tc_mode)
+        const int tcMode = score_tc_mode(MODEL, maxN, (int)slots, np, ctx->sm_count);
+        // second: phase 2 of a gated chunk has work only where the gate chose the fp32-filter kernel (otherwise phase 1 was
+        // the whole list), so the tensor-core launch -- thousands of CTAs that would return at once -- is skipped
+        auto score_range = [&](const int* dBegin, const int* dEnd, const int* gate, bool zeroed, bool second) -> int {
+            if (tcMode && !(second && gate)) {
+                const int rc = score_tc_run(ctx, st, MODEL, pf, pd, off, io.hOff + p0, p0, np, dModels, dSlotList, dEnd,
+                                            (int)slots, thr2, dCounts, gate, dBegin, second);
                 if (rc) return rc;
             }
             if (tcMode != 1) {
@@ -2079,11 +2124,39 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
                 int chunkPts = (int)((std::max<int64_t>(maxN, 1) + zs - 1) / zs);
                 zs = (int)((std::max<int64_t>(maxN, 1) + chunkPts - 1) / chunkPts);
                 if (gate) { zs = 1; chunkPts = (int)std::max<int64_t>(maxN, 1); }     // a gated chunk always fills the machine
-                if (zs > 1) MCV_CUDA_TRY(cudaMemsetAsync(dCounts, 0, (size_t)np * slots * 4, st));
+                if (zs > 1 && !zeroed) MCV_CUDA_TRY(cudaMemsetAsync(dCounts, 0, (size_t)np * slots * 4, st));
                 dim3 g(tiles, np, zs);
-                score_kernel<MODEL><<<g, 128, 0, st>>>(pf, pd, off, dModels, dSlotList, dNTotal, (int)slots,
-                                                       thr2, chunkPts, dCounts, gate);
+                score_kernel<MODEL><<<g, 128, 0, st>>>(pf, pd, off, dModels, dSlotList, dEnd, (int)slots,
+                                                       thr2, chunkPts, dCounts, gate, dBegin);
                 MCV_LAUNCH_CHECK();
+            }
+            return 0;
+        };
+        {
+            constexpr int K1 = 128;                       // iterations of phase 1
+            const bool twoPhase = prm.stopMode == MCV_STOP_ADAPTIVE && !io.dDbgCounts && !io.dInjModels && maxIters >= 4 * K1;
+            kt_begin(ctx, st, KT_SCORE);
+            const int* gate = nullptr;
+            if (tcMode == 2) {
+                gate = score_tc_pilot(ctx, st, MODEL, pf, pd, off, np, dModels, dSlotList, dNTotal, (int)slots, thr2);
+                if (!gate) return -1;
+            }
+            if (!twoPhase) {
+                if (score_range(nullptr, dNTotal, gate, false, false)) return -1;
+            } else {
+                if (ctx->ws[86].reserve((size_t)chunk * 8 + 64)) return -1;
+                int* dPhaseEnd = ctx->ws[86].as<int>();
+                int* dPhaseBegin = dPhaseEnd + chunk;
+                // counts zeroed once: small calls split a pair's correspondences over blocks that add their partial counts,
+                // and phase 2 must not wipe what phase 1 counted
+                MCV_CUDA_TRY(cudaMemsetAsync(dCounts, 0, (size_t)np * slots * 4, st));
+                phase_limit_kernel<<<(np + 127) / 128, 128, 0, st>>>(np, maxIters, K1, dNIter, dIterStart, dNTotal, gate, dPhaseEnd);
+                MCV_LAUNCH_CHECK();
+                if (score_range(nullptr, dPhaseEnd, gate, true, false)) return -1;
+                horizon_kernel<<<(np + 127) / 128, 128, 0, st>>>(off, np, maxIters, MAXM, MP, K1, prm.confidence, dNIter, dFlags,
+                                                                 dIterStart, dSlotList, dCounts, gate, dPhaseBegin, dPhaseEnd);
+                MCV_LAUNCH_CHECK();
+                if (score_range(dPhaseBegin, dPhaseEnd, gate, true, true)) return -1;
             }
             kt_end(ctx, st);
         }

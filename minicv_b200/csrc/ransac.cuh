@@ -59,7 +59,7 @@ int ransac_select(cudaStream_t st, const int64_t* dOff, int np, int maxIters, in
 
 // Scoring with the tensor-core first-level filter (score_tc.cu): counts [np][slots] over the compacted model lists,
 // identical to score_kernel's.  dOff / hOff point at the chunk's first pair (absolute offsets), pairBase = its index.
-// Uses ctx workspaces 80..85.
+// Uses ctx workspaces 80..85 (86: the two-phase scoring of ransac.cu).
 //   score_tc_mode: 0 = not for this chunk, 1 = tensor cores, 2 = decide on the device: score_tc_pilot scores the first 32
 //   models of every pair on 128 correspondences and leaves {models that fit, models looked at} in the gate; both scoring
 //   kernels are launched and the one the gate does not select returns at once (score_gate_dense).  Level 0 pays when
@@ -68,9 +68,12 @@ int ransac_select(cudaStream_t st, const int64_t* dOff, int np, int maxIters, in
 int score_tc_mode(int model, int64_t maxN, int slots, int np, int smCount);
 int* score_tc_pilot(Context* ctx, cudaStream_t st, int model, const float4* pf, const double* pd, const int64_t* dOff, int np,
                     const double* dModels, const int* dSlotList, const int* dNTotal, int slots, float thr2);
+// Models [dBegin[p], dNTotal[p]) of every pair's compacted list are scored (dBegin nullptr: from 0); haveFeatures: the
+// chunk's operand stages are already in the workspace (second call for the same chunk).
 int score_tc_run(Context* ctx, cudaStream_t st, int model, const float4* pf, const double* pd, const int64_t* dOff,
                  const int64_t* hOff, int64_t pairBase, int np, const double* dModels, const int* dSlotList,
-                 const int* dNTotal, int slots, float thr2, int* dCounts, const int* gate);
+                 const int* dNTotal, int slots, float thr2, int* dCounts, const int* gate, const int* dBegin,
+                 bool haveFeatures);
 // gate = {models that fit, models looked at}: "dense" when more than 1 in 32 of the sampled models fits
 __device__ __forceinline__ bool score_gate_dense(const int* gate) { return gate[0] * 32 > gate[1]; }
 

@@ -283,7 +283,7 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
                 const float* __restrict__ feat, const void* __restrict__ sortedRaw, const StageBox* __restrict__ boxes,
                 const double* __restrict__ models, const int* __restrict__ slotList, const int* __restrict__ nTotal,
                 int maxSlots, float thr2, int* __restrict__ counts, unsigned long long* __restrict__ audit,
-                const int* __restrict__ gate) {
+                const int* __restrict__ gate, const int* __restrict__ nBegin) {
     constexpr int isE = MODEL == RM_ESSENTIAL ? 1 : 0;
     constexpr bool isH = MODEL == RM_HOMOGRAPHY;
     constexpr int A_BYTES = ST_ROWS * ST_ROW_BYTES;           // 32 KB
@@ -291,8 +291,9 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
     constexpr int B_BYTES = ST_STAGE_BYTES;                   // 9 KB per stage: 64 operand rows + 64 coordinate quadruples
     const int p = blockIdx.y;
     const int total = nTotal[p];
+    const int begin = nBegin ? nBegin[p] : 0;               // models [begin, total) of the compacted list
     const int m0 = blockIdx.x * ST_ROWS;
-    if (m0 >= total) return;
+    if (m0 >= total || m0 + ST_ROWS <= begin) return;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -341,7 +342,7 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
     double fhA[AUDIT ? 9 : 1];
     double emA = 0;
     if (warp >= 2) {
-        active = m0 + row < total;
+        active = m0 + row < total && m0 + row >= begin;
         double m[9];
         int slot = 0;
         if (active) {
@@ -634,8 +635,8 @@ constexpr size_t ST_SMEM = 1024 + ST_ROWS * ST_ROW_BYTES + ST_STAGES * ST_STAGE_
 
 template <int MODEL>
 int run(Context* ctx, cudaStream_t st, const float4* pf, const double* pd, const int64_t* dOff, const int64_t* hOff,
-        int64_t pairBase, int np, const double* dModels, const int* dSlotList, const int* dNTotal, int slots, float thr2,
-        int* dCounts, float* auditOut, const int* gate) {
+        int64_t pairBase, int np, const double* dModels, const int* dSlotList, const int* dNTotal, int slots,
+        float thr2, int* dCounts, float* auditOut, const int* gate, const int* dBegin, bool haveFeatures) {
     // buffers of the pairs [0, np) of this chunk (dOff / hOff already point at the chunk's first pair), addressed relative
     // to the chunk's first pair
     const int64_t s0 = stage_base(hOff[0], pairBase), s1 = stage_base(hOff[np], pairBase + np) + 2;
@@ -649,14 +650,16 @@ int run(Context* ctx, cudaStream_t st, const float4* pf, const double* pd, const
     StageBox* boxes = ctx->ws[83].as<StageBox>() - s0;
     PairNorm* norms = ctx->ws[81].as<PairNorm>();
     unsigned long long* audit = ctx->ws[84].as<unsigned long long>();
-    score_tc_features_kernel<MODEL><<<np, 256, 0, st>>>(pf, pd, dOff, pairBase, norms, feat, raw, boxes, gate);
-    MCV_LAUNCH_CHECK();
+    if (!haveFeatures) {
+        score_tc_features_kernel<MODEL><<<np, 256, 0, st>>>(pf, pd, dOff, pairBase, norms, feat, raw, boxes, gate);
+        MCV_LAUNCH_CHECK();
+    }
     dim3 g((slots + ST_ROWS - 1) / ST_ROWS, np);
     if (auditOut) {
         MCV_CUDA_TRY(cudaMemsetAsync(audit, 0, 8, st));
         auto kern = score_tc_kernel<MODEL, true>;
         MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
-        kern<<<g, ST_THREADS, ST_SMEM, st>>>(dOff, pairBase, norms, feat, raw, boxes, dModels, dSlotList, dNTotal, slots, thr2, dCounts, audit, gate);
+        kern<<<g, ST_THREADS, ST_SMEM, st>>>(dOff, pairBase, norms, feat, raw, boxes, dModels, dSlotList, dNTotal, slots, thr2, dCounts, audit, gate, dBegin);
         MCV_LAUNCH_CHECK();
         unsigned long long h = 0;
         MCV_CUDA_TRY(cudaMemcpyAsync(&h, audit, 8, cudaMemcpyDeviceToHost, st));
@@ -668,7 +671,7 @@ int run(Context* ctx, cudaStream_t st, const float4* pf, const double* pd, const
     } else {
         auto kern = score_tc_kernel<MODEL, false>;
         MCV_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
-        kern<<<g, ST_THREADS, ST_SMEM, st>>>(dOff, pairBase, norms, feat, raw, boxes, dModels, dSlotList, dNTotal, slots, thr2, dCounts, audit, gate);
+        kern<<<g, ST_THREADS, ST_SMEM, st>>>(dOff, pairBase, norms, feat, raw, boxes, dModels, dSlotList, dNTotal, slots, thr2, dCounts, audit, gate, dBegin);
         MCV_LAUNCH_CHECK();
     }
     return 0;
@@ -751,16 +754,17 @@ int* score_tc_pilot(Context* ctx, cudaStream_t st, int model, const float4* pf, 
 
 int score_tc_run(Context* ctx, cudaStream_t st, int model, const float4* pf, const double* pd, const int64_t* dOff,
                  const int64_t* hOff, int64_t pairBase, int np, const double* dModels, const int* dSlotList,
-                 const int* dNTotal, int slots, float thr2, int* dCounts, const int* gate) {
+                 const int* dNTotal, int slots, float thr2, int* dCounts, const int* gate, const int* dBegin,
+                 bool haveFeatures) {
     float am = 0.f;
     float* ap = g_score_audit.load(std::memory_order_relaxed) ? &am : nullptr;
     int rc;
     if (model == RM_HOMOGRAPHY)
-        rc = run<RM_HOMOGRAPHY>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap, gate);
+        rc = run<RM_HOMOGRAPHY>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap, gate, dBegin, haveFeatures);
     else if (model == RM_FUNDAMENTAL)
-        rc = run<RM_FUNDAMENTAL>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap, gate);
+        rc = run<RM_FUNDAMENTAL>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap, gate, dBegin, haveFeatures);
     else
-        rc = run<RM_ESSENTIAL>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap, gate);
+        rc = run<RM_ESSENTIAL>(ctx, st, pf, pd, dOff, hOff, pairBase, np, dModels, dSlotList, dNTotal, slots, thr2, dCounts, ap, gate, dBegin, haveFeatures);
     if (ap) {
         uint32_t bits;
         memcpy(&bits, &am, 4);

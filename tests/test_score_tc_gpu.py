@@ -202,3 +202,39 @@ def test_auto_mode_selects_on_the_device(inlier_frac):
         np.testing.assert_array_equal(out[engine].masks, ref.masks)
         np.testing.assert_array_equal(out[engine].models, ref.models)
     assert ref.ok.all() and abs(ref.inliers.mean() / n - inlier_frac) < 0.1
+
+
+@pytest.mark.parametrize("model,kw,inlier_frac,n_pairs", [
+    (est.MODEL_H, dict(thr=3.0), 0.8, 40),
+    (est.MODEL_H, dict(thr=3.0), 0.3, 40),
+    (est.MODEL_H, dict(thr=3.0), 0.6, 3),
+    (est.MODEL_F, dict(thr=2.0), None, 24),
+    (est.MODEL_E, dict(thr=1.0, focal=800.0, pp=(320.0, 240.0)), None, 8),
+])
+def test_two_phase_adaptive_scoring_equals_one_pass(model, kw, inlier_frac, n_pairs):
+    """With OpenCV's adaptive stop the engine scores the first 128 iterations, replays the accept / RANSACUpdateNumIters rule
+    over them, cuts every pair's iteration count to the horizon that leaves and scores only what is below it.  The result
+    must be what one pass over all hypotheses gives (requesting the debug taps switches the two phases off): models, masks,
+    counts, the iteration the winner came from and the number of iterations OpenCV's loop would have run."""
+    n, iters = 700, 1024
+    A = np.empty((n_pairs * n, 2)); B = np.empty((n_pairs * n, 2))
+    for p in range(n_pairs):
+        r = synth.homography_pair(400 + p, n, inlier_frac=inlier_frac) if model == est.MODEL_H else synth.two_view_pair(400 + p, n)
+        A[p * n:(p + 1) * n] = r[0]; B[p * n:(p + 1) * n] = r[1]
+    off = np.arange(n_pairs + 1, dtype=np.int64) * n
+    args = dict(sample_mode=est.SAMPLE_MWC, stop_mode=est.STOP_ADAPTIVE, **{k: v for k, v in kw.items() if k != "thr"})
+    for engine in (est.SCORE_AUTO, est.SCORE_FP32_FILTER, est.SCORE_TENSOR):
+        est.set_score_engine(engine)
+        try:
+            one = est.ransac_batch(model, A, B, off, kw["thr"], iters, 0.995, debug=True, **args)
+            two = est.ransac_batch(model, A, B, off, kw["thr"], iters, 0.995, debug=False, **args)
+        finally:
+            est.set_score_engine(est.SCORE_AUTO)
+        np.testing.assert_array_equal(two.models, one.models)
+        np.testing.assert_array_equal(two.masks, one.masks)
+        np.testing.assert_array_equal(two.inliers, one.inliers)
+        np.testing.assert_array_equal(two.best, one.best)
+        np.testing.assert_array_equal(two.iters_run, one.iters_run)
+        np.testing.assert_array_equal(two.ok, one.ok)
+    if inlier_frac == 0.8:
+        assert (one.iters_run < 64).all()              # the horizon really is short here: phase 2 had nothing to do
