@@ -58,7 +58,7 @@ Nccl* nccl() {
     void* h = nullptr;
     for (const char* n : names) {
         if (!n || !*n) continue;
-        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        h = dlopen(n, RTLD_NOW | RTLD_LOCAL);          // every entry point is taken with dlsym: nothing leaks into the host's namespace
         if (h) break;
     }
     if (!h) return nullptr;

@@ -187,6 +187,25 @@ class PnpParams(C.Structure):
 _lib = None
 
 
+def _prefer_bundled_nccl() -> None:
+    """The library resolves NCCL at run time (dlopen).  In a Python process that may import torch later, it must pick the
+    SAME libnccl torch was built against: the loader de-duplicates by soname, so an older system libnccl.so.2 loaded
+    first would later be handed to libtorch_cuda.so (undefined symbol at `import torch`).  Point MINICV_NCCL_LIB at the
+    wheel-bundled copy when there is one and the caller has not chosen."""
+    if os.environ.get("MINICV_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations or []) if spec else []:
+            cand = Path(root) / "lib" / "libnccl.so.2"
+            if cand.exists():
+                os.environ["MINICV_NCCL_LIB"] = str(cand)
+                return
+    except Exception:
+        pass
+
+
 def load(path: os.PathLike | str | None = None) -> C.CDLL:
     """Load libMiniCVNative.so and attach signatures.  Raises if the library is absent."""
     global _lib
@@ -197,6 +216,7 @@ def load(path: os.PathLike | str | None = None) -> C.CDLL:
         raise NativeLibraryMissing(
             f"{p} not found: build it with `make` (or __graft_entry__.build()). "
             "minicv_b200 has no CPU fallback for the match/estimate path.")
+    _prefer_bundled_nccl()
     lib = C.CDLL(str(p))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here means header/library drift
