@@ -325,6 +325,12 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
         for (int s = 0; s < ST_STAGES; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1 + ST_EPI_WARPS); }
         for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, ST_EPI_WARPS * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the first operand stages are requested right away: they land while the epilogue threads convert their models
+        // (nothing but this thread has touched the barriers yet)
+        for (int j = 0; j < min(nStages, ST_STAGES); ++j) {
+            mbar_expect_tx(b_full + j, B_BYTES);
+            bulk_load_1d(sB + j * B_BYTES, img + (int64_t)j * B_BYTES, B_BYTES, b_full + j);
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)ST_TMEM_COLS) : "memory");
@@ -380,7 +386,7 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
 
     if (warp == 0) {
         if (elect_one()) {
-            for (int j = 0; j < nStages; ++j) {
+            for (int j = ST_STAGES; j < nStages; ++j) {   // stages 0 .. ST_STAGES - 1 were requested at CTA start
                 const int s = j % ST_STAGES;
                 mbar_wait_backoff(b_empty + s, ((j / ST_STAGES) & 1) ^ 1);
                 mbar_expect_tx(b_full + s, B_BYTES);
