@@ -31,7 +31,7 @@ RansacParams to_params(const McvRansacParams* p) {
     return r;
 }
 
-int stage_points(Staged& s, const McvPoint2d* a, const McvPoint2d* b, int64_t total, int nPairs) {
+int stage_alloc(Staged& s, int64_t total, int nPairs) {
     Context* c = s.ctx;
     const size_t tb = (size_t)std::max<int64_t>(total, 1);
     if (c->ws[30].reserve(tb * 16) || c->ws[31].reserve(tb * 16) || c->ws[32].reserve((size_t)nPairs * 72 + 72) ||
@@ -43,12 +43,50 @@ int stage_points(Staged& s, const McvPoint2d* a, const McvPoint2d* b, int64_t to
     s.dCnt = c->ws[34].as<int>(); s.dOk = c->ws[35].as<uint8_t>();
     s.dIters = c->ws[36].as<int>(); s.dBest = c->ws[37].as<int>();
     MCV_CUDA_TRY(cudaMemsetAsync(s.dModels, 0, (size_t)nPairs * 72, s.st));     // pairs without a model report a zero matrix
+    return 0;
+}
+
+int stage_points(Staged& s, const McvPoint2d* a, const McvPoint2d* b, int64_t total, int nPairs) {
+    if (stage_alloc(s, total, nPairs)) return -1;
     if (total > 0) {
         // pageable caller arrays (P/Invoke) go through the pinned ring, pinned ones are copied directly
-        if (h2d_copy(c, s.dA, a, (size_t)total * 16, s.st, host_is_pageable(a)) ||
-            h2d_copy(c, s.dB, b, (size_t)total * 16, s.st, host_is_pageable(b)))
+        if (h2d_copy(s.ctx, s.dA, a, (size_t)total * 16, s.st, host_is_pageable(a)) ||
+            h2d_copy(s.ctx, s.dB, b, (size_t)total * 16, s.st, host_is_pageable(b)))
             return -1;
     }
+    return 0;
+}
+
+// Host-buffer batches in PAGEABLE caller memory (what P/Invoke passes) are cut into up to four runs of whole pairs with
+// about the same number of correspondences: the points of run k + 1 go through the pinned staging ring while run k is
+// estimated (pairs are independent, so the result is the same).  Pinned arrays are copied in one piece: their copy is a
+// tenth of the call and four smaller launches cost more than the overlap returns (C3-H 133 k -> 116 k pairs/s when tried).
+// bounds: pair indices, front() = 0, back() = nPairs; one run when the batch is small.
+std::vector<int> pair_runs(const int64_t* off, int nPairs, bool pageable) {
+    const int64_t total = off[nPairs];
+    int runs = 4;
+    if (!pageable || nPairs < 8 || total * 32 < (8ll << 20)) runs = 1;
+    std::vector<int> b{0};
+    for (int r = 1; r < runs; ++r) {
+        const int64_t want = total * r / runs;
+        int p = b.back();
+        while (p < nPairs && off[p] < want) ++p;
+        if (p > b.back() && p < nPairs) b.push_back(p);
+    }
+    b.push_back(nPairs);
+    return b;
+}
+// the points of pairs [p0, p1) to the device on the context's copy stream; `ev` marks their arrival
+int stage_run(Staged& s, const McvPoint2d* a, const McvPoint2d* b, const int64_t* off, int p0, int p1, cudaEvent_t ev) {
+    const int64_t o0 = off[p0], o1 = off[p1];
+    cudaStream_t cs = s.ctx->stream2;
+    if (o1 > o0) {
+        if (h2d_copy(s.ctx, s.dA + 2 * o0, a + o0, (size_t)(o1 - o0) * 16, cs, host_is_pageable(a)) ||
+            h2d_copy(s.ctx, s.dB + 2 * o0, b + o0, (size_t)(o1 - o0) * 16, cs, host_is_pageable(b)))
+            return -1;
+    }
+    MCV_CUDA_TRY(cudaEventRecord(ev, cs));
+    MCV_CUDA_TRY(cudaStreamWaitEvent(s.st, ev, 0));
     return 0;
 }
 
@@ -174,8 +212,31 @@ MCV_API int cvRansacBatch(const McvRansacParams* p, const McvPoint2d* a, const M
     const int maxIters = std::max(prm.maxIters, 1);
     const int64_t total = offsets[nPairs];
     Staged s; s.ctx = ctx; s.st = ctx->stream;
-    if (stage_points(s, a, b, total, nPairs)) return -1;
+    const bool taps = injSamples || injModels || dbgCounts || dbgModels || dbgSamples;
+    const std::vector<int> runs = taps ? std::vector<int>{0, nPairs} : pair_runs(offsets, nPairs, host_is_pageable(a) || host_is_pageable(b));
+    const int nRuns = (int)runs.size() - 1;
+    if (nRuns > 1) {
+        // copy of run k + 1 under the estimation of run k
+        if (stage_alloc(s, total, nPairs)) return -1;
+        cudaEvent_t* ev = event_pool(ctx, nRuns);
+        if (!ev) { set_error("event pool"); return -1; }
+        std::vector<int64_t> roff;
+        for (int r = 0; r < nRuns; ++r) {
+            const int p0 = runs[r], p1 = runs[r + 1];
+            if (stage_run(s, a, b, offsets, p0, p1, ev[r])) return -1;
+            roff.assign(offsets + p0, offsets + p1 + 1);
+            for (auto& o : roff) o -= offsets[p0];
+            RansacIO io;
+            io.dA = s.dA + 2 * offsets[p0]; io.dB = s.dB + 2 * offsets[p0]; io.hOff = roff.data(); io.nPairs = p1 - p0;
+            io.dModels = s.dModels + 9 * (size_t)p0; io.dMasks = s.dMasks + offsets[p0]; io.dInlierCounts = s.dCnt + p0;
+            io.dOk = s.dOk + p0; io.dItersRun = s.dIters + p0; io.dBest = s.dBest + 2 * (size_t)p0;
+            RansacParams pr = prm;
+            pr.pairIndexBase += p0;                       // counter-based streams are keyed by the global pair index
+            if (ransac_batch_device(ctx, s.st, pr, io)) return -1;
+        }
+    }
     RansacIO io;
+    if (nRuns <= 1 && stage_points(s, a, b, total, nPairs)) return -1;
     io.dA = s.dA; io.dB = s.dB; io.hOff = offsets; io.nPairs = nPairs;
     io.dModels = s.dModels; io.dMasks = s.dMasks; io.dInlierCounts = s.dCnt; io.dOk = s.dOk;
     io.dItersRun = s.dIters; io.dBest = s.dBest;
@@ -193,7 +254,7 @@ MCV_API int cvRansacBatch(const McvRansacParams* p, const McvPoint2d* a, const M
     if (dbgCounts) { if (ctx->ws[40].reserve(nh * mm * 4)) return -1; io.dDbgCounts = ctx->ws[40].as<int>(); }
     if (dbgModels) { if (ctx->ws[41].reserve(nh * mm * 72)) return -1; io.dDbgModels = ctx->ws[41].as<double>(); }
     if (dbgSamples) { if (ctx->ws[42].reserve(nh * mp * 4)) return -1; io.dDbgSamples = ctx->ws[42].as<int>(); }
-    if (ransac_batch_device(ctx, s.st, prm, io)) return -1;
+    if (nRuns <= 1 && ransac_batch_device(ctx, s.st, prm, io)) return -1;
     MCV_CUDA_TRY(cudaMemcpyAsync(models, s.dModels, (size_t)nPairs * 72, cudaMemcpyDeviceToHost, s.st));
     MCV_CUDA_TRY(cudaMemcpyAsync(ok, s.dOk, (size_t)nPairs, cudaMemcpyDeviceToHost, s.st));
     if (masks && total > 0) MCV_CUDA_TRY(cudaMemcpyAsync(masks, s.dMasks, (size_t)total, cudaMemcpyDeviceToHost, s.st));
@@ -248,11 +309,13 @@ MCV_API int cvRecoverPoseBatch(const RecoverPoseConfig* cfg, const McvPoint2d* a
     if (!ctx) return -1;
     const int64_t total = offsets[nPairs];
     Staged s; s.ctx = ctx; s.st = ctx->stream;
-    if (stage_points(s, a, b, total, nPairs)) return -1;
     if (ctx->ws[43].reserve((size_t)nPairs * (72 + 24 + 4) + 64)) return -1;
     double* dR = ctx->ws[43].as<double>();
     double* dT = dR + 9 * (size_t)nPairs;
     int* dGood = reinterpret_cast<int*>(dT + 3 * (size_t)nPairs);
+    // (one piece: cut into runs of pairs like cvRansacBatch, the pageable C4 batch got slower, 33.7 k -> 31.3 k pairs/s --
+    // many more, shorter kernels per run than the H / F path)
+    if (stage_points(s, a, b, total, nPairs)) return -1;
     if (cvRecoverPoseBatchDevice(cfg, s.dA, s.dB, offsets, nPairs, sampleMode, maxIters, s.dModels, dR, dT,
                                  s.dMasks, dGood, s.dOk, ctx->device, s.st))
         return -1;

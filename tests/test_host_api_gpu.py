@@ -224,3 +224,62 @@ def test_multi_chunk_tensor_engine_vs_popc_and_oracle():
         idx, dist = bf_knn.bf_knn2_hamming(q[off[p]:off[p + 1]], t[off[p]:off[p + 1]])
         np.testing.assert_array_equal(r_tc.train_idx[off[p]:off[p + 1]], idx)
         np.testing.assert_array_equal(r_tc.distance[off[p]:off[p + 1]], dist)
+
+
+@pytest.mark.parametrize("sample_mode", ["mwc", "counter"])
+def test_host_buffer_batches_are_pipelined_in_runs_of_pairs(sample_mode):
+    """A host-buffer batch in pageable memory above 8 MB of points is estimated in up to four runs of whole pairs, run k + 1 travelling while
+    run k is estimated.  Pairs are independent (OpenCV's stream restarts per pair, the counter-based streams are keyed by
+    the global pair index), so the result must be the device-resident, single-run one -- ragged pair sizes included."""
+    import torch
+    from minicv_b200 import estimation as est, synth
+    rng = np.random.default_rng(5)
+    sizes = rng.integers(900, 2600, 170).tolist()
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    assert offs[-1] * 32 > (8 << 20)
+    A = np.empty((offs[-1], 2)); B = np.empty((offs[-1], 2))
+    for p, n in enumerate(sizes):
+        r = synth.homography_pair(600 + p, int(n))
+        A[offs[p]:offs[p + 1]] = r[0]; B[offs[p]:offs[p + 1]] = r[1]
+    sm = est.SAMPLE_MWC if sample_mode == "mwc" else est.SAMPLE_COUNTER
+    host = est.ransac_batch(est.MODEL_H, A, B, offs, 3.0, 256, 0.995, sample_mode=sm, stop_mode=est.STOP_ADAPTIVE, seed=11)
+    dev = torch.device("cuda:0")
+    dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
+    dM = torch.empty((len(sizes), 9), dtype=torch.float64, device=dev)
+    dMask = torch.empty(int(offs[-1]), dtype=torch.uint8, device=dev)
+    dCnt = torch.empty(len(sizes), dtype=torch.int32, device=dev); dOk = torch.empty(len(sizes), dtype=torch.uint8, device=dev)
+    est.ransac_batch_device(est.MODEL_H, dA, dB, offs, 3.0, 256, dM, dMask, dCnt, dOk, confidence=0.995, sample_mode=sm,
+                            stop_mode=est.STOP_ADAPTIVE, seed=11, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(host.models.reshape(-1, 9), dM.cpu().numpy())
+    np.testing.assert_array_equal(host.masks, dMask.cpu().numpy())
+    np.testing.assert_array_equal(host.inliers, dCnt.cpu().numpy())
+    np.testing.assert_array_equal(host.ok, dOk.cpu().numpy())
+    assert host.ok.all()
+
+
+def test_recover_pose_host_batch_equals_device_resident():
+    import torch
+    from minicv_b200 import estimation as est, synth
+    n_pairs, n = 96, 3000
+    A = np.empty((n_pairs * n, 2)); B = np.empty((n_pairs * n, 2))
+    for p in range(n_pairs):
+        r = synth.two_view_pair(700 + p, n)
+        A[p * n:(p + 1) * n] = r[0]; B[p * n:(p + 1) * n] = r[1]
+    off = np.arange(n_pairs + 1, dtype=np.int64) * n
+    assert off[-1] * 32 > (8 << 20)
+    cfg = est.RecoverPoseConfig(800.0, (320.0, 240.0), 0.999, 1.0)
+    R, t, ms, good, ok = est.recover_pose_batch(cfg, A, B, off, maxIters=300)
+    dev = torch.device("cuda:0")
+    dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
+    dE = torch.empty((n_pairs, 9), dtype=torch.float64, device=dev); dR = torch.empty((n_pairs, 9), dtype=torch.float64, device=dev)
+    dT = torch.empty((n_pairs, 3), dtype=torch.float64, device=dev); dMs = torch.empty(n_pairs * n, dtype=torch.uint8, device=dev)
+    dGood = torch.empty(n_pairs, dtype=torch.int32, device=dev); dOk = torch.empty(n_pairs, dtype=torch.uint8, device=dev)
+    est.recover_pose_batch_device(cfg, dA, dB, off, dE, dR, dT, dMs, dGood, dOk, maxIters=300,
+                                  stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(R.reshape(-1, 9), dR.cpu().numpy())
+    np.testing.assert_array_equal(t, dT.cpu().numpy())
+    np.testing.assert_array_equal(ms, dMs.cpu().numpy())
+    np.testing.assert_array_equal(good, dGood.cpu().numpy())
+    assert ok.all()
