@@ -1,4 +1,4 @@
-// filter0.cuh -- the arithmetic of the tensor-core first-level filter of the F / E scoring stage (score_tc.cu), as
+// filter0.cuh -- the arithmetic of the tensor-core first-level filter of the H / F / E scoring stage (score_tc.cu), as
 // __host__ __device__ functions so that the host build (tests/hostmath) can hammer the bound in the CPU suite.
 //
 // The residual of the epipolar constraint, r = x2' F x1, is bilinear: r = f . psi with the nine model entries f and the

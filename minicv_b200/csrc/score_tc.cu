@@ -1,13 +1,14 @@
-// score_tc.cu -- the scoring stage of the F / E RANSAC engine with a tensor-core first-level filter.
+// score_tc.cu -- the scoring stage of the H / F / E RANSAC engine with a tensor-core first-level filter.
 //
 // score_kernel<M> (ransac.cu) spends ~16 issue slots per (model, correspondence) evaluation, 10.5 of them in an fp32
 // filter whose only job is to prove "outlier" for the 98-99 % of evaluations that are outliers by a wide margin.  The
-// epipolar residual is bilinear in (model, correspondence), so the residuals of a whole tile are a small-K GEMM
+// epipolar residual (F, E) and the reprojection residual's diagonal component (H: filter0.cuh, "homography"; its survivors
+// get the float32 exact test directly, no classifier) are bilinear in (model, correspondence), so the residuals of a whole tile are a small-K GEMM
 // (filter0.cuh): here tcgen05.mma.kind::tf32 computes 128 models x 64 correspondences per instruction group into TMEM
 // (split-TF32 operands, K = 32) and the epilogue spends ONE comparison |r~| > T (+ one mask update) per evaluation, T
 // constant per (model, stage).  What survives level 0 (~3 %: near misses, inliers, anything non-finite) goes through a
 // two-sided fp32 classifier in the pair's coordinates (certainly outlier / certainly inlier; model and constants in
-// registers, coordinates from the stage's shared-memory image): the first two survivors of every lane in place, the
+// registers, coordinates from the stage's shared-memory image): the first three survivors of every lane in place, the
 // rest compacted ACROSS the warp into a shared-memory queue and drained 32 at a time.  The sliver the classifier cannot
 // decide (~1 % of the survivors) is queued once more and gets the reference's exact test of cvmath.cuh -- the counts
 // are the exact test's, bit for bit, as before.
@@ -25,6 +26,8 @@
 //                              CTA start (fp64 transform into the pair's coordinates, threshold constants, split-TF32
 //                              row written in the swizzled layout, fence.proxy.async).  Two CTAs per SM (256 TMEM
 //                              columns each).
+//   score_pilot_kernel        32 models x 128 correspondences per pair through the exact test: the device-side gate that
+//                              decides which scoring kernel takes the chunk (ransac.cuh, score_tc_mode)
 // Models with many survivors in a stage (a good model keeps its 30 % inliers) are resolved by the whole warp, one
 // correspondence per lane, as in filter_pass.cuh.
 #include "ransac.cuh"
