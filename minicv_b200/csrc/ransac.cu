@@ -255,27 +255,39 @@ sample_mwc_par_kernel(const float4* __restrict__ pf, const int64_t* __restrict__
 
 // Native mode: hypothesis (pair, it) draws from its own counter-based stream -- no sequential
 // dependency, same duplicate / degeneracy rules.
+// A subset that fails the degeneracy test is redrawn from the same stream (up to 64 attempts), and how often that happens
+// differs wildly between hypotheses (homography quadruples at 30 % inliers: a geometric tail; with one hypothesis per
+// thread the kernel ran with 9 of 32 lanes active).  So the lanes of a block share a pool of SC_POOL hypotheses: a lane
+// makes ONE attempt per trip and, when its hypothesis is settled, takes the next one from the pool.  Every hypothesis
+// still sees exactly its own stream and attempts, only who runs it changes.
+constexpr int SC_POOL = 1024;
 template <int MODEL>
 __global__ void __launch_bounds__(128)
 sample_counter_kernel(const float4* __restrict__ pf, const int64_t* __restrict__ off, int nPairs,
                       int maxIters, uint64_t seed, int64_t pairBase, int* __restrict__ samples,
                       int* __restrict__ nIter, int* __restrict__ flags) {
     constexpr int MP = MT<MODEL>::MP;
-    const int it = blockIdx.x * blockDim.x + threadIdx.x;
     const int p = blockIdx.y;
-    if (it >= maxIters) return;
+    const int it0 = blockIdx.x * SC_POOL, it1 = min(maxIters, it0 + SC_POOL);
     const int64_t base = off[p];
     const int n = (int)(off[p + 1] - base);
-    int* out = samples + ((int64_t)p * maxIters + it) * MP;
-    if (n < MP) { if (it == 0) { nIter[p] = 0; flags[p] = PAIR_FAIL; } return; }
-    if (n == MP) {
-        if (it == 0) { for (int i = 0; i < MP; ++i) out[i] = i; nIter[p] = 1; flags[p] = PAIR_DIRECT; }
+    int* outP = samples + (int64_t)p * maxIters * MP;
+    if (n <= MP) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (n < MP) { nIter[p] = 0; flags[p] = PAIR_FAIL; }
+            else { for (int i = 0; i < MP; ++i) outP[i] = i; nIter[p] = 1; flags[p] = PAIR_DIRECT; }
+        }
         return;
     }
-    if (it == 0) { nIter[p] = maxIters; flags[p] = 0; }
-    uint64_t ctr = mix64(seed ^ mix64((uint64_t)(pairBase + p) * 0x100000001B3ull + (uint64_t)it));
-    int idx[MP];
-    for (int attempt = 0; attempt < 64; ++attempt) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { nIter[p] = maxIters; flags[p] = 0; }
+    __shared__ int sNext;
+    if (threadIdx.x == 0) sNext = it0 + (int)blockDim.x;
+    __syncthreads();
+    int it = it0 + threadIdx.x, attempt = 0;
+    uint64_t ctr = 0;
+    if (it < it1) ctr = mix64(seed ^ mix64((uint64_t)(pairBase + p) * 0x100000001B3ull + (uint64_t)it));
+    while (it < it1) {
+        int idx[MP];
         for (int i = 0; i < MP; ++i) {
             int v;
             bool dup;
@@ -287,9 +299,15 @@ sample_counter_kernel(const float4* __restrict__ pf, const int64_t* __restrict__
             } while (dup);
             idx[i] = v;
         }
-        if (check_subset<MODEL>(pf, base, idx)) break;   // after 64 tries keep the last subset
+        ++attempt;
+        if (check_subset<MODEL>(pf, base, idx) || attempt == 64) {       // after 64 tries keep the last subset
+            int* out = outP + (int64_t)it * MP;
+            for (int i = 0; i < MP; ++i) out[i] = idx[i];
+            it = atomicAdd(&sNext, 1);
+            attempt = 0;
+            if (it < it1) ctr = mix64(seed ^ mix64((uint64_t)(pairBase + p) * 0x100000001B3ull + (uint64_t)it));
+        }
     }
-    for (int i = 0; i < MP; ++i) out[i] = idx[i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -2021,7 +2039,7 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             injected_setup_kernel<<<(np + 255) / 256, 256, 0, st>>>(off, np, maxIters, MP, dNIter, dFlags);
             MCV_LAUNCH_CHECK();
         } else if (prm.sampleMode == MCV_SAMPLE_COUNTER) {
-            dim3 g((maxIters + 127) / 128, np);
+            dim3 g((maxIters + SC_POOL - 1) / SC_POOL, np);
             sample_counter_kernel<MODEL><<<g, 128, 0, st>>>(pf, off, np, maxIters, prm.seed, prm.pairIndexBase + p0,
                                                             dSamples, dNIter, dFlags);
             MCV_LAUNCH_CHECK();
