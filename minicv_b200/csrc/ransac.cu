@@ -925,7 +925,7 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
              float thr2, int chunkPts, int* __restrict__ counts, const int* __restrict__ gate,
              const int* __restrict__ nBegin) {
     constexpr int TP = (MODEL == RM_ESSENTIAL) ? 512 : 1024;   // 16 KB per stage
-    if (gate && !score_gate_dense(gate)) return;               // the tensor-core kernel scores this chunk
+    if (gate && !score_gate_classic(gate)) return;             // the tensor-core kernel scores this chunk
     __shared__ __align__(16) unsigned char sraw[16384];
     __shared__ int smax[4];
     __shared__ __align__(16) float spair_e[(MODEL == RM_ESSENTIAL) ? 4 * 512 : 4];    // essential: fp32 rounding of the tile
@@ -934,7 +934,7 @@ score_kernel(const float4* __restrict__ pf, const double* __restrict__ pd,
     const int total = nTotal[p];
     const int k = blockIdx.x * 128 + threadIdx.x;
     const int begin = nBegin ? nBegin[p] : 0;                  // models [begin, total) of the compacted list
-    if (blockIdx.x * 128 >= total || blockIdx.x * 128 + 128 <= begin) return;
+    if (begin >= total || blockIdx.x * 128 >= total || blockIdx.x * 128 + 128 <= begin) return;
     const bool active = k < total && k >= begin;
     const int64_t base = off[p];
     const int n = (int)(off[p + 1] - base);
@@ -1913,7 +1913,7 @@ phase_limit_kernel(int np, int maxIters, int K, const int* __restrict__ nIter, c
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     // the pilot saw (almost) no fitting model: the horizon will not shrink, phase 1 is the whole list (no phase 2)
-    if (gate && !score_gate_dense(gate)) { phaseEnd[p] = nTotal[p]; return; }
+    if (gate && !score_gate_split(gate)) { phaseEnd[p] = nTotal[p]; return; }
     phaseEnd[p] = iterStart[(int64_t)p * (maxIters + 1) + min(min(K, nIter[p]), maxIters)];
 }
 __global__ void __launch_bounds__(128)
@@ -1926,7 +1926,7 @@ horizon_kernel(const int64_t* __restrict__ off, int np, int maxIters, int maxm, 
     const int* is = iterStart + (int64_t)p * (maxIters + 1);
     const int scored = phaseEnd[p];                      // models of the first K iterations (or all of them)
     phaseBegin[p] = scored;
-    if ((gate && !score_gate_dense(gate)) || (flags[p] & (PAIR_FAIL | PAIR_DIRECT))) { phaseEnd[p] = scored; return; }
+    if ((gate && !score_gate_split(gate)) || (flags[p] & (PAIR_FAIL | PAIR_DIRECT))) { phaseEnd[p] = scored; return; }
     const int n = (int)(off[p + 1] - off[p]);
     const int* c = counts + (int64_t)p * maxIters * maxm;
     const int* sl = slotList + (int64_t)p * maxIters * maxm;
@@ -2122,17 +2122,17 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             }
         } else {
         // ---- score: models [dBegin[p], dEnd[p]) of every pair's compacted list; slotsEff bounds dEnd (grid size)
-        // engine: tensor cores / fp32-filter kernel / both launched behind the device-side gate (score_tc_mode)
+        // engine: tensor cores (1) / fp32-filter kernel (0) / both launched behind the device-side gate (2) -- score_tc_mode
         const int tcMode = score_tc_mode(MODEL, maxN, (int)slots, np, ctx->sm_count);
-        // second: phase 2 of a gated chunk has work only where the gate chose the fp32-filter kernel (otherwise phase 1 was
-        // the whole list), so the tensor-core launch -- thousands of CTAs that would return at once -- is skipped
-        auto score_range = [&](const int* dBegin, const int* dEnd, const int* gate, bool zeroed, bool second) -> int {
-            if (tcMode && !(second && gate)) {
+        // models [dBegin, dEnd) of every pair; engineGate: the pilot's gate when the device picks the engine (else null)
+        auto score_range = [&](const int* dBegin, const int* dEnd, const int* engineGate, bool zeroed, bool useTc,
+                               bool useClassic) -> int {
+            if (useTc) {
                 const int rc = score_tc_run(ctx, st, MODEL, pf, pd, off, io.hOff + p0, p0, np, dModels, dSlotList, dEnd,
-                                            (int)slots, thr2, dCounts, gate, dBegin, second);
+                                            (int)slots, thr2, dCounts, engineGate, dBegin, false);
                 if (rc) return rc;
             }
-            if (tcMode != 1) {
+            if (useClassic) {
                 const int tiles = (int)((slots + 127) / 128);
                 int zs = 1;
                 const int64_t blocksXY = (int64_t)tiles * np;
@@ -2141,11 +2141,11 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
                 if (blocksXY < fill) zs = (int)std::min<int64_t>((fill + blocksXY - 1) / blocksXY, std::max<int64_t>(1, (maxN + TPmin - 1) / TPmin));
                 int chunkPts = (int)((std::max<int64_t>(maxN, 1) + zs - 1) / zs);
                 zs = (int)((std::max<int64_t>(maxN, 1) + chunkPts - 1) / chunkPts);
-                if (gate) { zs = 1; chunkPts = (int)std::max<int64_t>(maxN, 1); }     // a gated chunk always fills the machine
+                if (useTc) { zs = 1; chunkPts = (int)std::max<int64_t>(maxN, 1); }    // a chunk big enough for the tensor engine fills the machine
                 if (zs > 1 && !zeroed) MCV_CUDA_TRY(cudaMemsetAsync(dCounts, 0, (size_t)np * slots * 4, st));
                 dim3 g(tiles, np, zs);
                 score_kernel<MODEL><<<g, 128, 0, st>>>(pf, pd, off, dModels, dSlotList, dEnd, (int)slots,
-                                                       thr2, chunkPts, dCounts, gate, dBegin);
+                                                       thr2, chunkPts, dCounts, engineGate, dBegin);
                 MCV_LAUNCH_CHECK();
             }
             return 0;
@@ -2154,13 +2154,14 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
             constexpr int K1 = 128;                       // iterations of phase 1
             const bool twoPhase = prm.stopMode == MCV_STOP_ADAPTIVE && !io.dDbgCounts && !io.dInjModels && maxIters >= 4 * K1;
             kt_begin(ctx, st, KT_SCORE);
-            const int* gate = nullptr;
-            if (tcMode == 2) {
+            const int* gate = nullptr;                    // {models that fit, models looked at} of the pilot
+            if (tcMode == 2 || (tcMode == 1 && twoPhase)) {
                 gate = score_tc_pilot(ctx, st, MODEL, pf, pd, off, np, dModels, dSlotList, dNTotal, (int)slots, thr2);
                 if (!gate) return -1;
             }
+            const int* engineGate = tcMode == 2 ? gate : nullptr;
             if (!twoPhase) {
-                if (score_range(nullptr, dNTotal, gate, false, false)) return -1;
+                if (score_range(nullptr, dNTotal, engineGate, false, tcMode != 0, tcMode != 1)) return -1;
             } else {
                 if (ctx->ws[86].reserve((size_t)chunk * 8 + 64)) return -1;
                 int* dPhaseEnd = ctx->ws[86].as<int>();
@@ -2170,11 +2171,13 @@ int run_model(Context* ctx, cudaStream_t st, const RansacParams& prm, const Rans
                 MCV_CUDA_TRY(cudaMemsetAsync(dCounts, 0, (size_t)np * slots * 4, st));
                 phase_limit_kernel<<<(np + 127) / 128, 128, 0, st>>>(np, maxIters, K1, dNIter, dIterStart, dNTotal, gate, dPhaseEnd);
                 MCV_LAUNCH_CHECK();
-                if (score_range(nullptr, dPhaseEnd, gate, true, false)) return -1;
+                if (score_range(nullptr, dPhaseEnd, engineGate, true, tcMode != 0, tcMode != 1)) return -1;
                 horizon_kernel<<<(np + 127) / 128, 128, 0, st>>>(off, np, maxIters, MAXM, MP, K1, prm.confidence, dNIter, dFlags,
                                                                  dIterStart, dSlotList, dCounts, gate, dPhaseBegin, dPhaseEnd);
                 MCV_LAUNCH_CHECK();
-                if (score_range(dPhaseBegin, dPhaseEnd, gate, true, true)) return -1;
+                // phase 2 is a few iterations per pair when there is any at all: always the fp32-filter kernel (thousands of
+                // tensor-engine CTAs returning at once cost 0.45 ms per chunk when tried)
+                if (score_range(dPhaseBegin, dPhaseEnd, nullptr, true, false, true)) return -1;
             }
             kt_end(ctx, st);
         }

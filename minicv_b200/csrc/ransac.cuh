@@ -60,11 +60,15 @@ int ransac_select(cudaStream_t st, const int64_t* dOff, int np, int maxIters, in
 // Scoring with the tensor-core first-level filter (score_tc.cu): counts [np][slots] over the compacted model lists,
 // identical to score_kernel's.  dOff / hOff point at the chunk's first pair (absolute offsets), pairBase = its index.
 // Uses ctx workspaces 80..85 (86: the two-phase scoring of ransac.cu).
-//   score_tc_mode: 0 = not for this chunk, 1 = tensor cores, 2 = decide on the device: score_tc_pilot scores the first 32
-//   models of every pair on 128 correspondences and leaves {models that fit, models looked at} in the gate; both scoring
-//   kernels are launched and the one the gate does not select returns at once (score_gate_dense).  Level 0 pays when
-//   almost every model is wrong (a RANSAC batch at 30 % inliers); on ratio-tested matches, where every eighth minimal
-//   sample is clean and keeps most of the correspondences, the fp32-filter kernel's occupancy wins.
+//   score_tc_mode: 0 = not for this chunk, 1 = tensor cores, 2 = decide on the device (homography only): score_tc_pilot
+//   scores the first 32 models of every pair on 128 correspondences and leaves {models that fit, models looked at} in the
+//   gate; both scoring kernels are launched and the one the gate does not select returns at once.  Measured
+//   (tools/gate_probe.py, scoring stage of 256 pairs x 2000 x 4096, fp32-filter kernel vs tcgen05, by inlier ratio): H 0.3:
+//   1.61 / 1.01 ms, 0.5: 2.16 / 1.68, 0.6: 2.29 / 2.12, 0.7: 2.30 / 2.62, 0.85: 2.30 / 3.33 -- the crossover is where every
+//   sixth 4-point sample is clean; F 0.3: 3.87 / 2.69, 0.6: 8.51 / 4.50, 0.85: 19.0 / 8.57 -- the tensor engine at every
+//   ratio (its survivors are classified in fp32, the other kernel's dense lanes take the fp64 exact test), likewise E.
+//   The same gate, with a lower bar (1 fitting model in 32), tells the two-phase adaptive stop whether the horizon is
+//   going to shrink at all (ransac.cu).
 int score_tc_mode(int model, int64_t maxN, int slots, int np, int smCount);
 int* score_tc_pilot(Context* ctx, cudaStream_t st, int model, const float4* pf, const double* pd, const int64_t* dOff, int np,
                     const double* dModels, const int* dSlotList, const int* dNTotal, int slots, float thr2);
@@ -74,8 +78,9 @@ int score_tc_run(Context* ctx, cudaStream_t st, int model, const float4* pf, con
                  const int64_t* hOff, int64_t pairBase, int np, const double* dModels, const int* dSlotList,
                  const int* dNTotal, int slots, float thr2, int* dCounts, const int* gate, const int* dBegin,
                  bool haveFeatures);
-// gate = {models that fit, models looked at}: "dense" when more than 1 in 32 of the sampled models fits
-__device__ __forceinline__ bool score_gate_dense(const int* gate) { return gate[0] * 32 > gate[1]; }
+// gate = {models that fit, models looked at}
+__device__ __forceinline__ bool score_gate_classic(const int* gate) { return gate[0] * 6 > gate[1]; }    // engine (H)
+__device__ __forceinline__ bool score_gate_split(const int* gate) { return gate[0] * 32 > gate[1]; }     // two-phase stop
 
 // Asynchronous on `stream`.  Uses ctx workspaces 10..21 and pinned buffer 1.
 int ransac_batch_device(Context* ctx, cudaStream_t stream, const RansacParams& prm, const RansacIO& io);

@@ -91,7 +91,7 @@ score_tc_features_kernel(const float4* __restrict__ pf, const double* __restrict
                          void* __restrict__ sortedRaw, StageBox* __restrict__ boxes, const int* __restrict__ gate) {
     constexpr int isE = MODEL == RM_ESSENTIAL ? 1 : 0;
     constexpr bool isH = MODEL == RM_HOMOGRAPHY;
-    if (gate && score_gate_dense(gate)) return;               // the fp32-filter kernel scores this chunk
+    if (gate && score_gate_classic(gate)) return;             // the fp32-filter kernel scores this chunk
     const int p = blockIdx.x;
     const int64_t base = off[p];
     const int n = (int)(off[p + 1] - base);
@@ -297,13 +297,13 @@ score_tc_kernel(const int64_t* __restrict__ off, int64_t pairBase, const PairNor
     constexpr int isE = MODEL == RM_ESSENTIAL ? 1 : 0;
     constexpr bool isH = MODEL == RM_HOMOGRAPHY;
     constexpr int A_BYTES = ST_ROWS * ST_ROW_BYTES;           // 32 KB
-    if (gate && score_gate_dense(gate)) return;
+    if (gate && score_gate_classic(gate)) return;
     constexpr int B_BYTES = ST_STAGE_BYTES;                   // 9 KB per stage: 64 operand rows + 64 coordinate quadruples
     const int p = blockIdx.y;
     const int total = nTotal[p];
     const int begin = nBegin ? nBegin[p] : 0;               // models [begin, total) of the compacted list
     const int m0 = blockIdx.x * ST_ROWS;
-    if (m0 >= total || m0 + ST_ROWS <= begin) return;
+    if (begin >= total || m0 >= total || m0 + ST_ROWS <= begin) return;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -747,9 +747,10 @@ int score_tc_mode(int model, int64_t maxN, int slots, int np, int smCount) {
     if (maxN >= (1 << 26) || maxN < 1) return 0;
     if (eng == 2) return 1;
     // auto: enough (pair, 256-model) work items to fill the machine twice, enough correspondences per pair to amortise the
-    // per-CTA model conversion; then the device decides from what the models look like
+    // per-CTA model conversion; F / E then always take the tensor engine, H lets the device decide (ransac.cuh)
     const bool big = maxN >= 256 && slots >= 256 && (int64_t)np * ((slots + ST_ROWS - 1) / ST_ROWS) >= 2ll * smCount;
-    return big ? 2 : 0;
+    if (!big) return 0;
+    return model == RM_HOMOGRAPHY ? 2 : 1;
 }
 
 int* score_tc_pilot(Context* ctx, cudaStream_t st, int model, const float4* pf, const double* pd, const int64_t* dOff, int np,
