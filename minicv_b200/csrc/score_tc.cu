@@ -746,11 +746,15 @@ int score_tc_mode(int model, int64_t maxN, int slots, int np, int smCount) {
     if (eng == 1) return 0;
     if (maxN >= (1 << 26) || maxN < 1) return 0;
     if (eng == 2) return 1;
-    // auto: enough (pair, 256-model) work items to fill the machine twice, enough correspondences per pair to amortise the
-    // per-CTA model conversion; F / E then always take the tensor engine, H lets the device decide (ransac.cuh)
-    const bool big = maxN >= 256 && slots >= 256 && (int64_t)np * ((slots + ST_ROWS - 1) / ST_ROWS) >= 2ll * smCount;
-    if (!big) return 0;
-    return model == RM_HOMOGRAPHY ? 2 : 1;
+    // auto: enough correspondences per pair to amortise the per-CTA model conversion, and enough (pair, 256-model) work
+    // items: for H enough to fill the machine twice (below that the fp32-filter kernel, which can also split a pair's
+    // correspondences over blocks, is as fast or faster: tools/gate_probe.py at 1 .. 8 pairs), then the device decides
+    // (ransac.cuh); for F / E 64 items are enough -- at 2 pairs x 44 items the tensor engine costs 0.09 instead of 0.07 ms
+    // at 30 % inliers and 0.18 instead of 0.49 ms at 70 %, where the other kernel's dense lanes take the fp64 exact test
+    const int64_t items = (int64_t)np * ((slots + ST_ROWS - 1) / ST_ROWS);
+    if (maxN < 256 || slots < 256) return 0;
+    if (model == RM_HOMOGRAPHY) return items >= 2ll * smCount ? 2 : 0;
+    return items >= 64 ? 1 : 0;
 }
 
 int* score_tc_pilot(Context* ctx, cudaStream_t st, int model, const float4* pf, const double* pd, const int64_t* dOff, int np,
